@@ -1,0 +1,129 @@
+/*
+ * vtc_b200.h -- C ABI of the B200-native sparse-coding hot path.
+ *
+ * The reference (spencerkent/vision-transform-codes) has no FFI: its plug-in interface is "a Python module with a
+ * run(...) attribute" (vision_transform_codes/training/sparse_coding.py:389-439, called at :139 and :168). Each
+ * entry point below is what the drop-in module of the same dotted name binds through ctypes; the reference function
+ * it replaces is cited per entry point. INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *  - all matrix pointers are DEVICE pointers to row-major float32 (the reference's layout: images (b, n),
+ *    dictionary (s, n) with atoms as rows, codes (b, s));  ld_* are row pitches in elements;
+ *  - the caller owns every buffer, including the workspace (size from the *_workspace_bytes query); the library
+ *    never allocates or frees device memory;
+ *  - every call is enqueued on `stream` and returns without synchronising, except where stated;
+ *  - return value 0 = success; anything else is an error, text via vtc_last_error();
+ *  - there is no CPU fallback: without an sm_100 device every compute entry point fails with VTC_ERR_CUDA.
+ */
+#ifndef VTC_B200_H_
+#define VTC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VTC_OK 0
+#define VTC_ERR_ARG 1        /* bad argument -> AssertionError / ValueError in the Python shim */
+#define VTC_ERR_CUDA 2       /* CUDA runtime / driver failure */
+#define VTC_ERR_WORKSPACE 3  /* workspace too small or misaligned */
+#define VTC_ERR_UNSUPPORTED 4 /* -> NotImplementedError */
+#define VTC_ERR_NONFINITE 5  /* dictionary overflowed -> RuntimeError (ista_fista.py:75-79) */
+
+/* Arithmetic of the tensor-core contractions: number of bf16 x bf16 products per fp32 product.
+ * 1 = plain bf16 operands; 3 = hi/lo split (error ~2^-17, the default "fp32" path); 6 = three-way split (~fp32). */
+#define VTC_PRECISION_BF16 1
+#define VTC_PRECISION_BF16X3 3
+#define VTC_PRECISION_BF16X6 6
+
+#define VTC_VARIANT_ISTA 0
+#define VTC_VARIANT_FISTA 1
+
+typedef void* vtc_stream_t; /* a cudaStream_t */
+
+int vtc_version(void);
+const char* vtc_last_error(void);
+
+/* Number of SMs / compute capability of the current device (used by bench.py to size workloads). */
+int vtc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/*
+ * ISTA / FISTA code inference, fully connected, including the subspace (group-shrinkage) prox.
+ * Replaces analysis_transforms/fully_connected/ista_fista.py:14-148 (run) and, with group_size > 1,
+ * subspace_ista_fista.py:23-192 on a dictionary whose groups are runs of `group_size` adjacent atoms
+ * (the drop-in builds that "grouped dictionary" exactly as subspace_ista_fista.py:94-111 does).
+ *
+ *   images        (B, D) float32, pitch ld_images        -- never written
+ *   dictionary    (S, D) float32, dense                  -- never written
+ *   initial_codes (B, S) float32, pitch ld_codes, or NULL -- never written (tests/ista_fista_1.py:50-54)
+ *   codes_out     (B, S) float32, pitch ld_codes          -- the last thresholded iterate (ista_fista.py:148)
+ *   early_stopping_epsilon < 0 disables early stopping; otherwise the call synchronises the stream once per
+ *   iteration to test mean(|a_k - a_{k-1}|)/stepsize < eps and k > 1 (ista_fista.py:135-144).
+ *   iters_run, lipschitz_out: optional HOST outputs; passing lipschitz_out forces one stream synchronisation and
+ *   enables the non-finite-dictionary check (VTC_ERR_NONFINITE).
+ */
+size_t vtc_fista_workspace_bytes(int64_t B, int64_t S, int64_t D, int precision);
+int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary, const float* initial_codes,
+                 float* codes_out, int64_t ld_codes, int64_t B, int64_t S, int64_t D, float sparsity_weight,
+                 int num_iters, int variant, int nonnegative_only, int hard_threshold, int group_size,
+                 float early_stopping_epsilon, int precision, void* workspace, size_t workspace_bytes,
+                 int* iters_run, float* lipschitz_out, vtc_stream_t stream);
+
+/*
+ * Sparse-coding dictionary gradient  grad_sum = codes^T (codes * dictionary - images)   (S, D), NOT divided by B.
+ * First half of dict_update_rules/fully_connected/sc_cheap_quadratic_descent.py:43-44 (and sc_steepest_descent.py:
+ * 38-39). Kept separate from the apply step so that a data-parallel caller can all-reduce grad_sum in between.
+ */
+size_t vtc_dict_grad_workspace_bytes(int64_t B, int64_t S, int64_t D, int precision);
+int vtc_sc_dict_grad(const float* images, int64_t ld_images, const float* dictionary, const float* codes,
+                     int64_t ld_codes, float* grad_sum, int64_t B, int64_t S, int64_t D, int precision,
+                     void* workspace, size_t workspace_bytes, vtc_stream_t stream);
+
+/*
+ * Apply step, in place on `dictionary`:
+ *   U = stepsize * (grad_sum / batch_global); if hessian_diagonal: U /= (h + lowest_code_val); dictionary -= U;
+ *   if normalize: every row divided by its L2 norm.
+ * sc_cheap_quadratic_descent.py:43-48; hessian_diagonal == NULL gives sc_steepest_descent.py:37-41.
+ */
+int vtc_sc_dict_apply(float* dictionary, const float* grad_sum, const float* hessian_diagonal, int64_t S, int64_t D,
+                      int64_t batch_global, float stepsize, float lowest_code_val, int normalize,
+                      vtc_stream_t stream);
+
+/*
+ * Hessian-diagonal running average kept by the trainer (training/sparse_coding.py:154):
+ *   h <- 0.99 * h + colmean(codes^2) / 100, with the mean taken over batch_global rows.
+ * code_sq_sum (S,) receives sum_rows codes^2 of THIS shard (so it can be all-reduced); pass apply_ema = 1 to fold
+ * it into h directly (single GPU).
+ */
+int vtc_hessian_diag_update(const float* codes, int64_t ld_codes, int64_t B, int64_t S, int64_t batch_global,
+                            float* code_sq_sum, float* hessian_diagonal, int apply_ema, vtc_stream_t stream);
+
+/*
+ * Generic contraction exposed for tests and tools: out (M, N) = A (M, K) * B (N, K)^T [- sub (M, N)], float32 in and
+ * out, computed on the tcgen05 path with the requested precision.
+ */
+size_t vtc_matmul_nt_workspace_bytes(int64_t M, int64_t N, int64_t K, int precision);
+int vtc_matmul_nt(const float* A, const float* B, const float* sub, float* out, int64_t M, int64_t N, int64_t K,
+                  int precision, void* workspace, size_t workspace_bytes, vtc_stream_t stream);
+
+/* Largest eigenvalue of dictionary^T dictionary (ista_fista.py:72-74), written to a DEVICE float. */
+size_t vtc_lipschitz_workspace_bytes(int64_t S, int64_t D);
+int vtc_lipschitz(const float* dictionary, int64_t S, int64_t D, float* lipschitz_dev, void* workspace,
+                  size_t workspace_bytes, vtc_stream_t stream);
+
+/* Subspace helpers (subspace_ista_fista.py:94-111 and :184-190): gather dictionary rows into the padded grouped
+ * dictionary, gather initial codes, and scatter-add grouped codes back. index (n_slots,) int32 on the device holds
+ * the atom of each slot or -1 for padding. */
+int vtc_gather_rows(const float* src, int64_t ld_src, const int32_t* index, int64_t n_slots, int64_t D, float* dst,
+                    vtc_stream_t stream);
+int vtc_gather_cols(const float* src, int64_t ld_src, const int32_t* index, int64_t B, int64_t n_slots, float* dst,
+                    int64_t ld_dst, vtc_stream_t stream);
+int vtc_scatter_add_cols(const float* src, int64_t ld_src, const int32_t* index, int64_t B, int64_t n_slots,
+                         float* dst, int64_t ld_dst, int64_t S, vtc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTC_B200_H_ */

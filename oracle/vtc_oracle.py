@@ -1,0 +1,235 @@
+"""
+CPU oracle for the sparse-coding hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A restatement, in plain float32 (or float64) PyTorch on the CPU, of what the reference
+(spencerkent/vision-transform-codes) computes on this path. Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module; nothing under vision_transform_codes_b200/ does.
+
+Pinning: the reference's own tests hold no numeric golden vectors, so this oracle is pinned
+against OUTPUTS OF THE REFERENCE ITSELF, generated in the authoring container by tests/golden/make_golden.py (which
+imports /root/reference with a torch.symeig shim) and committed as tests/golden/*.npz; tests/test_oracle.py checks
+every function below against those files, plus closed-form known answers (orthonormal dictionary, groups of one).
+
+Reference lines followed (paths relative to vision_transform_codes/):
+  step size            analysis_transforms/fully_connected/ista_fista.py:72-80
+  gradient step        ista_fista.py:105-106
+  thresholds           ista_fista.py:107-121
+  FISTA momentum       ista_fista.py:123-133
+  early stopping       ista_fista.py:135-144
+  subspace grouping    analysis_transforms/fully_connected/subspace_ista_fista.py:94-123, :184-190
+  group shrinkage      subspace_ista_fista.py:144-156
+  dictionary update    dict_update_rules/fully_connected/sc_cheap_quadratic_descent.py:42-48, sc_steepest_descent.py:37-41
+  Hessian running mean training/sparse_coding.py:154
+  train step           training/sparse_coding.py:513-515
+"""
+import torch
+
+
+def lipschitz_constant(dictionary):
+  """Largest eigenvalue of dictionary^T dictionary (n x n), as the reference's symeig(...)[0][-1]."""
+  return torch.linalg.eigvalsh(torch.mm(dictionary.t(), dictionary))[-1]
+
+
+def momentum_coefficients(num_iters):
+  """beta_k = (t_k - 1) / t_{k+1}, t_1 = 1, t_{k+1} = (1 + sqrt(1 + 4 t_k^2)) / 2, in Python doubles."""
+  t_k, out = 1.0, []
+  for _ in range(num_iters):
+    t_next = (1 + (1 + (4 * t_k**2))**0.5) / 2
+    out.append((t_k - 1) / t_next)
+    t_k = t_next
+  return out
+
+
+def threshold(pre, cutoff, nonnegative_only=False, hard_threshold=False):
+  """The four scalar proximal maps of ista_fista.py:107-121, applied out of place."""
+  if hard_threshold:
+    out = pre.clone()
+    if nonnegative_only:
+      out[out < cutoff] = 0
+    else:
+      out[torch.abs(out) < cutoff] = 0
+    return out
+  if nonnegative_only:
+    return (pre - cutoff).clamp_(min=0.)
+  return torch.sign(pre) * (torch.abs(pre) - cutoff).clamp_(min=0.)
+
+
+def _iterate(images, synthesis, prox, num_iters, variant, start, early_stopping_epsilon, stepsize):
+  """
+  Common ISTA/FISTA loop: `synthesis` is the (possibly grouped) dictionary, `start` the first gradient-evaluation
+  point (flattened codes), `prox` maps the pre-threshold codes to the thresholded ones.
+  Returns (codes, iterations run).
+  """
+  assert variant in ['ista', 'fista']
+  eval_pt = start
+  previous = start.clone()
+  betas = momentum_coefficients(num_iters)
+  codes = None
+  done = 0
+  for k in range(num_iters):
+    residual = torch.mm(eval_pt, synthesis) - images
+    codes = prox(eval_pt - stepsize * torch.mm(residual, synthesis.t()))
+    change = codes - previous
+    if variant == 'fista':
+      eval_pt = codes + betas[k] * change
+    else:
+      eval_pt = codes
+    previous = codes
+    done = k + 1
+    if early_stopping_epsilon is not None:
+      if bool(torch.mean(torch.abs(change) / stepsize) < early_stopping_epsilon) and k > 0:
+        break
+  return codes, done
+
+
+def ista_fista(images, dictionary, sparsity_weight, num_iters, variant='fista', initial_codes=None,
+               early_stopping_epsilon=None, nonnegative_only=False, hard_threshold=False, return_iters=False):
+  """analysis_transforms/fully_connected/ista_fista.py:14-148."""
+  stepsize = 1. / lipschitz_constant(dictionary)
+  cutoff = sparsity_weight * stepsize
+  if initial_codes is None:
+    start = images.new_zeros(images.size(0), dictionary.size(0))
+  else:
+    start = initial_codes
+  codes, done = _iterate(images, dictionary, lambda pre: threshold(pre, cutoff, nonnegative_only, hard_threshold),
+                         num_iters, variant, start, early_stopping_epsilon, stepsize)
+  return (codes, done) if return_iters else codes
+
+
+def subspace_ista_fista(images, dictionary, group_assignments, sparsity_weight, num_iters, variant='fista',
+                        initial_codes=None, early_stopping_epsilon=None, return_iters=False):
+  """analysis_transforms/fully_connected/subspace_ista_fista.py:23-192 (soft group threshold, summed duplicates)."""
+  num_groups = len(group_assignments)
+  width = max(len(g) for g in group_assignments)
+  b = images.size(0)
+  # slot (g, j) of the padded layout holds atom group_assignments[g][j]; padding slots have a zero synthesis row
+  grouped_dictionary = images.new_zeros(num_groups * width, dictionary.size(1))
+  start = images.new_zeros(b, num_groups * width)
+  for g, members in enumerate(group_assignments):
+    members = list(members)
+    grouped_dictionary[g * width:g * width + len(members)] = dictionary[members]
+    if initial_codes is not None:
+      start[:, g * width:g * width + len(members)] = initial_codes[:, members]
+  stepsize = 1. / lipschitz_constant(grouped_dictionary)
+  cutoff = sparsity_weight * stepsize
+
+  def group_shrink(pre):
+    pre3 = pre.view(b, num_groups, width)
+    norms = torch.norm(pre3, p=2, dim=2, keepdim=True)
+    norms[norms == 0] = 1.0
+    return (pre3 * torch.clamp(1 - (cutoff / norms), min=0.)).reshape(b, num_groups * width)
+
+  grouped, done = _iterate(images, grouped_dictionary, group_shrink, num_iters, variant, start,
+                           early_stopping_epsilon, stepsize)
+  codes = images.new_zeros(b, dictionary.size(0))
+  for g, members in enumerate(group_assignments):
+    members = list(members)
+    codes[:, members] = codes[:, members] + grouped[:, g * width:g * width + len(members)]
+  return (codes, done) if return_iters else codes
+
+
+def sc_dictionary_update(images, dictionary, codes, hessian_diagonal=None, stepsize=0.001, num_iters=1,
+                         lowest_code_val=0.001, normalize_dictionary=True, batch_size=None, extra_gradient=None):
+  """
+  sc_cheap_quadratic_descent.py:42-48 (hessian_diagonal given) / sc_steepest_descent.py:37-41 (None).
+  Returns the updated dictionary (the reference updates in place; the oracle is functional).
+  batch_size overrides the divisor (global batch of a data-parallel step); extra_gradient is the summed gradient
+  contribution of the other shards for the FIRST iteration.
+  """
+  phi = dictionary.clone()
+  divisor = codes.size(0) if batch_size is None else batch_size
+  for it in range(num_iters):
+    gradient = torch.mm(codes.t(), torch.mm(codes, phi) - images)
+    if extra_gradient is not None and it == 0:
+      gradient = gradient + extra_gradient
+    update = stepsize * (gradient / divisor)
+    if hessian_diagonal is not None:
+      update = update / (hessian_diagonal[:, None] + lowest_code_val)
+    phi = phi - update
+    if normalize_dictionary:
+      phi = phi / phi.norm(p=2, dim=1)[:, None]
+  return phi
+
+
+def hessian_running_mean(hessian_diagonal, codes):
+  """training/sparse_coding.py:154 (functional)."""
+  return hessian_diagonal * 0.99 + torch.pow(codes, 2).mean(0) / 100
+
+
+def train_steps(batches, dictionary, sparsity_weight, num_iters, stepsize, variant='fista',
+                update_rule='sc_cheap_quadratic_descent', group_assignments=None):
+  """
+  The per-batch body of train_dictionary (training/sparse_coding.py:513-515 with :139, :154, :168): infer codes,
+  update the Hessian running mean, update the dictionary. Returns (dictionary, hessian_diagonal, last codes).
+  """
+  phi = dictionary.clone()
+  h = dictionary.new_zeros(dictionary.size(0))
+  codes = None
+  for x in batches:
+    if group_assignments is None:
+      codes = ista_fista(x, phi, sparsity_weight, num_iters, variant=variant)
+    else:
+      codes = subspace_ista_fista(x, phi, group_assignments, sparsity_weight, num_iters, variant=variant)
+    if update_rule.endswith('cheap_quadratic_descent'):
+      h = hessian_running_mean(h, codes)
+      phi = sc_dictionary_update(x, phi, codes, h, stepsize=stepsize)
+    else:
+      phi = sc_dictionary_update(x, phi, codes, None, stepsize=stepsize)
+  return phi, h, codes
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Seeded synthetic inputs; shared by tests, smoke() and bench.py so that the CUDA path and the
+# oracle always see identical tensors.
+def synthetic_dictionary(num_atoms, num_pixels, seed=1):
+  g = torch.Generator().manual_seed(seed)
+  phi = torch.randn(num_atoms, num_pixels, generator=g)
+  return phi / phi.norm(dim=1, keepdim=True)
+
+
+def synthetic_patches(batch, num_pixels, seed=0, kind='gaussian', std=0.3):
+  """'gaussian': x = std * randn.  'whitened': 1/f noise images passed through the reference's center-surround
+  whitening filter max(|f|,1e-3) * exp(-(|f| / 0.45)^8) (utils/image_processing.py:267-308), random crops,
+  globally rescaled to the requested per-pixel std."""
+  g = torch.Generator().manual_seed(seed)
+  if kind == 'gaussian':
+    return std * torch.randn(batch, num_pixels, generator=g)
+  side = int(round(num_pixels**0.5))
+  assert side * side == num_pixels, 'whitened patches must be square'
+  size = 256
+  fy = torch.fft.fftfreq(size)[:, None]
+  fx = torch.fft.fftfreq(size)[None, :]
+  rad = torch.sqrt(fy**2 + fx**2)
+  amp = 1.0 / torch.clamp(rad, min=1.0 / size)
+  whiten = torch.clamp(rad, min=1e-3) * torch.exp(-(rad / (0.5 * 0.9))**8)
+  per_image = 1024
+  num_images = (batch + per_image - 1) // per_image
+  out = torch.empty(num_images * per_image, num_pixels)
+  for i in range(num_images):
+    phase = torch.rand(size, size, generator=g) * 2 * torch.pi
+    spectrum = amp * torch.exp(1j * phase)
+    img = torch.fft.ifft2(spectrum).real
+    img = (img - img.min()) / (img.max() - img.min())
+    img = torch.fft.ifft2(torch.fft.fft2(img) * whiten).real
+    ys = torch.randint(5, size - side - 5, (per_image,), generator=g)
+    xs = torch.randint(5, size - side - 5, (per_image,), generator=g)
+    idx_y = ys[:, None, None] + torch.arange(side)[None, :, None]
+    idx_x = xs[:, None, None] + torch.arange(side)[None, None, :]
+    out[i * per_image:(i + 1) * per_image] = img[idx_y, idx_x].reshape(per_image, num_pixels)
+  out = out[:batch]
+  return (out * (std / out.std())).float().contiguous()
+
+
+def relative_l2(a, b):
+  return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-300))
+
+
+def support_mismatches(a, b, band=0.0):
+  """
+  Entries whose zero / non-zero status differs between a and b, as (total, outside_band): a flip whose non-zero
+  side is no larger than `band` is a tie at the threshold and is not counted in
+  outside_band.
+  """
+  flipped = (a != 0) != (b != 0)
+  magnitude = torch.maximum(a.abs(), b.abs())
+  return int(flipped.sum()), int((flipped & (magnitude > band)).sum())

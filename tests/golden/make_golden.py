@@ -1,0 +1,146 @@
+"""
+Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on the CPU in float32.
+
+Run in the authoring container only (the GPU box has no /root/reference):  python tests/golden/make_golden.py
+Two non-invasive shims are applied before import, neither edits the reference:
+  * torch.symeig (removed from torch) -> torch.linalg.eigvalsh with the same conventions
+  * utils.plotting stubbed in sys.modules (it imports skimage / matplotlib, absent here) for the trainer
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = '/root/reference/vision_transform_codes'
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+torch.symeig = lambda A, eigenvectors=False, upper=True: (
+    torch.linalg.eigvalsh(A, UPLO='U' if upper else 'L'), None)
+sys.modules['utils.plotting'] = types.ModuleType('utils.plotting')
+sys.path.insert(0, REF)
+
+from analysis_transforms.fully_connected import ista_fista  # noqa: E402
+from analysis_transforms.fully_connected import subspace_ista_fista  # noqa: E402
+from dict_update_rules.fully_connected import sc_cheap_quadratic_descent  # noqa: E402
+from dict_update_rules.fully_connected import sc_steepest_descent  # noqa: E402
+from training import sparse_coding  # noqa: E402
+
+torch.set_num_threads(4)
+
+
+def dictionary(s, n, seed=1):
+  g = torch.Generator().manual_seed(seed)
+  phi = torch.randn(s, n, generator=g)
+  return phi / phi.norm(dim=1, keepdim=True)
+
+
+def patches(b, n, seed=0, std=0.3):
+  g = torch.Generator().manual_seed(seed)
+  return std * torch.randn(b, n, generator=g)
+
+
+def save(name, **arrays):
+  out = {k: (v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in arrays.items()}
+  np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+  print(name, {k: v.shape for k, v in out.items()})
+
+
+def make_inference():
+  b, n, s, T, lam = 48, 64, 128, 60, 0.1
+  x, phi = patches(b, n), dictionary(s, n)
+  warm = ista_fista.run(x, phi, lam, 5, variant='fista')
+  save('inference_small', images=x, dictionary=phi, sparsity_weight=lam, num_iters=T, warm_start=warm,
+       fista=ista_fista.run(x, phi, lam, T, variant='fista'),
+       ista=ista_fista.run(x, phi, lam, T, variant='ista'),
+       fista_nonneg=ista_fista.run(x, phi, lam, T, variant='fista', nonnegative_only=True),
+       fista_hard=ista_fista.run(x, phi, lam, T, variant='fista', hard_threshold=True),
+       ista_hard_nonneg=ista_fista.run(x, phi, lam, T, variant='ista', hard_threshold=True, nonnegative_only=True),
+       fista_warm=ista_fista.run(x, phi, lam, T, variant='fista', initial_codes=warm),
+       ista_early=ista_fista.run(x, phi, lam, 1000, variant='ista', early_stopping_epsilon=1e-3),
+       fista_early=ista_fista.run(x, phi, lam, 1000, variant='fista', early_stopping_epsilon=1e-3))
+
+
+def make_config1():
+  # BASELINE.json configs[0]: 16x16 patches, 256 atoms, batch 250, 300 iterations, lambda 0.1
+  b, n, s, T, lam = 250, 256, 256, 300, 0.1
+  x, phi = patches(b, n), dictionary(s, n)
+  save('inference_config1', images=x, dictionary=phi, sparsity_weight=lam, num_iters=T,
+       fista=ista_fista.run(x, phi, lam, T, variant='fista'))
+
+
+def make_overcomplete():
+  # configs[1] shape (D=256, 1024 atoms) on a 96-patch sub-batch
+  b, n, s, T, lam = 96, 256, 1024, 300, 0.1
+  x, phi = patches(b, n), dictionary(s, n)
+  save('inference_overcomplete', images=x, dictionary=phi, sparsity_weight=lam, num_iters=T,
+       fista=ista_fista.run(x, phi, lam, T, variant='fista'))
+
+
+def make_subspace():
+  b, n, s, T, lam = 40, 48, 64, 50, 0.1
+  x, phi = patches(b, n), dictionary(s, n)
+  pairs = [list(g) for g in np.array_split(np.arange(s), s // 2)]
+  quads = [list(g) for g in np.array_split(np.arange(s), s // 4)]
+  ragged = [[0, 2, 5], [1], [2, 3, 4, 5], [6, 7, 8, 9, 10], [11, 12], [13, 14, 15, 16, 17, 18, 19]]
+  warm = subspace_ista_fista.run(x, phi, pairs, lam, 5)
+  save('subspace_small', images=x, dictionary=phi, sparsity_weight=lam, num_iters=T, warm_start=warm,
+       ragged_sizes=np.array([len(g) for g in ragged]), ragged_flat=np.concatenate([np.array(g) for g in ragged]),
+       pairs_fista=subspace_ista_fista.run(x, phi, pairs, lam, T, variant='fista'),
+       pairs_ista=subspace_ista_fista.run(x, phi, pairs, lam, T, variant='ista'),
+       quads_fista=subspace_ista_fista.run(x, phi, quads, lam, T, variant='fista'),
+       ragged_fista=subspace_ista_fista.run(x, phi, ragged, lam, T, variant='fista'),
+       pairs_warm=subspace_ista_fista.run(x, phi, pairs, lam, T, variant='fista', initial_codes=warm),
+       pairs_early=subspace_ista_fista.run(x, phi, pairs, lam, 1000, variant='ista', early_stopping_epsilon=1e-3))
+
+
+def make_dict_update():
+  b, n, s, lam = 96, 64, 128, 0.1
+  x, phi = patches(b, n), dictionary(s, n)
+  codes = ista_fista.run(x, phi, lam, 40)
+  h = torch.pow(codes, 2).mean(0) / 100
+  d1 = phi.clone()
+  sc_cheap_quadratic_descent.run(x, d1, codes, h, stepsize=0.1, num_iters=1)
+  d2 = phi.clone()
+  sc_cheap_quadratic_descent.run(x, d2, codes, h, stepsize=0.05, num_iters=3)
+  d3 = phi.clone()
+  sc_steepest_descent.run(x, d3, codes, stepsize=0.1, num_iters=1)
+  d4 = phi.clone()
+  sc_steepest_descent.run(x, d4, codes, stepsize=0.1, num_iters=2, normalize_dictionary=False)
+  save('dict_update_small', images=x, dictionary=phi, codes=codes, hessian_diagonal=h,
+       cheap_1=d1, cheap_3=d2, steepest_1=d3, steepest_2_unnormalized=d4)
+
+
+def make_training():
+  # 4 steps of the unmodified train_dictionary: fista(30) + cheap quadratic descent
+  nb, b, n, s = 4, 64, 64, 128
+  x = patches(nb * b, n).view(nb, b, n)
+  phi0 = dictionary(s, n)
+  params = {
+      'mode': 'fully-connected', 'num_epochs': 1,
+      'code_inference_algorithm': 'fista',
+      'inference_param_schedule': {0: {'sparsity_weight': 0.1, 'num_iters': 30}},
+      'dictionary_update_algorithm': 'sc_cheap_quadratic_descent',
+      'dict_update_param_schedule': {0: {'stepsize': 0.1, 'num_iters': 1}}}
+  phi = phi0.clone()
+  sparse_coding.train_dictionary(x, x[:1], phi, params)
+  params2 = dict(params, code_inference_algorithm='ista', dictionary_update_algorithm='sc_steepest_descent')
+  phi_b = phi0.clone()
+  sparse_coding.train_dictionary(x, x[:1], phi_b, params2)
+  pairs = [list(map(int, g)) for g in np.array_split(np.arange(s), s // 2)]
+  params3 = dict(params, code_inference_algorithm='subspace_fista',
+                 dictionary_update_algorithm='subspace_sc_cheap_quadratic_descent',
+                 group_assignments=pairs, subspace_alignment_penalty=0.0)
+  phi_c = phi0.clone()
+  sparse_coding.train_dictionary(x, x[:1], phi_c, params3)
+  save('training_small', batches=x, dictionary=phi0, fista_cheap=phi, ista_steepest=phi_b, subspace_cheap=phi_c)
+
+
+if __name__ == '__main__':
+  make_inference()
+  make_config1()
+  make_overcomplete()
+  make_subspace()
+  make_dict_update()
+  make_training()

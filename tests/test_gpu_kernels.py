@@ -1,0 +1,98 @@
+"""Building blocks on the GPU: the tcgen05 contraction, the Lipschitz constant, the subspace gathers."""
+import ctypes
+
+import pytest
+import torch
+
+from oracle import vtc_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def matmul_nt(a, b, sub=None, precision=3):
+  from vision_transform_codes_b200 import _lib
+  lib = _lib.load()
+  M, K = a.shape
+  N = b.shape[0]
+  out = torch.empty(M, N, device=a.device)
+  ws = _lib.workspace(lib.vtc_matmul_nt_workspace_bytes(M, N, K, precision), a.device, 'matmul')
+  _lib.check(lib.vtc_matmul_nt(_lib.ptr(a), _lib.ptr(b), _lib.ptr(sub), _lib.ptr(out), M, N, K, precision,
+                               _lib.ptr(ws), ws.numel(), _lib.stream_ptr(a.device)))
+  torch.cuda.synchronize()
+  return out
+
+
+# relative Frobenius error of the product for each arithmetic mode
+TOL = {1: 6e-3, 3: 3e-5, 6: 2e-6}
+
+
+@pytest.mark.parametrize('shape', [(128, 256, 64), (256, 512, 256), (250, 256, 256), (1000, 200, 72),
+                                   (37, 20, 10), (4096, 1024, 1024), (129, 257, 65)])
+@pytest.mark.parametrize('precision', [1, 3, 6])
+def test_matmul_nt_against_float64(shape, precision):
+  M, N, K = shape
+  g = torch.Generator().manual_seed(M + N + K)
+  a = torch.randn(M, K, generator=g).cuda()
+  b = torch.randn(N, K, generator=g).cuda()
+  want = a.double() @ b.double().t()
+  got = matmul_nt(a, b, precision=precision)
+  err = float((got.double() - want).norm() / want.norm())
+  assert err < TOL[precision], err
+
+
+def test_matmul_nt_subtracts_in_the_epilogue():
+  g = torch.Generator().manual_seed(0)
+  a, b = torch.randn(300, 96, generator=g).cuda(), torch.randn(520, 96, generator=g).cuda()
+  sub = torch.randn(300, 520, generator=g).cuda()
+  want = a.double() @ b.double().t() - sub.double()
+  got = matmul_nt(a, b, sub=sub, precision=6)
+  assert float((got.double() - want).norm() / want.norm()) < 2e-6
+
+
+def test_matmul_nt_is_deterministic():
+  g = torch.Generator().manual_seed(1)
+  a, b = torch.randn(512, 320, generator=g).cuda(), torch.randn(768, 320, generator=g).cuda()
+  assert torch.equal(matmul_nt(a, b), matmul_nt(a, b))
+
+
+@pytest.mark.parametrize('shape', [(256, 256), (1024, 256), (64, 48), (300, 100), (4096, 1024)])
+def test_lipschitz_constant(shape):
+  from vision_transform_codes_b200 import _lib
+  lib = _lib.load()
+  S, D = shape
+  phi = oracle.synthetic_dictionary(S, D).cuda()
+  out = torch.zeros(1, device='cuda')
+  ws = _lib.workspace(lib.vtc_lipschitz_workspace_bytes(S, D), phi.device, 'lip')
+  _lib.check(lib.vtc_lipschitz(_lib.ptr(phi), S, D, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                               _lib.stream_ptr(phi.device)))
+  want = torch.linalg.eigvalsh(phi.double().cpu().t() @ phi.double().cpu())[-1]
+  assert abs(float(out.item()) - float(want)) / float(want) < 1e-6
+
+
+def test_lipschitz_clustered_spectrum():
+  # two nearly equal top eigenvalues: the squaring iteration must still land inside the cluster
+  from vision_transform_codes_b200 import _lib
+  lib = _lib.load()
+  q, _ = torch.linalg.qr(torch.randn(64, 64, generator=torch.Generator().manual_seed(5)))
+  sv = torch.ones(64)
+  sv[0], sv[1] = 2.0, 2.0 * (1 - 1e-6)
+  phi = (q * sv[None, :]).cuda().contiguous()  # phi^T phi = diag(sv^2)
+  out = torch.zeros(1, device='cuda')
+  ws = _lib.workspace(lib.vtc_lipschitz_workspace_bytes(64, 64), phi.device, 'lip')
+  _lib.check(lib.vtc_lipschitz(_lib.ptr(phi), 64, 64, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                               _lib.stream_ptr(phi.device)))
+  assert abs(float(out.item()) - 4.0) / 4.0 < 5e-6
+
+
+def test_hessian_diagonal_running_mean():
+  from vision_transform_codes_b200 import _lib
+  lib = _lib.load()
+  g = torch.Generator().manual_seed(2)
+  codes = torch.randn(777, 130, generator=g).cuda()
+  h = torch.rand(130, generator=g).cuda()
+  want = oracle.hessian_running_mean(h.cpu(), codes.cpu())
+  sq = torch.empty(130, device='cuda')
+  _lib.check(lib.vtc_hessian_diag_update(_lib.ptr(codes), 130, 777, 130, 777, _lib.ptr(sq), _lib.ptr(h), 1,
+                                         _lib.stream_ptr(codes.device)))
+  torch.cuda.synchronize()
+  assert oracle.relative_l2(h.cpu(), want) < 1e-6

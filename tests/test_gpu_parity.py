@@ -1,0 +1,232 @@
+"""
+Parity of the CUDA path (called through the drop-in modules -> ctypes -> C ABI) with the oracle and with the
+committed outputs of the reference. Tolerances are the ones BASELINE.json's north_star states: relative L2 <= 1e-4
+on codes and reconstructions for the float32-parity path (bf16x3 arithmetic), identical supports outside a guard
+band around the threshold; the plain-bf16 path has its own, looser tolerance.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, ragged_groups
+from oracle import vtc_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+CODE_TOL = 1e-4       # north_star: relative L2 on codes, float32-parity path
+RECON_TOL = 1e-4      # north_star: relative L2 on reconstructions
+BF16_CODE_TOL = 5e-2  # separately toleranced plain-bf16 path
+BF16_RECON_TOL = 1e-2
+GUARD_BAND = 1e-4     # a support flip whose non-zero side is below this is a tie at the threshold
+
+
+@pytest.fixture(autouse=True)
+def default_precision():
+  import vision_transform_codes_b200 as pkg
+  saved = (pkg.config.precision, pkg.config.update_precision)
+  pkg.config.precision, pkg.config.update_precision = 'bf16x3', 'bf16x6'
+  yield
+  pkg.config.precision, pkg.config.update_precision = saved
+
+
+def modules():
+  from vision_transform_codes_b200.analysis_transforms.fully_connected import ista_fista, subspace_ista_fista
+  from vision_transform_codes_b200.dict_update_rules.fully_connected import (
+      sc_cheap_quadratic_descent, sc_steepest_descent, subspace_sc_cheap_quadratic_descent)
+  return ista_fista, subspace_ista_fista, sc_cheap_quadratic_descent, sc_steepest_descent, \
+      subspace_sc_cheap_quadratic_descent
+
+
+def check_codes(got, want, phi, tol=CODE_TOL, recon_tol=RECON_TOL, band=GUARD_BAND):
+  got = got.cpu()
+  assert got.shape == want.shape and got.dtype == torch.float32
+  assert torch.isfinite(got).all()
+  err = oracle.relative_l2(got, want)
+  rerr = oracle.relative_l2(got @ phi, want @ phi)
+  flips, outside = oracle.support_mismatches(got, want, band=band)
+  assert err <= tol, ('codes', err)
+  assert rerr <= recon_tol, ('recon', rerr)
+  if band is not None:
+    assert outside == 0, ('support', flips, outside)
+  return err, rerr, flips
+
+
+def test_inference_call_matrix_against_reference_outputs():
+  """The call matrix of the reference's tests/ista_fista_1.py on the committed reference outputs."""
+  ista_fista = modules()[0]
+  g = load_golden('inference_small')
+  x, phi, lam, T = g['images'], g['dictionary'], g['sparsity_weight'], g['num_iters']
+  xd, pd = x.cuda(), phi.cuda()
+  keep_x, keep_p = xd.clone(), pd.clone()
+  check_codes(ista_fista.run(xd, pd, lam, T), g['fista'], phi)
+  check_codes(ista_fista.run(xd, pd, lam, T, 'ista'), g['ista'], phi)
+  check_codes(ista_fista.run(xd, pd, lam, T, nonnegative_only=True), g['fista_nonneg'], phi)
+  # hard thresholding is discontinuous: a tie at the cutoff moves a whole coefficient, so compare away from ties
+  check_codes(ista_fista.run(xd, pd, lam, T, hard_threshold=True), g['fista_hard'], phi, tol=2e-2, recon_tol=2e-2,
+              band=None)
+  check_codes(ista_fista.run(xd, pd, lam, T, variant='ista', hard_threshold=True, nonnegative_only=True),
+              g['ista_hard_nonneg'], phi, tol=2e-2, recon_tol=2e-2, band=None)
+  warm = g['warm_start'].cuda()
+  keep_w = warm.clone()
+  out = ista_fista.run(xd, pd, lam, T, initial_codes=warm)
+  check_codes(out, g['fista_warm'], phi)
+  # the reference's own assertions (tests/ista_fista_1.py:45-54): nothing passed in is mutated
+  assert torch.equal(xd, keep_x) and torch.equal(pd, keep_p) and torch.equal(warm, keep_w)
+  assert not torch.allclose(out, warm)
+
+
+def test_early_stopping_matches_reference_outputs():
+  ista_fista = modules()[0]
+  g = load_golden('inference_small')
+  x, phi, lam = g['images'], g['dictionary'], g['sparsity_weight']
+  xd, pd = x.cuda(), phi.cuda()
+  for variant, key in (('ista', 'ista_early'), ('fista', 'fista_early')):
+    _, want_iters = oracle.ista_fista(x, phi, lam, 1000, variant=variant, early_stopping_epsilon=1e-3,
+                                      return_iters=True)
+    got, iters = ista_fista.infer(xd, pd, lam, 1000, variant, None, 1e-3, False, False, 1)
+    assert abs(iters - want_iters) <= 1, (iters, want_iters)
+    check_codes(got, g[key], phi, tol=2e-3, recon_tol=2e-3, band=None)
+
+
+@pytest.mark.parametrize('name', ['inference_config1', 'inference_overcomplete'])
+def test_baseline_config_shapes_against_reference_outputs(name):
+  ista_fista = modules()[0]
+  g = load_golden(name)
+  phi = g['dictionary']
+  got = ista_fista.run(g['images'].cuda(), phi.cuda(), g['sparsity_weight'], g['num_iters'])
+  check_codes(got, g['fista'], phi)
+
+
+@pytest.mark.parametrize('precision,tol,rtol', [('bf16x6', 2e-5, 1e-5), ('bf16x3', CODE_TOL, RECON_TOL),
+                                                ('bf16', BF16_CODE_TOL, BF16_RECON_TOL)])
+def test_precision_modes_on_overcomplete_shape(precision, tol, rtol):
+  import vision_transform_codes_b200 as pkg
+  ista_fista = modules()[0]
+  pkg.config.precision = precision
+  g = load_golden('inference_overcomplete')
+  phi = g['dictionary']
+  got = ista_fista.run(g['images'].cuda(), phi.cuda(), g['sparsity_weight'], g['num_iters'])
+  check_codes(got, g['fista'], phi, tol=tol, recon_tol=rtol, band=GUARD_BAND if precision != 'bf16' else None)
+
+
+def test_oracle_parity_on_seeded_whitened_patches():
+  """C2 shape (D=256, 1024 atoms, 300 FISTA iterations, lambda 0.1) on a 512-patch sub-batch of whitened patches."""
+  ista_fista = modules()[0]
+  phi = oracle.synthetic_dictionary(1024, 256)
+  x = oracle.synthetic_patches(512, 256, kind='whitened')
+  want = oracle.ista_fista(x, phi, 0.1, 300)
+  got = ista_fista.run(x.cuda(), phi.cuda(), 0.1, 300)
+  err, rerr, flips = check_codes(got, want, phi)
+  print('codes rel-L2 %.3e recon rel-L2 %.3e support flips %d / %d' % (err, rerr, flips, want.numel()))
+
+
+@pytest.mark.parametrize('shape', [(250, 256, 256), (130, 200, 100), (77, 36, 20), (300, 1000, 256)])
+def test_ragged_shapes_against_oracle(shape):
+  ista_fista = modules()[0]
+  B, S, D = shape
+  phi = oracle.synthetic_dictionary(S, D)
+  x = oracle.synthetic_patches(B, D)
+  want = oracle.ista_fista(x, phi, 0.1, 40)
+  got = ista_fista.run(x.cuda(), phi.cuda(), 0.1, 40)
+  check_codes(got, want, phi)
+
+
+def test_known_answer_orthonormal_dictionary():
+  ista_fista = modules()[0]
+  torch.manual_seed(3)
+  q, _ = torch.linalg.qr(torch.randn(64, 64))
+  x = 0.5 * torch.randn(100, 64)
+  want = oracle.threshold(x @ q.t(), 0.1)
+  for variant in ('ista', 'fista'):
+    got = ista_fista.run(x.cuda(), q.cuda(), 0.1, 5, variant=variant).cpu()
+    assert (got - want).abs().max() < 3e-5
+
+
+def test_error_behaviour_matches_reference():
+  ista_fista, subspace = modules()[:2]
+  x, phi = torch.zeros(8, 16).cuda(), torch.eye(16).cuda()
+  with pytest.raises(AssertionError):
+    ista_fista.run(x, phi, 0.1, 3, variant='lista')
+  with pytest.raises(UnboundLocalError):
+    ista_fista.run(x, phi, 0.1, 0)
+  with pytest.raises(NotImplementedError):
+    subspace.run(x, phi, [[0, 1], [2, 3]], 0.1, 3, hard_threshold=True)
+  with pytest.raises(NotImplementedError):
+    subspace.run(x, phi, [[0, 1], [2, 3]], 0.1, 3, ret_summed_gduplicates=False)
+  bad = phi.clone()
+  bad[3, 3] = float('inf')
+  with pytest.raises(RuntimeError):
+    ista_fista.run(x, bad, 0.1, 3)
+
+
+def test_subspace_against_reference_outputs():
+  """The call matrix of the reference's tests/ista_fista_3.py."""
+  subspace = modules()[1]
+  g = load_golden('subspace_small')
+  x, phi, lam, T = g['images'], g['dictionary'], g['sparsity_weight'], g['num_iters']
+  s = phi.size(0)
+  xd, pd = x.cuda(), phi.cuda()
+  pairs = [list(map(int, v)) for v in np.array_split(np.arange(s), s // 2)]
+  quads = [list(map(int, v)) for v in np.array_split(np.arange(s), s // 4)]
+  check_codes(subspace.run(xd, pd, pairs, lam, T), g['pairs_fista'], phi)
+  check_codes(subspace.run(xd, pd, pairs, lam, T, variant='ista'), g['pairs_ista'], phi)
+  check_codes(subspace.run(xd, pd, quads, lam, T), g['quads_fista'], phi)
+  check_codes(subspace.run(xd, pd, ragged_groups(g), lam, T), g['ragged_fista'], phi)
+  warm = g['warm_start'].cuda()
+  keep = warm.clone()
+  check_codes(subspace.run(xd, pd, pairs, lam, T, initial_codes=warm), g['pairs_warm'], phi)
+  assert torch.equal(warm, keep)
+  check_codes(subspace.run(xd, pd, pairs, lam, 1000, variant='ista', early_stopping_epsilon=1e-3), g['pairs_early'],
+              phi, tol=2e-3, recon_tol=2e-3, band=None)
+
+
+def test_subspace_groups_of_one_equal_vanilla():
+  ista_fista, subspace = modules()[:2]
+  phi = oracle.synthetic_dictionary(96, 48).cuda()
+  x = oracle.synthetic_patches(64, 48).cuda()
+  a = subspace.run(x, phi, [[i] for i in range(96)], 0.1, 30)
+  b = ista_fista.run(x, phi, 0.1, 30)
+  assert oracle.relative_l2(a.cpu(), b.cpu()) < 1e-6
+
+
+def test_dictionary_updates_against_reference_outputs():
+  _, _, cheap, steepest, sub_cheap = modules()
+  g = load_golden('dict_update_small')
+  x, phi, a, h = (g[k].cuda() for k in ('images', 'dictionary', 'codes', 'hessian_diagonal'))
+  keep = (x.clone(), a.clone(), h.clone())
+
+  def updated(fn, *args, **kw):
+    d = phi.clone()
+    assert fn(x, d, *args, **kw) is None  # in place, returns None
+    return d.cpu()
+
+  assert oracle.relative_l2(updated(cheap.run, a, h, stepsize=0.1), g['cheap_1']) < 1e-5
+  assert oracle.relative_l2(updated(cheap.run, a, h, stepsize=0.05, num_iters=3), g['cheap_3']) < 2e-5
+  assert oracle.relative_l2(updated(steepest.run, a, stepsize=0.1), g['steepest_1']) < 1e-5
+  assert oracle.relative_l2(updated(steepest.run, a, stepsize=0.1, num_iters=2, normalize_dictionary=False),
+                            g['steepest_2_unnormalized']) < 1e-5
+  assert oracle.relative_l2(updated(sub_cheap.run, a, [[0, 1]], h, 0.0, stepsize=0.1), g['cheap_1']) < 1e-5
+  with pytest.raises(NotImplementedError):
+    sub_cheap.run(x, phi.clone(), a, [[0, 1]], h, 0.5)
+  assert torch.equal(x, keep[0]) and torch.equal(a, keep[1]) and torch.equal(h, keep[2])
+
+
+def test_zero_codes_leave_dictionary_unchanged():
+  cheap = modules()[2]
+  phi = oracle.synthetic_dictionary(128, 64).cuda()
+  x = oracle.synthetic_patches(200, 64).cuda()
+  d = phi.clone()
+  cheap.run(x, d, torch.zeros(200, 128, device='cuda'), torch.zeros(128, device='cuda'), stepsize=0.1)
+  assert oracle.relative_l2(d.cpu(), phi.cpu()) < 1e-6
+
+
+def test_dictionary_update_larger_batch_against_oracle():
+  cheap = modules()[2]
+  phi = oracle.synthetic_dictionary(1024, 256)
+  x = oracle.synthetic_patches(4096, 256)
+  a = oracle.ista_fista(x[:256], phi, 0.1, 30).repeat(16, 1) * torch.linspace(0.5, 1.5, 4096)[:, None]
+  h = oracle.hessian_running_mean(torch.zeros(1024), a)
+  want = oracle.sc_dictionary_update(x, phi, a, h, stepsize=0.1)
+  d = phi.cuda()
+  cheap.run(x.cuda(), d, a.cuda(), h.cuda(), stepsize=0.1)
+  assert oracle.relative_l2(d.cpu(), want) < 1e-5

@@ -1,0 +1,117 @@
+"""The CPU oracle against outputs of the reference itself (tests/golden, made by make_golden.py) and closed forms."""
+import numpy as np
+import torch
+
+from conftest import load_golden, ragged_groups
+from oracle import vtc_oracle as oracle
+
+TIGHT = 2e-6  # same torch ops in the same order: only eigensolver / summation-order noise is left
+
+
+def close(a, b, tol=TIGHT):
+  assert a.shape == b.shape
+  err = oracle.relative_l2(a, b)
+  assert err <= tol, err
+
+
+def test_inference_matches_reference_outputs():
+  g = load_golden('inference_small')
+  x, phi, lam, T = g['images'], g['dictionary'], g['sparsity_weight'], g['num_iters']
+  close(oracle.ista_fista(x, phi, lam, T, variant='fista'), g['fista'])
+  close(oracle.ista_fista(x, phi, lam, T, variant='ista'), g['ista'])
+  close(oracle.ista_fista(x, phi, lam, T, nonnegative_only=True), g['fista_nonneg'])
+  close(oracle.ista_fista(x, phi, lam, T, hard_threshold=True), g['fista_hard'], 1e-5)
+  close(oracle.ista_fista(x, phi, lam, T, variant='ista', hard_threshold=True, nonnegative_only=True),
+        g['ista_hard_nonneg'], 1e-5)
+  close(oracle.ista_fista(x, phi, lam, T, initial_codes=g['warm_start']), g['fista_warm'])
+  close(oracle.ista_fista(x, phi, lam, 1000, variant='ista', early_stopping_epsilon=1e-3), g['ista_early'])
+  close(oracle.ista_fista(x, phi, lam, 1000, variant='fista', early_stopping_epsilon=1e-3), g['fista_early'])
+
+
+def test_inference_baseline_configs():
+  for name in ('inference_config1', 'inference_overcomplete'):
+    g = load_golden(name)
+    close(oracle.ista_fista(g['images'], g['dictionary'], g['sparsity_weight'], g['num_iters']), g['fista'], 1e-5)
+
+
+def test_subspace_matches_reference_outputs():
+  g = load_golden('subspace_small')
+  x, phi, lam, T = g['images'], g['dictionary'], g['sparsity_weight'], g['num_iters']
+  s = phi.size(0)
+  pairs = [list(map(int, v)) for v in np.array_split(np.arange(s), s // 2)]
+  quads = [list(map(int, v)) for v in np.array_split(np.arange(s), s // 4)]
+  close(oracle.subspace_ista_fista(x, phi, pairs, lam, T), g['pairs_fista'])
+  close(oracle.subspace_ista_fista(x, phi, pairs, lam, T, variant='ista'), g['pairs_ista'])
+  close(oracle.subspace_ista_fista(x, phi, quads, lam, T), g['quads_fista'])
+  close(oracle.subspace_ista_fista(x, phi, ragged_groups(g), lam, T), g['ragged_fista'])
+  close(oracle.subspace_ista_fista(x, phi, pairs, lam, T, initial_codes=g['warm_start']), g['pairs_warm'])
+  close(oracle.subspace_ista_fista(x, phi, pairs, lam, 1000, variant='ista', early_stopping_epsilon=1e-3),
+        g['pairs_early'])
+
+
+def test_dictionary_update_matches_reference_outputs():
+  g = load_golden('dict_update_small')
+  x, phi, a, h = g['images'], g['dictionary'], g['codes'], g['hessian_diagonal']
+  close(oracle.sc_dictionary_update(x, phi, a, h, stepsize=0.1), g['cheap_1'])
+  close(oracle.sc_dictionary_update(x, phi, a, h, stepsize=0.05, num_iters=3), g['cheap_3'])
+  close(oracle.sc_dictionary_update(x, phi, a, None, stepsize=0.1), g['steepest_1'])
+  close(oracle.sc_dictionary_update(x, phi, a, None, stepsize=0.1, num_iters=2, normalize_dictionary=False),
+        g['steepest_2_unnormalized'])
+
+
+def test_train_steps_match_reference_trainer():
+  g = load_golden('training_small')
+  batches, phi0 = g['batches'], g['dictionary']
+  s = phi0.size(0)
+  phi, _, _ = oracle.train_steps(batches, phi0, 0.1, 30, 0.1)
+  close(phi, g['fista_cheap'], 1e-5)
+  phi, _, _ = oracle.train_steps(batches, phi0, 0.1, 30, 0.1, variant='ista', update_rule='sc_steepest_descent')
+  close(phi, g['ista_steepest'], 1e-5)
+  pairs = [list(map(int, v)) for v in np.array_split(np.arange(s), s // 2)]
+  phi, _, _ = oracle.train_steps(batches, phi0, 0.1, 30, 0.1, group_assignments=pairs)
+  close(phi, g['subspace_cheap'], 1e-5)
+
+
+def test_known_answer_orthonormal_dictionary():
+  # Q orthonormal => L = 1, stepsize = 1, and one step from zero is already the fixed point soft(x Q^T, lambda)
+  torch.manual_seed(3)
+  q, _ = torch.linalg.qr(torch.randn(32, 32))
+  x = 0.5 * torch.randn(20, 32)
+  want = oracle.threshold(x @ q.t(), 0.1)
+  for variant in ('ista', 'fista'):
+    for iters in (1, 7):
+      got = oracle.ista_fista(x, q, 0.1, iters, variant=variant)
+      assert (got - want).abs().max() < 2e-5
+
+
+def test_known_answer_groups_of_one_equal_vanilla():
+  phi = oracle.synthetic_dictionary(48, 24)
+  x = oracle.synthetic_patches(16, 24)
+  groups = [[i] for i in range(48)]
+  a = oracle.subspace_ista_fista(x, phi, groups, 0.1, 40)
+  b = oracle.ista_fista(x, phi, 0.1, 40)
+  assert oracle.relative_l2(a, b) < 1e-5
+
+
+def test_known_answer_zero_codes_leave_dictionary_unchanged():
+  phi = oracle.synthetic_dictionary(16, 8)
+  x = oracle.synthetic_patches(10, 8)
+  out = oracle.sc_dictionary_update(x, phi, torch.zeros(10, 16), torch.zeros(16), stepsize=0.1)
+  assert oracle.relative_l2(out, phi) < 1e-6
+
+
+def test_inputs_not_mutated():
+  # the reference's own assertions: tests/ista_fista_1.py:45-54
+  phi = oracle.synthetic_dictionary(32, 16)
+  x = oracle.synthetic_patches(8, 16)
+  warm = oracle.ista_fista(x, phi, 0.1, 3)
+  keep = (x.clone(), phi.clone(), warm.clone())
+  out = oracle.ista_fista(x, phi, 0.1, 10, initial_codes=warm)
+  assert torch.equal(x, keep[0]) and torch.equal(phi, keep[1]) and torch.equal(warm, keep[2])
+  assert not torch.allclose(out, warm)
+
+
+def test_whitened_generator_statistics():
+  x = oracle.synthetic_patches(2048, 256, kind='whitened')
+  assert x.shape == (2048, 256)
+  assert abs(float(x.std()) - 0.3) < 1e-3

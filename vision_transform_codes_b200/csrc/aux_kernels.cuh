@@ -1,0 +1,270 @@
+// Small HBM-bound helper kernels around the tcgen05 GEMM: bf16 operand splitting, transposes, the Lipschitz constant
+// (largest eigenvalue of dictionary^T dictionary) in fp64, the dictionary apply step, gathers/scatters for subspaces.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vtc {
+
+// ------------------------------------------------------------------------------------------------------------
+// fp32 (R x C, pitch ld) -> bf16 parts (R x nparts*Cp): part p holds bf16(residual after removing parts < p);
+// columns [C, Cp) of every part are written as zero so that K-tail tiles contribute nothing.
+__global__ void split_rows_kernel(const float* __restrict__ in, int64_t ld, int64_t R, int64_t C, int64_t Cp,
+                                  int nparts, __nv_bfloat16* __restrict__ out) {
+  const int64_t half = Cp / 2;
+  const int64_t total = R * half;
+  const int64_t pitch = static_cast<int64_t>(nparts) * Cp;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / half;
+    const int64_t c = (i - r * half) * 2;
+    float v0 = (c < C) ? in[r * ld + c] : 0.f;
+    float v1 = (c + 1 < C) ? in[r * ld + c + 1] : 0.f;
+    for (int p = 0; p < nparts; ++p) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+      v0 = __fsub_rn(v0, __bfloat162float(h0));
+      v1 = __fsub_rn(v1, __bfloat162float(h1));
+      __nv_bfloat162 pk;
+      pk.x = h0;
+      pk.y = h1;
+      *reinterpret_cast<__nv_bfloat162*>(out + r * pitch + p * Cp + c) = pk;
+    }
+  }
+}
+
+// fp32 (R x C, pitch ld) -> bf16 parts of the TRANSPOSE: out is (C x nparts*Rp), zero in columns [R, Rp).
+// 32x32 tiles through shared memory so that both the read and the write are coalesced.
+__global__ void transpose_split_kernel(const float* __restrict__ in, int64_t ld, int64_t R, int64_t C, int64_t Rp,
+                                       int nparts, __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32;  // over Rp
+  const int64_t c0 = static_cast<int64_t>(blockIdx.y) * 32;  // over C
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  const int64_t pitch = static_cast<int64_t>(nparts) * Rp;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < Rp) {
+      float v = tile[threadIdx.x][i];
+      for (int p = 0; p < nparts; ++p) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        v = __fsub_rn(v, __bfloat162float(h));
+        out[c * pitch + p * Rp + r] = h;
+      }
+    }
+  }
+}
+
+// fp32 (R x C, pitch ld) -> fp32 transpose (C x R, pitch ldo)
+__global__ void transpose_f32_kernel(const float* __restrict__ in, int64_t ld, int64_t R, int64_t C,
+                                     float* __restrict__ out, int64_t ldo) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int64_t c0 = static_cast<int64_t>(blockIdx.y) * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R) out[c * ldo + r] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Lipschitz constant L = lambda_max(Phi^T Phi) (ista_fista.py:72-74), in fp64, without a host round trip:
+//   M = Phi^T Phi (n x n, n = D padded to 32);  A_0 = M;  A_{j+1} = (A_j / tr A_j)^2
+// After p squarings A_p / tr A_p is the projector onto the top eigenspace up to (lambda_2/lambda_1)^(2^p), and
+//   L = <A_p, M> / tr A_p   is the eigenvalue average under that weight (a Rayleigh quotient).
+__global__ void gram_fp64_kernel(const float* __restrict__ phi, int64_t S, int64_t D, int n, double* __restrict__ M,
+                                 double* __restrict__ trace_out) {
+  __shared__ double As[32][33], Bs[32][33];
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  double acc[4] = {0, 0, 0, 0};
+  for (int64_t s0 = 0; s0 < S; s0 += 32) {
+    for (int r = ty; r < 32; r += 8) {
+      const int64_t s = s0 + r;
+      As[r][tx] = (s < S && i0 + tx < D) ? static_cast<double>(phi[s * D + i0 + tx]) : 0.0;
+      Bs[r][tx] = (s < S && j0 + tx < D) ? static_cast<double>(phi[s * D + j0 + tx]) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const double b = Bs[k][tx];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] += As[k][ty + 8 * q] * b;
+    }
+    __syncthreads();
+  }
+  double tr = 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = i0 + ty + 8 * q, j = j0 + tx;
+    M[static_cast<int64_t>(i) * n + j] = acc[q];
+    if (i == j) tr += acc[q];
+  }
+  if (i0 == j0 && tr != 0.0) atomicAdd(trace_out, tr);
+}
+
+// C = (A / *trace_in)^2 for symmetric A (n x n, n % 32 == 0); accumulates tr C into *trace_out.
+__global__ void square_fp64_kernel(const double* __restrict__ A, int n, const double* __restrict__ trace_in,
+                                   double* __restrict__ C, double* __restrict__ trace_out) {
+  __shared__ double As[32][33], Bs[32][33];
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const double scale = 1.0 / *trace_in;
+  double acc[4] = {0, 0, 0, 0};
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    for (int r = ty; r < 32; r += 8) {
+      // A symmetric: A[i][k] read as row k0+r of column block i0 (coalesced)
+      As[r][tx] = A[static_cast<int64_t>(k0 + r) * n + i0 + tx] * scale;
+      Bs[r][tx] = A[static_cast<int64_t>(k0 + r) * n + j0 + tx] * scale;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const double b = Bs[k][tx];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] += As[k][ty + 8 * q] * b;
+    }
+    __syncthreads();
+  }
+  double tr = 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = i0 + ty + 8 * q, j = j0 + tx;
+    C[static_cast<int64_t>(i) * n + j] = acc[q];
+    if (i == j) tr += acc[q];
+  }
+  if (i0 == j0 && tr != 0.0) atomicAdd(trace_out, tr);
+}
+
+// scalars[0] = eta = 1/L, [1] = theta = lambda * eta, [2] = L, [3] = status bits (1 = non-finite / non-positive L)
+__global__ void lipschitz_finalize_kernel(const double* __restrict__ Ap, const double* __restrict__ M, int n,
+                                          const double* __restrict__ trace_p, float sparsity_weight,
+                                          float* __restrict__ scalars, float* __restrict__ lipschitz_out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  const int64_t total = static_cast<int64_t>(n) * n;
+  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) s += Ap[i] * M[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float L = static_cast<float>(red[0] / *trace_p);
+    if (lipschitz_out) *lipschitz_out = L;
+    if (scalars) {
+      const float eta = 1.f / L;  // stepsize = 1. / lipschitz_constant  (ista_fista.py:80), float32 arithmetic
+      scalars[0] = eta;
+      scalars[1] = sparsity_weight * eta;  // sparsity_weight * stepsize  (ista_fista.py:119)
+      scalars[2] = L;
+      scalars[3] = (isfinite(L) && L > 0.f) ? 0.f : 1.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// grad[s][d] = sum_z partial[z][s][d]   (fixed order -> deterministic)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nsplit, int64_t rows_per_split,
+                                       int64_t ldp, int64_t S, int64_t D, float* __restrict__ grad) {
+  const int64_t total = S * D;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t s = i / D, d = i - s * D;
+    float acc = 0.f;
+    for (int z = 0; z < nsplit; ++z) acc += partial[(z * rows_per_split + s) * ldp + d];
+    grad[i] = acc;
+  }
+}
+
+// One block per atom (row): sc_cheap_quadratic_descent.py:43-48 / sc_steepest_descent.py:37-41 after the contraction.
+__global__ void dict_apply_kernel(float* __restrict__ dict, const float* __restrict__ grad, const float* __restrict__ h,
+                                  int64_t D, float batch, float stepsize, float lowest, int normalize) {
+  __shared__ float red[256];
+  const int64_t s = blockIdx.x;
+  float* row = dict + s * D;
+  const float* g = grad + s * D;
+  const float denom = h ? (h[s] + lowest) : 1.f;
+  float ss = 0.f;
+  for (int64_t d = threadIdx.x; d < D; d += blockDim.x) {
+    float u = __fmul_rn(stepsize, __fdiv_rn(g[d], batch));  // stepsize * (mm / codes.size(0))
+    if (h) u = __fdiv_rn(u, denom);                                    // dict_update.div_(h[:, None] + lowest)
+    const float v = __fsub_rn(row[d], u);                              // dictionary.sub_(dict_update)
+    row[d] = v;
+    ss += v * v;
+  }
+  if (!normalize) return;
+  red[threadIdx.x] = ss;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float nrm = sqrtf(red[0]);
+  for (int64_t d = threadIdx.x; d < D; d += blockDim.x) row[d] = __fdiv_rn(row[d], nrm);
+}
+
+// code_sq_sum[s] += sum over this block's rows of codes[r][s]^2
+__global__ void col_sq_sum_kernel(const float* __restrict__ codes, int64_t ld, int64_t B, int64_t S,
+                                  int64_t rows_per_block, float* __restrict__ out) {
+  const int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+  const int64_t r1 = min(B, r0 + rows_per_block);
+  float acc = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float v = codes[r * ld + s];
+    acc += v * v;
+  }
+  atomicAdd(out + s, acc);
+}
+// h <- 0.99 h + (sum / batch) / 100      (training/sparse_coding.py:154)
+__global__ void hessian_ema_kernel(float* __restrict__ h, const float* __restrict__ sq_sum, int64_t S, float batch) {
+  const int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (s < S) h[s] = __fadd_rn(__fmul_rn(h[s], 0.99f), __fdiv_rn(__fdiv_rn(sq_sum[s], batch), 100.f));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Subspace regrouping (subspace_ista_fista.py:94-111, :184-190); index[j] = atom of slot j, or -1 for padding.
+__global__ void gather_rows_kernel(const float* __restrict__ src, int64_t ld, const int32_t* __restrict__ index,
+                                   int64_t n_slots, int64_t D, float* __restrict__ dst) {
+  const int64_t total = n_slots * D;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t j = i / D, d = i - j * D;
+    const int32_t a = index[j];
+    dst[i] = (a >= 0) ? src[static_cast<int64_t>(a) * ld + d] : 0.f;
+  }
+}
+__global__ void gather_cols_kernel(const float* __restrict__ src, int64_t ld, const int32_t* __restrict__ index,
+                                   int64_t B, int64_t n_slots, float* __restrict__ dst, int64_t ldd) {
+  const int64_t total = B * n_slots;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / n_slots, j = i - r * n_slots;
+    const int32_t a = index[j];
+    dst[r * ldd + j] = (a >= 0) ? src[r * ld + a] : 0.f;
+  }
+}
+// dst (B x S) must be zeroed by the caller; duplicates of an atom in several groups are summed.
+__global__ void scatter_add_cols_kernel(const float* __restrict__ src, int64_t ld, const int32_t* __restrict__ index,
+                                        int64_t B, int64_t n_slots, float* __restrict__ dst, int64_t ldd) {
+  const int64_t total = B * n_slots;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / n_slots, j = i - r * n_slots;
+    const int32_t a = index[j];
+    if (a >= 0) atomicAdd(dst + r * ldd + a, src[r * ld + j]);
+  }
+}
+
+}  // namespace vtc

@@ -1,0 +1,730 @@
+// C ABI (include/vtc_b200.h) and host-side orchestration of the sm_100a kernels.
+#include "../../include/vtc_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "gemm_kernel.cuh"
+
+namespace {
+
+using namespace vtc;
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess) return fail(VTC_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+#define TRY(expr)               \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != VTC_OK) return rc__; \
+  } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// ---------------------------------------------------------------------------------------------- device properties
+struct DeviceInfo {
+  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  bool ok = false;
+};
+int device_info(DeviceInfo* out) {
+  static thread_local DeviceInfo cache[64];
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(VTC_ERR_CUDA, "device ordinal %d out of range", dev);
+  if (!cache[dev].ok) {
+    CUDA_TRY(cudaDeviceGetAttribute(&cache[dev].sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&cache[dev].cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&cache[dev].cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    cache[dev].ok = true;
+  }
+  *out = cache[dev];
+  return VTC_OK;
+}
+int require_sm100(DeviceInfo* info) {
+  TRY(device_info(info));
+  if (info->cc_major != 10)
+    return fail(VTC_ERR_CUDA, "vtc_b200 needs an sm_100 (B200) device, found sm_%d%d; there is no fallback path",
+                info->cc_major, info->cc_minor);
+  return VTC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int get_encode(EncodeTiledFn* fn) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) return fail(VTC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    cached = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *fn = cached;
+  return VTC_OK;
+}
+int encode(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+           const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw, const char* what) {
+  EncodeTiledFn fn;
+  TRY(get_encode(&fn));
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(VTC_ERR_ARG, "%s: base pointer not 16-byte aligned", what);
+  for (int i = 0; i < rank - 1; ++i)
+    if (gstr[i] % 16 != 0) return fail(VTC_ERR_ARG, "%s: stride %llu not a multiple of 16 bytes", what, (unsigned long long)gstr[i]);
+  CUresult r = fn(m, dt, rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VTC_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return VTC_OK;
+}
+
+// A bf16 "parts" matrix: rows x (parts * Kp), part p = columns [p*Kp, p*Kp + K), zero padded to Kp (multiple of 64).
+struct PartsMat {
+  const void* ptr = nullptr;
+  int64_t rows = 0, K = 0, Kp = 0;
+  int parts = 0;
+  int64_t pitch_elems() const { return static_cast<int64_t>(parts) * Kp; }
+  size_t bytes() const { return static_cast<size_t>(rows) * pitch_elems() * 2; }
+};
+struct F32Mat {
+  const void* ptr = nullptr;
+  int64_t rows = 0, cols = 0, ld = 0;
+};
+
+int map_operand(CUtensorMap* m, const PartsMat& a, int box_rows, const char* what) {
+  const uint64_t dims[2] = {static_cast<uint64_t>(a.pitch_elems()), static_cast<uint64_t>(a.rows)};
+  const uint64_t str[1] = {static_cast<uint64_t>(a.pitch_elems()) * 2};
+  const uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(box_rows)};
+  return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.ptr, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, what);
+}
+int map_f32(CUtensorMap* m, const F32Mat& a, const char* what) {
+  const uint64_t dims[2] = {static_cast<uint64_t>(a.cols), static_cast<uint64_t>(a.rows)};
+  const uint64_t str[1] = {static_cast<uint64_t>(a.ld) * 4};
+  const uint32_t box[2] = {EPI_COLS, BLOCK_M};
+  return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.ptr, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, what);
+}
+// 3-D view (cols, parts, rows) of a parts matrix, for the epilogue's bf16 split store.
+int map_parts_out(CUtensorMap* m, const PartsMat& a, const char* what) {
+  const uint64_t dims[3] = {static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.parts), static_cast<uint64_t>(a.rows)};
+  const uint64_t str[2] = {static_cast<uint64_t>(a.Kp) * 2, static_cast<uint64_t>(a.pitch_elems()) * 2};
+  const uint32_t box[3] = {EPI_COLS, static_cast<uint32_t>(a.parts), BLOCK_M};
+  return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a.ptr, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, what);
+}
+
+// ---------------------------------------------------------------------------------------------- precision
+int parts_for(int precision) { return precision == VTC_PRECISION_BF16 ? 1 : precision == VTC_PRECISION_BF16X3 ? 2 : 3; }
+bool valid_precision(int p) { return p == VTC_PRECISION_BF16 || p == VTC_PRECISION_BF16X3 || p == VTC_PRECISION_BF16X6; }
+// (A part, B part) pairs, smallest-magnitude products first so that fp32 accumulation loses the least.
+int segments_for(int precision, int (*seg)[2]) {
+  if (precision == VTC_PRECISION_BF16) {
+    seg[0][0] = 0, seg[0][1] = 0;
+    return 1;
+  }
+  if (precision == VTC_PRECISION_BF16X3) {
+    const int s[3][2] = {{0, 1}, {1, 0}, {0, 0}};
+    memcpy(seg, s, sizeof(s));
+    return 3;
+  }
+  const int s[6][2] = {{0, 2}, {2, 0}, {1, 1}, {0, 1}, {1, 0}, {0, 0}};
+  memcpy(seg, s, sizeof(s));
+  return 6;
+}
+
+// ---------------------------------------------------------------------------------------------- GEMM launch
+struct GemmCall {
+  PartsMat A, B;         // D[M,N] = A[M,K] * B[N,K]^T
+  int precision = VTC_PRECISION_BF16X3;
+  int64_t M = 0, N = 0, K = 0;
+  F32Mat in[3];
+  int n_in = 0;
+  F32Mat out;            // fp32 output (optional)
+  bool store_out = false;
+  PartsMat parts_out;    // bf16 split output (optional)
+  int n_parts = 0;
+  int ksplits = 1;       // >1: fp32 partials stacked along rows of `out`, out_rows_per_split apart
+  int64_t out_rows_per_split = 0;
+  // FISTA epilogue
+  int prox = 0, group = 1, use_momentum = 0;
+  float beta_prev = 0.f, beta_next = 0.f;
+  const float* scalars = nullptr;
+  double* stat = nullptr;
+};
+
+template <int EPI>
+int launch_gemm(const GemmCall& c, cudaStream_t stream) {
+  DeviceInfo info;
+  TRY(require_sm100(&info));
+  if (c.M <= 0 || c.N <= 0 || c.K <= 0) return fail(VTC_ERR_ARG, "empty GEMM %lld x %lld x %lld", (long long)c.M, (long long)c.N, (long long)c.K);
+  if (c.A.K != c.K || c.B.K != c.K || c.A.Kp != c.B.Kp) return fail(VTC_ERR_ARG, "operand K mismatch");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  TRY(map_operand(&p.tmA, c.A, BLOCK_M, "A operand"));
+  TRY(map_operand(&p.tmB, c.B, BLOCK_N, "B operand"));
+  for (int i = 0; i < c.n_in; ++i) TRY(map_f32(&p.tmIn[i], c.in[i], "epilogue input"));
+  if (c.store_out) TRY(map_f32(&p.tmOut, c.out, "fp32 output"));
+  if (c.n_parts) TRY(map_parts_out(&p.tmParts, c.parts_out, "bf16 parts output"));
+  p.M = static_cast<int>(c.M);
+  p.N = static_cast<int>(c.N);
+  p.num_m_blocks = static_cast<int>(ceil_div(c.M, BLOCK_M));
+  p.num_n_blocks = static_cast<int>(ceil_div(c.N, BLOCK_N));
+  p.k_blocks = static_cast<int>(ceil_div(c.K, BLOCK_K));
+  int seg[MAX_SEG][2];
+  p.nseg = segments_for(c.precision, seg);
+  for (int s = 0; s < p.nseg; ++s) {
+    if (seg[s][0] >= c.A.parts || seg[s][1] >= c.B.parts) return fail(VTC_ERR_ARG, "operand has too few bf16 parts for precision %d", c.precision);
+    p.a_koff[s] = static_cast<int>(seg[s][0] * c.A.Kp);
+    p.b_koff[s] = static_cast<int>(seg[s][1] * c.B.Kp);
+  }
+  p.kb_per_split = static_cast<int>(ceil_div(p.k_blocks, c.ksplits));
+  p.ksplits = static_cast<int>(ceil_div(p.k_blocks, p.kb_per_split));
+  p.out_rows_per_split = static_cast<int>(c.out_rows_per_split);
+  p.n_in = c.n_in;
+  p.n_parts = c.n_parts;
+  p.store_out = c.store_out ? 1 : 0;
+  p.prox = c.prox;
+  p.group = c.group;
+  p.use_momentum = c.use_momentum;
+  p.beta_prev = c.beta_prev;
+  p.beta_next = c.beta_next;
+  p.scalars = c.scalars;
+  p.stat = c.stat;
+  const long long tiles = 1ll * p.num_m_blocks * p.num_n_blocks * p.ksplits;
+  if (tiles > 0x7fffffffll) return fail(VTC_ERR_ARG, "too many tiles");
+  static thread_local bool attr_set[2] = {false, false};
+  if (!attr_set[EPI]) {
+    CUDA_TRY(cudaFuncSetAttribute(vtc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+    attr_set[EPI] = true;
+  }
+  const int grid = static_cast<int>(tiles < info.sm_count ? tiles : info.sm_count);
+  vtc_gemm_kernel<EPI><<<grid, GEMM_THREADS, SMEM_ALLOC, stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- small launches
+int grid_for(int64_t work, int threads, int sm_count) {
+  int64_t g = ceil_div(work, threads);
+  const int64_t cap = static_cast<int64_t>(sm_count) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+int split_rows(const float* in, int64_t ld, int64_t R, int64_t C, const PartsMat& out, cudaStream_t st) {
+  DeviceInfo info;
+  TRY(device_info(&info));
+  split_rows_kernel<<<grid_for(R * out.Kp / 2, 256, info.sm_count), 256, 0, st>>>(
+      in, ld, R, C, out.Kp, out.parts, reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out.ptr)));
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+// out = parts of in^T : out.rows == C, out.K == R
+int transpose_split(const float* in, int64_t ld, int64_t R, int64_t C, const PartsMat& out, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>(out.Kp / 32), static_cast<unsigned>(ceil_div(C, 32)));
+  if (grid.y > 65535) return fail(VTC_ERR_ARG, "transpose_split: too many columns (%lld)", (long long)C);
+  transpose_split_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ld, R, C, out.Kp, out.parts,
+                                                       reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out.ptr)));
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+int transpose_f32(const float* in, int64_t ld, int64_t R, int64_t C, float* out, int64_t ldo, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>(ceil_div(R, 32)), static_cast<unsigned>(ceil_div(C, 32)));
+  if (grid.y > 65535) return fail(VTC_ERR_ARG, "transpose: too many columns (%lld)", (long long)C);
+  transpose_f32_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ld, R, C, out, ldo);
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- workspace carving
+struct Carver {
+  uint8_t* base;
+  size_t off = 0, cap;
+  bool dry;
+  Carver(void* b, size_t c) : base(static_cast<uint8_t*>(b)), cap(c), dry(b == nullptr) {}
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~size_t(1023);
+    void* p = dry ? nullptr : base + off;
+    off += bytes;
+    return p;
+  }
+  bool fits() const { return dry || off <= cap; }
+};
+PartsMat carve_parts(Carver& cv, int64_t rows, int64_t K, int parts) {
+  PartsMat m;
+  m.rows = rows;
+  m.K = K;
+  m.Kp = round_up(K, BLOCK_K);
+  m.parts = parts;
+  m.ptr = cv.take(m.bytes());
+  return m;
+}
+
+constexpr int kSquarings = 28;
+struct LipschitzWs {
+  double *M, *A0, *A1, *traces;
+  int n;
+};
+LipschitzWs carve_lipschitz(Carver& cv, int64_t D) {
+  LipschitzWs w;
+  w.n = static_cast<int>(round_up(D, 32));
+  const size_t mat = static_cast<size_t>(w.n) * w.n * sizeof(double);
+  w.M = static_cast<double*>(cv.take(mat));
+  w.A0 = static_cast<double*>(cv.take(mat));
+  w.A1 = static_cast<double*>(cv.take(mat));
+  w.traces = static_cast<double*>(cv.take((kSquarings + 2) * sizeof(double)));
+  return w;
+}
+// scalars (device float[4]) <- eta, theta, L, status ; lipschitz_dev (device float, optional) <- L
+int run_lipschitz(const float* dict, int64_t S, int64_t D, const LipschitzWs& w, float sparsity_weight, float* scalars,
+                  float* lipschitz_dev, cudaStream_t st) {
+  CUDA_TRY(cudaMemsetAsync(w.traces, 0, (kSquarings + 2) * sizeof(double), st));
+  const dim3 grid(w.n / 32, w.n / 32), block(32, 8);
+  gram_fp64_kernel<<<grid, block, 0, st>>>(dict, S, D, w.n, w.M, w.traces + 0);
+  const double* src = w.M;
+  double* dst = w.A0;
+  for (int j = 0; j < kSquarings; ++j) {
+    square_fp64_kernel<<<grid, block, 0, st>>>(src, w.n, w.traces + j, dst, w.traces + j + 1);
+    src = dst;
+    dst = (dst == w.A0) ? w.A1 : w.A0;
+  }
+  lipschitz_finalize_kernel<<<1, 256, 0, st>>>(src, w.M, w.n, w.traces + kSquarings, sparsity_weight, scalars,
+                                               lipschitz_dev);
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- FISTA
+struct FistaWs {
+  float* scalars;
+  double* stats;
+  LipschitzWs lip;
+  PartsMat phi_op, x_op, G_op, yop[2];
+  float *bvec, *X1, *X2, *init_pad;
+  int64_t ldS;
+};
+FistaWs carve_fista(Carver& cv, int64_t B, int64_t S, int64_t D, int precision) {
+  FistaWs w;
+  const int P = parts_for(precision);
+  w.scalars = static_cast<float*>(cv.take(64));
+  w.stats = static_cast<double*>(cv.take(8 * 4096));
+  w.lip = carve_lipschitz(cv, D);
+  w.phi_op = carve_parts(cv, S, D, 3);
+  w.x_op = carve_parts(cv, B, D, 3);
+  w.G_op = carve_parts(cv, S, S, P);
+  w.yop[0] = carve_parts(cv, B, S, P);
+  w.yop[1] = carve_parts(cv, B, S, P);
+  w.ldS = round_up(S, 4);
+  const size_t state = static_cast<size_t>(B) * w.ldS * 4;
+  w.bvec = static_cast<float*>(cv.take(state));
+  w.X1 = static_cast<float*>(cv.take(state));
+  w.X2 = static_cast<float*>(cv.take(state));
+  w.init_pad = static_cast<float*>(cv.take(state));
+  return w;
+}
+
+bool tma_ok(const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld % 4) == 0; }
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int vtc_version(void) { return 100; }
+const char* vtc_last_error(void) { return g_err; }
+
+int vtc_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  DeviceInfo info;
+  TRY(device_info(&info));
+  if (sm_count) *sm_count = info.sm_count;
+  if (cc_major) *cc_major = info.cc_major;
+  if (cc_minor) *cc_minor = info.cc_minor;
+  return VTC_OK;
+}
+
+size_t vtc_lipschitz_workspace_bytes(int64_t S, int64_t D) {
+  (void)S;
+  Carver cv(nullptr, 0);
+  carve_lipschitz(cv, D);
+  return cv.off + 1024;
+}
+int vtc_lipschitz(const float* dictionary, int64_t S, int64_t D, float* lipschitz_dev, void* workspace,
+                  size_t workspace_bytes, vtc_stream_t stream) {
+  if (!dictionary || !lipschitz_dev || S <= 0 || D <= 0) return fail(VTC_ERR_ARG, "vtc_lipschitz: bad argument");
+  Carver cv(workspace, workspace_bytes);
+  LipschitzWs w = carve_lipschitz(cv, D);
+  if (!workspace || !cv.fits()) return fail(VTC_ERR_WORKSPACE, "vtc_lipschitz: workspace too small");
+  return run_lipschitz(dictionary, S, D, w, 0.f, nullptr, lipschitz_dev, static_cast<cudaStream_t>(stream));
+}
+
+size_t vtc_fista_workspace_bytes(int64_t B, int64_t S, int64_t D, int precision) {
+  if (!valid_precision(precision) || B <= 0 || S <= 0 || D <= 0) return 0;
+  Carver cv(nullptr, 0);
+  carve_fista(cv, B, S, D, precision);
+  return cv.off + 1024;
+}
+
+int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary, const float* initial_codes,
+                 float* codes_out, int64_t ld_codes, int64_t B, int64_t S, int64_t D, float sparsity_weight,
+                 int num_iters, int variant, int nonnegative_only, int hard_threshold, int group_size,
+                 float early_stopping_epsilon, int precision, void* workspace, size_t workspace_bytes,
+                 int* iters_run, float* lipschitz_out, vtc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!images || !dictionary || !codes_out) return fail(VTC_ERR_ARG, "vtc_fista_fc: null pointer");
+  if (B <= 0 || S <= 0 || D <= 0 || ld_images < D || ld_codes < S) return fail(VTC_ERR_ARG, "vtc_fista_fc: bad shape");
+  if (variant != VTC_VARIANT_ISTA && variant != VTC_VARIANT_FISTA) return fail(VTC_ERR_ARG, "variant must be ista or fista");
+  if (!valid_precision(precision)) return fail(VTC_ERR_ARG, "precision must be 1, 3 or 6");
+  if (num_iters < 1) return fail(VTC_ERR_ARG, "num_iters must be >= 1");
+  if (group_size < 1) return fail(VTC_ERR_ARG, "group_size must be >= 1");
+  if (group_size > 1) {
+    if (hard_threshold) return fail(VTC_ERR_UNSUPPORTED, "hard threshold is not implemented for the subspace variant");
+    if (EPI_COLS % group_size != 0 || S % group_size != 0)
+      return fail(VTC_ERR_UNSUPPORTED, "group_size must divide 16 and the (grouped) code size; got %d", group_size);
+  }
+  if (S > (1 << 20) || B > (1ll << 31) - 256) return fail(VTC_ERR_ARG, "problem too large for 32-bit tile coordinates");
+  DeviceInfo info;
+  TRY(require_sm100(&info));
+  Carver cv(workspace, workspace_bytes);
+  FistaWs w = carve_fista(cv, B, S, D, precision);
+  if (!workspace || !cv.fits()) return fail(VTC_ERR_WORKSPACE, "vtc_fista_fc: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
+  const bool early = early_stopping_epsilon >= 0.f;
+  if (early && num_iters > 4096) return fail(VTC_ERR_UNSUPPORTED, "early stopping supports at most 4096 iterations");
+  const int P = parts_for(precision);
+
+  // ---- setup: step size, operand splits, Gram matrix G = Phi Phi^T (as bf16 parts), drive b = x Phi^T
+  TRY(run_lipschitz(dictionary, S, D, w.lip, sparsity_weight, w.scalars, nullptr, st));
+  TRY(split_rows(dictionary, D, S, D, w.phi_op, st));
+  TRY(split_rows(images, ld_images, B, D, w.x_op, st));
+  {
+    GemmCall g;
+    g.A = w.phi_op, g.B = w.phi_op;
+    g.precision = VTC_PRECISION_BF16X6;
+    g.M = S, g.N = S, g.K = D;
+    g.parts_out = w.G_op, g.n_parts = P;
+    CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.G_op.ptr), 0, w.G_op.bytes(), st));
+    TRY(launch_gemm<EPI_STORE>(g, st));
+  }
+  {
+    GemmCall g;
+    g.A = w.x_op, g.B = w.phi_op;
+    g.precision = VTC_PRECISION_BF16X6;
+    g.M = B, g.N = S, g.K = D;
+    g.out = F32Mat{w.bvec, B, S, w.ldS}, g.store_out = true;
+    TRY(launch_gemm<EPI_STORE>(g, st));
+  }
+
+  // ---- state buffers. a_k lives in X1 for odd k and X2 for even k; a_0 is `init`.
+  const bool direct_out = tma_ok(codes_out, ld_codes) && !early;
+  float* X1 = w.X1;
+  float* X2 = w.X2;
+  int64_t ld1 = w.ldS, ld2 = w.ldS;
+  if (direct_out) {
+    if (num_iters & 1) X1 = codes_out, ld1 = ld_codes;
+    else X2 = codes_out, ld2 = ld_codes;
+  }
+  const float* init;
+  int64_t ld_init;
+  CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[1].ptr), 0, w.yop[1].bytes(), st));
+  if (initial_codes) {
+    if (tma_ok(initial_codes, ld_codes)) {
+      init = initial_codes, ld_init = ld_codes;
+    } else {
+      CUDA_TRY(cudaMemcpy2DAsync(w.init_pad, w.ldS * 4, initial_codes, ld_codes * 4, S * 4, B, cudaMemcpyDeviceToDevice, st));
+      init = w.init_pad, ld_init = w.ldS;
+    }
+    TRY(split_rows(initial_codes, ld_codes, B, S, w.yop[0], st));
+  } else {
+    // a_0 = 0: X2 doubles as a_0 (it is only overwritten, in place, when a_2 is produced)
+    CUDA_TRY(cudaMemset2DAsync(X2, ld2 * 4, 0, S * 4, B, st));
+    CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[0].ptr), 0, w.yop[0].bytes(), st));
+    init = X2, ld_init = ld2;
+  }
+  if (early) CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * num_iters, st));
+
+  float eta_host = 0.f;
+  float sc_host[4] = {0, 0, 0, 0};
+  if (early || lipschitz_out) {
+    CUDA_TRY(cudaMemcpyAsync(sc_host, w.scalars, sizeof(sc_host), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    eta_host = sc_host[0];
+    if (lipschitz_out) *lipschitz_out = sc_host[2];
+    if (sc_host[3] != 0.f || !isfinite(sc_host[2]))
+      return fail(VTC_ERR_NONFINITE, "largest eigenvalue of dictionary^T dictionary is %g: a dictionary element overflowed", sc_host[2]);
+  }
+
+  // ---- iterations. beta_k = (t_k - 1) / t_{k+1} in double on the host (ista_fista.py:124-125), applied as float32.
+  double t_k = 1.0;
+  float beta_prev = 0.f;
+  int k_done = 0;
+  for (int k = 1; k <= num_iters; ++k) {
+    const double t_next = (1.0 + sqrt(1.0 + 4.0 * t_k * t_k)) / 2.0;
+    const float beta_k = (variant == VTC_VARIANT_FISTA) ? static_cast<float>((t_k - 1.0) / t_next) : 0.f;
+    t_k = t_next;
+    const float* a_prev = (k == 1) ? init : ((k - 1) & 1) ? X1 : X2;       // a_{k-1}
+    const int64_t ld_prev = (k == 1) ? ld_init : ((k - 1) & 1) ? ld1 : ld2;
+    const float* a_prev2 = (k <= 2) ? init : (k & 1) ? X1 : X2;            // a_{k-2}
+    const int64_t ld_prev2 = (k <= 2) ? ld_init : (k & 1) ? ld1 : ld2;
+    float* a_out = (k & 1) ? X1 : X2;
+    const int64_t ld_out = (k & 1) ? ld1 : ld2;
+    GemmCall g;
+    g.A = w.yop[(k - 1) & 1], g.B = w.G_op;
+    g.precision = precision;
+    g.M = B, g.N = S, g.K = S;
+    g.in[0] = F32Mat{a_prev, B, S, ld_prev};
+    g.in[1] = F32Mat{w.bvec, B, S, w.ldS};
+    g.n_in = 2;
+    if (variant == VTC_VARIANT_FISTA && beta_prev != 0.f) {
+      g.in[2] = F32Mat{a_prev2, B, S, ld_prev2};
+      g.n_in = 3;
+    }
+    g.out = F32Mat{a_out, B, S, ld_out}, g.store_out = true;
+    if (k < num_iters) g.parts_out = w.yop[k & 1], g.n_parts = P;
+    g.prox = (hard_threshold ? PROX_HARD : 0) | (nonnegative_only ? PROX_NONNEG : 0);
+    g.group = group_size;
+    g.use_momentum = (variant == VTC_VARIANT_FISTA);
+    g.beta_prev = beta_prev, g.beta_next = beta_k;
+    g.scalars = w.scalars;
+    g.stat = early ? w.stats + (k - 1) : nullptr;
+    TRY(launch_gemm<EPI_FISTA>(g, st));
+    beta_prev = beta_k;
+    k_done = k;
+    if (early) {
+      double sum_abs = 0.0;
+      CUDA_TRY(cudaMemcpyAsync(&sum_abs, w.stats + (k - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      const double avg = sum_abs / (static_cast<double>(B) * static_cast<double>(S)) / static_cast<double>(eta_host);
+      if (avg < static_cast<double>(early_stopping_epsilon) && k > 1) break;
+    }
+  }
+  const float* result = (k_done & 1) ? X1 : X2;
+  const int64_t ld_res = (k_done & 1) ? ld1 : ld2;
+  if (result != codes_out)
+    CUDA_TRY(cudaMemcpy2DAsync(codes_out, ld_codes * 4, result, ld_res * 4, S * 4, B, cudaMemcpyDeviceToDevice, st));
+  if (iters_run) *iters_run = k_done;
+  return VTC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- dictionary update
+namespace {
+struct GradWs {
+  PartsMat a_op, aT_op, phiT_op, RT_op;
+  float* xT;
+  int64_t ldB;
+  float* partial;
+  int ksplits;
+  int64_t rows_per_split, ldD;
+};
+GradWs carve_grad(Carver& cv, int64_t B, int64_t S, int64_t D, int precision, int sm_count) {
+  GradWs w;
+  const int P = parts_for(precision);
+  w.a_op = carve_parts(cv, B, S, P);
+  w.aT_op = carve_parts(cv, S, B, P);
+  w.phiT_op = carve_parts(cv, D, S, P);
+  w.RT_op = carve_parts(cv, D, B, P);
+  w.ldB = round_up(B, 4);
+  w.xT = static_cast<float*>(cv.take(static_cast<size_t>(D) * w.ldB * 4));
+  const int64_t tiles_mn = ceil_div(S, BLOCK_M) * ceil_div(D, BLOCK_N);
+  const int64_t kb = ceil_div(B, BLOCK_K);
+  int64_t ks = sm_count / tiles_mn;
+  if (ks < 1) ks = 1;
+  if (ks > kb) ks = kb;
+  w.ksplits = static_cast<int>(ks);
+  w.rows_per_split = ceil_div(S, BLOCK_M) * BLOCK_M;
+  w.ldD = round_up(D, 4);
+  w.partial = static_cast<float*>(cv.take(static_cast<size_t>(w.ksplits) * w.rows_per_split * w.ldD * 4));
+  return w;
+}
+}  // namespace
+
+size_t vtc_dict_grad_workspace_bytes(int64_t B, int64_t S, int64_t D, int precision) {
+  if (!valid_precision(precision) || B <= 0 || S <= 0 || D <= 0) return 0;
+  Carver cv(nullptr, 0);
+  carve_grad(cv, B, S, D, precision, 148);
+  return cv.off + 1024;
+}
+
+int vtc_sc_dict_grad(const float* images, int64_t ld_images, const float* dictionary, const float* codes,
+                     int64_t ld_codes, float* grad_sum, int64_t B, int64_t S, int64_t D, int precision,
+                     void* workspace, size_t workspace_bytes, vtc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!images || !dictionary || !codes || !grad_sum) return fail(VTC_ERR_ARG, "vtc_sc_dict_grad: null pointer");
+  if (B <= 0 || S <= 0 || D <= 0 || ld_images < D || ld_codes < S) return fail(VTC_ERR_ARG, "vtc_sc_dict_grad: bad shape");
+  if (!valid_precision(precision)) return fail(VTC_ERR_ARG, "precision must be 1, 3 or 6");
+  DeviceInfo info;
+  TRY(require_sm100(&info));
+  Carver cv(workspace, workspace_bytes);
+  // ksplits must not depend on the SM count used for the size query (148 is the B200 count the query assumes)
+  GradWs w = carve_grad(cv, B, S, D, precision, info.sm_count < 148 ? info.sm_count : 148);
+  if (!workspace || !cv.fits()) return fail(VTC_ERR_WORKSPACE, "vtc_sc_dict_grad: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
+
+  TRY(split_rows(codes, ld_codes, B, S, w.a_op, st));
+  TRY(transpose_split(codes, ld_codes, B, S, w.aT_op, st));
+  TRY(transpose_split(dictionary, D, S, D, w.phiT_op, st));
+  TRY(transpose_f32(images, ld_images, B, D, w.xT, w.ldB, st));
+  // R^T (D x B) = Phi^T a^T - x^T, emitted directly as bf16 parts (the K-major operand of the next contraction)
+  {
+    GemmCall g;
+    g.A = w.phiT_op, g.B = w.a_op;
+    g.precision = precision;
+    g.M = D, g.N = B, g.K = S;
+    g.in[0] = F32Mat{w.xT, D, B, w.ldB}, g.n_in = 1;
+    g.parts_out = w.RT_op, g.n_parts = w.RT_op.parts;
+    CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.RT_op.ptr), 0, w.RT_op.bytes(), st));
+    TRY(launch_gemm<EPI_STORE>(g, st));
+  }
+  // grad (S x D) = a^T R, contraction over the batch, split-K across the SMs
+  {
+    GemmCall g;
+    g.A = w.aT_op, g.B = w.RT_op;
+    g.precision = precision;
+    g.M = S, g.N = D, g.K = B;
+    g.ksplits = w.ksplits;
+    g.out_rows_per_split = w.rows_per_split;
+    g.out = F32Mat{w.partial, static_cast<int64_t>(w.ksplits) * w.rows_per_split, D, w.ldD}, g.store_out = true;
+    TRY(launch_gemm<EPI_STORE>(g, st));
+    // launch_gemm may have lowered the split count; recompute exactly as it does
+    const int64_t kb = ceil_div(B, BLOCK_K);
+    const int64_t per = ceil_div(kb, w.ksplits);
+    const int nsplit = static_cast<int>(ceil_div(kb, per));
+    reduce_partials_kernel<<<grid_for(S * D, 256, info.sm_count), 256, 0, st>>>(w.partial, nsplit, w.rows_per_split,
+                                                                                w.ldD, S, D, grad_sum);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return VTC_OK;
+}
+
+int vtc_sc_dict_apply(float* dictionary, const float* grad_sum, const float* hessian_diagonal, int64_t S, int64_t D,
+                      int64_t batch_global, float stepsize, float lowest_code_val, int normalize,
+                      vtc_stream_t stream) {
+  if (!dictionary || !grad_sum || S <= 0 || D <= 0 || batch_global <= 0) return fail(VTC_ERR_ARG, "vtc_sc_dict_apply: bad argument");
+  dict_apply_kernel<<<static_cast<unsigned>(S), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dictionary, grad_sum, hessian_diagonal, D, static_cast<float>(batch_global), stepsize, lowest_code_val, normalize);
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+int vtc_hessian_diag_update(const float* codes, int64_t ld_codes, int64_t B, int64_t S, int64_t batch_global,
+                            float* code_sq_sum, float* hessian_diagonal, int apply_ema, vtc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!codes || !code_sq_sum || B <= 0 || S <= 0 || batch_global <= 0) return fail(VTC_ERR_ARG, "vtc_hessian_diag_update: bad argument");
+  if (apply_ema && !hessian_diagonal) return fail(VTC_ERR_ARG, "vtc_hessian_diag_update: hessian_diagonal required");
+  DeviceInfo info;
+  TRY(device_info(&info));
+  CUDA_TRY(cudaMemsetAsync(code_sq_sum, 0, S * sizeof(float), st));
+  const int64_t col_blocks = ceil_div(S, 128);
+  int64_t row_blocks = (static_cast<int64_t>(info.sm_count) * 8) / col_blocks;
+  if (row_blocks < 1) row_blocks = 1;
+  if (row_blocks > B) row_blocks = B;
+  const int64_t rows_per_block = ceil_div(B, row_blocks);
+  row_blocks = ceil_div(B, rows_per_block);
+  col_sq_sum_kernel<<<dim3(static_cast<unsigned>(col_blocks), static_cast<unsigned>(row_blocks)), 128, 0, st>>>(
+      codes, ld_codes, B, S, rows_per_block, code_sq_sum);
+  if (apply_ema)
+    hessian_ema_kernel<<<static_cast<unsigned>(ceil_div(S, 256)), 256, 0, st>>>(hessian_diagonal, code_sq_sum, S,
+                                                                              static_cast<float>(batch_global));
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- generic matmul
+size_t vtc_matmul_nt_workspace_bytes(int64_t M, int64_t N, int64_t K, int precision) {
+  if (!valid_precision(precision) || M <= 0 || N <= 0 || K <= 0) return 0;
+  Carver cv(nullptr, 0);
+  carve_parts(cv, M, K, parts_for(precision));
+  carve_parts(cv, N, K, parts_for(precision));
+  cv.take(static_cast<size_t>(M) * round_up(N, 4) * 4);
+  cv.take(static_cast<size_t>(M) * round_up(N, 4) * 4);
+  return cv.off + 1024;
+}
+int vtc_matmul_nt(const float* A, const float* Bm, const float* sub, float* out, int64_t M, int64_t N, int64_t K,
+                  int precision, void* workspace, size_t workspace_bytes, vtc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!A || !Bm || !out || M <= 0 || N <= 0 || K <= 0) return fail(VTC_ERR_ARG, "vtc_matmul_nt: bad argument");
+  if (!valid_precision(precision)) return fail(VTC_ERR_ARG, "precision must be 1, 3 or 6");
+  Carver cv(workspace, workspace_bytes);
+  PartsMat a = carve_parts(cv, M, K, parts_for(precision));
+  PartsMat b = carve_parts(cv, N, K, parts_for(precision));
+  const int64_t ldN = round_up(N, 4);
+  float* out_pad = static_cast<float*>(cv.take(static_cast<size_t>(M) * ldN * 4));
+  float* sub_pad = static_cast<float*>(cv.take(static_cast<size_t>(M) * ldN * 4));
+  if (!workspace || !cv.fits()) return fail(VTC_ERR_WORKSPACE, "vtc_matmul_nt: workspace too small");
+  TRY(split_rows(A, K, M, K, a, st));
+  TRY(split_rows(Bm, K, N, K, b, st));
+  GemmCall g;
+  g.A = a, g.B = b;
+  g.precision = precision;
+  g.M = M, g.N = N, g.K = K;
+  const bool direct = tma_ok(out, N);
+  if (sub) {
+    const float* s = sub;
+    int64_t lds = N;
+    if (!tma_ok(sub, N)) {
+      CUDA_TRY(cudaMemcpy2DAsync(sub_pad, ldN * 4, sub, N * 4, N * 4, M, cudaMemcpyDeviceToDevice, st));
+      s = sub_pad, lds = ldN;
+    }
+    g.in[0] = F32Mat{s, M, N, lds}, g.n_in = 1;
+  }
+  g.out = direct ? F32Mat{out, M, N, N} : F32Mat{out_pad, M, N, ldN};
+  g.store_out = true;
+  TRY(launch_gemm<EPI_STORE>(g, st));
+  if (!direct) CUDA_TRY(cudaMemcpy2DAsync(out, N * 4, out_pad, ldN * 4, N * 4, M, cudaMemcpyDeviceToDevice, st));
+  return VTC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- subspace helpers
+int vtc_gather_rows(const float* src, int64_t ld_src, const int32_t* index, int64_t n_slots, int64_t D, float* dst,
+                    vtc_stream_t stream) {
+  if (!src || !index || !dst || n_slots <= 0 || D <= 0) return fail(VTC_ERR_ARG, "vtc_gather_rows: bad argument");
+  DeviceInfo info;
+  TRY(device_info(&info));
+  gather_rows_kernel<<<grid_for(n_slots * D, 256, info.sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, ld_src, index, n_slots, D, dst);
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+int vtc_gather_cols(const float* src, int64_t ld_src, const int32_t* index, int64_t B, int64_t n_slots, float* dst,
+                    int64_t ld_dst, vtc_stream_t stream) {
+  if (!src || !index || !dst || n_slots <= 0 || B <= 0) return fail(VTC_ERR_ARG, "vtc_gather_cols: bad argument");
+  DeviceInfo info;
+  TRY(device_info(&info));
+  gather_cols_kernel<<<grid_for(B * n_slots, 256, info.sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, ld_src, index, B, n_slots, dst, ld_dst);
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+int vtc_scatter_add_cols(const float* src, int64_t ld_src, const int32_t* index, int64_t B, int64_t n_slots,
+                         float* dst, int64_t ld_dst, int64_t S, vtc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!src || !index || !dst || n_slots <= 0 || B <= 0 || S <= 0) return fail(VTC_ERR_ARG, "vtc_scatter_add_cols: bad argument");
+  DeviceInfo info;
+  TRY(device_info(&info));
+  CUDA_TRY(cudaMemset2DAsync(dst, ld_dst * 4, 0, S * 4, B, st));
+  scatter_add_cols_kernel<<<grid_for(B * n_slots, 256, info.sm_count), 256, 0, st>>>(src, ld_src, index, B, n_slots,
+                                                                                      dst, ld_dst);
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+}  // extern "C"
