@@ -1,0 +1,283 @@
+"""
+bench.py -- the reference's headline metric on B200: FISTA patches/sec (300 iterations) on BASELINE.json configs[1]
+(16x16 whitened patches, D=256, 1024 atoms, batch 65,536 per GPU, lambda 0.1), plus train steps/sec on configs[2].
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16x3|bf16|bf16x6]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full inference call (step size, Gram/drive GEMMs, 300 fused iterations) on one batch per GPU.
+Inference needs no communication, so N GPUs run N independent shards of an N-times larger batch (weak scaling);
+`value` is the whole-job patches/sec with inputs resident in HBM, timed with CUDA events on the launching stream
+between barriers, max over ranks. `e2e` is the same call made through the public drop-in API from pinned HOST
+buffers, host<->device copies inside the timed region. `--impl reference` times the CPU float32 restatement of the
+reference (oracle/vtc_oracle.py; the reference itself is Python/torch and is not on the GPU box) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+B_PER_GPU, S, D, T, LAM = 65536, 1024, 256, 300, 0.1
+TRAIN_GLOBAL_BATCH = 524288
+WORKLOAD = ('configs[1]: fully-connected FISTA, 16x16 whitened patches (D=256), 1024 atoms, '
+            'batch 65536 per GPU, 300 iters, lambda 0.1')
+CPU_SAMPLE = 2048
+
+
+def peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    p = json.load(open(path))
+    return {'bf16_sustained': p.get('bf16_tflops_sustained'), 'bf16_burst': p.get('bf16_tflops'),
+            'hbm_gbs': p.get('hbm_gbs'), 'source': 'measured'}
+  return {'bf16_sustained': 1400.0, 'bf16_burst': 1590.0, 'hbm_gbs': 6650.0, 'source': 'fallback'}
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+  FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+            'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+            'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                                    '--format=csv,noheader,nounits', '-lms', '100'],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except OSError:
+      return
+    self.thread = threading.Thread(target=self._read, daemon=True)
+    self.thread.start()
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(',')])
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    self.proc.terminate()
+    self.thread.join(timeout=2)
+    sm, smax, reasons = [], None, set()
+    for r in self.rows:
+      try:
+        sm.append(float(r[0]))
+        smax = float(r[1])
+      except (ValueError, IndexError):
+        continue
+      for name, cell in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+        if cell.lower().startswith('active'):
+          reasons.add(name)
+    busy = [v for v in sm if smax and v > 0.3 * smax] or sm
+    return {'sm_mhz': statistics.median(busy) if busy else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons),
+            'samples': len(sm)}
+
+
+def cpu_reference_patches_per_sec(sample, repeats=1):
+  """The reference's float32 CPU path (restated in oracle/vtc_oracle.py) on `sample` patches of the same workload."""
+  from oracle import vtc_oracle as oracle
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  phi = oracle.synthetic_dictionary(S, D)
+  x = oracle.synthetic_patches(sample, D, kind='whitened')
+  oracle.ista_fista(x[:64], phi, LAM, 3)  # warm the thread pool
+  best = float('inf')
+  for _ in range(repeats):
+    t0 = time.perf_counter()
+    oracle.ista_fista(x, phi, LAM, T)
+    best = min(best, time.perf_counter() - t0)
+  return sample / best, cores, best
+
+
+def run_reference(args, rank):
+  if rank != 0:
+    return
+  steps = max(1, args.steps)
+  for _ in range(max(0, min(args.warmup, 1))):
+    cpu_reference_patches_per_sec(256)
+  vals, secs, cores = [], [], 1
+  for _ in range(steps):
+    v, cores, s = cpu_reference_patches_per_sec(CPU_SAMPLE)
+    vals.append(v)
+    secs.append(s)
+  value = CPU_SAMPLE * len(vals) / sum(secs)
+  line = {
+      'impl': 'reference', 'metric': 'fista_patches_per_sec', 'value': value, 'unit': 'patches/s',
+      'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(secs) / len(secs),
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': WORKLOAD, 'note': 'CPU float32 torch path of the reference (oracle port), all host '
+                 'threads; each step is a %d-patch sample of the workload, throughput is linear in the batch'
+                 % CPU_SAMPLE},
+      'cpu_baseline': {'value': value, 'unit': 'patches/s', 'cores': cores, 'kind': 'port',
+                       'sample': '%d of 65536 patches x 300 iterations per step' % CPU_SAMPLE},
+      'e2e': {'value': value, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+      'gpu_launches': 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=5)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--precision', default=os.environ.get('VTC_B200_PRECISION', 'bf16x3'))
+  ap.add_argument('--batch', type=int, default=B_PER_GPU, help='patches per GPU (default: the BASELINE config)')
+  ap.add_argument('--no-extras', action='store_true', help='skip the bf16-path, train-step and CPU side measurements')
+  args = ap.parse_args()
+
+  rank = int(os.environ.get('RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if args.impl == 'reference':
+    run_reference(args, rank)
+    return
+
+  import torch.distributed as dist
+  import vision_transform_codes_b200 as pkg
+  from oracle import vtc_oracle as oracle  # inputs only (seeded generators shared with the tests) + cpu_baseline
+  from vision_transform_codes_b200 import _lib
+  from vision_transform_codes_b200.analysis_transforms.fully_connected import ista_fista
+
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a B200: the CUDA path has no CPU fallback')
+  dev = torch.device('cuda', local_rank)
+  torch.cuda.set_device(dev)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  lib = _lib.load()
+  pkg.config.precision = args.precision
+  pkg.config.check_finite = False  # no host synchronisation inside the timed region of `value`
+  Bn = args.batch
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def max_over_ranks(ms):
+    if world == 1:
+      return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+  phi = oracle.synthetic_dictionary(S, D).to(dev)
+  x_host = oracle.synthetic_patches(Bn, D, seed=rank, kind='whitened').pin_memory()
+  x = x_host.to(dev)
+
+  def timed(fn, steps, warmup):
+    for _ in range(warmup):
+      fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = lib.vtc_launch_count()
+    e0.record()
+    for _ in range(steps):
+      fn()
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1)), lib.vtc_launch_count() - n0
+
+  # ---- headline: inputs resident in HBM
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  total_ms, launches = timed(lambda: ista_fista.run(x, phi, LAM, T), args.steps, args.warmup)
+  clocks = sampler.stop() if rank == 0 else None
+  ms_per_step = total_ms / args.steps
+  value = world * Bn / (ms_per_step * 1e-3)
+
+  # ---- the dominant kernel (one fused FISTA iteration = one launch): CUDA events recorded by the library around
+  #      the 300 iteration launches of one more call, on the launching stream
+  lib.vtc_profile_enable(1)
+  ista_fista.run(x, phi, LAM, T)
+  import ctypes
+  setup_ms, iter_ms, iter_launches = ctypes.c_float(), ctypes.c_float(), ctypes.c_int()
+  _lib.check(lib.vtc_profile_last(ctypes.byref(setup_ms), ctypes.byref(iter_ms), ctypes.byref(iter_launches)))
+  lib.vtc_profile_enable(0)
+  pk = peaks()
+  nprod = pkg.PRECISIONS[args.precision]
+  launch_ms = iter_ms.value / max(1, iter_launches.value)
+  flops_per_launch = 2.0 * Bn * S * S  # algorithmic Gram-form flops of one iteration (2*S^2 per patch)
+  achieved = flops_per_launch / (launch_ms * 1e-3) / 1e12
+  roofline = {
+      'bound': 'tensor', 'kernel': 'vtc_gemm_kernel<EPI_FISTA>', 'achieved': achieved, 'peak': pk['bf16_sustained'],
+      'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_sustained'], 'traffic': None,
+      'peak_source': pk['source'] + ' bf16_tflops_sustained', 'launch_ms': launch_ms,
+      'launches_per_step': iter_launches.value, 'setup_ms_per_step': setup_ms.value,
+      'algorithmic_flops_per_launch': flops_per_launch, 'executed_mma_flops_per_launch': nprod * flops_per_launch,
+      'executed_frac': nprod * achieved / pk['bf16_sustained'],
+      'hbm_bytes_per_launch_model': Bn * S * (12 + 4 + 2 * (2 if nprod == 3 else 3 if nprod == 6 else 1) * 2),
+      'reference_form_flops_per_launch': 4.0 * Bn * S * D,
+  }
+
+  # ---- end to end through the public API from pinned host memory
+  codes_host = torch.empty((Bn, S), dtype=torch.float32).pin_memory()
+  pkg.config.check_finite = True  # the default user-facing behaviour
+
+  def e2e_step():
+    xd = x_host.to(dev, non_blocking=True)
+    codes = ista_fista.run(xd, phi, LAM, T)
+    codes_host.copy_(codes, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+
+  e2e_ms, _ = timed(e2e_step, max(2, min(args.steps, 3)), 1)
+  e2e_ms /= max(2, min(args.steps, 3))
+  e2e = {'value': world * Bn / (e2e_ms * 1e-3), 'unit': 'patches/s', 'ms_per_step': e2e_ms,
+         'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': codes_host.numel() * 4}
+  pkg.config.check_finite = False
+
+  line = {
+      'metric': 'fista_patches_per_sec', 'value': value, 'unit': 'patches/s', 'n_gpus': world, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': args.precision + ' (bf16 products, fp32 accumulate)', 'data': 'synthetic',
+      'config': {'workload': WORKLOAD, 'batch_per_gpu': Bn, 'atoms': S, 'pixels': D, 'iters': T,
+                 'precision': args.precision, 'parallelism': 'batch sharded over %d GPU(s), dictionary replicated, '
+                 'no data-path collective' % world,
+                 'l2': 'inputs larger than L2 (per-iteration state %.0f MB vs 126 MB L2)' % (Bn * S * 4 * 3 / 1e6)},
+      'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'clocks': clocks,
+  }
+
+  if not args.no_extras:
+    # separately toleranced plain-bf16 path (1 MMA pass per product)
+    if args.precision != 'bf16':
+      pkg.config.precision = 'bf16'
+      ms, _ = timed(lambda: ista_fista.run(x, phi, LAM, T), 3, 2)
+      ms /= 3
+      line['bf16_path'] = {'value': world * Bn / (ms * 1e-3), 'unit': 'patches/s', 'ms_per_step': ms,
+                           'achieved_tflops_whole_call': (T * flops_per_launch) / (ms * 1e-3) / 1e12,
+                           'frac_of_peak_whole_call': (T * flops_per_launch) / (ms * 1e-3) / 1e12 / pk['bf16_sustained']}
+      pkg.config.precision = args.precision
+    try:
+      from vision_transform_codes_b200.training import sparse_coding as trainer
+      line['train_step'] = trainer.benchmark_train_step(TRAIN_GLOBAL_BATCH, S, D, T, LAM, world, rank, dev, timed)
+    except ImportError:
+      pass
+    if rank == 0 and world == 1:
+      v, cores, secs = cpu_reference_patches_per_sec(CPU_SAMPLE)
+      line['cpu_baseline'] = {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': 'port',
+                              'sample': '%d of %d patches x %d iterations (%.1f s), float32 torch on the host'
+                              % (CPU_SAMPLE, Bn, T, secs)}
+  if rank == 0:
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

@@ -46,6 +46,13 @@ typedef void* vtc_stream_t; /* a cudaStream_t */
 int vtc_version(void);
 const char* vtc_last_error(void);
 
+/* Measurement hooks (bench.py): cumulative number of kernels this library has launched in this process, and
+ * CUDA-event timing of the last vtc_fista_fc call: setup (step size, splits, Gram and drive GEMMs) and the
+ * iteration launches, recorded on the call's own stream. vtc_profile_last synchronises on the last event. */
+long long vtc_launch_count(void);
+int vtc_profile_enable(int on);
+int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches);
+
 /* Number of SMs / compute capability of the current device (used by bench.py to size workloads). */
 int vtc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

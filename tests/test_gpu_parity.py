@@ -43,7 +43,7 @@ def check_codes(got, want, phi, tol=CODE_TOL, recon_tol=RECON_TOL, band=GUARD_BA
   assert torch.isfinite(got).all()
   err = oracle.relative_l2(got, want)
   rerr = oracle.relative_l2(got @ phi, want @ phi)
-  flips, outside = oracle.support_mismatches(got, want, band=band)
+  flips, outside = oracle.support_mismatches(got, want, band=0.0 if band is None else band)
   assert err <= tol, ('codes', err)
   assert rerr <= recon_tol, ('recon', rerr)
   if band is not None:
@@ -61,11 +61,13 @@ def test_inference_call_matrix_against_reference_outputs():
   check_codes(ista_fista.run(xd, pd, lam, T), g['fista'], phi)
   check_codes(ista_fista.run(xd, pd, lam, T, 'ista'), g['ista'], phi)
   check_codes(ista_fista.run(xd, pd, lam, T, nonnegative_only=True), g['fista_nonneg'], phi)
-  # hard thresholding is discontinuous: a tie at the cutoff moves a whole coefficient, so compare away from ties
-  check_codes(ista_fista.run(xd, pd, lam, T, hard_threshold=True), g['fista_hard'], phi, tol=2e-2, recon_tol=2e-2,
-              band=None)
-  check_codes(ista_fista.run(xd, pd, lam, T, variant='ista', hard_threshold=True, nonnegative_only=True),
-              g['ista_hard_nonneg'], phi, tol=2e-2, recon_tol=2e-2, band=None)
+  # hard thresholding is discontinuous: one tie at the cutoff moves a whole coefficient and the iteration amplifies
+  # it, so the comparison is loose on values and asks for agreement of (almost) the whole support instead
+  for kw, key in (({'hard_threshold': True}, 'fista_hard'),
+                  ({'variant': 'ista', 'hard_threshold': True, 'nonnegative_only': True}, 'ista_hard_nonneg')):
+    got = ista_fista.run(xd, pd, lam, T, **kw)
+    _, _, flips = check_codes(got, g[key], phi, tol=8e-2, recon_tol=8e-2, band=None)
+    assert flips <= 0.002 * got.numel(), flips
   warm = g['warm_start'].cuda()
   keep_w = warm.clone()
   out = ista_fista.run(xd, pd, lam, T, initial_codes=warm)

@@ -16,6 +16,9 @@ _i64, _int, _f32, _ptr, _size = _c.c_int64, _c.c_int, _c.c_float, _c.c_void_p, _
 SIGNATURES = {
     'vtc_version': (_int, []),
     'vtc_last_error': (_c.c_char_p, []),
+    'vtc_launch_count': (_c.c_longlong, []),
+    'vtc_profile_enable': (_int, [_int]),
+    'vtc_profile_last': (_int, [_c.POINTER(_f32), _c.POINTER(_f32), _c.POINTER(_int)]),
     'vtc_device_info': (_int, [_c.POINTER(_int)] * 3),
     'vtc_fista_workspace_bytes': (_size, [_i64, _i64, _i64, _int]),
     'vtc_fista_fc': (_int, [_ptr, _i64, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _f32, _int, _int, _int, _int, _int,

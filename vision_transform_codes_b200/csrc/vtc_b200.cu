@@ -36,6 +36,17 @@ int fail(int code, const char* fmt, ...) {
     if (rc__ != VTC_OK) return rc__; \
   } while (0)
 
+// every kernel launch of this library goes through COUNT_LAUNCH so that callers can report how many ran
+long long g_launches = 0;
+#define COUNT_LAUNCH() (++g_launches)
+
+struct Profile {
+  bool on = false, valid = false;
+  cudaEvent_t begin = nullptr, iter_begin = nullptr, iter_end = nullptr;
+  int iter_launches = 0;
+};
+Profile g_prof;
+
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
 
@@ -221,6 +232,7 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
   }
   const int grid = static_cast<int>(tiles < info.sm_count ? tiles : info.sm_count);
   vtc_gemm_kernel<EPI><<<grid, GEMM_THREADS, SMEM_ALLOC, stream>>>(p);
+  COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
 }
@@ -238,6 +250,7 @@ int split_rows(const float* in, int64_t ld, int64_t R, int64_t C, const PartsMat
   TRY(device_info(&info));
   split_rows_kernel<<<grid_for(R * out.Kp / 2, 256, info.sm_count), 256, 0, st>>>(
       in, ld, R, C, out.Kp, out.parts, reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out.ptr)));
+  COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
 }
@@ -247,6 +260,7 @@ int transpose_split(const float* in, int64_t ld, int64_t R, int64_t C, const Par
   if (grid.y > 65535) return fail(VTC_ERR_ARG, "transpose_split: too many columns (%lld)", (long long)C);
   transpose_split_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ld, R, C, out.Kp, out.parts,
                                                        reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out.ptr)));
+  COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
 }
@@ -254,6 +268,7 @@ int transpose_f32(const float* in, int64_t ld, int64_t R, int64_t C, float* out,
   dim3 grid(static_cast<unsigned>(ceil_div(R, 32)), static_cast<unsigned>(ceil_div(C, 32)));
   if (grid.y > 65535) return fail(VTC_ERR_ARG, "transpose: too many columns (%lld)", (long long)C);
   transpose_f32_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ld, R, C, out, ldo);
+  COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
 }
@@ -303,15 +318,18 @@ int run_lipschitz(const float* dict, int64_t S, int64_t D, const LipschitzWs& w,
   CUDA_TRY(cudaMemsetAsync(w.traces, 0, (kSquarings + 2) * sizeof(double), st));
   const dim3 grid(w.n / 32, w.n / 32), block(32, 8);
   gram_fp64_kernel<<<grid, block, 0, st>>>(dict, S, D, w.n, w.M, w.traces + 0);
+  COUNT_LAUNCH();
   const double* src = w.M;
   double* dst = w.A0;
   for (int j = 0; j < kSquarings; ++j) {
     square_fp64_kernel<<<grid, block, 0, st>>>(src, w.n, w.traces + j, dst, w.traces + j + 1);
+    COUNT_LAUNCH();
     src = dst;
     dst = (dst == w.A0) ? w.A1 : w.A0;
   }
   lipschitz_finalize_kernel<<<1, 256, 0, st>>>(src, w.M, w.n, w.traces + kSquarings, sparsity_weight, scalars,
                                                lipschitz_dev);
+  COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
 }
@@ -353,6 +371,23 @@ bool tma_ok(const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) 
 extern "C" {
 
 int vtc_version(void) { return 100; }
+long long vtc_launch_count(void) { return g_launches; }
+int vtc_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.valid = false;
+  return VTC_OK;
+}
+int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches) {
+  if (!g_prof.valid) return fail(VTC_ERR_ARG, "vtc_profile_last: no profiled vtc_fista_fc call");
+  CUDA_TRY(cudaEventSynchronize(g_prof.iter_end));
+  float a = 0.f, b = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&a, g_prof.begin, g_prof.iter_begin));
+  CUDA_TRY(cudaEventElapsedTime(&b, g_prof.iter_begin, g_prof.iter_end));
+  if (setup_ms) *setup_ms = a;
+  if (iter_ms) *iter_ms = b;
+  if (iter_launches) *iter_launches = g_prof.iter_launches;
+  return VTC_OK;
+}
 const char* vtc_last_error(void) { return g_err; }
 
 int vtc_device_info(int* sm_count, int* cc_major, int* cc_minor) {
@@ -413,6 +448,15 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   if (early && num_iters > 4096) return fail(VTC_ERR_UNSUPPORTED, "early stopping supports at most 4096 iterations");
   const int P = parts_for(precision);
 
+  if (g_prof.on) {
+    if (!g_prof.begin) {
+      CUDA_TRY(cudaEventCreate(&g_prof.begin));
+      CUDA_TRY(cudaEventCreate(&g_prof.iter_begin));
+      CUDA_TRY(cudaEventCreate(&g_prof.iter_end));
+    }
+    g_prof.valid = false;
+    CUDA_TRY(cudaEventRecord(g_prof.begin, st));
+  }
   // ---- setup: step size, operand splits, Gram matrix G = Phi Phi^T (as bf16 parts), drive b = x Phi^T
   TRY(run_lipschitz(dictionary, S, D, w.lip, sparsity_weight, w.scalars, nullptr, st));
   TRY(split_rows(dictionary, D, S, D, w.phi_op, st));
@@ -478,6 +522,7 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   double t_k = 1.0;
   float beta_prev = 0.f;
   int k_done = 0;
+  if (g_prof.on) CUDA_TRY(cudaEventRecord(g_prof.iter_begin, st));
   for (int k = 1; k <= num_iters; ++k) {
     const double t_next = (1.0 + sqrt(1.0 + 4.0 * t_k * t_k)) / 2.0;
     const float beta_k = (variant == VTC_VARIANT_FISTA) ? static_cast<float>((t_k - 1.0) / t_next) : 0.f;
@@ -517,6 +562,11 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
       const double avg = sum_abs / (static_cast<double>(B) * static_cast<double>(S)) / static_cast<double>(eta_host);
       if (avg < static_cast<double>(early_stopping_epsilon) && k > 1) break;
     }
+  }
+  if (g_prof.on) {
+    CUDA_TRY(cudaEventRecord(g_prof.iter_end, st));
+    g_prof.iter_launches = k_done;
+    g_prof.valid = true;
   }
   const float* result = (k_done & 1) ? X1 : X2;
   const int64_t ld_res = (k_done & 1) ? ld1 : ld2;
@@ -610,6 +660,7 @@ int vtc_sc_dict_grad(const float* images, int64_t ld_images, const float* dictio
     const int nsplit = static_cast<int>(ceil_div(kb, per));
     reduce_partials_kernel<<<grid_for(S * D, 256, info.sm_count), 256, 0, st>>>(w.partial, nsplit, w.rows_per_split,
                                                                                 w.ldD, S, D, grad_sum);
+    COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
   }
   return VTC_OK;
@@ -621,6 +672,7 @@ int vtc_sc_dict_apply(float* dictionary, const float* grad_sum, const float* hes
   if (!dictionary || !grad_sum || S <= 0 || D <= 0 || batch_global <= 0) return fail(VTC_ERR_ARG, "vtc_sc_dict_apply: bad argument");
   dict_apply_kernel<<<static_cast<unsigned>(S), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       dictionary, grad_sum, hessian_diagonal, D, static_cast<float>(batch_global), stepsize, lowest_code_val, normalize);
+  COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
 }
@@ -641,9 +693,12 @@ int vtc_hessian_diag_update(const float* codes, int64_t ld_codes, int64_t B, int
   row_blocks = ceil_div(B, rows_per_block);
   col_sq_sum_kernel<<<dim3(static_cast<unsigned>(col_blocks), static_cast<unsigned>(row_blocks)), 128, 0, st>>>(
       codes, ld_codes, B, S, rows_per_block, code_sq_sum);
-  if (apply_ema)
+  COUNT_LAUNCH();
+  if (apply_ema) {
     hessian_ema_kernel<<<static_cast<unsigned>(ceil_div(S, 256)), 256, 0, st>>>(hessian_diagonal, code_sq_sum, S,
                                                                               static_cast<float>(batch_global));
+    COUNT_LAUNCH();
+  }
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
 }
@@ -701,6 +756,7 @@ int vtc_gather_rows(const float* src, int64_t ld_src, const int32_t* index, int6
   TRY(device_info(&info));
   gather_rows_kernel<<<grid_for(n_slots * D, 256, info.sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, ld_src, index, n_slots, D, dst);
+  COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
 }
@@ -711,6 +767,7 @@ int vtc_gather_cols(const float* src, int64_t ld_src, const int32_t* index, int6
   TRY(device_info(&info));
   gather_cols_kernel<<<grid_for(B * n_slots, 256, info.sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, ld_src, index, B, n_slots, dst, ld_dst);
+  COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
 }
@@ -723,6 +780,7 @@ int vtc_scatter_add_cols(const float* src, int64_t ld_src, const int32_t* index,
   CUDA_TRY(cudaMemset2DAsync(dst, ld_dst * 4, 0, S * 4, B, st));
   scatter_add_cols_kernel<<<grid_for(B * n_slots, 256, info.sm_count), 256, 0, st>>>(src, ld_src, index, B, n_slots,
                                                                                       dst, ld_dst);
+  COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
 }
