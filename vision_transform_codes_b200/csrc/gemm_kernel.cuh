@@ -1,17 +1,24 @@
-// Persistent, warp-specialised tcgen05 GEMM with a fused, TMA-staged epilogue (sm_100a).
+// Persistent, warp-specialised tcgen05 GEMM on CTA pairs (cta_group::2) with a fused, TMA-staged epilogue (sm_100a).
 //
-//   D[M,N] = sum_seg  A[:, a_koff[seg] : +K] * B[:, b_koff[seg] : +K]^T        (bf16 operands, fp32 accumulate in TMEM)
+//   D[M,N] = sum over (pa, pb) in PAIRS  A_pa[M,K] * B_pb[N,K]^T            bf16 operands, fp32 accumulate in TMEM
 //
-// Both operands are K-major bf16 matrices whose rows hold several "parts" of an fp32 matrix side by side
-// (hi | mid | lo of a bf16 split, each padded to a multiple of 64 columns). A list of (A part, B part) segment
-// pairs selects the precision: 1 segment = plain bf16, 3 = bf16x3 (~2^-17), 6 = bf16x6 (~fp32).
+// A and B are K-major bf16 "parts" matrices: each row holds P parts of an fp32 matrix side by side (hi | mid | lo of a
+// bf16 split, each padded to a multiple of 64 columns). P = 1: plain bf16 (1 product), P = 2: bf16x3 (hi*lo + lo*hi +
+// hi*hi, error ~2^-17), P = 3: bf16x6 (~fp32). For every K block ALL parts of A and B are staged once and every
+// product of the list is issued from that stage, so the x3 / x6 modes move 2x / 3x the operand bytes of plain bf16,
+// not 3x / 6x.
 //
-// Warp roles (256 threads, one CTA per SM, static round-robin tile schedule):
-//   warp 0 lane 0 : TMA producer for the A/B operand ring            (full/empty mbarriers)
-//   warp 1 lane 0 : tcgen05.mma issuer, accumulators double-buffered in TMEM (tmem_full/tmem_empty)
-//   warp 2        : TMEM allocator / deallocator
-//   warp 3 lane 0 : epilogue DMA: TMA-loads the fp32 state tiles a sub-tile ahead, TMA-stores the results
-//   warps 4..7    : epilogue math: tcgen05.ld 16 columns -> fused update -> swizzled st.shared
+// One CTA pair (cluster of 2, one CTA per SM) owns a 256 x 256 output tile: each CTA holds its own 128 rows of A and
+// half (128 rows) of the B tile, the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) and both tensor cores read
+// both halves of B. Accumulators are double-buffered in TMEM (2 x 256 columns).
+//
+// Warp roles (384 threads):
+//   warp 0 lane 0 : TMA producer of the operand ring (full / empty mbarriers; full lives in the leader CTA)
+//   warp 1 lane 0 : tcgen05.mma issuer (leader CTA only); commits are multicast to both CTAs
+//   warp 2        : TMEM allocator; lane 0 then drives the TMA stores of the epilogue (out ring)
+//   warp 3 lane 0 : TMA loader of the epilogue's fp32 state tiles (in ring), running ahead of the math warps
+//   warps 4..11   : epilogue math, two groups of four warps working on alternate 16-column sub-tiles:
+//                   tcgen05.ld -> fused update -> swizzled st.shared -> TMA store
 //
 // Epilogues:
 //   EPI_STORE : out = acc [- in0]; optionally also emitted as bf16 parts (split of the fp32 value)
@@ -27,43 +34,63 @@
 
 namespace vtc {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_N = 256;
-constexpr int BLOCK_K = 64;     // 64 bf16 = one 128-byte swizzle span
+constexpr int BLOCK_M = 128;        // rows per CTA
+constexpr int PAIR_M = 256;         // rows per CTA pair (UMMA M)
+constexpr int BLOCK_N = 256;        // UMMA N; each CTA stages half of it
+constexpr int HALF_N = 128;
 constexpr int UMMA_K = 16;
-constexpr int NUM_STAGES = 3;   // operand ring
-constexpr int EPI_COLS = 16;    // epilogue sub-tile width (fp32 columns)
-constexpr int EPI_STAGES = 3;   // epilogue state ring
-constexpr int MAX_SEG = 6;
+constexpr int EPI_COLS = 16;        // epilogue sub-tile width (fp32 columns)
 constexpr int MAX_PARTS = 3;
+constexpr int GEMM_THREADS = 384;
+constexpr int NUM_MATH_WARPS = 8;
+constexpr int TMEM_COLS = 2 * BLOCK_N;
+constexpr int EPI_ARRAY_BYTES = BLOCK_M * EPI_COLS * 4;  // 8 KB: one fp32 [128 x 16] sub-tile
+constexpr int EPI_PART_BYTES = BLOCK_M * EPI_COLS * 2;   // 4 KB: one bf16 [128 x 16] sub-tile
+constexpr int IN_STAGE_BYTES = 3 * EPI_ARRAY_BYTES;      // 24 KB
 
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;                 // 16 KB
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;                 // 32 KB
-constexpr int EPI_ARRAY_BYTES = BLOCK_M * EPI_COLS * 4;              // 8 KB : one fp32 [128 x 16] sub-tile
-constexpr int EPI_STAGE_BYTES = 3 * EPI_ARRAY_BYTES;                 // 24 KB: {in0,in1,in2} then {out | parts}
-constexpr int SMEM_A_OFF = 0;
-constexpr int SMEM_B_OFF = SMEM_A_OFF + NUM_STAGES * A_STAGE_BYTES;
-constexpr int SMEM_EPI_OFF = SMEM_B_OFF + NUM_STAGES * B_STAGE_BYTES;
-constexpr int SMEM_BAR_OFF = SMEM_EPI_OFF + EPI_STAGES * EPI_STAGE_BYTES;
-constexpr int NUM_BARRIERS = 2 * NUM_STAGES + 4 + 2 * EPI_STAGES;
-constexpr int SMEM_TOTAL = SMEM_BAR_OFF + NUM_BARRIERS * 8 + 16;
-constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;  // slack to align the dynamic base to 1024 B
-constexpr int GEMM_THREADS = 256;
-constexpr int TMEM_COLS = 2 * BLOCK_N;         // two accumulators
+// Compile-time configuration for P staged parts per operand.
+template <int P>
+struct Cfg {
+  static constexpr int BK = (P == 1) ? 64 : 32;                 // K extent of a stage
+  static constexpr int SPAN = BK * 2;                           // bytes per operand row = swizzle span (128 / 64)
+  static constexpr int TILE_BYTES = BLOCK_M * SPAN;             // one part tile of A, or of this CTA's half of B
+  static constexpr int STAGE_BYTES = 2 * P * TILE_BYTES;        // P A tiles + P B tiles
+  static constexpr int OP_STAGES = (P == 1) ? 4 : (P == 2) ? 3 : 2;
+  static constexpr int IN_STAGES = (P == 2) ? 4 : 3;
+  static constexpr int OUT_STAGES = 2;
+  static constexpr int OUT_STAGE_BYTES = EPI_ARRAY_BYTES + P * EPI_PART_BYTES;
+  static constexpr int NPAIRS = (P == 1) ? 1 : (P == 2) ? 3 : 6;
+  static constexpr int OFF_OP = 0;
+  static constexpr int OFF_IN = OFF_OP + OP_STAGES * STAGE_BYTES;
+  static constexpr int OFF_OUT = OFF_IN + IN_STAGES * IN_STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_OUT + OUT_STAGES * OUT_STAGE_BYTES;
+  static constexpr int NUM_BARRIERS = 2 * OP_STAGES + 4 + 2 * IN_STAGES + 2 * OUT_STAGES;
+  static constexpr int SMEM_TOTAL = OFF_BAR + NUM_BARRIERS * 8 + 16;
+  static constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;          // slack to align the dynamic base to 1024 B
+  static_assert(SMEM_ALLOC <= 232448, "over the 227 KB shared memory limit");
+};
+// (A part, B part) products of each mode, smallest magnitude first so fp32 accumulation loses the least:
+//   P = 2: (hi,lo) (lo,hi) (hi,hi)        P = 3: (0,2) (2,0) (1,1) (0,1) (1,0) (0,0)
+__host__ __device__ constexpr int pair_a(int P, int i) {
+  return P == 1 ? 0 : P == 2 ? (i == 1 ? 1 : 0) : (i == 1 ? 2 : (i == 2 || i == 4) ? 1 : 0);
+}
+__host__ __device__ constexpr int pair_b(int P, int i) {
+  return P == 1 ? 0 : P == 2 ? (i == 0 ? 1 : 0) : (i == 0 ? 2 : (i == 2 || i == 3) ? 1 : 0);
+}
 
 enum EpiKind { EPI_STORE = 0, EPI_FISTA = 1 };
 enum ProxFlags { PROX_HARD = 1, PROX_NONNEG = 2 };
 
 struct GemmParams {
-  CUtensorMap tmA, tmB;    // bf16 operands, 2-D (cols, rows), box 64 x 128 / 64 x 256, SWIZZLE_128B
+  CUtensorMap tmA, tmB;    // bf16 operands, 2-D (cols, rows), box BK x 128, swizzle = row span
   CUtensorMap tmIn[3];     // fp32 epilogue inputs, 2-D, box 16 x 128, SWIZZLE_64B
   CUtensorMap tmOut;       // fp32 output, 2-D, box 16 x 128, SWIZZLE_64B
-  CUtensorMap tmParts;     // bf16 parts output, 3-D (cols, parts, rows), box 16 x n_parts x 128, no swizzle
+  CUtensorMap tmParts;     // bf16 parts output, 2-D over (n_parts * Kp) columns, box 16 x 128, SWIZZLE_32B
   int M, N;
-  int num_m_blocks, num_n_blocks;
-  int k_blocks;            // ceil(K / 64) per segment
-  int nseg;
-  int a_koff[MAX_SEG], b_koff[MAX_SEG];
+  int num_m_blocks, num_n_blocks;   // in units of 256 x 256 pair tiles
+  int k_blocks;            // ceil(K / BK)
+  int a_part_stride, b_part_stride;   // column offset between parts of A / B (their padded K)
+  int out_part_stride;     // column offset between parts of the bf16 output
   int ksplits, kb_per_split;
   int out_rows_per_split;  // fp32 partial outputs are stacked along rows
   int n_in, n_parts, store_out;
@@ -77,13 +104,13 @@ struct GemmParams {
 struct TileCoord {
   int m0, n0, kb0, kb1, out_row0, nsub;
 };
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int w) {
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int w, int cta_rank) {
   const int n_blk = w % p.num_n_blocks;
   const int t = w / p.num_n_blocks;
   const int m_blk = t % p.num_m_blocks;
   const int z = t / p.num_m_blocks;
   TileCoord c;
-  c.m0 = m_blk * BLOCK_M;
+  c.m0 = m_blk * PAIR_M + cta_rank * BLOCK_M;
   c.n0 = n_blk * BLOCK_N;
   c.kb0 = z * p.kb_per_split;
   c.kb1 = min(p.k_blocks, c.kb0 + p.kb_per_split);
@@ -114,24 +141,30 @@ __device__ __forceinline__ void group_shrink(const float (&u)[16], float (&o)[16
   }
 }
 
-template <int EPI>
+template <int EPI, int P>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<P>;
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operand tiles need a 1024-byte aligned base.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t sA = sbase + SMEM_A_OFF, sB = sbase + SMEM_B_OFF, sE = sbase + SMEM_EPI_OFF;
-  const uint32_t bar0 = sbase + SMEM_BAR_OFF;
+  // swizzled TMA / UMMA tiles need a 1024-byte aligned base; the offset is identical in both CTAs of the pair
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sOp = sbase + C::OFF_OP, sIn = sbase + C::OFF_IN, sOut = sbase + C::OFF_OUT;
+  const uint32_t bar0 = sbase + C::OFF_BAR;
   auto full_bar = [&](int s) { return bar0 + 8 * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8 * (NUM_STAGES + s); };
-  auto tmem_full_bar = [&](int a) { return bar0 + 8 * (2 * NUM_STAGES + a); };
-  auto tmem_empty_bar = [&](int a) { return bar0 + 8 * (2 * NUM_STAGES + 2 + a); };
-  auto epi_full_bar = [&](int e) { return bar0 + 8 * (2 * NUM_STAGES + 4 + e); };
-  auto epi_done_bar = [&](int e) { return bar0 + 8 * (2 * NUM_STAGES + 4 + EPI_STAGES + e); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR_OFF + NUM_BARRIERS * 8);
+  auto empty_bar = [&](int s) { return bar0 + 8 * (C::OP_STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar0 + 8 * (2 * C::OP_STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar0 + 8 * (2 * C::OP_STAGES + 2 + a); };
+  auto in_full_bar = [&](int e) { return bar0 + 8 * (2 * C::OP_STAGES + 4 + e); };
+  auto in_free_bar = [&](int e) { return bar0 + 8 * (2 * C::OP_STAGES + 4 + C::IN_STAGES + e); };
+  auto out_full_bar = [&](int o) { return bar0 + 8 * (2 * C::OP_STAGES + 4 + 2 * C::IN_STAGES + o); };
+  auto out_free_bar = [&](int o) { return bar0 + 8 * (2 * C::OP_STAGES + 4 + 2 * C::IN_STAGES + C::OUT_STAGES + o); };
+  const uint32_t tmem_slot = bar0 + C::NUM_BARRIERS * 8;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = static_cast<int>(cluster_ctarank());
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
   const int total_tiles = p.num_m_blocks * p.num_n_blocks * p.ksplits;
 
   if (warp == 0 && lane == 0) {
@@ -142,125 +175,141 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     if (p.n_parts) tma_prefetch_desc(&p.tmParts);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NUM_STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < C::OP_STAGES; ++s) {
+      mbar_init(full_bar(s), 2);   // one arrive per CTA's producer (used in the leader only)
+      mbar_init(empty_bar(s), 1);  // multicast tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 128);
+      mbar_init(tmem_full_bar(a), 1);                     // multicast tcgen05.commit
+      mbar_init(tmem_empty_bar(a), 2 * NUM_MATH_WARPS);   // every math warp of both CTAs (used in the leader only)
     }
-    for (int e = 0; e < EPI_STAGES; ++e) {
-      mbar_init(epi_full_bar(e), 1);
-      mbar_init(epi_done_bar(e), 128);
+    for (int e = 0; e < C::IN_STAGES; ++e) {
+      mbar_init(in_full_bar(e), 1);
+      mbar_init(in_free_bar(e), 4);   // the four warps of the math group that consumed the stage
+    }
+    for (int o = 0; o < C::OUT_STAGES; ++o) {
+      mbar_init(out_full_bar(o), 4);
+      mbar_init(out_free_bar(o), 1);
     }
     fence_barrier_init();
   }
+  __syncwarp();
   if (warp == 2) {
-    tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tmem_relinquish_pair();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0 && lane == 0) {
-    // ================================ operand producer ================================
+    // ================================ operand producer (both CTAs) ================================
     uint32_t it = 0;
-    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
-      const TileCoord c = decode_tile(p, w);
-      for (int seg = 0; seg < p.nseg; ++seg) {
-        for (int kb = c.kb0; kb < c.kb1; ++kb, ++it) {
-          const int s = it % NUM_STAGES;
-          const uint32_t ph = (it / NUM_STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_arrive_expect_tx(full_bar(s), A_STAGE_BYTES + B_STAGE_BYTES);
-          tma_load_2d(sA + s * A_STAGE_BYTES, &p.tmA, full_bar(s), p.a_koff[seg] + kb * BLOCK_K, c.m0, kEvictNormal);
-          tma_load_2d(sB + s * B_STAGE_BYTES, &p.tmB, full_bar(s), p.b_koff[seg] + kb * BLOCK_K, c.n0, kEvictLast);
-        }
+    for (int w = cluster_id; w < total_tiles; w += num_clusters) {
+      const TileCoord c = decode_tile(p, w, cta_rank);
+      for (int kb = c.kb0; kb < c.kb1; ++kb, ++it) {
+        const int s = it % C::OP_STAGES;
+        const uint32_t ph = (it / C::OP_STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
+        else mbar_arrive_remote(full_bar(s), 0);
+        const uint32_t dst = sOp + s * C::STAGE_BYTES;
+#pragma unroll
+        for (int q = 0; q < P; ++q)
+          tma_load_2d_pair(dst + q * C::TILE_BYTES, &p.tmA, full_bar(s), q * p.a_part_stride + kb * C::BK, c.m0,
+                           kEvictNormal);
+#pragma unroll
+        for (int q = 0; q < P; ++q)
+          tma_load_2d_pair(dst + (P + q) * C::TILE_BYTES, &p.tmB, full_bar(s), q * p.b_part_stride + kb * C::BK,
+                           c.n0 + cta_rank * HALF_N, kEvictLast);
       }
     }
   } else if (warp == 1 && lane == 0) {
-    // ================================ MMA issuer ================================
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
-    uint32_t it = 0, tile_iter = 0;
-    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++tile_iter) {
-      const TileCoord c = decode_tile(p, w);
-      const int acc = tile_iter & 1;
-      const uint32_t acc_ph = (tile_iter >> 1) & 1;
-      mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      uint32_t accumulate = 0;
-      for (int seg = 0; seg < p.nseg; ++seg) {
+    // ================================ MMA issuer (leader CTA) ================================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR_M, BLOCK_N);
+      uint32_t it = 0, tile_iter = 0;
+      for (int w = cluster_id; w < total_tiles; w += num_clusters, ++tile_iter) {
+        const TileCoord c = decode_tile(p, w, cta_rank);
+        const int acc = tile_iter & 1;
+        const uint32_t acc_ph = (tile_iter >> 1) & 1;
+        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        uint32_t accumulate = 0;
         for (int kb = c.kb0; kb < c.kb1; ++kb, ++it) {
-          const int s = it % NUM_STAGES;
-          const uint32_t ph = (it / NUM_STAGES) & 1;
+          const int s = it % C::OP_STAGES;
+          const uint32_t ph = (it / C::OP_STAGES) & 1;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint64_t adesc = make_kmajor_sw128_desc(sA + s * A_STAGE_BYTES);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sB + s * B_STAGE_BYTES);
+          const uint32_t stage = sOp + s * C::STAGE_BYTES;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // +32 bytes (UMMA_K bf16) per step inside the 128-byte swizzle span -> +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
-            accumulate = 1;
+          for (int pr = 0; pr < C::NPAIRS; ++pr) {
+            const uint64_t adesc = make_kmajor_desc(stage + pair_a(P, pr) * C::TILE_BYTES, C::SPAN);
+            const uint64_t bdesc = make_kmajor_desc(stage + (P + pair_b(P, pr)) * C::TILE_BYTES, C::SPAN);
+#pragma unroll
+            for (int k = 0; k < C::BK / UMMA_K; ++k) {
+              // +32 bytes (16 bf16) per K step inside the swizzle span -> +2 in the (address >> 4) field
+              umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+              accumulate = 1;
+            }
           }
-          umma_commit(empty_bar(s));  // smem slot is free once these MMAs have drained
+          umma_commit_pair(empty_bar(s), 3);  // both CTAs' slots are free once these MMAs have drained
         }
+        umma_commit_pair(tmem_full_bar(acc), 3);  // accumulator ready for both epilogues
       }
-      umma_commit(tmem_full_bar(acc));  // accumulator ready for the epilogue
     }
   } else if (warp == 3 && lane == 0) {
-    // ================================ epilogue DMA ================================
+    // ================================ epilogue loader ================================
     const uint32_t in_bytes = p.n_in * EPI_ARRAY_BYTES;
-    // load cursor
-    int wl = blockIdx.x, jl = 0;
-    TileCoord cl = decode_tile(p, wl < total_tiles ? wl : 0);
-    uint32_t ql = 0;
-    auto issue_load = [&]() {  // arm stage (ql % EPI_STAGES) with sub-tile (wl, jl); returns false past the end
-      if (wl >= total_tiles) return false;
-      const int e = ql % EPI_STAGES;
-      const uint32_t dst = sE + e * EPI_STAGE_BYTES;
-      if (p.n_in > 0) {
-        mbar_arrive_expect_tx(epi_full_bar(e), in_bytes);
-        for (int i = 0; i < p.n_in; ++i)
-          tma_load_2d(dst + i * EPI_ARRAY_BYTES, &p.tmIn[i], epi_full_bar(e), cl.n0 + jl * EPI_COLS, cl.m0,
-                      kEvictFirst);
-      } else {
-        mbar_arrive(epi_full_bar(e));  // nothing to load: just hand the stage to the math warps
-      }
-      ++ql;
-      if (++jl == cl.nsub) {
-        jl = 0;
-        wl += gridDim.x;
-        if (wl < total_tiles) cl = decode_tile(p, wl);
-      }
-      return true;
-    };
-    for (int i = 0; i < EPI_STAGES; ++i) issue_load();
     uint32_t q = 0;
-    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
-      const TileCoord c = decode_tile(p, w);
+    for (int w = cluster_id; w < total_tiles; w += num_clusters) {
+      const TileCoord c = decode_tile(p, w, cta_rank);
       for (int j = 0; j < c.nsub; ++j, ++q) {
-        const int e = q % EPI_STAGES;
-        const uint32_t ph = (q / EPI_STAGES) & 1;
-        mbar_wait(epi_done_bar(e), ph);  // math warps have written {out | parts} of sub-tile q
-        const uint32_t src = sE + e * EPI_STAGE_BYTES;
+        const int e = q % C::IN_STAGES;
+        const uint32_t ph = (q / C::IN_STAGES) & 1;
+        mbar_wait(in_free_bar(e), ph ^ 1);
+        if (p.n_in > 0) {
+          mbar_arrive_expect_tx(in_full_bar(e), in_bytes);
+          for (int i = 0; i < p.n_in; ++i)
+            tma_load_2d(sIn + e * IN_STAGE_BYTES + i * EPI_ARRAY_BYTES, &p.tmIn[i], in_full_bar(e),
+                        c.n0 + j * EPI_COLS, c.m0, kEvictFirst);
+        } else {
+          mbar_arrive(in_full_bar(e));
+        }
+      }
+    }
+  } else if (warp == 2 && lane == 0) {
+    // ================================ epilogue storer ================================
+    uint32_t q = 0;
+    for (int w = cluster_id; w < total_tiles; w += num_clusters) {
+      const TileCoord c = decode_tile(p, w, cta_rank);
+      for (int j = 0; j < c.nsub; ++j, ++q) {
+        const int o = q % C::OUT_STAGES;
+        const uint32_t ph = (q / C::OUT_STAGES) & 1;
+        mbar_wait(out_full_bar(o), ph);  // a math group has written {out | parts} of sub-tile q
+        const uint32_t src = sOut + o * C::OUT_STAGE_BYTES;
         if (p.store_out) tma_store_2d(&p.tmOut, src, c.n0 + j * EPI_COLS, c.out_row0);
-        if (p.n_parts) tma_store_3d(&p.tmParts, src + EPI_ARRAY_BYTES, c.n0 + j * EPI_COLS, 0, c.m0);
+        for (int part = 0; part < p.n_parts; ++part)
+          tma_store_2d(&p.tmParts, src + EPI_ARRAY_BYTES + part * EPI_PART_BYTES,
+                       part * p.out_part_stride + c.n0 + j * EPI_COLS, c.m0);
         bulk_commit();
-        bulk_wait_read<0>();  // stage memory may be overwritten again
-        issue_load();         // refill this stage with sub-tile q + EPI_STAGES
+        if (q > 0) {
+          bulk_wait_read<1>();  // everything but the group just committed has left shared memory
+          mbar_arrive(out_free_bar((q - 1) % C::OUT_STAGES));
+        }
       }
     }
     bulk_wait<0>();
   } else if (warp >= 4) {
     // ================================ epilogue math ================================
+    const uint32_t group = (warp - 4) >> 2;  // 0 or 1: which alternate sub-tiles this warp works on
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;     // row inside the 128-row tile
-    const uint32_t sw = (row >> 1) & 3;      // SWIZZLE_64B: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)
+    const int row = quarter * 32 + lane;     // row inside this CTA's 128-row tile
+    const uint32_t sw64 = (row >> 1) & 3;    // SWIZZLE_64B: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)
+    const uint32_t sw32 = (row >> 2) & 1;    // SWIZZLE_32B: chunk c of row r lives at chunk c ^ ((r >> 2) & 1)
     float eta = 0.f, theta = 0.f;
     if (EPI == EPI_FISTA) {
       eta = __ldg(p.scalars + 0);
@@ -268,32 +317,48 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     }
     float stat_local = 0.f;
     uint32_t q = 0, tile_iter = 0;
-    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++tile_iter) {
-      const TileCoord c = decode_tile(p, w);
+    for (int w = cluster_id; w < total_tiles; w += num_clusters, ++tile_iter) {
+      const TileCoord c = decode_tile(p, w, cta_rank);
       const int acc = tile_iter & 1;
       const uint32_t acc_ph = (tile_iter >> 1) & 1;
       mbar_wait(tmem_full_bar(acc), acc_ph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      // last sub-tile of this tile that belongs to this warp's group (-1: none)
+      int j_last = c.nsub - 1;
+      if (((q + j_last) & 1) != group) --j_last;
+      if (j_last < 0) {
+        __syncwarp();
+        if (lane == 0) {
+          tc_fence_before();
+          mbar_arrive_remote(tmem_empty_bar(acc), 0);
+        }
+      }
       for (int j = 0; j < c.nsub; ++j, ++q) {
-        const int e = q % EPI_STAGES;
-        const uint32_t ph = (q / EPI_STAGES) & 1;
+        if ((q & 1) != group) continue;
+        const int e = q % C::IN_STAGES;
+        const uint32_t in_ph = (q / C::IN_STAGES) & 1;
+        const int o = q % C::OUT_STAGES;
+        const uint32_t out_ph = (q / C::OUT_STAGES) & 1;
         uint32_t v[16];
         tmem_ld16(t_row + j * EPI_COLS, v);
-        mbar_wait(epi_full_bar(e), ph);
+        mbar_wait(in_full_bar(e), in_ph);
         tmem_ld_wait();
-        if (j == c.nsub - 1) {  // accumulator fully drained into registers: hand TMEM back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(tmem_empty_bar(acc));
+        if (j == j_last) {  // this warp has drained its share of the accumulator
+          __syncwarp();
+          if (lane == 0) {
+            tc_fence_before();
+            mbar_arrive_remote(tmem_empty_bar(acc), 0);
+          }
         }
-        uint8_t* stage = smem + SMEM_EPI_OFF + e * EPI_STAGE_BYTES;
+        const uint32_t in_stage = sIn + e * IN_STAGE_BYTES;
         float in[3][16];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           if (i < p.n_in) {
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
-              const float4 t = *reinterpret_cast<const float4*>(stage + i * EPI_ARRAY_BYTES + row * 64 + ((ch ^ sw) << 4));
+              const float4 t = lds128(in_stage + i * EPI_ARRAY_BYTES + row * 64 + ((ch ^ sw64) << 4));
               in[i][4 * ch + 0] = t.x; in[i][4 * ch + 1] = t.y; in[i][4 * ch + 2] = t.z; in[i][4 * ch + 3] = t.w;
             }
           } else {
@@ -336,7 +401,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
               outv[x] = a;
             }
           } else {
-            // subspace shrinkage over `group` adjacent columns (group divides 16)
             switch (p.group) {
               case 2: group_shrink<2>(u, outv, theta); break;
               case 4: group_shrink<4>(u, outv, theta); break;
@@ -352,16 +416,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
             if (p.stat) stat_local += fabsf(d);
           }
         }
-        named_bar_sync(1, 128);  // every math thread has finished reading this stage's inputs
+        // every lane has consumed its inputs: hand the in stage back to the loader
+        __syncwarp();
+        if (lane == 0) mbar_arrive(in_free_bar(e));
+        mbar_wait(out_free_bar(o), out_ph ^ 1);
+        const uint32_t out_stage = sOut + o * C::OUT_STAGE_BYTES;
         if (p.store_out) {
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch)
-            *reinterpret_cast<float4*>(stage + row * 64 + ((ch ^ sw) << 4)) =
-                make_float4(outv[4 * ch], outv[4 * ch + 1], outv[4 * ch + 2], outv[4 * ch + 3]);
+            sts128(out_stage + row * 64 + ((ch ^ sw64) << 4), outv[4 * ch], outv[4 * ch + 1], outv[4 * ch + 2],
+                   outv[4 * ch + 3]);
         }
         if (p.n_parts) {
-          // smem box layout [row][part][16 bf16]
-          uint8_t* prow = stage + EPI_ARRAY_BYTES + row * (p.n_parts * 32);
           float r[16];
 #pragma unroll
           for (int x = 0; x < 16; ++x) r[x] = partv[x];
@@ -377,12 +443,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
               r[2 * x + 1] = __fsub_rn(r[2 * x + 1], __bfloat162float(h1));
               w32[x] = pack_bf16x2(h0, h1);
             }
-            *reinterpret_cast<uint4*>(prow + part * 32) = make_uint4(w32[0], w32[1], w32[2], w32[3]);
-            *reinterpret_cast<uint4*>(prow + part * 32 + 16) = make_uint4(w32[4], w32[5], w32[6], w32[7]);
+            const uint32_t prow = out_stage + EPI_ARRAY_BYTES + part * EPI_PART_BYTES + row * 32;
+            sts128u(prow + ((0 ^ sw32) << 4), w32[0], w32[1], w32[2], w32[3]);
+            sts128u(prow + ((1 ^ sw32) << 4), w32[4], w32[5], w32[6], w32[7]);
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(epi_done_bar(e));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(out_full_bar(o));
       }
     }
     if (EPI == EPI_FISTA && p.stat) {
@@ -392,9 +460,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     }
   }
 
+  __syncwarp();
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
 }
 
 }  // namespace vtc

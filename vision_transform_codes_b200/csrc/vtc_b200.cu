@@ -126,11 +126,12 @@ struct F32Mat {
   int64_t rows = 0, cols = 0, ld = 0;
 };
 
-int map_operand(CUtensorMap* m, const PartsMat& a, int box_rows, const char* what) {
+int map_operand(CUtensorMap* m, const PartsMat& a, int block_k, const char* what) {
   const uint64_t dims[2] = {static_cast<uint64_t>(a.pitch_elems()), static_cast<uint64_t>(a.rows)};
   const uint64_t str[1] = {static_cast<uint64_t>(a.pitch_elems()) * 2};
-  const uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(box_rows)};
-  return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.ptr, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, what);
+  const uint32_t box[2] = {static_cast<uint32_t>(block_k), BLOCK_M};
+  return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.ptr, dims, str, box,
+                block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, what);
 }
 int map_f32(CUtensorMap* m, const F32Mat& a, const char* what) {
   const uint64_t dims[2] = {static_cast<uint64_t>(a.cols), static_cast<uint64_t>(a.rows)};
@@ -138,32 +139,20 @@ int map_f32(CUtensorMap* m, const F32Mat& a, const char* what) {
   const uint32_t box[2] = {EPI_COLS, BLOCK_M};
   return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.ptr, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, what);
 }
-// 3-D view (cols, parts, rows) of a parts matrix, for the epilogue's bf16 split store.
+// The epilogue's bf16 split store: part p of sub-tile (row0, col0) goes to columns p * Kp + col0. Columns in a part's
+// zero padding [K, Kp) may be written, always with zeros (the accumulator and every input are zero there).
 int map_parts_out(CUtensorMap* m, const PartsMat& a, const char* what) {
-  const uint64_t dims[3] = {static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.parts), static_cast<uint64_t>(a.rows)};
-  const uint64_t str[2] = {static_cast<uint64_t>(a.Kp) * 2, static_cast<uint64_t>(a.pitch_elems()) * 2};
-  const uint32_t box[3] = {EPI_COLS, static_cast<uint32_t>(a.parts), BLOCK_M};
-  return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a.ptr, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, what);
+  const uint64_t dims[2] = {static_cast<uint64_t>(a.pitch_elems()), static_cast<uint64_t>(a.rows)};
+  const uint64_t str[1] = {static_cast<uint64_t>(a.pitch_elems()) * 2};
+  const uint32_t box[2] = {EPI_COLS, BLOCK_M};
+  return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.ptr, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B, what);
 }
 
 // ---------------------------------------------------------------------------------------------- precision
 int parts_for(int precision) { return precision == VTC_PRECISION_BF16 ? 1 : precision == VTC_PRECISION_BF16X3 ? 2 : 3; }
 bool valid_precision(int p) { return p == VTC_PRECISION_BF16 || p == VTC_PRECISION_BF16X3 || p == VTC_PRECISION_BF16X6; }
-// (A part, B part) pairs, smallest-magnitude products first so that fp32 accumulation loses the least.
-int segments_for(int precision, int (*seg)[2]) {
-  if (precision == VTC_PRECISION_BF16) {
-    seg[0][0] = 0, seg[0][1] = 0;
-    return 1;
-  }
-  if (precision == VTC_PRECISION_BF16X3) {
-    const int s[3][2] = {{0, 1}, {1, 0}, {0, 0}};
-    memcpy(seg, s, sizeof(s));
-    return 3;
-  }
-  const int s[6][2] = {{0, 2}, {2, 0}, {1, 1}, {0, 1}, {1, 0}, {0, 0}};
-  memcpy(seg, s, sizeof(s));
-  return 6;
-}
+// K blocks the kernel walks for a padded K extent: 64 columns per stage for plain bf16, 32 for the split modes.
+int64_t k_blocks_for(int64_t Kp, int precision) { return Kp / (parts_for(precision) == 1 ? 64 : 32); }
 
 // ---------------------------------------------------------------------------------------------- GEMM launch
 struct GemmCall {
@@ -185,31 +174,24 @@ struct GemmCall {
   double* stat = nullptr;
 };
 
-template <int EPI>
-int launch_gemm(const GemmCall& c, cudaStream_t stream) {
-  DeviceInfo info;
-  TRY(require_sm100(&info));
-  if (c.M <= 0 || c.N <= 0 || c.K <= 0) return fail(VTC_ERR_ARG, "empty GEMM %lld x %lld x %lld", (long long)c.M, (long long)c.N, (long long)c.K);
-  if (c.A.K != c.K || c.B.K != c.K || c.A.Kp != c.B.Kp) return fail(VTC_ERR_ARG, "operand K mismatch");
+template <int EPI, int P>
+int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream) {
+  using Cf = Cfg<P>;
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  TRY(map_operand(&p.tmA, c.A, BLOCK_M, "A operand"));
-  TRY(map_operand(&p.tmB, c.B, BLOCK_N, "B operand"));
+  TRY(map_operand(&p.tmA, c.A, Cf::BK, "A operand"));
+  TRY(map_operand(&p.tmB, c.B, Cf::BK, "B operand"));
   for (int i = 0; i < c.n_in; ++i) TRY(map_f32(&p.tmIn[i], c.in[i], "epilogue input"));
   if (c.store_out) TRY(map_f32(&p.tmOut, c.out, "fp32 output"));
   if (c.n_parts) TRY(map_parts_out(&p.tmParts, c.parts_out, "bf16 parts output"));
   p.M = static_cast<int>(c.M);
   p.N = static_cast<int>(c.N);
-  p.num_m_blocks = static_cast<int>(ceil_div(c.M, BLOCK_M));
+  p.num_m_blocks = static_cast<int>(ceil_div(c.M, PAIR_M));
   p.num_n_blocks = static_cast<int>(ceil_div(c.N, BLOCK_N));
-  p.k_blocks = static_cast<int>(ceil_div(c.K, BLOCK_K));
-  int seg[MAX_SEG][2];
-  p.nseg = segments_for(c.precision, seg);
-  for (int s = 0; s < p.nseg; ++s) {
-    if (seg[s][0] >= c.A.parts || seg[s][1] >= c.B.parts) return fail(VTC_ERR_ARG, "operand has too few bf16 parts for precision %d", c.precision);
-    p.a_koff[s] = static_cast<int>(seg[s][0] * c.A.Kp);
-    p.b_koff[s] = static_cast<int>(seg[s][1] * c.B.Kp);
-  }
+  p.k_blocks = static_cast<int>(ceil_div(c.A.Kp, Cf::BK));  // Kp is a multiple of 64; the padding is zero
+  p.a_part_stride = static_cast<int>(c.A.Kp);
+  p.b_part_stride = static_cast<int>(c.B.Kp);
+  p.out_part_stride = static_cast<int>(c.parts_out.Kp);
   p.kb_per_split = static_cast<int>(ceil_div(p.k_blocks, c.ksplits));
   p.ksplits = static_cast<int>(ceil_div(p.k_blocks, p.kb_per_split));
   p.out_rows_per_split = static_cast<int>(c.out_rows_per_split);
@@ -225,16 +207,46 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
   p.stat = c.stat;
   const long long tiles = 1ll * p.num_m_blocks * p.num_n_blocks * p.ksplits;
   if (tiles > 0x7fffffffll) return fail(VTC_ERR_ARG, "too many tiles");
-  static thread_local bool attr_set[2] = {false, false};
-  if (!attr_set[EPI]) {
-    CUDA_TRY(cudaFuncSetAttribute(vtc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
-    attr_set[EPI] = true;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(vtc_gemm_kernel<EPI, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
+    attr_set = true;
   }
-  const int grid = static_cast<int>(tiles < info.sm_count ? tiles : info.sm_count);
-  vtc_gemm_kernel<EPI><<<grid, GEMM_THREADS, SMEM_ALLOC, stream>>>(p);
+  const long long max_pairs = info.sm_count / 2;
+  const int pairs = static_cast<int>(tiles < max_pairs ? tiles : max_pairs);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cf::SMEM_ALLOC;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_gemm_kernel<EPI, P>, p));
   COUNT_LAUNCH();
-  CUDA_TRY(cudaGetLastError());
   return VTC_OK;
+}
+
+template <int EPI>
+int launch_gemm(const GemmCall& c, cudaStream_t stream) {
+  DeviceInfo info;
+  TRY(require_sm100(&info));
+  if (c.M <= 0 || c.N <= 0 || c.K <= 0) return fail(VTC_ERR_ARG, "empty GEMM %lld x %lld x %lld", (long long)c.M, (long long)c.N, (long long)c.K);
+  if (c.A.K != c.K || c.B.K != c.K || c.A.Kp != c.B.Kp) return fail(VTC_ERR_ARG, "operand K mismatch");
+  const int P = parts_for(c.precision);
+  if (c.A.parts < P || c.B.parts < P) return fail(VTC_ERR_ARG, "operand has too few bf16 parts for precision %d", c.precision);
+  if (c.n_parts > MAX_PARTS || (c.n_parts && c.parts_out.parts < c.n_parts)) return fail(VTC_ERR_ARG, "bad parts output");
+  if (c.n_parts > P) return fail(VTC_ERR_ARG, "at most %d output parts at precision %d", P, c.precision);
+  switch (P) {
+    case 1: return launch_gemm_p<EPI, 1>(c, info, stream);
+    case 2: return launch_gemm_p<EPI, 2>(c, info, stream);
+    default: return launch_gemm_p<EPI, 3>(c, info, stream);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- small launches
@@ -291,7 +303,7 @@ PartsMat carve_parts(Carver& cv, int64_t rows, int64_t K, int parts) {
   PartsMat m;
   m.rows = rows;
   m.K = K;
-  m.Kp = round_up(K, BLOCK_K);
+  m.Kp = round_up(K, 64);
   m.parts = parts;
   m.ptr = cv.take(m.bytes());
   return m;
@@ -595,13 +607,13 @@ GradWs carve_grad(Carver& cv, int64_t B, int64_t S, int64_t D, int precision, in
   w.RT_op = carve_parts(cv, D, B, P);
   w.ldB = round_up(B, 4);
   w.xT = static_cast<float*>(cv.take(static_cast<size_t>(D) * w.ldB * 4));
-  const int64_t tiles_mn = ceil_div(S, BLOCK_M) * ceil_div(D, BLOCK_N);
-  const int64_t kb = ceil_div(B, BLOCK_K);
-  int64_t ks = sm_count / tiles_mn;
+  const int64_t tiles_mn = ceil_div(S, PAIR_M) * ceil_div(D, BLOCK_N);
+  const int64_t kb = k_blocks_for(round_up(B, 64), precision);
+  int64_t ks = (sm_count / 2) / tiles_mn;
   if (ks < 1) ks = 1;
   if (ks > kb) ks = kb;
   w.ksplits = static_cast<int>(ks);
-  w.rows_per_split = ceil_div(S, BLOCK_M) * BLOCK_M;
+  w.rows_per_split = ceil_div(S, PAIR_M) * PAIR_M;
   w.ldD = round_up(D, 4);
   w.partial = static_cast<float*>(cv.take(static_cast<size_t>(w.ksplits) * w.rows_per_split * w.ldD * 4));
   return w;
@@ -655,7 +667,7 @@ int vtc_sc_dict_grad(const float* images, int64_t ld_images, const float* dictio
     g.out = F32Mat{w.partial, static_cast<int64_t>(w.ksplits) * w.rows_per_split, D, w.ldD}, g.store_out = true;
     TRY(launch_gemm<EPI_STORE>(g, st));
     // launch_gemm may have lowered the split count; recompute exactly as it does
-    const int64_t kb = ceil_div(B, BLOCK_K);
+    const int64_t kb = k_blocks_for(round_up(B, 64), precision);
     const int64_t per = ceil_div(kb, w.ksplits);
     const int nsplit = static_cast<int>(ceil_div(kb, per));
     reduce_partials_kernel<<<grid_for(S * D, 256, info.sm_count), 256, 0, st>>>(w.partial, nsplit, w.rows_per_split,
