@@ -80,6 +80,15 @@ __host__ __device__ constexpr int pair_b(int P, int i) {
 
 enum EpiKind { EPI_STORE = 0, EPI_FISTA = 1 };
 enum ProxFlags { PROX_HARD = 1, PROX_NONNEG = 2 };
+// Tuning switches (VTC_B200_FLAGS). All default to off; the measured effect of each on configs[1] is in DESIGN.md.
+enum TuneFlags {
+  TUNE_CONTIGUOUS = 1,          // contiguous tile range per cluster instead of round-robin        (measured: slower)
+  TUNE_PREFETCH_OPERANDS = 2,   // TMA L2 prefetch of the A panel, 8-12 K blocks ahead              (measured: slower)
+  TUNE_PREFETCH_STATE = 4,      // TMA L2 prefetch of the fp32 state tiles, 16 sub-tiles ahead      (measured: slower)
+  TUNE_STATE_EVICT_FIRST = 8,   // evict-first hint on state loads: neighbours fetched in the same 128-byte line are
+                                // dropped before their own sub-tile asks for them (+45 % HBM reads) (measured: slower)
+  TUNE_PROMO_256 = 16,          // 256-byte L2 promotion on the fp32 tensor maps                     (measured: slower)
+};
 
 struct GemmParams {
   CUtensorMap tmA, tmB;    // bf16 operands, 2-D (cols, rows), box BK x 128, swizzle = row span
@@ -99,6 +108,7 @@ struct GemmParams {
   float beta_prev, beta_next;
   const float* scalars;    // device: [0]=eta, [1]=theta
   double* stat;            // optional: += sum |a_new - a_k| (early stopping statistic)
+  int flags;               // tuning switches, see TuneFlags
 };
 
 struct TileCoord {
@@ -166,6 +176,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
   const int total_tiles = p.num_m_blocks * p.num_n_blocks * p.ksplits;
+  // Each cluster walks a contiguous range of tiles (n fastest): the 256-row A panel of an m block is fetched from
+  // HBM once, for the first of its n tiles, and is L2-resident for the others.
+  const bool contiguous = (p.flags & TUNE_CONTIGUOUS) != 0;
+  const int tiles_per_cluster = (total_tiles + num_clusters - 1) / num_clusters;
+  const int w_begin = contiguous ? min(total_tiles, cluster_id * tiles_per_cluster) : cluster_id;
+  const int w_end = contiguous ? min(total_tiles, w_begin + tiles_per_cluster) : total_tiles;
+  const int w_step = contiguous ? 1 : num_clusters;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -206,12 +223,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
 
   if (warp == 0 && lane == 0) {
     // ================================ operand producer (both CTAs) ================================
+    // A second cursor runs PF_OP K blocks ahead and prefetches the A panel into L2 (no shared memory needed), so that
+    // the first n tile of every m block does not expose HBM latency to the tensor core.
+    constexpr int PF_OP = (P == 1) ? 12 : 8;
+    int pw = w_begin, pkb = 0;
+    TileCoord pc = decode_tile(p, pw < w_end ? pw : 0, cta_rank);
+    pkb = pc.kb0;
+    auto prefetch_step = [&]() {
+      if (pw >= w_end) return;
+      if (!contiguous || pw == w_begin || (pw % p.num_n_blocks) == 0) {
+#pragma unroll
+        for (int q = 0; q < P; ++q) tma_prefetch_2d(&p.tmA, q * p.a_part_stride + pkb * C::BK, pc.m0);
+      }
+      if (++pkb >= pc.kb1) {
+        if ((pw += w_step) < w_end) {
+          pc = decode_tile(p, pw, cta_rank);
+          pkb = pc.kb0;
+        }
+      }
+    };
+    const bool pf_op = (p.flags & TUNE_PREFETCH_OPERANDS) != 0;
+    if (pf_op)
+      for (int i = 0; i < PF_OP; ++i) prefetch_step();
     uint32_t it = 0;
-    for (int w = cluster_id; w < total_tiles; w += num_clusters) {
+    for (int w = w_begin; w < w_end; w += w_step) {
       const TileCoord c = decode_tile(p, w, cta_rank);
       for (int kb = c.kb0; kb < c.kb1; ++kb, ++it) {
         const int s = it % C::OP_STAGES;
         const uint32_t ph = (it / C::OP_STAGES) & 1;
+        if (pf_op) prefetch_step();
         mbar_wait(empty_bar(s), ph ^ 1);
         if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
         else mbar_arrive_remote(full_bar(s), 0);
@@ -231,7 +271,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(PAIR_M, BLOCK_N);
       uint32_t it = 0, tile_iter = 0;
-      for (int w = cluster_id; w < total_tiles; w += num_clusters, ++tile_iter) {
+      for (int w = w_begin; w < w_end; w += w_step, ++tile_iter) {
         const TileCoord c = decode_tile(p, w, cta_rank);
         const int acc = tile_iter & 1;
         const uint32_t acc_ph = (tile_iter >> 1) & 1;
@@ -263,19 +303,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     }
   } else if (warp == 3 && lane == 0) {
     // ================================ epilogue loader ================================
+    // The fp32 state tiles always come from HBM. A cursor PF_EPI sub-tiles ahead prefetches them into L2 so that the
+    // in ring only has to cover L2 latency, not HBM latency times bandwidth.
+    constexpr int PF_EPI = 16;
     const uint32_t in_bytes = p.n_in * EPI_ARRAY_BYTES;
+    int pw = w_begin, pj = 0;
+    TileCoord pc = decode_tile(p, pw < w_end ? pw : 0, cta_rank);
+    auto prefetch_step = [&]() {
+      if (pw >= w_end) return;
+      for (int i = 0; i < p.n_in; ++i) tma_prefetch_2d(&p.tmIn[i], pc.n0 + pj * EPI_COLS, pc.m0);
+      if (++pj >= pc.nsub) {
+        pj = 0;
+        if ((pw += w_step) < w_end) pc = decode_tile(p, pw, cta_rank);
+      }
+    };
+    const bool pf_epi = p.n_in > 0 && (p.flags & TUNE_PREFETCH_STATE) != 0;
+    if (pf_epi)
+      for (int i = 0; i < PF_EPI; ++i) prefetch_step();
     uint32_t q = 0;
-    for (int w = cluster_id; w < total_tiles; w += num_clusters) {
+    for (int w = w_begin; w < w_end; w += w_step) {
       const TileCoord c = decode_tile(p, w, cta_rank);
       for (int j = 0; j < c.nsub; ++j, ++q) {
         const int e = q % C::IN_STAGES;
         const uint32_t ph = (q / C::IN_STAGES) & 1;
+        if (pf_epi) prefetch_step();
         mbar_wait(in_free_bar(e), ph ^ 1);
         if (p.n_in > 0) {
           mbar_arrive_expect_tx(in_full_bar(e), in_bytes);
           for (int i = 0; i < p.n_in; ++i)
             tma_load_2d(sIn + e * IN_STAGE_BYTES + i * EPI_ARRAY_BYTES, &p.tmIn[i], in_full_bar(e),
-                        c.n0 + j * EPI_COLS, c.m0, kEvictFirst);
+                        c.n0 + j * EPI_COLS, c.m0, (p.flags & TUNE_STATE_EVICT_FIRST) ? kEvictFirst : kEvictNormal);
         } else {
           mbar_arrive(in_full_bar(e));
         }
@@ -284,7 +341,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
   } else if (warp == 2 && lane == 0) {
     // ================================ epilogue storer ================================
     uint32_t q = 0;
-    for (int w = cluster_id; w < total_tiles; w += num_clusters) {
+    for (int w = w_begin; w < w_end; w += w_step) {
       const TileCoord c = decode_tile(p, w, cta_rank);
       for (int j = 0; j < c.nsub; ++j, ++q) {
         const int o = q % C::OUT_STAGES;
@@ -317,7 +374,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     }
     float stat_local = 0.f;
     uint32_t q = 0, tile_iter = 0;
-    for (int w = cluster_id; w < total_tiles; w += num_clusters, ++tile_iter) {
+    for (int w = w_begin; w < w_end; w += w_step, ++tile_iter) {
       const TileCoord c = decode_tile(p, w, cta_rank);
       const int acc = tile_iter & 1;
       const uint32_t acc_ph = (tile_iter >> 1) & 1;

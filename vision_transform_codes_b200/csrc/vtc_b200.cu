@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -77,6 +78,8 @@ int require_sm100(DeviceInfo* info) {
   return VTC_OK;
 }
 
+int tune_flags();
+
 // ---------------------------------------------------------------------------------------------- tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -107,8 +110,11 @@ int encode(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, c
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(VTC_ERR_ARG, "%s: base pointer not 16-byte aligned", what);
   for (int i = 0; i < rank - 1; ++i)
     if (gstr[i] % 16 != 0) return fail(VTC_ERR_ARG, "%s: stride %llu not a multiple of 16 bytes", what, (unsigned long long)gstr[i]);
+  // operands (re-read from L2 by several tiles): 256-byte promotion; fp32 state tiles (64-byte rows, read once): none
+  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT32 && !(tune_flags() & TUNE_PROMO_256)) promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;
   CUresult r = fn(m, dt, rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(VTC_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
   return VTC_OK;
 }
@@ -151,6 +157,16 @@ int map_parts_out(CUtensorMap* m, const PartsMat& a, const char* what) {
 // ---------------------------------------------------------------------------------------------- precision
 int parts_for(int precision) { return precision == VTC_PRECISION_BF16 ? 1 : precision == VTC_PRECISION_BF16X3 ? 2 : 3; }
 bool valid_precision(int p) { return p == VTC_PRECISION_BF16 || p == VTC_PRECISION_BF16X3 || p == VTC_PRECISION_BF16X6; }
+// Tuning switches of the GEMM kernel (TuneFlags); VTC_B200_FLAGS overrides the default for experiments.
+int tune_flags() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("VTC_B200_FLAGS");
+    cached = e ? atoi(e) : 0;
+  }
+  return cached;
+}
+
 // K blocks the kernel walks for a padded K extent: 64 columns per stage for plain bf16, 32 for the split modes.
 int64_t k_blocks_for(int64_t Kp, int precision) { return Kp / (parts_for(precision) == 1 ? 64 : 32); }
 
@@ -205,6 +221,7 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   p.beta_next = c.beta_next;
   p.scalars = c.scalars;
   p.stat = c.stat;
+  p.flags = tune_flags();
   const long long tiles = 1ll * p.num_m_blocks * p.num_n_blocks * p.ksplits;
   if (tiles > 0x7fffffffll) return fail(VTC_ERR_ARG, "too many tiles");
   static thread_local bool attr_set = false;
