@@ -107,6 +107,10 @@ int vtc_sc_dict_apply(float* dictionary, const float* grad_sum, const float* hes
 int vtc_hessian_diag_update(const float* codes, int64_t ld_codes, int64_t B, int64_t S, int64_t batch_global,
                             float* code_sq_sum, float* hessian_diagonal, int apply_ema, vtc_stream_t stream);
 
+/* Second half of the running mean when code_sq_sum has been summed over shards: h <- 0.99 h + (sum/batch)/100. */
+int vtc_hessian_ema(float* hessian_diagonal, const float* code_sq_sum, int64_t S, int64_t batch_global,
+                    vtc_stream_t stream);
+
 /*
  * Generic contraction exposed for tests and tools: out (M, N) = A (M, K) * B (N, K)^T [- sub (M, N)], float32 in and
  * out, computed on the tcgen05 path with the requested precision.

@@ -732,6 +732,16 @@ int vtc_hessian_diag_update(const float* codes, int64_t ld_codes, int64_t B, int
   return VTC_OK;
 }
 
+int vtc_hessian_ema(float* hessian_diagonal, const float* code_sq_sum, int64_t S, int64_t batch_global,
+                    vtc_stream_t stream) {
+  if (!hessian_diagonal || !code_sq_sum || S <= 0 || batch_global <= 0) return fail(VTC_ERR_ARG, "vtc_hessian_ema: bad argument");
+  hessian_ema_kernel<<<static_cast<unsigned>(ceil_div(S, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      hessian_diagonal, code_sq_sum, S, static_cast<float>(batch_global));
+  COUNT_LAUNCH();
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- generic matmul
 size_t vtc_matmul_nt_workspace_bytes(int64_t M, int64_t N, int64_t K, int precision) {
   if (!valid_precision(precision) || M <= 0 || N <= 0 || K <= 0) return 0;

@@ -1,0 +1,211 @@
+"""
+Sparse-coding dictionary training on B200: the per-batch hot path of the reference trainer, optionally data parallel.
+
+The reference's ``training/sparse_coding.py`` (train_dictionary, :9-519) is the CALLER of the hot path and keeps
+working unmodified on top of the drop-in modules (``vision_transform_codes_b200.install()``). This module is the
+lean equivalent for when the reference tree is not on the machine, and the only trainer that is correct under data
+parallelism: it mirrors the reference's parameter dictionary and per-batch body (:460-465 schedules, :513-515
+infer -> update, :154 Hessian running mean, :170-175 pickle checkpoints) and leaves out what is not on the hot path
+(tensorboard visualisation :177-271, dictionary-element reset/prune :522-764), which raise NotImplementedError.
+
+Data parallel (``vision_transform_codes_b200.enable_data_parallel()``): every rank holds a replica of the
+dictionary and its contiguous shard of each batch. Inference needs no communication. Per dictionary-update
+iteration there is exactly one collective: a sum all-reduce of [gradient sum | sum of squared codes] (S*D + S
+floats), after which every rank applies the identical update, so the replicas stay bit-identical.
+"""
+import pickle
+import time
+
+import torch
+
+from vision_transform_codes_b200 import _lib, config
+from vision_transform_codes_b200.analysis_transforms.fully_connected import ista_fista, subspace_ista_fista
+from vision_transform_codes_b200.dict_update_rules.fully_connected import _common
+
+CHEAP_QUADRATIC = ('sc_cheap_quadratic_descent', 'subspace_sc_cheap_quadratic_descent')
+UPDATE_RULES = ('sc_steepest_descent', 'sc_cheap_quadratic_descent', 'subspace_sc_steepest_descent',
+                'subspace_sc_cheap_quadratic_descent')
+
+
+def infer_codes(images, dictionary, code_inf_alg, sparsity_weight, num_iters, nonnegative_only=False,
+                hard_threshold=False, group_assignments=None):
+  """training/sparse_coding.py:124-140."""
+  if code_inf_alg in ('subspace_ista', 'subspace_fista'):
+    return subspace_ista_fista.run(images, dictionary, group_assignments, sparsity_weight, num_iters,
+                                   variant=code_inf_alg[9:], hard_threshold=hard_threshold)
+  return ista_fista.run(images, dictionary, sparsity_weight, num_iters, variant=code_inf_alg,
+                        nonnegative_only=nonnegative_only, hard_threshold=hard_threshold)
+
+
+class _UpdateState:
+  """Buffers reused across steps: packed [gradient sum | sum of squared codes] for the single all-reduce."""
+
+  def __init__(self, dictionary):
+    S, D = dictionary.shape
+    self.packed = torch.empty(S * D + S, dtype=torch.float32, device=dictionary.device)
+    self.grad = self.packed[:S * D].view(S, D)
+    self.sq_sum = self.packed[S * D:]
+    self.batch_global = None
+
+
+def allreduce_update_buffers(state, with_code_squares):
+  """The one collective of a data-parallel update step: sum over ranks of [gradient sum | sum of squared codes]."""
+  import torch.distributed as dist
+  dist.all_reduce(state.packed if with_code_squares else state.grad, op=dist.ReduceOp.SUM,
+                  group=config.process_group)
+
+
+def update_dictionary(images, dictionary, codes, hessian_diag, stepsize, num_iters, state, lowest_code_val=0.001,
+                      normalize_dictionary=True, batch_global=None):
+  """
+  training/sparse_coding.py:142-168 for the fully-connected rules: the Hessian running mean (:154, when
+  hessian_diag is given) followed by num_iters descent steps, with ONE all-reduce per step when data parallel.
+  """
+  lib = _lib.load()
+  device = dictionary.device
+  S, D = dictionary.shape
+  B = codes.size(0)
+  if batch_global is None:
+    if state.batch_global is None or state.batch_global[0] != B:
+      state.batch_global = (B, _common.global_batch_size(B, device))
+    batch_global = state.batch_global[1]
+  codes_rm, ld_codes = _lib.row_major(codes)
+  with torch.cuda.device(device):
+    st = _lib.stream_ptr(device)
+    for it in range(int(num_iters)):
+      _common.dictionary_gradient(images, dictionary, codes, out=state.grad)
+      first = it == 0 and hessian_diag is not None
+      if first:
+        _lib.check(lib.vtc_hessian_diag_update(_lib.ptr(codes_rm), ld_codes, B, S, batch_global,
+                                               _lib.ptr(state.sq_sum), 0, 0, st))
+      if config.data_parallel:
+        allreduce_update_buffers(state, first)
+      if first:
+        _lib.check(lib.vtc_hessian_ema(_lib.ptr(hessian_diag), _lib.ptr(state.sq_sum), S, batch_global, st))
+      _lib.check(lib.vtc_sc_dict_apply(_lib.ptr(dictionary), _lib.ptr(state.grad), _lib.ptr(hessian_diag), S, D,
+                                       int(batch_global), float(stepsize), float(lowest_code_val),
+                                       int(bool(normalize_dictionary)), st))
+
+
+def train_dictionary(training_image_dataset, validation_image_dataset, init_dictionary, all_params):
+  """
+  Train a sparse coding dictionary (fully-connected mode), in place on ``init_dictionary``.
+
+  Same arguments as the reference's train_dictionary (training/sparse_coding.py:9-117). Under data parallelism
+  ``training_image_dataset`` yields THIS rank's shard of every batch.
+  """
+  assert 0 in all_params['inference_param_schedule']
+  assert 0 in all_params['dict_update_param_schedule']
+  coding_mode = all_params['mode']
+  num_epochs = all_params['num_epochs']
+  code_inf_alg = all_params['code_inference_algorithm']
+  inf_param_schedule = all_params['inference_param_schedule']
+  dict_update_alg = all_params['dictionary_update_algorithm']
+  dict_update_param_schedule = all_params['dict_update_param_schedule']
+  assert coding_mode in ['fully-connected', 'convolutional']
+  assert code_inf_alg in ['ista', 'fista', 'subspace_ista', 'subspace_fista']
+  assert dict_update_alg in UPDATE_RULES
+  if coding_mode != 'fully-connected':
+    raise NotImplementedError('the B200 path covers fully-connected sparse coding')
+  for key in ('training_visualization_schedule', 'dict_element_rp_schedule'):
+    if key in all_params:
+      raise NotImplementedError('%s is host-side orchestration outside the B200 hot path; run the reference '
+                                'trainer on top of vision_transform_codes_b200.install() for it' % key)
+  if dict_update_alg == 'subspace_sc_steepest_descent':
+    raise ImportError('dict_update_rules.fully_connected.subspace_sc_steepest_descent does not exist in the '
+                      'reference either')
+  nonneg_only = all_params.get('nonnegative_only', False)
+  hard_threshold = all_params.get('hard_threshold', False)
+  group_assignments = all_params.get('group_assignments')
+  if group_assignments is not None:
+    assert all([len(set(x)) == len(x) for x in group_assignments])
+    group_assignments = [list(map(int, x)) for x in group_assignments]
+  if code_inf_alg.startswith('subspace'):
+    assert group_assignments is not None
+  if dict_update_alg.startswith('subspace') and all_params.get('subspace_alignment_penalty', 0.0) != 0:
+    raise NotImplementedError('subspace_alignment_penalty != 0 is not implemented on the B200 path')
+  if all_params.get('renormalize_dictionary', True):
+    norms = init_dictionary.norm(p=2, dim=1)
+    assert torch.allclose(norms, torch.ones_like(norms)), 'Please ensure the initial dictionary is already normalized'
+  ckpt_sched = all_params.get('checkpoint_schedule')
+  logging_path = all_params.get('logging_folder_fullpath')
+  if ckpt_sched is not None:
+    assert logging_path is not None and not isinstance(logging_path, str), 'should be pathlib.Path'
+    logging_path.mkdir(parents=True, exist_ok=True)
+  print_interval = all_params.get('stdout_print_interval', 1000)
+
+  dictionary = init_dictionary  # no copying, just a new reference
+  hessian_diag = None
+  if dict_update_alg in CHEAP_QUADRATIC:
+    hessian_diag = init_dictionary.new_zeros(init_dictionary.shape[0])
+  state = _UpdateState(dictionary)
+  rank0 = (not config.data_parallel) or torch.distributed.get_rank(config.process_group) == 0
+
+  starttime = time.time()
+  total_iter_idx = 0
+  for epoch_idx in range(num_epochs):
+    for t_batch_images in training_image_dataset:
+      if total_iter_idx % print_interval == 0 and total_iter_idx != 0 and rank0:
+        print(total_iter_idx, 'iterations complete')
+        print('Time elapsed:', '{:.1f}'.format(time.time() - starttime), 'seconds')
+        print('-----')
+      if total_iter_idx in inf_param_schedule:
+        sparsity_weight = inf_param_schedule[total_iter_idx]['sparsity_weight']
+        inf_num_iters = inf_param_schedule[total_iter_idx]['num_iters']
+      if total_iter_idx in dict_update_param_schedule:
+        d_upd_stp = dict_update_param_schedule[total_iter_idx]['stepsize']
+        d_upd_niters = dict_update_param_schedule[total_iter_idx]['num_iters']
+      if ckpt_sched is not None and total_iter_idx in ckpt_sched and rank0:
+        pickle.dump(dictionary.cpu().numpy(),
+                    open(logging_path / ('checkpoint_dictionary_iter_' + str(total_iter_idx)), 'wb'))
+      if dictionary.device != t_batch_images.device:
+        t_batch_images = t_batch_images.to(dictionary.device)
+      t_codes = infer_codes(t_batch_images, dictionary, code_inf_alg, sparsity_weight, inf_num_iters, nonneg_only,
+                            hard_threshold, group_assignments)
+      update_dictionary(t_batch_images, dictionary, t_codes, hessian_diag, d_upd_stp, d_upd_niters, state)
+      total_iter_idx += 1
+    if rank0:
+      print("Epoch", epoch_idx + 1, "finished")
+  return hessian_diag
+
+
+def benchmark_train_step(global_batch, S, D, num_iters, sparsity_weight, world, rank, device, timed, steps=2):
+  """
+  bench.py helper: BASELINE.json configs[2], one full train step = FISTA inference on this rank's shard of a
+  524,288-patch batch + Hessian running mean + cheap-quadratic dictionary update with one all-reduce.
+  Strong scaling: the global batch is fixed and sharded over `world` GPUs.
+  """
+  g = torch.Generator().manual_seed(1)
+  phi = torch.randn(S, D, generator=g)
+  phi = (phi / phi.norm(dim=1, keepdim=True)).to(device)
+  shard = global_batch // world
+  gx = torch.Generator(device=device).manual_seed(100 + rank)
+  x = 0.3 * torch.randn(shard, D, generator=gx, device=device)
+  h = torch.zeros(S, device=device)
+  state = _UpdateState(phi)
+  was_parallel = config.data_parallel
+  if world > 1:
+    config.data_parallel, config.process_group = True, None
+
+  def step():
+    codes = ista_fista.run(x, phi, sparsity_weight, num_iters)
+    update_dictionary(x, phi, codes, h, 0.1, 1, state, batch_global=global_batch)
+
+  try:
+    ms, launches = timed(step, steps, 1)
+  finally:
+    config.data_parallel = was_parallel
+  ms /= steps
+  replicas_identical = None
+  if world > 1:
+    import torch.distributed as dist
+    ref = phi.clone()
+    dist.broadcast(ref, src=0)
+    same = torch.tensor([int(torch.equal(ref, phi))], device=device)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    replicas_identical = bool(same.item())
+  return {'steps_per_sec': 1e3 / ms, 'ms_per_step': ms, 'global_batch': global_batch, 'shard_per_gpu': shard,
+          'scaling': 'strong', 'update_rule': 'sc_cheap_quadratic_descent', 'allreduce_bytes_per_step': 4 * (S * D + S),
+          'patches_per_sec': global_batch * 1e3 / ms, 'gpu_launches': int(launches),
+          'replicas_bit_identical': replicas_identical,
+          'workload': 'configs[2]: FISTA-300 inference + SC quadratic-descent update, 16x16 patches, 1024 atoms'}
