@@ -53,6 +53,12 @@ long long vtc_launch_count(void);
 int vtc_profile_enable(int on);
 int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches);
 
+/* Contraction used by one ISTA/FISTA iteration: 1 = Gram form (y G - b, G = Phi Phi^T; 2*S*S flops per patch, one
+ * launch), 2 = synthesis/analysis form ((y Phi - x) Phi^T as in ista_fista.py:105-106; 4*S*D flops, two launches),
+ * 0 = automatic (synthesis when S > 2 D). Both give the same iterates up to rounding. Also VTC_B200_FORMULATION. */
+int vtc_set_formulation(int formulation);
+int vtc_get_formulation(int64_t S, int64_t D);
+
 /* Number of SMs / compute capability of the current device (used by bench.py to size workloads). */
 int vtc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

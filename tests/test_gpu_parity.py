@@ -111,6 +111,50 @@ def test_precision_modes_on_overcomplete_shape(precision, tol, rtol):
   check_codes(got, g['fista'], phi, tol=tol, recon_tol=rtol, band=GUARD_BAND if precision != 'bf16' else None)
 
 
+@pytest.fixture
+def formulation():
+  from vision_transform_codes_b200 import _lib
+  lib = _lib.load()
+
+  def choose(which):
+    _lib.check(lib.vtc_set_formulation({'auto': 0, 'gram': 1, 'synthesis': 2}[which]))
+  yield choose
+  lib.vtc_set_formulation(0)
+
+
+@pytest.mark.parametrize('which', ['gram', 'synthesis'])
+@pytest.mark.parametrize('name', ['inference_small', 'inference_config1', 'inference_overcomplete'])
+def test_both_formulations_against_reference_outputs(formulation, which, name):
+  """Gram form (y G - b) and synthesis form ((y Phi - x) Phi^T) are two contractions of the same iteration."""
+  ista_fista = modules()[0]
+  formulation(which)
+  g = load_golden(name)
+  phi = g['dictionary']
+  got = ista_fista.run(g['images'].cuda(), phi.cuda(), g['sparsity_weight'], g['num_iters'])
+  check_codes(got, g['fista'], phi)
+
+
+@pytest.mark.parametrize('which', ['gram', 'synthesis'])
+def test_formulations_cover_variants_and_ragged_shapes(formulation, which):
+  ista_fista, subspace = modules()[:2]
+  formulation(which)
+  B, S, D = 130, 200, 100
+  phi = oracle.synthetic_dictionary(S, D)
+  x = oracle.synthetic_patches(B, D)
+  for kw in ({'variant': 'ista'}, {'nonnegative_only': True}, {}):
+    want = oracle.ista_fista(x, phi, 0.1, 40, **kw)
+    check_codes(ista_fista.run(x.cuda(), phi.cuda(), 0.1, 40, **kw), want, phi)
+  groups = [list(range(i, i + 4)) for i in range(0, S, 4)]
+  want = oracle.subspace_ista_fista(x, phi, groups, 0.1, 40)
+  check_codes(subspace.run(x.cuda(), phi.cuda(), groups, 0.1, 40), want, phi)
+  warm = oracle.ista_fista(x, phi, 0.1, 5)
+  want = oracle.ista_fista(x, phi, 0.1, 40, initial_codes=warm)
+  check_codes(ista_fista.run(x.cuda(), phi.cuda(), 0.1, 40, initial_codes=warm.cuda()), want, phi)
+  _, want_iters = oracle.ista_fista(x, phi, 0.1, 500, variant='ista', early_stopping_epsilon=1e-3, return_iters=True)
+  _, iters = ista_fista.infer(x.cuda(), phi.cuda(), 0.1, 500, 'ista', None, 1e-3, False, False, 1)
+  assert abs(iters - want_iters) <= 1
+
+
 def test_oracle_parity_on_seeded_whitened_patches():
   """C2 shape (D=256, 1024 atoms, 300 FISTA iterations, lambda 0.1) on a 512-patch sub-batch of whitened patches."""
   ista_fista = modules()[0]

@@ -102,7 +102,8 @@ struct GemmParams {
   int out_part_stride;     // column offset between parts of the bf16 output
   int ksplits, kb_per_split;
   int out_rows_per_split;  // fp32 partial outputs are stacked along rows
-  int n_in, n_parts, store_out;
+  int in_mask;             // bit i set: epilogue input slot i is loaded (FISTA: 0 = a_k, 1 = b, 2 = a_{k-1})
+  int n_parts, store_out;
   int prox, group;         // ProxFlags; group size for subspace shrinkage (1 = scalar prox)
   int use_momentum;        // FISTA (1) or ISTA (0)
   float beta_prev, beta_next;
@@ -187,7 +188,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
-    for (int i = 0; i < p.n_in; ++i) tma_prefetch_desc(&p.tmIn[i]);
+    for (int i = 0; i < 3; ++i)
+      if (p.in_mask & (1 << i)) tma_prefetch_desc(&p.tmIn[i]);
     if (p.store_out) tma_prefetch_desc(&p.tmOut);
     if (p.n_parts) tma_prefetch_desc(&p.tmParts);
   }
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ================================ operand producer (both CTAs) ================================
     // A second cursor runs PF_OP K blocks ahead and prefetches the A panel into L2 (no shared memory needed), so that
     // the first n tile of every m block does not expose HBM latency to the tensor core.
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
       }
     };
     const bool pf_op = (p.flags & TUNE_PREFETCH_OPERANDS) != 0;
-    if (pf_op)
+    if (pf_op && lane == 0)
       for (int i = 0; i < PF_OP; ++i) prefetch_step();
     uint32_t it = 0;
     for (int w = w_begin; w < w_end; w += w_step) {
@@ -251,22 +253,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
       for (int kb = c.kb0; kb < c.kb1; ++kb, ++it) {
         const int s = it % C::OP_STAGES;
         const uint32_t ph = (it / C::OP_STAGES) & 1;
-        if (pf_op) prefetch_step();
+        if (pf_op && lane == 0) prefetch_step();
         mbar_wait(empty_bar(s), ph ^ 1);
-        if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
-        else mbar_arrive_remote(full_bar(s), 0);
-        const uint32_t dst = sOp + s * C::STAGE_BYTES;
+        if (elect_one_sync()) {
+          if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
+          else mbar_arrive_remote(full_bar(s), 0);
+          const uint32_t dst = sOp + s * C::STAGE_BYTES;
 #pragma unroll
-        for (int q = 0; q < P; ++q)
-          tma_load_2d_pair(dst + q * C::TILE_BYTES, &p.tmA, full_bar(s), q * p.a_part_stride + kb * C::BK, c.m0,
-                           kEvictNormal);
+          for (int q = 0; q < P; ++q)
+            tma_load_2d_pair(dst + q * C::TILE_BYTES, &p.tmA, full_bar(s), q * p.a_part_stride + kb * C::BK, c.m0,
+                             kEvictNormal);
 #pragma unroll
-        for (int q = 0; q < P; ++q)
-          tma_load_2d_pair(dst + (P + q) * C::TILE_BYTES, &p.tmB, full_bar(s), q * p.b_part_stride + kb * C::BK,
-                           c.n0 + cta_rank * HALF_N, kEvictLast);
+          for (int q = 0; q < P; ++q)
+            tma_load_2d_pair(dst + (P + q) * C::TILE_BYTES, &p.tmB, full_bar(s), q * p.b_part_stride + kb * C::BK,
+                             c.n0 + cta_rank * HALF_N, kEvictLast);
+        }
+        __syncwarp();
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA) ================================
     if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(PAIR_M, BLOCK_N);
@@ -285,40 +290,46 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t stage = sOp + s * C::STAGE_BYTES;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int pr = 0; pr < C::NPAIRS; ++pr) {
-            const uint64_t adesc = make_kmajor_desc(stage + pair_a(P, pr) * C::TILE_BYTES, C::SPAN);
-            const uint64_t bdesc = make_kmajor_desc(stage + (P + pair_b(P, pr)) * C::TILE_BYTES, C::SPAN);
+            for (int pr = 0; pr < C::NPAIRS; ++pr) {
+              const uint64_t adesc = make_kmajor_desc(stage + pair_a(P, pr) * C::TILE_BYTES, C::SPAN);
+              const uint64_t bdesc = make_kmajor_desc(stage + (P + pair_b(P, pr)) * C::TILE_BYTES, C::SPAN);
 #pragma unroll
-            for (int k = 0; k < C::BK / UMMA_K; ++k) {
-              // +32 bytes (16 bf16) per K step inside the swizzle span -> +2 in the (address >> 4) field
-              umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
-              accumulate = 1;
+              for (int k = 0; k < C::BK / UMMA_K; ++k) {
+                // +32 bytes (16 bf16) per K step inside the swizzle span -> +2 in the (address >> 4) field
+                umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                accumulate = 1;
+              }
             }
+            umma_commit_pair(empty_bar(s), 3);  // both CTAs' slots are free once these MMAs have drained
           }
-          umma_commit_pair(empty_bar(s), 3);  // both CTAs' slots are free once these MMAs have drained
+          accumulate = 1;
+          __syncwarp();
         }
-        umma_commit_pair(tmem_full_bar(acc), 3);  // accumulator ready for both epilogues
+        if (elect_one_sync()) umma_commit_pair(tmem_full_bar(acc), 3);  // accumulator ready for both epilogues
+        __syncwarp();
       }
     }
-  } else if (warp == 3 && lane == 0) {
+  } else if (warp == 3) {
     // ================================ epilogue loader ================================
     // The fp32 state tiles always come from HBM. A cursor PF_EPI sub-tiles ahead prefetches them into L2 so that the
     // in ring only has to cover L2 latency, not HBM latency times bandwidth.
     constexpr int PF_EPI = 16;
-    const uint32_t in_bytes = p.n_in * EPI_ARRAY_BYTES;
+    const uint32_t in_bytes = __popc(p.in_mask) * EPI_ARRAY_BYTES;
     int pw = w_begin, pj = 0;
     TileCoord pc = decode_tile(p, pw < w_end ? pw : 0, cta_rank);
     auto prefetch_step = [&]() {
       if (pw >= w_end) return;
-      for (int i = 0; i < p.n_in; ++i) tma_prefetch_2d(&p.tmIn[i], pc.n0 + pj * EPI_COLS, pc.m0);
+      for (int i = 0; i < 3; ++i)
+        if (p.in_mask & (1 << i)) tma_prefetch_2d(&p.tmIn[i], pc.n0 + pj * EPI_COLS, pc.m0);
       if (++pj >= pc.nsub) {
         pj = 0;
         if ((pw += w_step) < w_end) pc = decode_tile(p, pw, cta_rank);
       }
     };
-    const bool pf_epi = p.n_in > 0 && (p.flags & TUNE_PREFETCH_STATE) != 0;
-    if (pf_epi)
+    const bool pf_epi = p.in_mask != 0 && (p.flags & TUNE_PREFETCH_STATE) != 0;
+    if (pf_epi && lane == 0)
       for (int i = 0; i < PF_EPI; ++i) prefetch_step();
     uint32_t q = 0;
     for (int w = w_begin; w < w_end; w += w_step) {
@@ -326,19 +337,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
       for (int j = 0; j < c.nsub; ++j, ++q) {
         const int e = q % C::IN_STAGES;
         const uint32_t ph = (q / C::IN_STAGES) & 1;
-        if (pf_epi) prefetch_step();
+        if (pf_epi && lane == 0) prefetch_step();
         mbar_wait(in_free_bar(e), ph ^ 1);
-        if (p.n_in > 0) {
-          mbar_arrive_expect_tx(in_full_bar(e), in_bytes);
-          for (int i = 0; i < p.n_in; ++i)
-            tma_load_2d(sIn + e * IN_STAGE_BYTES + i * EPI_ARRAY_BYTES, &p.tmIn[i], in_full_bar(e),
-                        c.n0 + j * EPI_COLS, c.m0, (p.flags & TUNE_STATE_EVICT_FIRST) ? kEvictFirst : kEvictNormal);
-        } else {
-          mbar_arrive(in_full_bar(e));
+        if (elect_one_sync()) {
+          if (p.in_mask != 0) {
+            mbar_arrive_expect_tx(in_full_bar(e), in_bytes);
+            for (int i = 0; i < 3; ++i)
+              if (p.in_mask & (1 << i))
+                tma_load_2d(sIn + e * IN_STAGE_BYTES + i * EPI_ARRAY_BYTES, &p.tmIn[i], in_full_bar(e),
+                          c.n0 + j * EPI_COLS, c.m0, (p.flags & TUNE_STATE_EVICT_FIRST) ? kEvictFirst : kEvictNormal);
+          } else {
+            mbar_arrive(in_full_bar(e));
+          }
         }
+        __syncwarp();
       }
     }
-  } else if (warp == 2 && lane == 0) {
+  } else if (warp == 2) {
     // ================================ epilogue storer ================================
     uint32_t q = 0;
     for (int w = w_begin; w < w_end; w += w_step) {
@@ -348,18 +363,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
         const uint32_t ph = (q / C::OUT_STAGES) & 1;
         mbar_wait(out_full_bar(o), ph);  // a math group has written {out | parts} of sub-tile q
         const uint32_t src = sOut + o * C::OUT_STAGE_BYTES;
-        if (p.store_out) tma_store_2d(&p.tmOut, src, c.n0 + j * EPI_COLS, c.out_row0);
-        for (int part = 0; part < p.n_parts; ++part)
-          tma_store_2d(&p.tmParts, src + EPI_ARRAY_BYTES + part * EPI_PART_BYTES,
-                       part * p.out_part_stride + c.n0 + j * EPI_COLS, c.m0);
-        bulk_commit();
-        if (q > 0) {
-          bulk_wait_read<1>();  // everything but the group just committed has left shared memory
-          mbar_arrive(out_free_bar((q - 1) % C::OUT_STAGES));
+        if (elect_one_sync()) {  // bulk groups are per thread: the same elected lane issues, commits and waits
+          if (p.store_out) tma_store_2d(&p.tmOut, src, c.n0 + j * EPI_COLS, c.out_row0);
+          for (int part = 0; part < p.n_parts; ++part)
+            tma_store_2d(&p.tmParts, src + EPI_ARRAY_BYTES + part * EPI_PART_BYTES,
+                         part * p.out_part_stride + c.n0 + j * EPI_COLS, c.m0);
+          bulk_commit();
+          if (q > 0) {
+            bulk_wait_read<1>();  // everything but the group just committed has left shared memory
+            mbar_arrive(out_free_bar((q - 1) % C::OUT_STAGES));
+          }
         }
+        __syncwarp();
       }
     }
-    bulk_wait<0>();
+    if (elect_one_sync()) bulk_wait<0>();
+    __syncwarp();
   } else if (warp >= 4) {
     // ================================ epilogue math ================================
     const uint32_t group = (warp - 4) >> 2;  // 0 or 1: which alternate sub-tiles this warp works on
@@ -412,7 +431,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
         float in[3][16];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          if (i < p.n_in) {
+          if (p.in_mask & (1 << i)) {
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
               const float4 t = lds128(in_stage + i * EPI_ARRAY_BYTES + row * 64 + ((ch ^ sw64) << 4));
@@ -432,13 +451,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
             partv[x] = outv[x];
           }
         } else {
-          // in[0] = a_k, in[1] = b, in[2] = a_{k-1} (only loaded when the momentum term is non-zero)
+          // in[0] = a_k, in[1] = b (absent -> 0: the accumulator already is the full gradient),
+          // in[2] = a_{k-1} (only loaded when the momentum term is non-zero)
           float u[16];
 #pragma unroll
           for (int x = 0; x < 16; ++x) {
             const float ak = in[0][x];
             float y = ak;
-            if (p.n_in == 3) y = __fadd_rn(ak, __fmul_rn(p.beta_prev, __fsub_rn(ak, in[2][x])));
+            if (p.in_mask & 4) y = __fadd_rn(ak, __fmul_rn(p.beta_prev, __fsub_rn(ak, in[2][x])));
             const float g = __fsub_rn(__uint_as_float(v[x]), in[1][x]);
             u[x] = __fsub_rn(y, __fmul_rn(eta, g));
           }

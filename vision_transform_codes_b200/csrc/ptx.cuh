@@ -22,6 +22,22 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// One lane of a fully converged warp (always the same one for the full mask). Keeping the surrounding control flow
+// warp-uniform and predicating only the issuing instructions lets the compiler hold TMA / UMMA operands in uniform
+// registers instead of broadcasting them out of a divergent lane for every instruction.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -244,12 +260,9 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
 // K-major operand tile whose rows are one swizzle span of `span_bytes` (128 or 64): 8-row groups are
 // 8 * span_bytes apart (SBO); layout_type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t span_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>(((8 * span_bytes) >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(span_bytes == 128 ? 2 : 4) << 61;
-  return d;
+  const uint32_t hi = (((8 * span_bytes) >> 4) & 0x3FFF) | (1u << 14) | ((span_bytes == 128 ? 2u : 4u) << 29);
+  const uint32_t lo = (smem_addr >> 4) & 0x3FFF;
+  return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
 }  // namespace vtc

@@ -44,7 +44,7 @@ long long g_launches = 0;
 struct Profile {
   bool on = false, valid = false;
   cudaEvent_t begin = nullptr, iter_begin = nullptr, iter_end = nullptr;
-  int iter_launches = 0;
+  int iter_launches = 0, iters = 0;
 };
 Profile g_prof;
 
@@ -167,6 +167,22 @@ int tune_flags() {
   return cached;
 }
 
+// How one ISTA/FISTA iteration is contracted:
+//   gram      : acc = y G,  G = Phi Phi^T, b = x Phi^T precomputed        2*S*S flops per patch, 1 launch
+//   synthesis : r = y Phi - x, then acc = r Phi^T (the reference's own form, ista_fista.py:105-106)
+//                                                                          4*S*D flops per patch, 2 launches
+// auto picks the cheaper one: synthesis when S > 2 D.
+enum Formulation { FORM_AUTO = 0, FORM_GRAM = 1, FORM_SYNTHESIS = 2 };
+int g_formulation = -1;
+int formulation_for(int64_t S, int64_t D) {
+  if (g_formulation < 0) {
+    const char* e = getenv("VTC_B200_FORMULATION");
+    g_formulation = e ? atoi(e) : FORM_AUTO;
+  }
+  if (g_formulation == FORM_GRAM || g_formulation == FORM_SYNTHESIS) return g_formulation;
+  return S > 2 * D ? FORM_SYNTHESIS : FORM_GRAM;
+}
+
 // K blocks the kernel walks for a padded K extent: 64 columns per stage for plain bf16, 32 for the split modes.
 int64_t k_blocks_for(int64_t Kp, int precision) { return Kp / (parts_for(precision) == 1 ? 64 : 32); }
 
@@ -176,7 +192,7 @@ struct GemmCall {
   int precision = VTC_PRECISION_BF16X3;
   int64_t M = 0, N = 0, K = 0;
   F32Mat in[3];
-  int n_in = 0;
+  int in_mask = 0;       // bit i: in[i] is loaded by the epilogue
   F32Mat out;            // fp32 output (optional)
   bool store_out = false;
   PartsMat parts_out;    // bf16 split output (optional)
@@ -197,7 +213,8 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   memset(&p, 0, sizeof(p));
   TRY(map_operand(&p.tmA, c.A, Cf::BK, "A operand"));
   TRY(map_operand(&p.tmB, c.B, Cf::BK, "B operand"));
-  for (int i = 0; i < c.n_in; ++i) TRY(map_f32(&p.tmIn[i], c.in[i], "epilogue input"));
+  for (int i = 0; i < 3; ++i)
+    if (c.in_mask & (1 << i)) TRY(map_f32(&p.tmIn[i], c.in[i], "epilogue input"));
   if (c.store_out) TRY(map_f32(&p.tmOut, c.out, "fp32 output"));
   if (c.n_parts) TRY(map_parts_out(&p.tmParts, c.parts_out, "bf16 parts output"));
   p.M = static_cast<int>(c.M);
@@ -211,7 +228,7 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   p.kb_per_split = static_cast<int>(ceil_div(p.k_blocks, c.ksplits));
   p.ksplits = static_cast<int>(ceil_div(p.k_blocks, p.kb_per_split));
   p.out_rows_per_split = static_cast<int>(c.out_rows_per_split);
-  p.n_in = c.n_in;
+  p.in_mask = c.in_mask;
   p.n_parts = c.n_parts;
   p.store_out = c.store_out ? 1 : 0;
   p.prox = c.prox;
@@ -368,9 +385,9 @@ struct FistaWs {
   float* scalars;
   double* stats;
   LipschitzWs lip;
-  PartsMat phi_op, x_op, G_op, yop[2];
-  float *bvec, *X1, *X2, *init_pad;
-  int64_t ldS;
+  PartsMat phi_op, x_op, G_op, yop[2], phiT_op, r_op;
+  float *bvec, *X1, *X2, *init_pad, *x_pad;
+  int64_t ldS, ldD;
 };
 FistaWs carve_fista(Carver& cv, int64_t B, int64_t S, int64_t D, int precision) {
   FistaWs w;
@@ -379,13 +396,23 @@ FistaWs carve_fista(Carver& cv, int64_t B, int64_t S, int64_t D, int precision) 
   w.stats = static_cast<double*>(cv.take(8 * 4096));
   w.lip = carve_lipschitz(cv, D);
   w.phi_op = carve_parts(cv, S, D, 3);
-  w.x_op = carve_parts(cv, B, D, 3);
-  w.G_op = carve_parts(cv, S, S, P);
+  const bool gram = formulation_for(S, D) == FORM_GRAM;
+  w.ldS = round_up(S, 4);
+  w.ldD = round_up(D, 4);
+  const size_t state = static_cast<size_t>(B) * w.ldS * 4;
+  if (gram) {
+    w.x_op = carve_parts(cv, B, D, 3);
+    w.G_op = carve_parts(cv, S, S, P);
+    w.bvec = static_cast<float*>(cv.take(state));
+    w.x_pad = nullptr;
+  } else {
+    w.phiT_op = carve_parts(cv, D, S, 3);
+    w.r_op = carve_parts(cv, B, D, P);
+    w.x_pad = static_cast<float*>(cv.take(static_cast<size_t>(B) * w.ldD * 4));
+    w.bvec = nullptr;
+  }
   w.yop[0] = carve_parts(cv, B, S, P);
   w.yop[1] = carve_parts(cv, B, S, P);
-  w.ldS = round_up(S, 4);
-  const size_t state = static_cast<size_t>(B) * w.ldS * 4;
-  w.bvec = static_cast<float*>(cv.take(state));
   w.X1 = static_cast<float*>(cv.take(state));
   w.X2 = static_cast<float*>(cv.take(state));
   w.init_pad = static_cast<float*>(cv.take(state));
@@ -406,6 +433,12 @@ int vtc_profile_enable(int on) {
   g_prof.valid = false;
   return VTC_OK;
 }
+int vtc_set_formulation(int formulation) {
+  if (formulation < 0 || formulation > 2) return fail(VTC_ERR_ARG, "formulation must be 0 (auto), 1 (gram) or 2 (synthesis)");
+  g_formulation = formulation;
+  return VTC_OK;
+}
+int vtc_get_formulation(int64_t S, int64_t D) { return formulation_for(S, D); }
 int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches) {
   if (!g_prof.valid) return fail(VTC_ERR_ARG, "vtc_profile_last: no profiled vtc_fista_fc call");
   CUDA_TRY(cudaEventSynchronize(g_prof.iter_end));
@@ -486,26 +519,38 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
     g_prof.valid = false;
     CUDA_TRY(cudaEventRecord(g_prof.begin, st));
   }
-  // ---- setup: step size, operand splits, Gram matrix G = Phi Phi^T (as bf16 parts), drive b = x Phi^T
+  // ---- setup: step size and operand splits; Gram form additionally G = Phi Phi^T (as bf16 parts) and b = x Phi^T
+  const bool gram = formulation_for(S, D) == FORM_GRAM;
   TRY(run_lipschitz(dictionary, S, D, w.lip, sparsity_weight, w.scalars, nullptr, st));
   TRY(split_rows(dictionary, D, S, D, w.phi_op, st));
-  TRY(split_rows(images, ld_images, B, D, w.x_op, st));
-  {
-    GemmCall g;
-    g.A = w.phi_op, g.B = w.phi_op;
-    g.precision = VTC_PRECISION_BF16X6;
-    g.M = S, g.N = S, g.K = D;
-    g.parts_out = w.G_op, g.n_parts = P;
-    CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.G_op.ptr), 0, w.G_op.bytes(), st));
-    TRY(launch_gemm<EPI_STORE>(g, st));
-  }
-  {
-    GemmCall g;
-    g.A = w.x_op, g.B = w.phi_op;
-    g.precision = VTC_PRECISION_BF16X6;
-    g.M = B, g.N = S, g.K = D;
-    g.out = F32Mat{w.bvec, B, S, w.ldS}, g.store_out = true;
-    TRY(launch_gemm<EPI_STORE>(g, st));
+  const float* x_in = images;  // synthesis form: the fp32 images are an epilogue input of the first contraction
+  int64_t ld_x = ld_images;
+  if (gram) {
+    TRY(split_rows(images, ld_images, B, D, w.x_op, st));
+    {
+      GemmCall g;
+      g.A = w.phi_op, g.B = w.phi_op;
+      g.precision = VTC_PRECISION_BF16X6;
+      g.M = S, g.N = S, g.K = D;
+      g.parts_out = w.G_op, g.n_parts = P;
+      CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.G_op.ptr), 0, w.G_op.bytes(), st));
+      TRY(launch_gemm<EPI_STORE>(g, st));
+    }
+    {
+      GemmCall g;
+      g.A = w.x_op, g.B = w.phi_op;
+      g.precision = VTC_PRECISION_BF16X6;
+      g.M = B, g.N = S, g.K = D;
+      g.out = F32Mat{w.bvec, B, S, w.ldS}, g.store_out = true;
+      TRY(launch_gemm<EPI_STORE>(g, st));
+    }
+  } else {
+    TRY(transpose_split(dictionary, D, S, D, w.phiT_op, st));
+    CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.r_op.ptr), 0, w.r_op.bytes(), st));
+    if (!tma_ok(images, ld_images)) {
+      CUDA_TRY(cudaMemcpy2DAsync(w.x_pad, w.ldD * 4, images, ld_images * 4, D * 4, B, cudaMemcpyDeviceToDevice, st));
+      x_in = w.x_pad, ld_x = w.ldD;
+    }
   }
 
   // ---- state buffers. a_k lives in X1 for odd k and X2 for even k; a_0 is `init`.
@@ -563,15 +608,29 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
     float* a_out = (k & 1) ? X1 : X2;
     const int64_t ld_out = (k & 1) ? ld1 : ld2;
     GemmCall g;
-    g.A = w.yop[(k - 1) & 1], g.B = w.G_op;
     g.precision = precision;
-    g.M = B, g.N = S, g.K = S;
     g.in[0] = F32Mat{a_prev, B, S, ld_prev};
-    g.in[1] = F32Mat{w.bvec, B, S, w.ldS};
-    g.n_in = 2;
+    g.in_mask = 1;
+    if (gram) {
+      g.A = w.yop[(k - 1) & 1], g.B = w.G_op;
+      g.M = B, g.N = S, g.K = S;
+      g.in[1] = F32Mat{w.bvec, B, S, w.ldS};
+      g.in_mask |= 2;
+    } else {
+      // r = y Phi - x, emitted as bf16 parts; then the fused contraction acc = r Phi^T is the whole gradient
+      GemmCall r;
+      r.precision = precision;
+      r.A = w.yop[(k - 1) & 1], r.B = w.phiT_op;
+      r.M = B, r.N = D, r.K = S;
+      r.in[0] = F32Mat{x_in, B, D, ld_x}, r.in_mask = 1;
+      r.parts_out = w.r_op, r.n_parts = P;
+      TRY(launch_gemm<EPI_STORE>(r, st));
+      g.A = w.r_op, g.B = w.phi_op;
+      g.M = B, g.N = S, g.K = D;
+    }
     if (variant == VTC_VARIANT_FISTA && beta_prev != 0.f) {
       g.in[2] = F32Mat{a_prev2, B, S, ld_prev2};
-      g.n_in = 3;
+      g.in_mask |= 4;
     }
     g.out = F32Mat{a_out, B, S, ld_out}, g.store_out = true;
     if (k < num_iters) g.parts_out = w.yop[k & 1], g.n_parts = P;
@@ -594,7 +653,8 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   }
   if (g_prof.on) {
     CUDA_TRY(cudaEventRecord(g_prof.iter_end, st));
-    g_prof.iter_launches = k_done;
+    g_prof.iter_launches = k_done * (gram ? 1 : 2);
+    g_prof.iters = k_done;
     g_prof.valid = true;
   }
   const float* result = (k_done & 1) ? X1 : X2;
@@ -668,7 +728,7 @@ int vtc_sc_dict_grad(const float* images, int64_t ld_images, const float* dictio
     g.A = w.phiT_op, g.B = w.a_op;
     g.precision = precision;
     g.M = D, g.N = B, g.K = S;
-    g.in[0] = F32Mat{w.xT, D, B, w.ldB}, g.n_in = 1;
+    g.in[0] = F32Mat{w.xT, D, B, w.ldB}, g.in_mask = 1;
     g.parts_out = w.RT_op, g.n_parts = w.RT_op.parts;
     CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.RT_op.ptr), 0, w.RT_op.bytes(), st));
     TRY(launch_gemm<EPI_STORE>(g, st));
@@ -778,7 +838,7 @@ int vtc_matmul_nt(const float* A, const float* Bm, const float* sub, float* out,
       CUDA_TRY(cudaMemcpy2DAsync(sub_pad, ldN * 4, sub, N * 4, N * 4, M, cudaMemcpyDeviceToDevice, st));
       s = sub_pad, lds = ldN;
     }
-    g.in[0] = F32Mat{s, M, N, lds}, g.n_in = 1;
+    g.in[0] = F32Mat{s, M, N, lds}, g.in_mask = 1;
   }
   g.out = direct ? F32Mat{out, M, N, N} : F32Mat{out_pad, M, N, ldN};
   g.store_out = true;
