@@ -47,11 +47,14 @@ int vtc_version(void);
 const char* vtc_last_error(void);
 
 /* Measurement hooks (bench.py): cumulative number of kernels this library has launched in this process, and
- * CUDA-event timing of the last vtc_fista_fc call: setup (step size, splits, Gram and drive GEMMs) and the
- * iteration launches, recorded on the call's own stream. vtc_profile_last synchronises on the last event. */
+ * CUDA-event timing of the last vtc_fista_fc call, recorded on the call's own stream: setup (step size, splits,
+ * Gram-form GEMMs), all iteration launches together, and the mean duration of 16 sampled launches of the fused
+ * ISTA/FISTA kernel (plus, in the synthesis form, of the r = y Phi - x launch before it).
+ * vtc_profile_last synchronises on the last event. */
 long long vtc_launch_count(void);
 int vtc_profile_enable(int on);
-int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches);
+int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches, int* iters, float* fused_launch_ms,
+                     float* first_launch_ms);
 
 /* Contraction used by one ISTA/FISTA iteration: 1 = Gram form (y G - b, G = Phi Phi^T; 2*S*S flops per patch, one
  * launch), 2 = synthesis/analysis form ((y Phi - x) Phi^T as in ista_fista.py:105-106; 4*S*D flops, two launches),

@@ -18,7 +18,8 @@ SIGNATURES = {
     'vtc_last_error': (_c.c_char_p, []),
     'vtc_launch_count': (_c.c_longlong, []),
     'vtc_profile_enable': (_int, [_int]),
-    'vtc_profile_last': (_int, [_c.POINTER(_f32), _c.POINTER(_f32), _c.POINTER(_int)]),
+    'vtc_profile_last': (_int, [_c.POINTER(_f32), _c.POINTER(_f32), _c.POINTER(_int), _c.POINTER(_int),
+                                _c.POINTER(_f32), _c.POINTER(_f32)]),
     'vtc_set_formulation': (_int, [_int]),
     'vtc_get_formulation': (_int, [_i64, _i64]),
     'vtc_device_info': (_int, [_c.POINTER(_int)] * 3),

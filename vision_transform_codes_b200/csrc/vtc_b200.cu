@@ -41,10 +41,13 @@ int fail(int code, const char* fmt, ...) {
 long long g_launches = 0;
 #define COUNT_LAUNCH() (++g_launches)
 
+constexpr int kProfSamples = 16;
 struct Profile {
   bool on = false, valid = false;
   cudaEvent_t begin = nullptr, iter_begin = nullptr, iter_end = nullptr;
-  int iter_launches = 0, iters = 0;
+  cudaEvent_t k1_begin[kProfSamples], k1_end[kProfSamples], k2_end[kProfSamples];  // sampled iterations
+  int iter_launches = 0, iters = 0, samples = 0;
+  bool two_launches = false;
 };
 Profile g_prof;
 
@@ -439,7 +442,8 @@ int vtc_set_formulation(int formulation) {
   return VTC_OK;
 }
 int vtc_get_formulation(int64_t S, int64_t D) { return formulation_for(S, D); }
-int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches) {
+int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches, int* iters, float* fused_launch_ms,
+                     float* first_launch_ms) {
   if (!g_prof.valid) return fail(VTC_ERR_ARG, "vtc_profile_last: no profiled vtc_fista_fc call");
   CUDA_TRY(cudaEventSynchronize(g_prof.iter_end));
   float a = 0.f, b = 0.f;
@@ -448,6 +452,19 @@ int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches) {
   if (setup_ms) *setup_ms = a;
   if (iter_ms) *iter_ms = b;
   if (iter_launches) *iter_launches = g_prof.iter_launches;
+  if (iters) *iters = g_prof.iters;
+  // mean duration of the sampled launches: the fused ISTA/FISTA launch, and (synthesis form) the launch before it
+  float fused = 0.f, first = 0.f;
+  for (int i = 0; i < g_prof.samples; ++i) {
+    float t1 = 0.f, t2 = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t1, g_prof.k1_begin[i], g_prof.k1_end[i]));
+    CUDA_TRY(cudaEventElapsedTime(&t2, g_prof.k1_end[i], g_prof.k2_end[i]));
+    if (g_prof.two_launches) first += t1, fused += t2;
+    else fused += t1;
+  }
+  if (g_prof.samples > 0) fused /= g_prof.samples, first /= g_prof.samples;
+  if (fused_launch_ms) *fused_launch_ms = fused;
+  if (first_launch_ms) *first_launch_ms = first;
   return VTC_OK;
 }
 const char* vtc_last_error(void) { return g_err; }
@@ -515,7 +532,13 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
       CUDA_TRY(cudaEventCreate(&g_prof.begin));
       CUDA_TRY(cudaEventCreate(&g_prof.iter_begin));
       CUDA_TRY(cudaEventCreate(&g_prof.iter_end));
+      for (int i = 0; i < kProfSamples; ++i) {
+        CUDA_TRY(cudaEventCreate(&g_prof.k1_begin[i]));
+        CUDA_TRY(cudaEventCreate(&g_prof.k1_end[i]));
+        CUDA_TRY(cudaEventCreate(&g_prof.k2_end[i]));
+      }
     }
+    g_prof.samples = 0;
     g_prof.valid = false;
     CUDA_TRY(cudaEventRecord(g_prof.begin, st));
   }
@@ -607,6 +630,8 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
     const int64_t ld_prev2 = (k <= 2) ? ld_init : (k & 1) ? ld1 : ld2;
     float* a_out = (k & 1) ? X1 : X2;
     const int64_t ld_out = (k & 1) ? ld1 : ld2;
+    const int sample = (g_prof.on && k > num_iters / 2 && g_prof.samples < kProfSamples) ? g_prof.samples : -1;
+    if (sample >= 0) CUDA_TRY(cudaEventRecord(g_prof.k1_begin[sample], st));
     GemmCall g;
     g.precision = precision;
     g.in[0] = F32Mat{a_prev, B, S, ld_prev};
@@ -625,6 +650,7 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
       r.in[0] = F32Mat{x_in, B, D, ld_x}, r.in_mask = 1;
       r.parts_out = w.r_op, r.n_parts = P;
       TRY(launch_gemm<EPI_STORE>(r, st));
+      if (sample >= 0) CUDA_TRY(cudaEventRecord(g_prof.k1_end[sample], st));
       g.A = w.r_op, g.B = w.phi_op;
       g.M = B, g.N = S, g.K = D;
     }
@@ -641,6 +667,12 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
     g.scalars = w.scalars;
     g.stat = early ? w.stats + (k - 1) : nullptr;
     TRY(launch_gemm<EPI_FISTA>(g, st));
+    if (sample >= 0) {
+      if (gram) CUDA_TRY(cudaEventRecord(g_prof.k1_end[sample], st));
+      CUDA_TRY(cudaEventRecord(g_prof.k2_end[sample], st));
+      g_prof.samples = sample + 1;
+      g_prof.two_launches = !gram;
+    }
     beta_prev = beta_k;
     k_done = k;
     if (early) {
