@@ -276,3 +276,21 @@ def test_dictionary_update_larger_batch_against_oracle():
   d = phi.cuda()
   cheap.run(x.cuda(), d, a.cuda(), h.cuda(), stepsize=0.1)
   assert oracle.relative_l2(d.cpu(), want) < 1e-5
+
+
+def test_size_independent_properties_at_benchmark_shape():
+  """BASELINE configs[1] shape at a batch the oracle cannot cover: determinism, batch-shard independence (what
+  multi-GPU sharding relies on), fixed point of the converged code, and oracle parity on a sub-batch."""
+  ista_fista = modules()[0]
+  B, S, D, T = 16384, 1024, 256, 300
+  phi = oracle.synthetic_dictionary(S, D)
+  x = oracle.synthetic_patches(B, D, kind='whitened')
+  xd, pd = x.cuda(), phi.cuda()
+  a = ista_fista.run(xd, pd, 0.1, T)
+  assert torch.equal(a, ista_fista.run(xd, pd, 0.1, T))
+  assert torch.equal(a[B // 2:], ista_fista.run(xd[B // 2:], pd, 0.1, T))
+  assert torch.equal(a[1000:1300], ista_fista.run(xd[1000:1300], pd, 0.1, T))
+  more = ista_fista.run(xd, pd, 0.1, 1, variant='ista', initial_codes=a)
+  assert oracle.relative_l2(more.cpu(), a.cpu()) < 1e-4
+  want = oracle.ista_fista(x[:384], phi, 0.1, T)
+  check_codes(a[:384], want, phi)
