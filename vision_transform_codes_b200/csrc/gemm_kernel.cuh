@@ -46,17 +46,24 @@ constexpr int NUM_MATH_WARPS = 8;
 constexpr int TMEM_COLS = 2 * BLOCK_N;
 constexpr int EPI_ARRAY_BYTES = BLOCK_M * EPI_COLS * 4;  // 8 KB: one fp32 [128 x 16] sub-tile
 constexpr int EPI_PART_BYTES = BLOCK_M * EPI_COLS * 2;   // 4 KB: one bf16 [128 x 16] sub-tile
-constexpr int IN_STAGE_BYTES = 3 * EPI_ARRAY_BYTES;      // 24 KB
 
-// Compile-time configuration for P staged parts per operand.
-template <int P>
+// Compile-time configuration for P staged parts per operand and NIN fp32 epilogue inputs per sub-tile. Shared memory
+// (227 KB) is split between the operand ring and the epilogue's input ring according to what bounds the launch:
+// NIN = 1 (plain GEMMs, K large): deep operand ring; NIN = 2 (fused update after the short K = D contraction of the
+// synthesis form, HBM-bound): shallow operand ring, 5-8 input stages in flight; NIN = 3 (Gram-form fused update).
+template <int P, int NIN>
 struct Cfg {
   static constexpr int BK = (P == 1) ? 64 : 32;                 // K extent of a stage
   static constexpr int SPAN = BK * 2;                           // bytes per operand row = swizzle span (128 / 64)
   static constexpr int TILE_BYTES = BLOCK_M * SPAN;             // one part tile of A, or of this CTA's half of B
   static constexpr int STAGE_BYTES = 2 * P * TILE_BYTES;        // P A tiles + P B tiles
-  static constexpr int OP_STAGES = (P == 1) ? 4 : (P == 2) ? 3 : 2;
-  static constexpr int IN_STAGES = (P == 2) ? 4 : 3;
+  static constexpr int IN_STAGE_BYTES = NIN * EPI_ARRAY_BYTES;
+  static constexpr int OP_STAGES = NIN == 3 ? ((P == 1) ? 4 : (P == 2) ? 3 : 2)
+                                 : NIN == 2 ? 2
+                                            : ((P == 3) ? 3 : 4);
+  static constexpr int IN_STAGES = NIN == 3 ? ((P == 2) ? 4 : 3)
+                                 : NIN == 2 ? ((P == 3) ? 5 : 8)
+                                            : ((P == 3) ? 5 : 8);
   static constexpr int OUT_STAGES = 2;
   static constexpr int OUT_STAGE_BYTES = EPI_ARRAY_BYTES + P * EPI_PART_BYTES;
   static constexpr int NPAIRS = (P == 1) ? 1 : (P == 2) ? 3 : 6;
@@ -152,9 +159,10 @@ __device__ __forceinline__ void group_shrink(const float (&u)[16], float (&o)[16
   }
 }
 
-template <int EPI, int P>
+template <int EPI, int P, int NIN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<P>;
+  using C = Cfg<P, NIN>;
+  constexpr int IN_STAGE_BYTES = C::IN_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // swizzled TMA / UMMA tiles need a 1024-byte aligned base; the offset is identical in both CTAs of the pair
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -343,8 +351,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
           if (p.in_mask != 0) {
             mbar_arrive_expect_tx(in_full_bar(e), in_bytes);
             for (int i = 0; i < 3; ++i)
-              if (p.in_mask & (1 << i))
-                tma_load_2d(sIn + e * IN_STAGE_BYTES + i * EPI_ARRAY_BYTES, &p.tmIn[i], in_full_bar(e),
+              if (p.in_mask & (1 << i))  // inputs are packed into the stage in slot order
+                tma_load_2d(sIn + e * IN_STAGE_BYTES + __popc(p.in_mask & ((1 << i) - 1)) * EPI_ARRAY_BYTES,
+                            &p.tmIn[i], in_full_bar(e),
                           c.n0 + j * EPI_COLS, c.m0, (p.flags & TUNE_STATE_EVICT_FIRST) ? kEvictFirst : kEvictNormal);
           } else {
             mbar_arrive(in_full_bar(e));
@@ -434,7 +443,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
           if (p.in_mask & (1 << i)) {
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
-              const float4 t = lds128(in_stage + i * EPI_ARRAY_BYTES + row * 64 + ((ch ^ sw64) << 4));
+              const float4 t = lds128(in_stage + __popc(p.in_mask & ((1 << i) - 1)) * EPI_ARRAY_BYTES + row * 64 +
+                                      ((ch ^ sw64) << 4));
               in[i][4 * ch + 0] = t.x; in[i][4 * ch + 1] = t.y; in[i][4 * ch + 2] = t.z; in[i][4 * ch + 3] = t.w;
             }
           } else {

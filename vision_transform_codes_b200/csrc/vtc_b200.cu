@@ -209,9 +209,9 @@ struct GemmCall {
   double* stat = nullptr;
 };
 
-template <int EPI, int P>
+template <int EPI, int P, int NIN>
 int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream) {
-  using Cf = Cfg<P>;
+  using Cf = Cfg<P, NIN>;
   GemmParams p;
   memset(&p, 0, sizeof(p));
   TRY(map_operand(&p.tmA, c.A, Cf::BK, "A operand"));
@@ -244,9 +244,12 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   p.flags = tune_flags();
   const long long tiles = 1ll * p.num_m_blocks * p.num_n_blocks * p.ksplits;
   if (tiles > 0x7fffffffll) return fail(VTC_ERR_ARG, "too many tiles");
-  static thread_local bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // the attribute is per device
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  bool& attr_set = attr_set_dev[dev & 63];
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(vtc_gemm_kernel<EPI, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
+    CUDA_TRY(cudaFuncSetAttribute(vtc_gemm_kernel<EPI, P, NIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
     attr_set = true;
   }
   const long long max_pairs = info.sm_count / 2;
@@ -264,7 +267,7 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_gemm_kernel<EPI, P>, p));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_gemm_kernel<EPI, P, NIN>, p));
   COUNT_LAUNCH();
   return VTC_OK;
 }
@@ -279,10 +282,27 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
   if (c.A.parts < P || c.B.parts < P) return fail(VTC_ERR_ARG, "operand has too few bf16 parts for precision %d", c.precision);
   if (c.n_parts > MAX_PARTS || (c.n_parts && c.parts_out.parts < c.n_parts)) return fail(VTC_ERR_ARG, "bad parts output");
   if (c.n_parts > P) return fail(VTC_ERR_ARG, "at most %d output parts at precision %d", P, c.precision);
+  // epilogue input slots in use: plain GEMMs at most 1, fused update 2 (synthesis form) or 3 (Gram form, reads b)
+  const int nin = __builtin_popcount(c.in_mask);
+  if (EPI == EPI_STORE) {
+    if (nin > 1) return fail(VTC_ERR_ARG, "EPI_STORE takes at most one epilogue input");
+    switch (P) {
+      case 1: return launch_gemm_p<EPI_STORE, 1, 1>(c, info, stream);
+      case 2: return launch_gemm_p<EPI_STORE, 2, 1>(c, info, stream);
+      default: return launch_gemm_p<EPI_STORE, 3, 1>(c, info, stream);
+    }
+  }
+  if (nin <= 2) {
+    switch (P) {
+      case 1: return launch_gemm_p<EPI_FISTA, 1, 2>(c, info, stream);
+      case 2: return launch_gemm_p<EPI_FISTA, 2, 2>(c, info, stream);
+      default: return launch_gemm_p<EPI_FISTA, 3, 2>(c, info, stream);
+    }
+  }
   switch (P) {
-    case 1: return launch_gemm_p<EPI, 1>(c, info, stream);
-    case 2: return launch_gemm_p<EPI, 2>(c, info, stream);
-    default: return launch_gemm_p<EPI, 3>(c, info, stream);
+    case 1: return launch_gemm_p<EPI_FISTA, 1, 3>(c, info, stream);
+    case 2: return launch_gemm_p<EPI_FISTA, 2, 3>(c, info, stream);
+    default: return launch_gemm_p<EPI_FISTA, 3, 3>(c, info, stream);
   }
 }
 
