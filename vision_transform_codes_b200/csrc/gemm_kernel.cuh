@@ -58,13 +58,13 @@ struct Cfg {
   static constexpr int TILE_BYTES = BLOCK_M * SPAN;             // one part tile of A, or of this CTA's half of B
   static constexpr int STAGE_BYTES = 2 * P * TILE_BYTES;        // P A tiles + P B tiles
   static constexpr int IN_STAGE_BYTES = NIN * EPI_ARRAY_BYTES;
-  static constexpr int OP_STAGES = NIN == 3 ? ((P == 1) ? 4 : (P == 2) ? 3 : 2)
+  static constexpr int OP_STAGES = NIN == 3 ? ((P == 3) ? 2 : 3)
                                  : NIN == 2 ? 2
                                             : ((P == 3) ? 3 : 4);
-  static constexpr int IN_STAGES = NIN == 3 ? ((P == 2) ? 4 : 3)
-                                 : NIN == 2 ? ((P == 3) ? 5 : 8)
-                                            : ((P == 3) ? 5 : 8);
-  static constexpr int OUT_STAGES = 2;
+  static constexpr int IN_STAGES = NIN == 3 ? ((P == 3) ? 2 : 3)
+                                 : NIN == 2 ? ((P == 3) ? 4 : 7)
+                                            : ((P == 3) ? 2 : 6);
+  static constexpr int OUT_STAGES = 3;
   static constexpr int OUT_STAGE_BYTES = EPI_ARRAY_BYTES + P * EPI_PART_BYTES;
   static constexpr int NPAIRS = (P == 1) ? 1 : (P == 2) ? 3 : 6;
   static constexpr int OFF_OP = 0;
@@ -378,9 +378,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
             tma_store_2d(&p.tmParts, src + EPI_ARRAY_BYTES + part * EPI_PART_BYTES,
                          part * p.out_part_stride + c.n0 + j * EPI_COLS, c.m0);
           bulk_commit();
-          if (q > 0) {
-            bulk_wait_read<1>();  // everything but the group just committed has left shared memory
-            mbar_arrive(out_free_bar((q - 1) % C::OUT_STAGES));
+          if (q >= C::OUT_STAGES - 1) {
+            // all but the OUT_STAGES-1 most recent store groups have left shared memory: recycle the oldest stage
+            bulk_wait_read<C::OUT_STAGES - 1>();
+            mbar_arrive(out_free_bar((q - (C::OUT_STAGES - 1)) % C::OUT_STAGES));
           }
         }
         __syncwarp();
