@@ -95,6 +95,7 @@ enum TuneFlags {
   TUNE_STATE_EVICT_FIRST = 8,   // evict-first hint on state loads: neighbours fetched in the same 128-byte line are
                                 // dropped before their own sub-tile asks for them (+45 % HBM reads) (measured: slower)
   TUNE_PROMO_256 = 16,          // 256-byte L2 promotion on the fp32 tensor maps                     (measured: slower)
+  TUNE_NO_PDL = 32,             // launch without programmatic stream serialization
 };
 
 struct GemmParams {
@@ -228,6 +229,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the tail of the previous launch
+  // in the stream; global memory written by it is only touched after this point.
+  pdl_launch_dependents();
+  pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 

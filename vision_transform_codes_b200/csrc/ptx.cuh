@@ -185,6 +185,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
          | ((M >> 4) << 24);  // m_dim
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel in the stream may start occupying SMs as this grid's CTAs retire;
+// wait: block until the previous grid has completed and its memory is visible (no-op without the launch attribute).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- explicit shared-space vector access
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;

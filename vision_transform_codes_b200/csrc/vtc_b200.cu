@@ -260,13 +260,15 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cf::SMEM_ALLOC;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // prologue overlaps the previous launch's tail
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (tune_flags() & TUNE_NO_PDL) ? 1 : 2;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_gemm_kernel<EPI, P, NIN>, p));
   COUNT_LAUNCH();
   return VTC_OK;
