@@ -246,8 +246,12 @@ def main():
                 'frac': achieved / pk['bf16_sustained'], 'peak_source': pk['source'] + ' bf16_tflops_sustained',
                 'algorithmic_flops_per_launch': flops_fused,
                 'executed_frac': nprod * achieved / pk['bf16_sustained']}
+  traffic = None  # DRAM bytes per launch of this kernel from the committed ncu --set full capture of the same shape
+  tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+  if os.path.exists(tpath) and form == 'synthesis' and Bn == B_PER_GPU:
+    traffic = json.load(open(tpath)).get(args.precision, {}).get('fused_bytes')
   roofline.update({
-      'kernel': 'vtc_gemm_kernel<EPI_FISTA,%d> (%s form)' % (nparts, form), 'traffic': None,
+      'kernel': 'vtc_gemm_kernel<EPI_FISTA,%d> (%s form)' % (nparts, form), 'traffic': traffic,
       'launch_ms': fused_ms, 'first_launch_ms': first_ms if form == 'synthesis' else None,
       'formulation': form, 'launches_per_iteration': n_launch // max(1, n_iter), 'ms_per_iteration': iter_ms_each,
       'setup_ms_per_step': setup_ms,
