@@ -17,7 +17,7 @@
 //   warp 1 lane 0 : tcgen05.mma issuer (leader CTA only); commits are multicast to both CTAs
 //   warp 2        : TMEM allocator; lane 0 then drives the TMA stores of the epilogue (out ring)
 //   warp 3 lane 0 : TMA loader of the epilogue's fp32 state tiles (in ring), running ahead of the math warps
-//   warps 4..11   : epilogue math, two groups of four warps working on alternate 16-column sub-tiles:
+//   warps 4..11   : epilogue math, two groups of four warps taking 16-column sub-tiles round-robin:
 //                   tcgen05.ld -> fused update -> swizzled st.shared -> TMA store
 //
 // Epilogues:
@@ -41,8 +41,10 @@ constexpr int HALF_N = 128;
 constexpr int UMMA_K = 16;
 constexpr int EPI_COLS = 16;        // epilogue sub-tile width (fp32 columns)
 constexpr int MAX_PARTS = 3;
-constexpr int GEMM_THREADS = 384;
-constexpr int NUM_MATH_WARPS = 8;
+constexpr int NUM_MATH_GROUPS = 2;   // groups of four warps (one per TMEM lane quarter) taking sub-tiles round-robin
+                                    // (three groups measured no faster: the fused launch is not issue-bound)
+constexpr int NUM_MATH_WARPS = 4 * NUM_MATH_GROUPS;
+constexpr int GEMM_THREADS = 128 + 32 * NUM_MATH_WARPS;
 constexpr int TMEM_COLS = 2 * BLOCK_N;
 constexpr int EPI_ARRAY_BYTES = BLOCK_M * EPI_COLS * 4;  // 8 KB: one fp32 [128 x 16] sub-tile
 constexpr int EPI_PART_BYTES = BLOCK_M * EPI_COLS * 2;   // 4 KB: one bf16 [128 x 16] sub-tile
@@ -61,10 +63,13 @@ struct Cfg {
   static constexpr int OP_STAGES = NIN == 3 ? ((P == 3) ? 2 : 3)
                                  : NIN == 2 ? 2
                                             : ((P == 3) ? 3 : 4);
-  static constexpr int IN_STAGES = NIN == 3 ? ((P == 3) ? 2 : 3)
-                                 : NIN == 2 ? ((P == 3) ? 4 : 7)
+  // IN_STAGES is a multiple of NUM_MATH_GROUPS: every input stage is always consumed by the same math group, so a
+  // group sees the phases of "its" stages strictly in order (parity waits must never run a whole phase ahead).
+  static constexpr int IN_STAGES = NIN == 3 ? ((P == 3) ? 2 : 4)
+                                 : NIN == 2 ? ((P == 3) ? 4 : 6)
                                             : ((P == 3) ? 2 : 6);
-  static constexpr int OUT_STAGES = 3;
+  static constexpr int OUT_STAGES = (NIN == 3 && P != 3) ? 2 : 3;
+  static_assert(IN_STAGES % NUM_MATH_GROUPS == 0, "input stages must have a fixed owner group");
   static constexpr int OUT_STAGE_BYTES = EPI_ARRAY_BYTES + P * EPI_PART_BYTES;
   static constexpr int NPAIRS = (P == 1) ? 1 : (P == 2) ? 3 : 6;
   static constexpr int OFF_OP = 0;
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     __syncwarp();
   } else if (warp >= 4) {
     // ================================ epilogue math ================================
-    const uint32_t group = (warp - 4) >> 2;  // 0 or 1: which alternate sub-tiles this warp works on
+    const uint32_t group = (warp - 4) >> 2;  // which sub-tiles (q mod NUM_MATH_GROUPS) this warp works on
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;     // row inside this CTA's 128-row tile
     const uint32_t sw64 = (row >> 1) & 3;    // SWIZZLE_64B: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)
@@ -416,8 +421,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
       // last sub-tile of this tile that belongs to this warp's group (-1: none)
-      int j_last = c.nsub - 1;
-      if (((q + j_last) & 1) != group) --j_last;
+      int j_last = -1;
+      for (int j = c.nsub - 1; j >= 0 && j >= c.nsub - NUM_MATH_GROUPS; --j)
+        if ((q + j) % NUM_MATH_GROUPS == group) {
+          j_last = j;
+          break;
+        }
       if (j_last < 0) {
         __syncwarp();
         if (lane == 0) {
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
         }
       }
       for (int j = 0; j < c.nsub; ++j, ++q) {
-        if ((q & 1) != group) continue;
+        if (q % NUM_MATH_GROUPS != group) continue;
         const int e = q % C::IN_STAGES;
         const uint32_t in_ph = (q / C::IN_STAGES) & 1;
         const int o = q % C::OUT_STAGES;
