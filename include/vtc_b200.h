@@ -99,13 +99,25 @@ int vtc_sc_dict_grad(const float* images, int64_t ld_images, const float* dictio
 
 /*
  * Apply step, in place on `dictionary`:
- *   U = stepsize * (grad_sum / batch_global); if hessian_diagonal: U /= (h + lowest_code_val); dictionary -= U;
- *   if normalize: every row divided by its L2 norm.
- * sc_cheap_quadratic_descent.py:43-48; hessian_diagonal == NULL gives sc_steepest_descent.py:37-41.
+ *   U = stepsize * (grad_sum / batch_global [+ alignment_penalty * alignment_grad]);
+ *   if hessian_diagonal: U /= (h + lowest_code_val); dictionary -= U; if normalize: every row divided by its L2 norm.
+ * sc_cheap_quadratic_descent.py:43-48; hessian_diagonal == NULL gives sc_steepest_descent.py:37-41; alignment_grad
+ * (S, D) != NULL adds the regulariser of subspace_sc_cheap_quadratic_descent.py:71-75.
  */
-int vtc_sc_dict_apply(float* dictionary, const float* grad_sum, const float* hessian_diagonal, int64_t S, int64_t D,
+int vtc_sc_dict_apply(float* dictionary, const float* grad_sum, const float* hessian_diagonal,
+                      const float* alignment_grad, float alignment_penalty, int64_t S, int64_t D,
                       int64_t batch_global, float stepsize, float lowest_code_val, int normalize,
                       vtc_stream_t stream);
+
+/*
+ * Gradient of the within-group alignment penalty (sum over pairs in a group of |cos(phi_i, phi_j)|),
+ * subspace_sc_cheap_quadratic_descent.py:59-70 and :91-127. group_slots (num_groups * group_width) int32 on the device:
+ * atom of each (group, position) slot, -1 for padding; atoms in several groups accumulate. alignment_grad (S, D) is
+ * overwritten. dictionary_is_normalized selects the reference's shortcut for unit-norm atoms (its dict_is_normalized).
+ */
+int vtc_subspace_alignment_grad(const float* dictionary, int64_t S, int64_t D, const int32_t* group_slots,
+                                int64_t num_groups, int64_t group_width, int dictionary_is_normalized,
+                                float* alignment_grad, vtc_stream_t stream);
 
 /*
  * Hessian-diagonal running average kept by the trainer (training/sparse_coding.py:154):

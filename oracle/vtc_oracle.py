@@ -128,8 +128,29 @@ def subspace_ista_fista(images, dictionary, group_assignments, sparsity_weight, 
   return (codes, done) if return_iters else codes
 
 
+def alignment_regularization_gradients(group_rows, dict_is_normalized):
+  """
+  Gradient of sum_{i != j} |cos(phi_i, phi_j)| over the rows of one group
+  (dict_update_rules/fully_connected/subspace_sc_cheap_quadratic_descent.py:91-127).
+  """
+  m = group_rows.size(0)
+  inner = torch.mm(group_rows, group_rows.t())
+  if dict_is_normalized:
+    cos = inner[:, :, None]
+    own = cos * group_rows[:, None, :].expand(m, m, -1)       # depends on phi_i
+    other = group_rows[None, :, :].expand(m, m, -1)           # depends on phi_j
+  else:
+    norms = torch.norm(group_rows, p=2, dim=1, keepdim=True)
+    outer = torch.mm(norms, norms.t())
+    cos = (inner / outer)[:, :, None]
+    own = (cos / (norms**2)[:, None]) * group_rows[:, None, :].expand(m, m, -1)
+    other = group_rows[None, :, :].expand(m, m, -1) / outer[:, :, None]
+  return torch.sum(torch.sign(cos) * (other - own), dim=1)
+
+
 def sc_dictionary_update(images, dictionary, codes, hessian_diagonal=None, stepsize=0.001, num_iters=1,
-                         lowest_code_val=0.001, normalize_dictionary=True, batch_size=None, extra_gradient=None):
+                         lowest_code_val=0.001, normalize_dictionary=True, batch_size=None, extra_gradient=None,
+                         group_assignments=None, alignment_penalty=0.0):
   """
   sc_cheap_quadratic_descent.py:42-48 (hessian_diagonal given) / sc_steepest_descent.py:37-41 (None).
   Returns the updated dictionary (the reference updates in place; the oracle is functional).
@@ -142,7 +163,15 @@ def sc_dictionary_update(images, dictionary, codes, hessian_diagonal=None, steps
     gradient = torch.mm(codes.t(), torch.mm(codes, phi) - images)
     if extra_gradient is not None and it == 0:
       gradient = gradient + extra_gradient
-    update = stepsize * (gradient / divisor)
+    data_term = gradient / divisor
+    if alignment_penalty != 0:
+      # subspace_sc_cheap_quadratic_descent.py:59-75: per-group gradients accumulated over groups
+      reg = torch.zeros_like(phi)
+      for members in group_assignments:
+        members = list(members)
+        reg[members] = reg[members] + alignment_regularization_gradients(phi[members], normalize_dictionary)
+      data_term = data_term + alignment_penalty * reg
+    update = stepsize * data_term
     if hessian_diagonal is not None:
       update = update / (hessian_diagonal[:, None] + lowest_code_val)
     phi = phi - update
@@ -157,7 +186,7 @@ def hessian_running_mean(hessian_diagonal, codes):
 
 
 def train_steps(batches, dictionary, sparsity_weight, num_iters, stepsize, variant='fista',
-                update_rule='sc_cheap_quadratic_descent', group_assignments=None):
+                update_rule='sc_cheap_quadratic_descent', group_assignments=None, alignment_penalty=0.0):
   """
   The per-batch body of train_dictionary (training/sparse_coding.py:513-515 with :139, :154, :168): infer codes,
   update the Hessian running mean, update the dictionary. Returns (dictionary, hessian_diagonal, last codes).
@@ -172,7 +201,8 @@ def train_steps(batches, dictionary, sparsity_weight, num_iters, stepsize, varia
       codes = subspace_ista_fista(x, phi, group_assignments, sparsity_weight, num_iters, variant=variant)
     if update_rule.endswith('cheap_quadratic_descent'):
       h = hessian_running_mean(h, codes)
-      phi = sc_dictionary_update(x, phi, codes, h, stepsize=stepsize)
+      phi = sc_dictionary_update(x, phi, codes, h, stepsize=stepsize, group_assignments=group_assignments,
+                                 alignment_penalty=alignment_penalty)
     else:
       phi = sc_dictionary_update(x, phi, codes, None, stepsize=stepsize)
   return phi, h, codes

@@ -25,6 +25,7 @@ from analysis_transforms.fully_connected import ista_fista  # noqa: E402
 from analysis_transforms.fully_connected import subspace_ista_fista  # noqa: E402
 from dict_update_rules.fully_connected import sc_cheap_quadratic_descent  # noqa: E402
 from dict_update_rules.fully_connected import sc_steepest_descent  # noqa: E402
+from dict_update_rules.fully_connected import subspace_sc_cheap_quadratic_descent  # noqa: E402
 from training import sparse_coding  # noqa: E402
 
 torch.set_num_threads(4)
@@ -108,8 +109,19 @@ def make_dict_update():
   sc_steepest_descent.run(x, d3, codes, stepsize=0.1, num_iters=1)
   d4 = phi.clone()
   sc_steepest_descent.run(x, d4, codes, stepsize=0.1, num_iters=2, normalize_dictionary=False)
+  pairs = [list(map(int, g)) for g in np.array_split(np.arange(s), s // 2)]
+  overlapping = [[0, 2, 5], [1, 7], [2, 3, 4, 5], [6, 7, 8, 9, 10], [11, 12]]
+  d5 = phi.clone()
+  subspace_sc_cheap_quadratic_descent.run(x, d5, codes, pairs, h, 0.5, stepsize=0.1, num_iters=1)
+  d6 = phi.clone()
+  subspace_sc_cheap_quadratic_descent.run(x, d6, codes, overlapping, h, 0.25, stepsize=0.05, num_iters=2)
+  d7 = phi.clone() * torch.linspace(0.5, 2.0, s)[:, None]
+  d7_in = d7.clone()
+  subspace_sc_cheap_quadratic_descent.run(x, d7, codes, overlapping, h, 0.25, stepsize=0.05, num_iters=1,
+                                          normalize_dictionary=False)
   save('dict_update_small', images=x, dictionary=phi, codes=codes, hessian_diagonal=h,
-       cheap_1=d1, cheap_3=d2, steepest_1=d3, steepest_2_unnormalized=d4)
+       cheap_1=d1, cheap_3=d2, steepest_1=d3, steepest_2_unnormalized=d4,
+       aligned_pairs=d5, aligned_overlapping_2=d6, unnormalized_in=d7_in, aligned_unnormalized=d7)
 
 
 def make_training():
@@ -134,7 +146,11 @@ def make_training():
                  group_assignments=pairs, subspace_alignment_penalty=0.0)
   phi_c = phi0.clone()
   sparse_coding.train_dictionary(x, x[:1], phi_c, params3)
-  save('training_small', batches=x, dictionary=phi0, fista_cheap=phi, ista_steepest=phi_b, subspace_cheap=phi_c)
+  params4 = dict(params3, subspace_alignment_penalty=0.3)
+  phi_d = phi0.clone()
+  sparse_coding.train_dictionary(x, x[:1], phi_d, params4)
+  save('training_small', batches=x, dictionary=phi0, fista_cheap=phi, ista_steepest=phi_b, subspace_cheap=phi_c,
+       subspace_cheap_aligned=phi_d)
 
 
 if __name__ == '__main__':

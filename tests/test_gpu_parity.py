@@ -252,8 +252,16 @@ def test_dictionary_updates_against_reference_outputs():
   assert oracle.relative_l2(updated(steepest.run, a, stepsize=0.1, num_iters=2, normalize_dictionary=False),
                             g['steepest_2_unnormalized']) < 1e-5
   assert oracle.relative_l2(updated(sub_cheap.run, a, [[0, 1]], h, 0.0, stepsize=0.1), g['cheap_1']) < 1e-5
-  with pytest.raises(NotImplementedError):
-    sub_cheap.run(x, phi.clone(), a, [[0, 1]], h, 0.5)
+  # within-group alignment penalty (reference subspace_sc_cheap_quadratic_descent.py:59-79, :91-127)
+  s = phi.size(0)
+  pairs = [list(map(int, v)) for v in np.array_split(np.arange(s), s // 2)]
+  overlapping = [[0, 2, 5], [1, 7], [2, 3, 4, 5], [6, 7, 8, 9, 10], [11, 12]]
+  assert oracle.relative_l2(updated(sub_cheap.run, a, pairs, h, 0.5, stepsize=0.1), g['aligned_pairs']) < 1e-5
+  assert oracle.relative_l2(updated(sub_cheap.run, a, overlapping, h, 0.25, stepsize=0.05, num_iters=2),
+                            g['aligned_overlapping_2']) < 2e-5
+  d = g['unnormalized_in'].cuda()
+  sub_cheap.run(x, d, a, overlapping, h, 0.25, stepsize=0.05, num_iters=1, normalize_dictionary=False)
+  assert oracle.relative_l2(d.cpu(), g['aligned_unnormalized']) < 1e-5
   assert torch.equal(x, keep[0]) and torch.equal(a, keep[1]) and torch.equal(h, keep[2])
 
 

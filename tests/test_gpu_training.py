@@ -39,6 +39,11 @@ def test_trainer_matches_reference_trainer_outputs(capsys):
                            params('subspace_fista', 'subspace_sc_cheap_quadratic_descent', group_assignments=pairs,
                                   subspace_alignment_penalty=0.0))
   assert oracle.relative_l2(phi.cpu(), g['subspace_cheap']) < 1e-4
+  phi = phi0.cuda()
+  trainer.train_dictionary(batches, batches[:1], phi,
+                           params('subspace_fista', 'subspace_sc_cheap_quadratic_descent', group_assignments=pairs,
+                                  subspace_alignment_penalty=0.3))
+  assert oracle.relative_l2(phi.cpu(), g['subspace_cheap_aligned']) < 1e-4
 
 
 def test_checkpoint_format_matches_reference(tmp_path):

@@ -57,6 +57,15 @@ def test_dictionary_update_matches_reference_outputs():
   close(oracle.sc_dictionary_update(x, phi, a, None, stepsize=0.1), g['steepest_1'])
   close(oracle.sc_dictionary_update(x, phi, a, None, stepsize=0.1, num_iters=2, normalize_dictionary=False),
         g['steepest_2_unnormalized'])
+  s = phi.size(0)
+  pairs = [list(map(int, v)) for v in np.array_split(np.arange(s), s // 2)]
+  overlapping = [[0, 2, 5], [1, 7], [2, 3, 4, 5], [6, 7, 8, 9, 10], [11, 12]]
+  close(oracle.sc_dictionary_update(x, phi, a, h, stepsize=0.1, group_assignments=pairs, alignment_penalty=0.5),
+        g['aligned_pairs'])
+  close(oracle.sc_dictionary_update(x, phi, a, h, stepsize=0.05, num_iters=2, group_assignments=overlapping,
+                                    alignment_penalty=0.25), g['aligned_overlapping_2'])
+  close(oracle.sc_dictionary_update(x, g['unnormalized_in'], a, h, stepsize=0.05, normalize_dictionary=False,
+                                    group_assignments=overlapping, alignment_penalty=0.25), g['aligned_unnormalized'])
 
 
 def test_train_steps_match_reference_trainer():
@@ -70,6 +79,9 @@ def test_train_steps_match_reference_trainer():
   pairs = [list(map(int, v)) for v in np.array_split(np.arange(s), s // 2)]
   phi, _, _ = oracle.train_steps(batches, phi0, 0.1, 30, 0.1, group_assignments=pairs)
   close(phi, g['subspace_cheap'], 1e-5)
+  phi, _, _ = oracle.train_steps(batches, phi0, 0.1, 30, 0.1, group_assignments=pairs,
+                                 update_rule='subspace_sc_cheap_quadratic_descent', alignment_penalty=0.3)
+  close(phi, g['subspace_cheap_aligned'], 1e-5)
 
 
 def test_known_answer_orthonormal_dictionary():

@@ -28,7 +28,8 @@ SIGNATURES = {
                             _f32, _int, _ptr, _size, _c.POINTER(_int), _c.POINTER(_f32), _ptr]),
     'vtc_dict_grad_workspace_bytes': (_size, [_i64, _i64, _i64, _int]),
     'vtc_sc_dict_grad': (_int, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _int, _ptr, _size, _ptr]),
-    'vtc_sc_dict_apply': (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _f32, _f32, _int, _ptr]),
+    'vtc_sc_dict_apply': (_int, [_ptr, _ptr, _ptr, _ptr, _f32, _i64, _i64, _i64, _f32, _f32, _int, _ptr]),
+    'vtc_subspace_alignment_grad': (_int, [_ptr, _i64, _i64, _ptr, _i64, _i64, _int, _ptr, _ptr]),
     'vtc_hessian_diag_update': (_int, [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _int, _ptr]),
     'vtc_hessian_ema': (_int, [_ptr, _ptr, _i64, _i64, _ptr]),
     'vtc_matmul_nt_workspace_bytes': (_size, [_i64, _i64, _i64, _int]),

@@ -186,9 +186,65 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int ns
   }
 }
 
+// Gradient of the within-group alignment penalty sum_{i != j in group} |cos(phi_i, phi_j)|
+// (subspace_sc_cheap_quadratic_descent.py:91-127). One block per group; slots[g*W + i] is the atom of member i or -1.
+//   normalised dictionary:  grad_i = sum_j sign(c_ij) (phi_j - c_ij phi_i),            c = phi phi^T
+//   general:                grad_i = sum_j sign(c_ij) (phi_j / (n_i n_j) - c_ij / n_i^2 phi_i),  c_ij = phi_i.phi_j / (n_i n_j)
+// Contributions are accumulated with atomics because an atom may belong to several groups (:66-70).
+__global__ void alignment_grad_kernel(const float* __restrict__ dict, int64_t D, const int32_t* __restrict__ slots,
+                                      int W, int normalized, float* __restrict__ accum) {
+  extern __shared__ float sm[];
+  float* rows = sm;                 // [W][D]
+  float* dots = sm + static_cast<size_t>(W) * D;  // [W][W]
+  float* norms = dots + W * W;      // [W]
+  const int g = blockIdx.x;
+  const int32_t* members = slots + static_cast<int64_t>(g) * W;
+  for (int64_t i = threadIdx.x; i < static_cast<int64_t>(W) * D; i += blockDim.x) {
+    const int m = static_cast<int>(i / D);
+    const int32_t a = members[m];
+    rows[i] = (a >= 0) ? dict[static_cast<int64_t>(a) * D + (i - m * D)] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int pair = warp; pair < W * W; pair += nwarps) {
+    const int i = pair / W, j = pair % W;
+    float acc = 0.f;
+    for (int64_t d = lane; d < D; d += 32) acc += rows[i * D + d] * rows[j * D + d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) dots[pair] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < W) norms[threadIdx.x] = sqrtf(dots[threadIdx.x * W + threadIdx.x]);
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < static_cast<int64_t>(W) * D; i += blockDim.x) {
+    const int m = static_cast<int>(i / D);
+    const int64_t d = i - static_cast<int64_t>(m) * D;
+    const int32_t a = members[m];
+    if (a < 0) continue;
+    float grad = 0.f;
+    for (int j = 0; j < W; ++j) {
+      if (members[j] < 0) continue;
+      float c, t;
+      if (normalized) {
+        c = dots[m * W + j];
+        t = rows[j * D + d] - c * rows[m * D + d];
+      } else {
+        const float nn = norms[m] * norms[j];
+        c = dots[m * W + j] / nn;
+        t = rows[j * D + d] / nn - (c / (norms[m] * norms[m])) * rows[m * D + d];
+      }
+      const float sgn = (c > 0.f) ? 1.f : (c < 0.f) ? -1.f : 0.f;
+      grad += sgn * t;
+    }
+    atomicAdd(accum + static_cast<int64_t>(a) * D + d, grad);
+  }
+}
+
 // One block per atom (row): sc_cheap_quadratic_descent.py:43-48 / sc_steepest_descent.py:37-41 after the contraction.
 __global__ void dict_apply_kernel(float* __restrict__ dict, const float* __restrict__ grad, const float* __restrict__ h,
-                                  int64_t D, float batch, float stepsize, float lowest, int normalize) {
+                                  const float* __restrict__ reg, float penalty, int64_t D, float batch, float stepsize,
+                                  float lowest, int normalize) {
   __shared__ float red[256];
   const int64_t s = blockIdx.x;
   float* row = dict + s * D;
@@ -196,7 +252,9 @@ __global__ void dict_apply_kernel(float* __restrict__ dict, const float* __restr
   const float denom = h ? (h[s] + lowest) : 1.f;
   float ss = 0.f;
   for (int64_t d = threadIdx.x; d < D; d += blockDim.x) {
-    float u = __fmul_rn(stepsize, __fdiv_rn(g[d], batch));  // stepsize * (mm / codes.size(0))
+    float data_term = __fdiv_rn(g[d], batch);               // mm / codes.size(0)
+    if (reg) data_term = __fadd_rn(data_term, __fmul_rn(penalty, reg[s * D + d]));  // + alignment_penalty * reg. grads
+    float u = __fmul_rn(stepsize, data_term);
     if (h) u = __fdiv_rn(u, denom);                                    // dict_update.div_(h[:, None] + lowest)
     const float v = __fsub_rn(row[d], u);                              // dictionary.sub_(dict_update)
     row[d] = v;

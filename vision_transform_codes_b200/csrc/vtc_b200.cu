@@ -809,12 +809,32 @@ int vtc_sc_dict_grad(const float* images, int64_t ld_images, const float* dictio
   return VTC_OK;
 }
 
-int vtc_sc_dict_apply(float* dictionary, const float* grad_sum, const float* hessian_diagonal, int64_t S, int64_t D,
+int vtc_sc_dict_apply(float* dictionary, const float* grad_sum, const float* hessian_diagonal,
+                      const float* alignment_grad, float alignment_penalty, int64_t S, int64_t D,
                       int64_t batch_global, float stepsize, float lowest_code_val, int normalize,
                       vtc_stream_t stream) {
   if (!dictionary || !grad_sum || S <= 0 || D <= 0 || batch_global <= 0) return fail(VTC_ERR_ARG, "vtc_sc_dict_apply: bad argument");
   dict_apply_kernel<<<static_cast<unsigned>(S), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dictionary, grad_sum, hessian_diagonal, D, static_cast<float>(batch_global), stepsize, lowest_code_val, normalize);
+      dictionary, grad_sum, hessian_diagonal, alignment_grad, alignment_penalty, D, static_cast<float>(batch_global),
+      stepsize, lowest_code_val, normalize);
+  COUNT_LAUNCH();
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+int vtc_subspace_alignment_grad(const float* dictionary, int64_t S, int64_t D, const int32_t* group_slots,
+                                int64_t num_groups, int64_t group_width, int dictionary_is_normalized,
+                                float* alignment_grad, vtc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!dictionary || !group_slots || !alignment_grad || S <= 0 || D <= 0 || num_groups <= 0 || group_width <= 0)
+    return fail(VTC_ERR_ARG, "vtc_subspace_alignment_grad: bad argument");
+  const size_t smem = (static_cast<size_t>(group_width) * D + group_width * group_width + group_width) * sizeof(float);
+  if (smem > 200 * 1024) return fail(VTC_ERR_UNSUPPORTED, "group of %lld atoms x %lld pixels does not fit in shared memory", (long long)group_width, (long long)D);
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(alignment_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  CUDA_TRY(cudaMemsetAsync(alignment_grad, 0, static_cast<size_t>(S) * D * sizeof(float), st));
+  alignment_grad_kernel<<<static_cast<unsigned>(num_groups), 256, smem, st>>>(
+      dictionary, D, group_slots, static_cast<int>(group_width), dictionary_is_normalized, alignment_grad);
   COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;

@@ -2,9 +2,9 @@
 Dictionary update for subspace sparse coding (cheap quadratic descent), on B200.
 
 Drop-in for vision_transform_codes/dict_update_rules/fully_connected/subspace_sc_cheap_quadratic_descent.py:13-88.
-With ``alignment_penalty == 0`` the rule is exactly sc_cheap_quadratic_descent (reference :80-88) and runs on the
-CUDA path. The within-group alignment regulariser (reference :59-79, :91-127) is not on the B200 hot path yet
- and raises NotImplementedError rather than silently dropping the term.
+With ``alignment_penalty == 0`` the rule is exactly sc_cheap_quadratic_descent (reference :80-88). Otherwise the
+gradient of the within-group alignment penalty (reference :59-79, :91-127) is computed by ``vtc_subspace_alignment_grad``
+(one thread block per group) and folded into the apply step.
 """
 import os
 import sys
@@ -28,13 +28,11 @@ def run(images, dictionary, codes, group_assignments, hessian_diagonal,
   dictionary : torch.Tensor(float32, size=(s, n))
   codes : torch.Tensor(float32, size=(b, s))
   group_assignments : list(array_like)
-      Only used by the alignment penalty.
+      Groups of dictionary elements; an element may belong to several groups.
   hessian_diagonal : torch.Tensor(float32, size=(s,))
   alignment_penalty : float
-      Weight of the within-group alignment regulariser; must be 0 here.
+      Weight of the within-group alignment regulariser.
   stepsize, num_iters, lowest_code_val, normalize_dictionary : see sc_cheap_quadratic_descent.run
   """
-  if alignment_penalty != 0:
-    raise NotImplementedError('alignment_penalty != 0 is not implemented on the B200 path')
   _common.descend(images, dictionary, codes, hessian_diagonal, stepsize, num_iters, lowest_code_val,
-                  normalize_dictionary)
+                  normalize_dictionary, group_assignments=group_assignments, alignment_penalty=alignment_penalty)

@@ -46,6 +46,7 @@ class _UpdateState:
     self.grad = self.packed[:S * D].view(S, D)
     self.sq_sum = self.packed[S * D:]
     self.batch_global = None
+    self.slots, self.width, self.reg = None, 0, None  # subspace alignment penalty
 
 
 def allreduce_update_buffers(state, with_code_squares):
@@ -56,7 +57,7 @@ def allreduce_update_buffers(state, with_code_squares):
 
 
 def update_dictionary(images, dictionary, codes, hessian_diag, stepsize, num_iters, state, lowest_code_val=0.001,
-                      normalize_dictionary=True, batch_global=None):
+                      normalize_dictionary=True, batch_global=None, group_assignments=None, alignment_penalty=0.0):
   """
   training/sparse_coding.py:142-168 for the fully-connected rules: the Hessian running mean (:154, when
   hessian_diag is given) followed by num_iters descent steps, with ONE all-reduce per step when data parallel.
@@ -82,9 +83,18 @@ def update_dictionary(images, dictionary, codes, hessian_diag, stepsize, num_ite
         allreduce_update_buffers(state, first)
       if first:
         _lib.check(lib.vtc_hessian_ema(_lib.ptr(hessian_diag), _lib.ptr(state.sq_sum), S, batch_global, st))
-      _lib.check(lib.vtc_sc_dict_apply(_lib.ptr(dictionary), _lib.ptr(state.grad), _lib.ptr(hessian_diag), S, D,
-                                       int(batch_global), float(stepsize), float(lowest_code_val),
-                                       int(bool(normalize_dictionary)), st))
+      reg = None
+      if alignment_penalty != 0:
+        if state.slots is None:
+          state.slots, state.width = _common.group_slot_table(group_assignments, S, device)
+          state.reg = torch.empty((S, D), dtype=torch.float32, device=device)
+        reg = state.reg
+        _lib.check(lib.vtc_subspace_alignment_grad(_lib.ptr(dictionary), S, D, _lib.ptr(state.slots),
+                                                   state.slots.size(0), state.width, int(bool(normalize_dictionary)),
+                                                   _lib.ptr(reg), st))
+      _lib.check(lib.vtc_sc_dict_apply(_lib.ptr(dictionary), _lib.ptr(state.grad), _lib.ptr(hessian_diag),
+                                       _lib.ptr(reg), float(alignment_penalty), S, D, int(batch_global),
+                                       float(stepsize), float(lowest_code_val), int(bool(normalize_dictionary)), st))
 
 
 def train_dictionary(training_image_dataset, validation_image_dataset, init_dictionary, all_params):
@@ -122,8 +132,10 @@ def train_dictionary(training_image_dataset, validation_image_dataset, init_dict
     group_assignments = [list(map(int, x)) for x in group_assignments]
   if code_inf_alg.startswith('subspace'):
     assert group_assignments is not None
-  if dict_update_alg.startswith('subspace') and all_params.get('subspace_alignment_penalty', 0.0) != 0:
-    raise NotImplementedError('subspace_alignment_penalty != 0 is not implemented on the B200 path')
+  alignment_penalty = 0.0
+  if dict_update_alg.startswith('subspace'):
+    assert group_assignments is not None
+    alignment_penalty = all_params['subspace_alignment_penalty']
   if all_params.get('renormalize_dictionary', True):
     norms = init_dictionary.norm(p=2, dim=1)
     assert torch.allclose(norms, torch.ones_like(norms)), 'Please ensure the initial dictionary is already normalized'
@@ -162,7 +174,8 @@ def train_dictionary(training_image_dataset, validation_image_dataset, init_dict
         t_batch_images = t_batch_images.to(dictionary.device)
       t_codes = infer_codes(t_batch_images, dictionary, code_inf_alg, sparsity_weight, inf_num_iters, nonneg_only,
                             hard_threshold, group_assignments)
-      update_dictionary(t_batch_images, dictionary, t_codes, hessian_diag, d_upd_stp, d_upd_niters, state)
+      update_dictionary(t_batch_images, dictionary, t_codes, hessian_diag, d_upd_stp, d_upd_niters, state,
+                        group_assignments=group_assignments, alignment_penalty=alignment_penalty)
       total_iter_idx += 1
     if rank0:
       print("Epoch", epoch_idx + 1, "finished")
