@@ -207,6 +207,7 @@ struct GemmCall {
   float beta_prev = 0.f, beta_next = 0.f;
   const float* scalars = nullptr;
   double* stat = nullptr;
+  int max_pairs = 0;     // cap on the SM pairs used (0 = all): concurrent chains share the chip
 };
 
 template <int EPI, int P, int NIN>
@@ -252,7 +253,8 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
     CUDA_TRY(cudaFuncSetAttribute(vtc_gemm_kernel<EPI, P, NIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
     attr_set = true;
   }
-  const long long max_pairs = info.sm_count / 2;
+  long long max_pairs = info.sm_count / 2;
+  if (c.max_pairs > 0 && c.max_pairs < max_pairs) max_pairs = c.max_pairs;
   const int pairs = static_cast<int>(tiles < max_pairs ? tiles : max_pairs);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -515,12 +517,223 @@ int vtc_lipschitz(const float* dictionary, int64_t S, int64_t D, float* lipschit
   return run_lipschitz(dictionary, S, D, w, 0.f, nullptr, lipschitz_dev, static_cast<cudaStream_t>(stream));
 }
 
+// ---- chains -----------------------------------------------------------------------------------------------------
+// In the synthesis form an iteration is a tensor-bound launch (r = y Phi - x) followed by an HBM-bound one
+// (r Phi^T + fused update). Rows are independent, so a large batch is cut into two "chains" (contiguous halves) that
+// run on two streams with half of the SM pairs each: while one chain is in its tensor-bound launch the other streams
+// its state through HBM. Launches are issued alternately so that neither chain starts late.
+}  // extern "C"  (helpers below have C++ linkage)
+
+namespace {
+
+struct FistaCommon {
+  const float* dictionary;
+  int64_t S, D;
+  float sparsity_weight;
+  int num_iters, variant, prox, group_size, precision, P;
+  bool gram, early;
+};
+
+struct FistaChain {
+  // caller's buffers for this chain's rows
+  const float* images;
+  const float* initial_codes;
+  float* codes_out;
+  int64_t ld_images, ld_codes, B;
+  cudaStream_t st;
+  int max_pairs;       // SM pairs this chain's GEMM launches may occupy (0 = all)
+  FistaWs w;
+  // state
+  float *X1, *X2;
+  int64_t ld1, ld2;
+  const float* init;
+  int64_t ld_init;
+  const float* x_in;
+  int64_t ld_x;
+};
+
+int chains_for(int64_t B, int64_t S, int64_t D) {
+  static int requested = -1;
+  if (requested < 0) {
+    const char* e = getenv("VTC_B200_CHAINS");
+    requested = e ? atoi(e) : 2;
+    if (requested < 1) requested = 1;
+    if (requested > 2) requested = 2;
+  }
+  // only where the two launches of an iteration stress different resources, and each chain still fills its SMs
+  if (requested == 2 && formulation_for(S, D) == FORM_SYNTHESIS && B >= 2 * 37 * PAIR_M) return 2;
+  return 1;
+}
+int64_t chain_rows(int64_t B, int chains, int c) {
+  if (chains == 1) return B;
+  const int64_t first = round_up((B + 1) / 2, PAIR_M);
+  return c == 0 ? first : B - first;
+}
+
+int chain_setup(const FistaCommon& cm, FistaChain& ch) {
+  FistaWs& w = ch.w;
+  cudaStream_t st = ch.st;
+  const int64_t B = ch.B, S = cm.S, D = cm.D;
+  // step size and operand splits; Gram form additionally G = Phi Phi^T (as bf16 parts) and b = x Phi^T
+  TRY(run_lipschitz(cm.dictionary, S, D, w.lip, cm.sparsity_weight, w.scalars, nullptr, st));
+  TRY(split_rows(cm.dictionary, D, S, D, w.phi_op, st));
+  ch.x_in = ch.images;  // synthesis form: the fp32 images are an epilogue input of the first contraction
+  ch.ld_x = ch.ld_images;
+  if (cm.gram) {
+    TRY(split_rows(ch.images, ch.ld_images, B, D, w.x_op, st));
+    {
+      GemmCall g;
+      g.A = w.phi_op, g.B = w.phi_op;
+      g.precision = VTC_PRECISION_BF16X6;
+      g.M = S, g.N = S, g.K = D;
+      g.parts_out = w.G_op, g.n_parts = cm.P;
+      g.max_pairs = ch.max_pairs;
+      CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.G_op.ptr), 0, w.G_op.bytes(), st));
+      TRY(launch_gemm<EPI_STORE>(g, st));
+    }
+    {
+      GemmCall g;
+      g.A = w.x_op, g.B = w.phi_op;
+      g.precision = VTC_PRECISION_BF16X6;
+      g.M = B, g.N = S, g.K = D;
+      g.out = F32Mat{w.bvec, B, S, w.ldS}, g.store_out = true;
+      g.max_pairs = ch.max_pairs;
+      TRY(launch_gemm<EPI_STORE>(g, st));
+    }
+  } else {
+    TRY(transpose_split(cm.dictionary, D, S, D, w.phiT_op, st));
+    CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.r_op.ptr), 0, w.r_op.bytes(), st));
+    if (!tma_ok(ch.images, ch.ld_images)) {
+      CUDA_TRY(cudaMemcpy2DAsync(w.x_pad, w.ldD * 4, ch.images, ch.ld_images * 4, D * 4, B, cudaMemcpyDeviceToDevice, st));
+      ch.x_in = w.x_pad, ch.ld_x = w.ldD;
+    }
+  }
+  // state buffers. a_k lives in X1 for odd k and X2 for even k; a_0 is `init`.
+  const bool direct_out = tma_ok(ch.codes_out, ch.ld_codes) && !cm.early;
+  ch.X1 = w.X1, ch.X2 = w.X2;
+  ch.ld1 = w.ldS, ch.ld2 = w.ldS;
+  if (direct_out) {
+    if (cm.num_iters & 1) ch.X1 = ch.codes_out, ch.ld1 = ch.ld_codes;
+    else ch.X2 = ch.codes_out, ch.ld2 = ch.ld_codes;
+  }
+  CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[1].ptr), 0, w.yop[1].bytes(), st));
+  if (ch.initial_codes) {
+    if (tma_ok(ch.initial_codes, ch.ld_codes)) {
+      ch.init = ch.initial_codes, ch.ld_init = ch.ld_codes;
+    } else {
+      CUDA_TRY(cudaMemcpy2DAsync(w.init_pad, w.ldS * 4, ch.initial_codes, ch.ld_codes * 4, S * 4, B, cudaMemcpyDeviceToDevice, st));
+      ch.init = w.init_pad, ch.ld_init = w.ldS;
+    }
+    TRY(split_rows(ch.initial_codes, ch.ld_codes, B, S, w.yop[0], st));
+  } else {
+    // a_0 = 0: X2 doubles as a_0 (it is only overwritten, in place, when a_2 is produced)
+    CUDA_TRY(cudaMemset2DAsync(ch.X2, ch.ld2 * 4, 0, S * 4, B, st));
+    CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[0].ptr), 0, w.yop[0].bytes(), st));
+    ch.init = ch.X2, ch.ld_init = ch.ld2;
+  }
+  if (cm.early) CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * cm.num_iters, st));
+  return VTC_OK;
+}
+
+// iteration k (1-based) of one chain; `sample` >= 0 records profile events around its launches
+int chain_iterate(const FistaCommon& cm, FistaChain& ch, int k, float beta_prev, float beta_k, int sample) {
+  FistaWs& w = ch.w;
+  cudaStream_t st = ch.st;
+  const int64_t B = ch.B, S = cm.S, D = cm.D;
+  const float* a_prev = (k == 1) ? ch.init : ((k - 1) & 1) ? ch.X1 : ch.X2;       // a_{k-1}
+  const int64_t ld_prev = (k == 1) ? ch.ld_init : ((k - 1) & 1) ? ch.ld1 : ch.ld2;
+  const float* a_prev2 = (k <= 2) ? ch.init : (k & 1) ? ch.X1 : ch.X2;            // a_{k-2}
+  const int64_t ld_prev2 = (k <= 2) ? ch.ld_init : (k & 1) ? ch.ld1 : ch.ld2;
+  float* a_out = (k & 1) ? ch.X1 : ch.X2;
+  const int64_t ld_out = (k & 1) ? ch.ld1 : ch.ld2;
+  if (sample >= 0) CUDA_TRY(cudaEventRecord(g_prof.k1_begin[sample], st));
+  GemmCall g;
+  g.precision = cm.precision;
+  g.max_pairs = ch.max_pairs;
+  g.in[0] = F32Mat{a_prev, B, S, ld_prev};
+  g.in_mask = 1;
+  if (cm.gram) {
+    g.A = w.yop[(k - 1) & 1], g.B = w.G_op;
+    g.M = B, g.N = S, g.K = S;
+    g.in[1] = F32Mat{w.bvec, B, S, w.ldS};
+    g.in_mask |= 2;
+  } else {
+    // r = y Phi - x, emitted as bf16 parts; then the fused contraction acc = r Phi^T is the whole gradient
+    GemmCall r;
+    r.precision = cm.precision;
+    r.max_pairs = ch.max_pairs;
+    r.A = w.yop[(k - 1) & 1], r.B = w.phiT_op;
+    r.M = B, r.N = D, r.K = S;
+    r.in[0] = F32Mat{ch.x_in, B, D, ch.ld_x}, r.in_mask = 1;
+    r.parts_out = w.r_op, r.n_parts = cm.P;
+    TRY(launch_gemm<EPI_STORE>(r, st));
+    if (sample >= 0) CUDA_TRY(cudaEventRecord(g_prof.k1_end[sample], st));
+    g.A = w.r_op, g.B = w.phi_op;
+    g.M = B, g.N = S, g.K = D;
+  }
+  if (cm.variant == VTC_VARIANT_FISTA && beta_prev != 0.f) {
+    g.in[2] = F32Mat{a_prev2, B, S, ld_prev2};
+    g.in_mask |= 4;
+  }
+  g.out = F32Mat{a_out, B, S, ld_out}, g.store_out = true;
+  if (k < cm.num_iters) g.parts_out = w.yop[k & 1], g.n_parts = cm.P;
+  g.prox = cm.prox;
+  g.group = cm.group_size;
+  g.use_momentum = (cm.variant == VTC_VARIANT_FISTA);
+  g.beta_prev = beta_prev, g.beta_next = beta_k;
+  g.scalars = w.scalars;
+  g.stat = cm.early ? w.stats + (k - 1) : nullptr;
+  TRY(launch_gemm<EPI_FISTA>(g, st));
+  if (sample >= 0) {
+    if (cm.gram) CUDA_TRY(cudaEventRecord(g_prof.k1_end[sample], st));
+    CUDA_TRY(cudaEventRecord(g_prof.k2_end[sample], st));
+  }
+  return VTC_OK;
+}
+
+int chain_finish(const FistaCommon& cm, FistaChain& ch, int k_done) {
+  const float* result = (k_done & 1) ? ch.X1 : ch.X2;
+  const int64_t ld_res = (k_done & 1) ? ch.ld1 : ch.ld2;
+  if (result != ch.codes_out)
+    CUDA_TRY(cudaMemcpy2DAsync(ch.codes_out, ch.ld_codes * 4, result, ld_res * 4, cm.S * 4, ch.B, cudaMemcpyDeviceToDevice, ch.st));
+  return VTC_OK;
+}
+
+// side stream + fork/join events of the second chain, one set per device
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+int side_stream(SideStream** out) {
+  static SideStream per_device[64];
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  SideStream& s = per_device[dev & 63];
+  if (!s.stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return VTC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 size_t vtc_fista_workspace_bytes(int64_t B, int64_t S, int64_t D, int precision) {
   if (!valid_precision(precision) || B <= 0 || S <= 0 || D <= 0) return 0;
-  Carver cv(nullptr, 0);
-  carve_fista(cv, B, S, D, precision);
-  return cv.off + 1024;
+  // enough for either schedule: one chain over all rows (always used with early stopping) or two half-batch chains
+  Carver one(nullptr, 0);
+  carve_fista(one, B, S, D, precision);
+  Carver two(nullptr, 0);
+  const int chains = chains_for(B, S, D);
+  for (int c = 0; c < chains; ++c) carve_fista(two, chain_rows(B, chains, c), S, D, precision);
+  return (one.off > two.off ? one.off : two.off) + 2048;
 }
+
+int vtc_get_chains(int64_t B, int64_t S, int64_t D) { return chains_for(B, S, D); }
 
 int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary, const float* initial_codes,
                  float* codes_out, int64_t ld_codes, int64_t B, int64_t S, int64_t D, float sparsity_weight,
@@ -542,12 +755,37 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   if (S > (1 << 20) || B > (1ll << 31) - 256) return fail(VTC_ERR_ARG, "problem too large for 32-bit tile coordinates");
   DeviceInfo info;
   TRY(require_sm100(&info));
+  FistaCommon cm;
+  cm.dictionary = dictionary;
+  cm.S = S, cm.D = D;
+  cm.sparsity_weight = sparsity_weight;
+  cm.num_iters = num_iters, cm.variant = variant;
+  cm.prox = (hard_threshold ? PROX_HARD : 0) | (nonnegative_only ? PROX_NONNEG : 0);
+  cm.group_size = group_size;
+  cm.precision = precision, cm.P = parts_for(precision);
+  cm.gram = formulation_for(S, D) == FORM_GRAM;
+  cm.early = early_stopping_epsilon >= 0.f;
+  if (cm.early && num_iters > 4096) return fail(VTC_ERR_UNSUPPORTED, "early stopping supports at most 4096 iterations");
+
+  // the early-stopping statistic is global over the batch: one chain then
+  const int chains = cm.early ? 1 : chains_for(B, S, D);
+  FistaChain ch[2];
   Carver cv(workspace, workspace_bytes);
-  FistaWs w = carve_fista(cv, B, S, D, precision);
+  SideStream* side = nullptr;
+  if (chains == 2) TRY(side_stream(&side));
+  int64_t row0 = 0;
+  for (int c = 0; c < chains; ++c) {
+    const int64_t rows = chain_rows(B, chains, c);
+    ch[c].images = images + row0 * ld_images;
+    ch[c].initial_codes = initial_codes ? initial_codes + row0 * ld_codes : nullptr;
+    ch[c].codes_out = codes_out + row0 * ld_codes;
+    ch[c].ld_images = ld_images, ch[c].ld_codes = ld_codes, ch[c].B = rows;
+    ch[c].st = (c == 0) ? st : side->stream;
+    ch[c].max_pairs = (chains == 2) ? info.sm_count / 4 : 0;
+    ch[c].w = carve_fista(cv, rows, S, D, precision);
+    row0 += rows;
+  }
   if (!workspace || !cv.fits()) return fail(VTC_ERR_WORKSPACE, "vtc_fista_fc: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
-  const bool early = early_stopping_epsilon >= 0.f;
-  if (early && num_iters > 4096) return fail(VTC_ERR_UNSUPPORTED, "early stopping supports at most 4096 iterations");
-  const int P = parts_for(precision);
 
   if (g_prof.on) {
     if (!g_prof.begin) {
@@ -564,77 +802,23 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
     g_prof.valid = false;
     CUDA_TRY(cudaEventRecord(g_prof.begin, st));
   }
-  // ---- setup: step size and operand splits; Gram form additionally G = Phi Phi^T (as bf16 parts) and b = x Phi^T
-  const bool gram = formulation_for(S, D) == FORM_GRAM;
-  TRY(run_lipschitz(dictionary, S, D, w.lip, sparsity_weight, w.scalars, nullptr, st));
-  TRY(split_rows(dictionary, D, S, D, w.phi_op, st));
-  const float* x_in = images;  // synthesis form: the fp32 images are an epilogue input of the first contraction
-  int64_t ld_x = ld_images;
-  if (gram) {
-    TRY(split_rows(images, ld_images, B, D, w.x_op, st));
-    {
-      GemmCall g;
-      g.A = w.phi_op, g.B = w.phi_op;
-      g.precision = VTC_PRECISION_BF16X6;
-      g.M = S, g.N = S, g.K = D;
-      g.parts_out = w.G_op, g.n_parts = P;
-      CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.G_op.ptr), 0, w.G_op.bytes(), st));
-      TRY(launch_gemm<EPI_STORE>(g, st));
-    }
-    {
-      GemmCall g;
-      g.A = w.x_op, g.B = w.phi_op;
-      g.precision = VTC_PRECISION_BF16X6;
-      g.M = B, g.N = S, g.K = D;
-      g.out = F32Mat{w.bvec, B, S, w.ldS}, g.store_out = true;
-      TRY(launch_gemm<EPI_STORE>(g, st));
-    }
-  } else {
-    TRY(transpose_split(dictionary, D, S, D, w.phiT_op, st));
-    CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.r_op.ptr), 0, w.r_op.bytes(), st));
-    if (!tma_ok(images, ld_images)) {
-      CUDA_TRY(cudaMemcpy2DAsync(w.x_pad, w.ldD * 4, images, ld_images * 4, D * 4, B, cudaMemcpyDeviceToDevice, st));
-      x_in = w.x_pad, ld_x = w.ldD;
-    }
+  if (chains == 2) {  // fork: the side stream starts after everything already queued on the caller's stream
+    CUDA_TRY(cudaEventRecord(side->fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(side->stream, side->fork, 0));
   }
-
-  // ---- state buffers. a_k lives in X1 for odd k and X2 for even k; a_0 is `init`.
-  const bool direct_out = tma_ok(codes_out, ld_codes) && !early;
-  float* X1 = w.X1;
-  float* X2 = w.X2;
-  int64_t ld1 = w.ldS, ld2 = w.ldS;
-  if (direct_out) {
-    if (num_iters & 1) X1 = codes_out, ld1 = ld_codes;
-    else X2 = codes_out, ld2 = ld_codes;
-  }
-  const float* init;
-  int64_t ld_init;
-  CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[1].ptr), 0, w.yop[1].bytes(), st));
-  if (initial_codes) {
-    if (tma_ok(initial_codes, ld_codes)) {
-      init = initial_codes, ld_init = ld_codes;
-    } else {
-      CUDA_TRY(cudaMemcpy2DAsync(w.init_pad, w.ldS * 4, initial_codes, ld_codes * 4, S * 4, B, cudaMemcpyDeviceToDevice, st));
-      init = w.init_pad, ld_init = w.ldS;
-    }
-    TRY(split_rows(initial_codes, ld_codes, B, S, w.yop[0], st));
-  } else {
-    // a_0 = 0: X2 doubles as a_0 (it is only overwritten, in place, when a_2 is produced)
-    CUDA_TRY(cudaMemset2DAsync(X2, ld2 * 4, 0, S * 4, B, st));
-    CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[0].ptr), 0, w.yop[0].bytes(), st));
-    init = X2, ld_init = ld2;
-  }
-  if (early) CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * num_iters, st));
+  for (int c = 0; c < chains; ++c) TRY(chain_setup(cm, ch[c]));
 
   float eta_host = 0.f;
   float sc_host[4] = {0, 0, 0, 0};
-  if (early || lipschitz_out) {
-    CUDA_TRY(cudaMemcpyAsync(sc_host, w.scalars, sizeof(sc_host), cudaMemcpyDeviceToHost, st));
+  if (cm.early || lipschitz_out) {
+    CUDA_TRY(cudaMemcpyAsync(sc_host, ch[0].w.scalars, sizeof(sc_host), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     eta_host = sc_host[0];
     if (lipschitz_out) *lipschitz_out = sc_host[2];
-    if (sc_host[3] != 0.f || !isfinite(sc_host[2]))
+    if (sc_host[3] != 0.f || !isfinite(sc_host[2])) {
+      if (chains == 2) cudaStreamSynchronize(side->stream);
       return fail(VTC_ERR_NONFINITE, "largest eigenvalue of dictionary^T dictionary is %g: a dictionary element overflowed", sc_host[2]);
+    }
   }
 
   // ---- iterations. beta_k = (t_k - 1) / t_{k+1} in double on the host (ista_fista.py:124-125), applied as float32.
@@ -646,75 +830,33 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
     const double t_next = (1.0 + sqrt(1.0 + 4.0 * t_k * t_k)) / 2.0;
     const float beta_k = (variant == VTC_VARIANT_FISTA) ? static_cast<float>((t_k - 1.0) / t_next) : 0.f;
     t_k = t_next;
-    const float* a_prev = (k == 1) ? init : ((k - 1) & 1) ? X1 : X2;       // a_{k-1}
-    const int64_t ld_prev = (k == 1) ? ld_init : ((k - 1) & 1) ? ld1 : ld2;
-    const float* a_prev2 = (k <= 2) ? init : (k & 1) ? X1 : X2;            // a_{k-2}
-    const int64_t ld_prev2 = (k <= 2) ? ld_init : (k & 1) ? ld1 : ld2;
-    float* a_out = (k & 1) ? X1 : X2;
-    const int64_t ld_out = (k & 1) ? ld1 : ld2;
     const int sample = (g_prof.on && k > num_iters / 2 && g_prof.samples < kProfSamples) ? g_prof.samples : -1;
-    if (sample >= 0) CUDA_TRY(cudaEventRecord(g_prof.k1_begin[sample], st));
-    GemmCall g;
-    g.precision = precision;
-    g.in[0] = F32Mat{a_prev, B, S, ld_prev};
-    g.in_mask = 1;
-    if (gram) {
-      g.A = w.yop[(k - 1) & 1], g.B = w.G_op;
-      g.M = B, g.N = S, g.K = S;
-      g.in[1] = F32Mat{w.bvec, B, S, w.ldS};
-      g.in_mask |= 2;
-    } else {
-      // r = y Phi - x, emitted as bf16 parts; then the fused contraction acc = r Phi^T is the whole gradient
-      GemmCall r;
-      r.precision = precision;
-      r.A = w.yop[(k - 1) & 1], r.B = w.phiT_op;
-      r.M = B, r.N = D, r.K = S;
-      r.in[0] = F32Mat{x_in, B, D, ld_x}, r.in_mask = 1;
-      r.parts_out = w.r_op, r.n_parts = P;
-      TRY(launch_gemm<EPI_STORE>(r, st));
-      if (sample >= 0) CUDA_TRY(cudaEventRecord(g_prof.k1_end[sample], st));
-      g.A = w.r_op, g.B = w.phi_op;
-      g.M = B, g.N = S, g.K = D;
-    }
-    if (variant == VTC_VARIANT_FISTA && beta_prev != 0.f) {
-      g.in[2] = F32Mat{a_prev2, B, S, ld_prev2};
-      g.in_mask |= 4;
-    }
-    g.out = F32Mat{a_out, B, S, ld_out}, g.store_out = true;
-    if (k < num_iters) g.parts_out = w.yop[k & 1], g.n_parts = P;
-    g.prox = (hard_threshold ? PROX_HARD : 0) | (nonnegative_only ? PROX_NONNEG : 0);
-    g.group = group_size;
-    g.use_momentum = (variant == VTC_VARIANT_FISTA);
-    g.beta_prev = beta_prev, g.beta_next = beta_k;
-    g.scalars = w.scalars;
-    g.stat = early ? w.stats + (k - 1) : nullptr;
-    TRY(launch_gemm<EPI_FISTA>(g, st));
+    for (int c = 0; c < chains; ++c) TRY(chain_iterate(cm, ch[c], k, beta_prev, beta_k, c == 0 ? sample : -1));
     if (sample >= 0) {
-      if (gram) CUDA_TRY(cudaEventRecord(g_prof.k1_end[sample], st));
-      CUDA_TRY(cudaEventRecord(g_prof.k2_end[sample], st));
       g_prof.samples = sample + 1;
-      g_prof.two_launches = !gram;
+      g_prof.two_launches = !cm.gram;
     }
     beta_prev = beta_k;
     k_done = k;
-    if (early) {
+    if (cm.early) {
       double sum_abs = 0.0;
-      CUDA_TRY(cudaMemcpyAsync(&sum_abs, w.stats + (k - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(&sum_abs, ch[0].w.stats + (k - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
       const double avg = sum_abs / (static_cast<double>(B) * static_cast<double>(S)) / static_cast<double>(eta_host);
       if (avg < static_cast<double>(early_stopping_epsilon) && k > 1) break;
     }
   }
+  for (int c = 0; c < chains; ++c) TRY(chain_finish(cm, ch[c], k_done));
+  if (chains == 2) {  // join: the caller's stream continues only after the side chain is done
+    CUDA_TRY(cudaEventRecord(side->join, side->stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
+  }
   if (g_prof.on) {
     CUDA_TRY(cudaEventRecord(g_prof.iter_end, st));
-    g_prof.iter_launches = k_done * (gram ? 1 : 2);
+    g_prof.iter_launches = k_done * (cm.gram ? 1 : 2) * chains;
     g_prof.iters = k_done;
     g_prof.valid = true;
   }
-  const float* result = (k_done & 1) ? X1 : X2;
-  const int64_t ld_res = (k_done & 1) ? ld1 : ld2;
-  if (result != codes_out)
-    CUDA_TRY(cudaMemcpy2DAsync(codes_out, ld_codes * 4, result, ld_res * 4, S * 4, B, cudaMemcpyDeviceToDevice, st));
   if (iters_run) *iters_run = k_done;
   return VTC_OK;
 }
