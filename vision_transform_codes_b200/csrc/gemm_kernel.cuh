@@ -165,6 +165,29 @@ __device__ __forceinline__ void group_shrink(const float (&u)[16], float (&o)[16
   }
 }
 
+// Scalar soft-threshold update of 16 columns with the iteration's structure fixed at compile time (the common case):
+// no per-element selects on run-time flags. HASB: the drive b is an input (Gram form); PREV: a_{k-1} is an input
+// (momentum term non-zero); MOM: FISTA extrapolation of the new iterate.
+template <bool HASB, bool PREV, bool MOM>
+__device__ __forceinline__ void soft_update16(const uint32_t (&v)[16], const float (&in)[3][16], float eta, float theta,
+                                              float beta_prev, float beta_next, float (&outv)[16],
+                                              float (&partv)[16], float& stat_local, bool want_stat) {
+#pragma unroll
+  for (int x = 0; x < 16; ++x) {
+    const float ak = in[0][x];
+    float y = ak;
+    if (PREV) y = __fadd_rn(ak, __fmul_rn(beta_prev, __fsub_rn(ak, in[2][x])));
+    float g = __uint_as_float(v[x]);
+    if (HASB) g = __fsub_rn(g, in[1][x]);
+    const float u = __fsub_rn(y, __fmul_rn(eta, g));
+    const float a = copysignf(fmaxf(__fsub_rn(fabsf(u), theta), 0.f), u);
+    outv[x] = a;
+    const float d = __fsub_rn(a, ak);
+    partv[x] = MOM ? __fadd_rn(a, __fmul_rn(beta_next, d)) : a;
+    if (want_stat) stat_local += fabsf(d);
+  }
+}
+
 template <int EPI, int P, int NIN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<P, NIN>;
@@ -475,8 +498,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
             outv[x] = __uint_as_float(v[x]) - in[0][x];
             partv[x] = outv[x];
           }
+        } else if (p.prox == 0 && p.group <= 1) {
+          // fast paths: scalar soft threshold (ista_fista.py:117-120) with the iteration structure known at compile time
+          const bool prev = (p.in_mask & 4) != 0;
+          const bool want_stat = p.stat != nullptr;
+#define VTC_SOFT(HASB, PREV, MOM) \
+  soft_update16<HASB, PREV, MOM>(v, in, eta, theta, p.beta_prev, p.beta_next, outv, partv, stat_local, want_stat)
+          if (p.in_mask & 2) {  // Gram form: b is an input
+            if (!p.use_momentum) VTC_SOFT(true, false, false);
+            else if (!prev) VTC_SOFT(true, false, true);
+            else VTC_SOFT(true, true, true);
+          } else {              // synthesis form: the accumulator already is the whole gradient
+            if (!p.use_momentum) VTC_SOFT(false, false, false);
+            else if (!prev) VTC_SOFT(false, false, true);
+            else VTC_SOFT(false, true, true);
+          }
+#undef VTC_SOFT
         } else {
-          // in[0] = a_k, in[1] = b (absent -> 0: the accumulator already is the full gradient),
+          // general path. in[0] = a_k, in[1] = b (absent -> 0: the accumulator already is the full gradient),
           // in[2] = a_{k-1} (only loaded when the momentum term is non-zero)
           float u[16];
 #pragma unroll
@@ -495,10 +534,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
               if (p.prox & PROX_HARD) {
                 const float mag = (p.prox & PROX_NONNEG) ? ux : fabsf(ux);
                 a = (mag < theta) ? 0.f : ux;
-              } else if (p.prox & PROX_NONNEG) {
-                a = fmaxf(__fsub_rn(ux, theta), 0.f);
               } else {
-                a = copysignf(fmaxf(__fsub_rn(fabsf(ux), theta), 0.f), ux);
+                a = fmaxf(__fsub_rn(ux, theta), 0.f);
               }
               outv[x] = a;
             }
@@ -539,11 +576,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
             uint32_t w32[8];
 #pragma unroll
             for (int x = 0; x < 8; ++x) {
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(r[2 * x]);
-              const __nv_bfloat16 h1 = __float2bfloat16_rn(r[2 * x + 1]);
-              r[2 * x] = __fsub_rn(r[2 * x], __bfloat162float(h0));
-              r[2 * x + 1] = __fsub_rn(r[2 * x + 1], __bfloat162float(h1));
-              w32[x] = pack_bf16x2(h0, h1);
+              // one cvt.rn.bf16x2.f32 packs two columns; the bf16 -> fp32 widening is a shift / mask of that word
+              const __nv_bfloat162 h = __floats2bfloat162_rn(r[2 * x], r[2 * x + 1]);
+              w32[x] = *reinterpret_cast<const uint32_t*>(&h);
+              if (part + 1 < p.n_parts) {
+                r[2 * x] = __fsub_rn(r[2 * x], __uint_as_float(w32[x] << 16));
+                r[2 * x + 1] = __fsub_rn(r[2 * x + 1], __uint_as_float(w32[x] & 0xffff0000u));
+              }
             }
             const uint32_t prow = out_stage + EPI_ARRAY_BYTES + part * EPI_PART_BYTES + row * 32;
             sts128u(prow + ((0 ^ sw32) << 4), w32[0], w32[1], w32[2], w32[3]);
