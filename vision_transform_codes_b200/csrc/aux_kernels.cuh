@@ -10,8 +10,10 @@ namespace vtc {
 // ------------------------------------------------------------------------------------------------------------
 // fp32 (R x C, pitch ld) -> bf16 parts (R x nparts*Cp): part p holds bf16(residual after removing parts < p);
 // columns [C, Cp) of every part are written as zero so that K-tail tiles contribute nothing.
+// block == 0: row-major, part p in columns [p*Cp, (p+1)*Cp). block > 0 (even, divides Cp): tile-contiguous layout
+// [part][Cp/block][R][block], so that a (128 rows x block columns) operand tile is one contiguous span.
 __global__ void split_rows_kernel(const float* __restrict__ in, int64_t ld, int64_t R, int64_t C, int64_t Cp,
-                                  int nparts, __nv_bfloat16* __restrict__ out) {
+                                  int nparts, int block, __nv_bfloat16* __restrict__ out) {
   const int64_t half = Cp / 2;
   const int64_t total = R * half;
   const int64_t pitch = static_cast<int64_t>(nparts) * Cp;
@@ -28,8 +30,20 @@ __global__ void split_rows_kernel(const float* __restrict__ in, int64_t ld, int6
       __nv_bfloat162 pk;
       pk.x = h0;
       pk.y = h1;
-      *reinterpret_cast<__nv_bfloat162*>(out + r * pitch + p * Cp + c) = pk;
+      const int64_t idx = block ? ((p * (Cp / block) + c / block) * R + r) * block + c % block : r * pitch + p * Cp + c;
+      *reinterpret_cast<__nv_bfloat162*>(out + idx) = pk;
     }
+  }
+}
+
+// tile-contiguous fp32 [ceil(C/16)][R][16]  ->  row-major (R x C, pitch ld)
+__global__ void unblock_f32_kernel(const float* __restrict__ in, int64_t R, int64_t C, float* __restrict__ out,
+                                   int64_t ld) {
+  const int64_t total = R * C;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / C, c = i - r * C;
+    out[r * ld + c] = in[((c / 16) * R + r) * 16 + (c % 16)];
   }
 }
 

@@ -92,11 +92,11 @@ __host__ __device__ constexpr int pair_b(int P, int i) {
 
 enum EpiKind { EPI_STORE = 0, EPI_FISTA = 1 };
 enum ProxFlags { PROX_HARD = 1, PROX_NONNEG = 2 };
-// Tuning switches (VTC_B200_FLAGS). All default to off; the measured effect of each on configs[1] is in DESIGN.md.
+// Tuning switches (VTC_B200_FLAGS). All default to off; the measured effect of each on configs[1] is in
+// profiles/README.md. (Bits 2 and 4 were TMA L2 prefetch cursors for operands / state tiles: measured 8-37 % slower,
+// removed.)
 enum TuneFlags {
   TUNE_CONTIGUOUS = 1,          // contiguous tile range per cluster instead of round-robin        (measured: slower)
-  TUNE_PREFETCH_OPERANDS = 2,   // TMA L2 prefetch of the A panel, 8-12 K blocks ahead              (measured: slower)
-  TUNE_PREFETCH_STATE = 4,      // TMA L2 prefetch of the fp32 state tiles, 16 sub-tiles ahead      (measured: slower)
   TUNE_STATE_EVICT_FIRST = 8,   // evict-first hint on state loads: neighbours fetched in the same 128-byte line are
                                 // dropped before their own sub-tile asks for them (+45 % HBM reads) (measured: slower)
   TUNE_PROMO_256 = 16,          // 256-byte L2 promotion on the fp32 tensor maps                     (measured: slower)
@@ -123,7 +123,15 @@ struct GemmParams {
   const float* scalars;    // device: [0]=eta, [1]=theta
   double* stat;            // optional: += sum |a_new - a_k| (early stopping statistic)
   int flags;               // tuning switches, see TuneFlags
+  // Blocked ("tile-contiguous") global layouts: instead of row-major, a matrix is stored as [column block][row][W] so
+  // that a (128 rows x W columns) TMA box is ONE contiguous span of HBM. bit i (0..2): tmIn[i]; bit 3: tmOut;
+  // bit 4: tmParts; bit 5: tmA. Such maps are 3-D (W, rows, blocks); fp32 state uses W = 16, operands W = BK.
+  int blocked_mask;
+  int a_blocks_per_part;      // blocked A: column blocks per part
+  int parts_block_w;          // blocked parts output: block width (the consumer's BK) ...
+  int parts_blocks_per_part;  // ... and column blocks per part
 };
+enum BlockedBits { BLK_IN0 = 1, BLK_OUT = 8, BLK_PARTS = 16, BLK_A = 32 };
 
 struct TileCoord {
   int m0, n0, kb0, kb1, out_row0, nsub;
@@ -266,44 +274,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
 
   if (warp == 0) {
     // ================================ operand producer (both CTAs) ================================
-    // A second cursor runs PF_OP K blocks ahead and prefetches the A panel into L2 (no shared memory needed), so that
-    // the first n tile of every m block does not expose HBM latency to the tensor core.
-    constexpr int PF_OP = (P == 1) ? 12 : 8;
-    int pw = w_begin, pkb = 0;
-    TileCoord pc = decode_tile(p, pw < w_end ? pw : 0, cta_rank);
-    pkb = pc.kb0;
-    auto prefetch_step = [&]() {
-      if (pw >= w_end) return;
-      if (!contiguous || pw == w_begin || (pw % p.num_n_blocks) == 0) {
-#pragma unroll
-        for (int q = 0; q < P; ++q) tma_prefetch_2d(&p.tmA, q * p.a_part_stride + pkb * C::BK, pc.m0);
-      }
-      if (++pkb >= pc.kb1) {
-        if ((pw += w_step) < w_end) {
-          pc = decode_tile(p, pw, cta_rank);
-          pkb = pc.kb0;
-        }
-      }
-    };
-    const bool pf_op = (p.flags & TUNE_PREFETCH_OPERANDS) != 0;
-    if (pf_op && lane == 0)
-      for (int i = 0; i < PF_OP; ++i) prefetch_step();
+    const bool a_blocked = (p.blocked_mask & BLK_A) != 0;
     uint32_t it = 0;
     for (int w = w_begin; w < w_end; w += w_step) {
       const TileCoord c = decode_tile(p, w, cta_rank);
       for (int kb = c.kb0; kb < c.kb1; ++kb, ++it) {
         const int s = it % C::OP_STAGES;
         const uint32_t ph = (it / C::OP_STAGES) & 1;
-        if (pf_op && lane == 0) prefetch_step();
         mbar_wait(empty_bar(s), ph ^ 1);
         if (elect_one_sync()) {
           if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
           else mbar_arrive_remote(full_bar(s), 0);
           const uint32_t dst = sOp + s * C::STAGE_BYTES;
 #pragma unroll
-          for (int q = 0; q < P; ++q)
-            tma_load_2d_pair(dst + q * C::TILE_BYTES, &p.tmA, full_bar(s), q * p.a_part_stride + kb * C::BK, c.m0,
-                             kEvictNormal);
+          for (int q = 0; q < P; ++q) {
+            if (a_blocked)
+              tma_load_3d_pair(dst + q * C::TILE_BYTES, &p.tmA, full_bar(s), 0, c.m0, q * p.a_blocks_per_part + kb,
+                               kEvictNormal);
+            else
+              tma_load_2d_pair(dst + q * C::TILE_BYTES, &p.tmA, full_bar(s), q * p.a_part_stride + kb * C::BK, c.m0,
+                               kEvictNormal);
+          }
 #pragma unroll
           for (int q = 0; q < P; ++q)
             tma_load_2d_pair(dst + (P + q) * C::TILE_BYTES, &p.tmB, full_bar(s), q * p.b_part_stride + kb * C::BK,
@@ -354,40 +345,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     }
   } else if (warp == 3) {
     // ================================ epilogue loader ================================
-    // The fp32 state tiles always come from HBM. A cursor PF_EPI sub-tiles ahead prefetches them into L2 so that the
-    // in ring only has to cover L2 latency, not HBM latency times bandwidth.
-    constexpr int PF_EPI = 16;
     const uint32_t in_bytes = __popc(p.in_mask) * EPI_ARRAY_BYTES;
-    int pw = w_begin, pj = 0;
-    TileCoord pc = decode_tile(p, pw < w_end ? pw : 0, cta_rank);
-    auto prefetch_step = [&]() {
-      if (pw >= w_end) return;
-      for (int i = 0; i < 3; ++i)
-        if (p.in_mask & (1 << i)) tma_prefetch_2d(&p.tmIn[i], pc.n0 + pj * EPI_COLS, pc.m0);
-      if (++pj >= pc.nsub) {
-        pj = 0;
-        if ((pw += w_step) < w_end) pc = decode_tile(p, pw, cta_rank);
-      }
-    };
-    const bool pf_epi = p.in_mask != 0 && (p.flags & TUNE_PREFETCH_STATE) != 0;
-    if (pf_epi && lane == 0)
-      for (int i = 0; i < PF_EPI; ++i) prefetch_step();
     uint32_t q = 0;
     for (int w = w_begin; w < w_end; w += w_step) {
       const TileCoord c = decode_tile(p, w, cta_rank);
       for (int j = 0; j < c.nsub; ++j, ++q) {
         const int e = q % C::IN_STAGES;
         const uint32_t ph = (q / C::IN_STAGES) & 1;
-        if (pf_epi && lane == 0) prefetch_step();
         mbar_wait(in_free_bar(e), ph ^ 1);
         if (elect_one_sync()) {
           if (p.in_mask != 0) {
             mbar_arrive_expect_tx(in_full_bar(e), in_bytes);
-            for (int i = 0; i < 3; ++i)
-              if (p.in_mask & (1 << i))  // inputs are packed into the stage in slot order
-                tma_load_2d(sIn + e * IN_STAGE_BYTES + __popc(p.in_mask & ((1 << i) - 1)) * EPI_ARRAY_BYTES,
-                            &p.tmIn[i], in_full_bar(e),
-                          c.n0 + j * EPI_COLS, c.m0, (p.flags & TUNE_STATE_EVICT_FIRST) ? kEvictFirst : kEvictNormal);
+            const uint64_t hint = (p.flags & TUNE_STATE_EVICT_FIRST) ? kEvictFirst : kEvictNormal;
+            for (int i = 0; i < 3; ++i) {
+              if (!(p.in_mask & (1 << i))) continue;  // inputs are packed into the stage in slot order
+              const uint32_t dst = sIn + e * IN_STAGE_BYTES + __popc(p.in_mask & ((1 << i) - 1)) * EPI_ARRAY_BYTES;
+              const int col = c.n0 + j * EPI_COLS;
+              if (p.blocked_mask & (BLK_IN0 << i)) tma_load_3d(dst, &p.tmIn[i], in_full_bar(e), 0, c.m0, col / EPI_COLS, hint);
+              else tma_load_2d(dst, &p.tmIn[i], in_full_bar(e), col, c.m0, hint);
+            }
           } else {
             mbar_arrive(in_full_bar(e));
           }
@@ -406,10 +382,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
         mbar_wait(out_full_bar(o), ph);  // a math group has written {out | parts} of sub-tile q
         const uint32_t src = sOut + o * C::OUT_STAGE_BYTES;
         if (elect_one_sync()) {  // bulk groups are per thread: the same elected lane issues, commits and waits
-          if (p.store_out) tma_store_2d(&p.tmOut, src, c.n0 + j * EPI_COLS, c.out_row0);
-          for (int part = 0; part < p.n_parts; ++part)
-            tma_store_2d(&p.tmParts, src + EPI_ARRAY_BYTES + part * EPI_PART_BYTES,
-                         part * p.out_part_stride + c.n0 + j * EPI_COLS, c.m0);
+          const int col = c.n0 + j * EPI_COLS;
+          if (p.store_out) {
+            if (p.blocked_mask & BLK_OUT) tma_store_3d(&p.tmOut, src, 0, c.out_row0, col / EPI_COLS);
+            else tma_store_2d(&p.tmOut, src, col, c.out_row0);
+          }
+          for (int part = 0; part < p.n_parts; ++part) {
+            const uint32_t psrc = src + EPI_ARRAY_BYTES + part * EPI_PART_BYTES;
+            if (p.blocked_mask & BLK_PARTS)
+              tma_store_3d(&p.tmParts, psrc, col % p.parts_block_w, c.m0,
+                           part * p.parts_blocks_per_part + col / p.parts_block_w);
+            else
+              tma_store_2d(&p.tmParts, psrc, part * p.out_part_stride + col, c.m0);
+          }
           bulk_commit();
           if (q >= C::OUT_STAGES - 1) {
             // all but the OUT_STAGES-1 most recent store groups have left shared memory: recycle the oldest stage

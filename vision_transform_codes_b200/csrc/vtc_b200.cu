@@ -127,15 +127,26 @@ struct PartsMat {
   const void* ptr = nullptr;
   int64_t rows = 0, K = 0, Kp = 0;
   int parts = 0;
+  int block = 0;  // 0: row-major; else tile-contiguous [part][Kp/block][rows][block] (same size in bytes)
   int64_t pitch_elems() const { return static_cast<int64_t>(parts) * Kp; }
   size_t bytes() const { return static_cast<size_t>(rows) * pitch_elems() * 2; }
 };
 struct F32Mat {
   const void* ptr = nullptr;
   int64_t rows = 0, cols = 0, ld = 0;
+  bool blocked = false;  // tile-contiguous [ceil(cols/16)][rows][16] instead of row-major with pitch ld
 };
 
 int map_operand(CUtensorMap* m, const PartsMat& a, int block_k, const char* what) {
+  if (a.block) {
+    if (a.block != block_k) return fail(VTC_ERR_ARG, "%s: blocked operand of width %d read with K block %d", what, a.block, block_k);
+    const uint64_t dims[3] = {static_cast<uint64_t>(a.block), static_cast<uint64_t>(a.rows),
+                              static_cast<uint64_t>(a.parts * (a.Kp / a.block))};
+    const uint64_t str[2] = {static_cast<uint64_t>(a.block) * 2, static_cast<uint64_t>(a.rows) * a.block * 2};
+    const uint32_t box[3] = {static_cast<uint32_t>(block_k), BLOCK_M, 1};
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a.ptr, dims, str, box,
+                  block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, what);
+  }
   const uint64_t dims[2] = {static_cast<uint64_t>(a.pitch_elems()), static_cast<uint64_t>(a.rows)};
   const uint64_t str[1] = {static_cast<uint64_t>(a.pitch_elems()) * 2};
   const uint32_t box[2] = {static_cast<uint32_t>(block_k), BLOCK_M};
@@ -143,6 +154,12 @@ int map_operand(CUtensorMap* m, const PartsMat& a, int block_k, const char* what
                 block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, what);
 }
 int map_f32(CUtensorMap* m, const F32Mat& a, const char* what) {
+  if (a.blocked) {
+    const uint64_t dims[3] = {EPI_COLS, static_cast<uint64_t>(a.rows), static_cast<uint64_t>(ceil_div(a.cols, EPI_COLS))};
+    const uint64_t str[2] = {EPI_COLS * 4, static_cast<uint64_t>(a.rows) * EPI_COLS * 4};
+    const uint32_t box[3] = {EPI_COLS, BLOCK_M, 1};
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a.ptr, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, what);
+  }
   const uint64_t dims[2] = {static_cast<uint64_t>(a.cols), static_cast<uint64_t>(a.rows)};
   const uint64_t str[1] = {static_cast<uint64_t>(a.ld) * 4};
   const uint32_t box[2] = {EPI_COLS, BLOCK_M};
@@ -151,6 +168,13 @@ int map_f32(CUtensorMap* m, const F32Mat& a, const char* what) {
 // The epilogue's bf16 split store: part p of sub-tile (row0, col0) goes to columns p * Kp + col0. Columns in a part's
 // zero padding [K, Kp) may be written, always with zeros (the accumulator and every input are zero there).
 int map_parts_out(CUtensorMap* m, const PartsMat& a, const char* what) {
+  if (a.block) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(a.block), static_cast<uint64_t>(a.rows),
+                              static_cast<uint64_t>(a.parts * (a.Kp / a.block))};
+    const uint64_t str[2] = {static_cast<uint64_t>(a.block) * 2, static_cast<uint64_t>(a.rows) * a.block * 2};
+    const uint32_t box[3] = {EPI_COLS, BLOCK_M, 1};
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a.ptr, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B, what);
+  }
   const uint64_t dims[2] = {static_cast<uint64_t>(a.pitch_elems()), static_cast<uint64_t>(a.rows)};
   const uint64_t str[1] = {static_cast<uint64_t>(a.pitch_elems()) * 2};
   const uint32_t box[2] = {EPI_COLS, BLOCK_M};
@@ -243,6 +267,18 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   p.scalars = c.scalars;
   p.stat = c.stat;
   p.flags = tune_flags();
+  for (int i = 0; i < 3; ++i)
+    if ((c.in_mask & (1 << i)) && c.in[i].blocked) p.blocked_mask |= (BLK_IN0 << i);
+  if (c.store_out && c.out.blocked) p.blocked_mask |= BLK_OUT;
+  if (c.n_parts && c.parts_out.block) {
+    p.blocked_mask |= BLK_PARTS;
+    p.parts_block_w = c.parts_out.block;
+    p.parts_blocks_per_part = static_cast<int>(c.parts_out.Kp / c.parts_out.block);
+  }
+  if (c.A.block) {
+    p.blocked_mask |= BLK_A;
+    p.a_blocks_per_part = static_cast<int>(c.A.Kp / c.A.block);
+  }
   const long long tiles = 1ll * p.num_m_blocks * p.num_n_blocks * p.ksplits;
   if (tiles > 0x7fffffffll) return fail(VTC_ERR_ARG, "too many tiles");
   static bool attr_set_dev[64] = {};  // the attribute is per device
@@ -322,7 +358,7 @@ int split_rows(const float* in, int64_t ld, int64_t R, int64_t C, const PartsMat
   DeviceInfo info;
   TRY(device_info(&info));
   split_rows_kernel<<<grid_for(R * out.Kp / 2, 256, info.sm_count), 256, 0, st>>>(
-      in, ld, R, C, out.Kp, out.parts, reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out.ptr)));
+      in, ld, R, C, out.Kp, out.parts, out.block, reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out.ptr)));
   COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
@@ -360,12 +396,13 @@ struct Carver {
   }
   bool fits() const { return dry || off <= cap; }
 };
-PartsMat carve_parts(Carver& cv, int64_t rows, int64_t K, int parts) {
+PartsMat carve_parts(Carver& cv, int64_t rows, int64_t K, int parts, int block = 0) {
   PartsMat m;
   m.rows = rows;
   m.K = K;
   m.Kp = round_up(K, 64);
   m.parts = parts;
+  m.block = block;
   m.ptr = cv.take(m.bytes());
   return m;
 }
@@ -413,12 +450,15 @@ struct FistaWs {
   double* stats;
   LipschitzWs lip;
   PartsMat phi_op, x_op, G_op, yop[2], phiT_op, r_op;
-  float *bvec, *X1, *X2, *init_pad, *x_pad;
+  // bvec, X1, X2: tile-contiguous fp32 state [ceil(S/16)][B][16]; init_pad / out_pad / x_pad: row-major staging for
+  // caller buffers that TMA cannot address directly (unaligned base or pitch)
+  float *bvec, *X1, *X2, *init_pad, *out_pad, *x_pad;
   int64_t ldS, ldD;
 };
 FistaWs carve_fista(Carver& cv, int64_t B, int64_t S, int64_t D, int precision) {
   FistaWs w;
   const int P = parts_for(precision);
+  const int bk = (P == 1) ? 64 : 32;  // K block of the iteration GEMMs = block width of the streamed A operands
   w.scalars = static_cast<float*>(cv.take(64));
   w.stats = static_cast<double*>(cv.take(8 * 4096));
   w.lip = carve_lipschitz(cv, D);
@@ -426,23 +466,25 @@ FistaWs carve_fista(Carver& cv, int64_t B, int64_t S, int64_t D, int precision) 
   const bool gram = formulation_for(S, D) == FORM_GRAM;
   w.ldS = round_up(S, 4);
   w.ldD = round_up(D, 4);
-  const size_t state = static_cast<size_t>(B) * w.ldS * 4;
+  const size_t state_rm = static_cast<size_t>(B) * w.ldS * 4;                 // row-major, padded pitch
+  const size_t state_blk = static_cast<size_t>(B) * round_up(S, EPI_COLS) * 4;  // tile-contiguous
   if (gram) {
     w.x_op = carve_parts(cv, B, D, 3);
     w.G_op = carve_parts(cv, S, S, P);
-    w.bvec = static_cast<float*>(cv.take(state));
+    w.bvec = static_cast<float*>(cv.take(state_blk));
     w.x_pad = nullptr;
   } else {
     w.phiT_op = carve_parts(cv, D, S, 3);
-    w.r_op = carve_parts(cv, B, D, P);
+    w.r_op = carve_parts(cv, B, D, P, bk);
     w.x_pad = static_cast<float*>(cv.take(static_cast<size_t>(B) * w.ldD * 4));
     w.bvec = nullptr;
   }
-  w.yop[0] = carve_parts(cv, B, S, P);
-  w.yop[1] = carve_parts(cv, B, S, P);
-  w.X1 = static_cast<float*>(cv.take(state));
-  w.X2 = static_cast<float*>(cv.take(state));
-  w.init_pad = static_cast<float*>(cv.take(state));
+  w.yop[0] = carve_parts(cv, B, S, P, bk);
+  w.yop[1] = carve_parts(cv, B, S, P, bk);
+  w.X1 = static_cast<float*>(cv.take(state_blk));
+  w.X2 = static_cast<float*>(cv.take(state_blk));
+  w.init_pad = static_cast<float*>(cv.take(state_rm));
+  w.out_pad = static_cast<float*>(cv.take(state_rm));
   return w;
 }
 
@@ -543,11 +585,9 @@ struct FistaChain {
   cudaStream_t st;
   int max_pairs;       // SM pairs this chain's GEMM launches may occupy (0 = all)
   FistaWs w;
-  // state
-  float *X1, *X2;
-  int64_t ld1, ld2;
-  const float* init;
-  int64_t ld_init;
+  // state: a_k lives in the tile-contiguous buffer X1 for odd k and X2 for even k; a_0 is `init` (row-major caller
+  // data, or X2 zeroed); the last iterate is written row-major to `final_out`
+  F32Mat X1, X2, init, final_out;
   const float* x_in;
   int64_t ld_x;
 };
@@ -596,7 +636,7 @@ int chain_setup(const FistaCommon& cm, FistaChain& ch) {
       g.A = w.x_op, g.B = w.phi_op;
       g.precision = VTC_PRECISION_BF16X6;
       g.M = B, g.N = S, g.K = D;
-      g.out = F32Mat{w.bvec, B, S, w.ldS}, g.store_out = true;
+      g.out = F32Mat{w.bvec, B, S, 0, true}, g.store_out = true;
       g.max_pairs = ch.max_pairs;
       TRY(launch_gemm<EPI_STORE>(g, st));
     }
@@ -608,28 +648,25 @@ int chain_setup(const FistaCommon& cm, FistaChain& ch) {
       ch.x_in = w.x_pad, ch.ld_x = w.ldD;
     }
   }
-  // state buffers. a_k lives in X1 for odd k and X2 for even k; a_0 is `init`.
-  const bool direct_out = tma_ok(ch.codes_out, ch.ld_codes) && !cm.early;
-  ch.X1 = w.X1, ch.X2 = w.X2;
-  ch.ld1 = w.ldS, ch.ld2 = w.ldS;
-  if (direct_out) {
-    if (cm.num_iters & 1) ch.X1 = ch.codes_out, ch.ld1 = ch.ld_codes;
-    else ch.X2 = ch.codes_out, ch.ld2 = ch.ld_codes;
-  }
+  // state buffers
+  ch.X1 = F32Mat{w.X1, B, S, 0, true};
+  ch.X2 = F32Mat{w.X2, B, S, 0, true};
+  ch.final_out = tma_ok(ch.codes_out, ch.ld_codes) ? F32Mat{ch.codes_out, B, S, ch.ld_codes, false}
+                                                    : F32Mat{w.out_pad, B, S, w.ldS, false};
   CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[1].ptr), 0, w.yop[1].bytes(), st));
   if (ch.initial_codes) {
     if (tma_ok(ch.initial_codes, ch.ld_codes)) {
-      ch.init = ch.initial_codes, ch.ld_init = ch.ld_codes;
+      ch.init = F32Mat{ch.initial_codes, B, S, ch.ld_codes, false};
     } else {
       CUDA_TRY(cudaMemcpy2DAsync(w.init_pad, w.ldS * 4, ch.initial_codes, ch.ld_codes * 4, S * 4, B, cudaMemcpyDeviceToDevice, st));
-      ch.init = w.init_pad, ch.ld_init = w.ldS;
+      ch.init = F32Mat{w.init_pad, B, S, w.ldS, false};
     }
     TRY(split_rows(ch.initial_codes, ch.ld_codes, B, S, w.yop[0], st));
   } else {
     // a_0 = 0: X2 doubles as a_0 (it is only overwritten, in place, when a_2 is produced)
-    CUDA_TRY(cudaMemset2DAsync(ch.X2, ch.ld2 * 4, 0, S * 4, B, st));
+    CUDA_TRY(cudaMemsetAsync(w.X2, 0, static_cast<size_t>(B) * round_up(S, EPI_COLS) * 4, st));
     CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[0].ptr), 0, w.yop[0].bytes(), st));
-    ch.init = ch.X2, ch.ld_init = ch.ld2;
+    ch.init = ch.X2;
   }
   if (cm.early) CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * cm.num_iters, st));
   return VTC_OK;
@@ -640,22 +677,21 @@ int chain_iterate(const FistaCommon& cm, FistaChain& ch, int k, float beta_prev,
   FistaWs& w = ch.w;
   cudaStream_t st = ch.st;
   const int64_t B = ch.B, S = cm.S, D = cm.D;
-  const float* a_prev = (k == 1) ? ch.init : ((k - 1) & 1) ? ch.X1 : ch.X2;       // a_{k-1}
-  const int64_t ld_prev = (k == 1) ? ch.ld_init : ((k - 1) & 1) ? ch.ld1 : ch.ld2;
-  const float* a_prev2 = (k <= 2) ? ch.init : (k & 1) ? ch.X1 : ch.X2;            // a_{k-2}
-  const int64_t ld_prev2 = (k <= 2) ? ch.ld_init : (k & 1) ? ch.ld1 : ch.ld2;
-  float* a_out = (k & 1) ? ch.X1 : ch.X2;
-  const int64_t ld_out = (k & 1) ? ch.ld1 : ch.ld2;
+  const F32Mat& a_prev = (k == 1) ? ch.init : ((k - 1) & 1) ? ch.X1 : ch.X2;  // a_{k-1}
+  const F32Mat& a_prev2 = (k <= 2) ? ch.init : (k & 1) ? ch.X1 : ch.X2;       // a_{k-2}
+  // a_k overwrites a_{k-2} in place (same tile reads before it writes); the last iterate of a run without early
+  // stopping goes straight to the caller's row-major buffer
+  const F32Mat& a_out = (k == cm.num_iters && !cm.early) ? ch.final_out : (k & 1) ? ch.X1 : ch.X2;
   if (sample >= 0) CUDA_TRY(cudaEventRecord(g_prof.k1_begin[sample], st));
   GemmCall g;
   g.precision = cm.precision;
   g.max_pairs = ch.max_pairs;
-  g.in[0] = F32Mat{a_prev, B, S, ld_prev};
+  g.in[0] = a_prev;
   g.in_mask = 1;
   if (cm.gram) {
     g.A = w.yop[(k - 1) & 1], g.B = w.G_op;
     g.M = B, g.N = S, g.K = S;
-    g.in[1] = F32Mat{w.bvec, B, S, w.ldS};
+    g.in[1] = F32Mat{w.bvec, B, S, 0, true};
     g.in_mask |= 2;
   } else {
     // r = y Phi - x, emitted as bf16 parts; then the fused contraction acc = r Phi^T is the whole gradient
@@ -672,10 +708,10 @@ int chain_iterate(const FistaCommon& cm, FistaChain& ch, int k, float beta_prev,
     g.M = B, g.N = S, g.K = D;
   }
   if (cm.variant == VTC_VARIANT_FISTA && beta_prev != 0.f) {
-    g.in[2] = F32Mat{a_prev2, B, S, ld_prev2};
+    g.in[2] = a_prev2;
     g.in_mask |= 4;
   }
-  g.out = F32Mat{a_out, B, S, ld_out}, g.store_out = true;
+  g.out = a_out, g.store_out = true;
   if (k < cm.num_iters) g.parts_out = w.yop[k & 1], g.n_parts = cm.P;
   g.prox = cm.prox;
   g.group = cm.group_size;
@@ -692,10 +728,20 @@ int chain_iterate(const FistaCommon& cm, FistaChain& ch, int k, float beta_prev,
 }
 
 int chain_finish(const FistaCommon& cm, FistaChain& ch, int k_done) {
-  const float* result = (k_done & 1) ? ch.X1 : ch.X2;
-  const int64_t ld_res = (k_done & 1) ? ch.ld1 : ch.ld2;
-  if (result != ch.codes_out)
-    CUDA_TRY(cudaMemcpy2DAsync(ch.codes_out, ch.ld_codes * 4, result, ld_res * 4, cm.S * 4, ch.B, cudaMemcpyDeviceToDevice, ch.st));
+  const int64_t B = ch.B, S = cm.S;
+  if (cm.early) {
+    // the stopping iteration was not known in advance: the result sits in a tile-contiguous state buffer
+    DeviceInfo info;
+    TRY(device_info(&info));
+    const F32Mat& res = (k_done & 1) ? ch.X1 : ch.X2;
+    unblock_f32_kernel<<<grid_for(B * S, 256, info.sm_count), 256, 0, ch.st>>>(
+        static_cast<const float*>(res.ptr), B, S, ch.codes_out, ch.ld_codes);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+  } else if (ch.final_out.ptr != ch.codes_out) {
+    CUDA_TRY(cudaMemcpy2DAsync(ch.codes_out, ch.ld_codes * 4, ch.final_out.ptr, ch.final_out.ld * 4, S * 4, B,
+                               cudaMemcpyDeviceToDevice, ch.st));
+  }
   return VTC_OK;
 }
 
