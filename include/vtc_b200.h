@@ -62,8 +62,8 @@ int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches, int* i
 int vtc_set_formulation(int formulation);
 int vtc_get_formulation(int64_t S, int64_t D);
 
-/* Number of concurrent half-batch chains vtc_fista_fc uses for this problem (1 or 2; synthesis form and large batches
- * only; VTC_B200_CHAINS=1 disables). With 2, the tensor-bound and the HBM-bound launch of an iteration overlap across
+/* Number of concurrent half-batch chains vtc_fista_fc uses for this problem (1 unless VTC_B200_CHAINS=2 asks for two;
+ * synthesis form and large batches only; measured neutral, hence opt-in). With 2, the tensor-bound and the HBM-bound launch of an iteration overlap across
  * the two halves of the batch, each on half of the SMs, on the caller's stream and an internal side stream that is
  * forked from and joined back into the caller's stream inside the call. */
 int vtc_get_chains(int64_t B, int64_t S, int64_t D);
