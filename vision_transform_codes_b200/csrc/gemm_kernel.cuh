@@ -36,8 +36,7 @@ namespace vtc {
 
 constexpr int BLOCK_M = 128;        // rows per CTA
 constexpr int PAIR_M = 256;         // rows per CTA pair (UMMA M)
-constexpr int BLOCK_N = 256;        // UMMA N; each CTA stages half of it
-constexpr int HALF_N = 128;
+constexpr int BLOCK_N = 256;        // default UMMA N (a kernel template parameter BN: 256 or 128); each CTA stages half
 constexpr int UMMA_K = 16;
 constexpr int EPI_COLS = 16;        // epilogue sub-tile width (fp32 columns)
 constexpr int MAX_PARTS = 3;
@@ -45,7 +44,6 @@ constexpr int NUM_MATH_GROUPS = 2;   // groups of four warps (one per TMEM lane 
                                     // (three groups measured no faster: the fused launch is not issue-bound)
 constexpr int NUM_MATH_WARPS = 4 * NUM_MATH_GROUPS;
 constexpr int GEMM_THREADS = 128 + 32 * NUM_MATH_WARPS;
-constexpr int TMEM_COLS = 2 * BLOCK_N;
 constexpr int EPI_ARRAY_BYTES = BLOCK_M * EPI_COLS * 4;  // 8 KB: one fp32 [128 x 16] sub-tile
 constexpr int EPI_PART_BYTES = BLOCK_M * EPI_COLS * 2;   // 4 KB: one bf16 [128 x 16] sub-tile
 
@@ -53,12 +51,16 @@ constexpr int EPI_PART_BYTES = BLOCK_M * EPI_COLS * 2;   // 4 KB: one bf16 [128 
 // (227 KB) is split between the operand ring and the epilogue's input ring according to what bounds the launch:
 // NIN = 1 (plain GEMMs, K large): deep operand ring; NIN = 2 (fused update after the short K = D contraction of the
 // synthesis form, HBM-bound): shallow operand ring, 5-8 input stages in flight; NIN = 3 (Gram-form fused update).
-template <int P, int NIN>
+template <int P, int NIN, int BN>
 struct Cfg {
+  static_assert(BN == 256 || BN == 128, "tile width");
+  static constexpr int HALF_N = BN / 2;                         // B rows staged by each CTA of the pair
+  static constexpr int TMEM_COLS = 2 * BN;                      // two accumulators
   static constexpr int BK = (P == 1) ? 64 : 32;                 // K extent of a stage
   static constexpr int SPAN = BK * 2;                           // bytes per operand row = swizzle span (128 / 64)
-  static constexpr int TILE_BYTES = BLOCK_M * SPAN;             // one part tile of A, or of this CTA's half of B
-  static constexpr int STAGE_BYTES = 2 * P * TILE_BYTES;        // P A tiles + P B tiles
+  static constexpr int TILE_BYTES = BLOCK_M * SPAN;             // one part tile of A
+  static constexpr int B_TILE_BYTES = HALF_N * SPAN;            // one part tile of this CTA's half of B
+  static constexpr int STAGE_BYTES = P * (TILE_BYTES + B_TILE_BYTES);
   static constexpr int IN_STAGE_BYTES = NIN * EPI_ARRAY_BYTES;
   static constexpr int OP_STAGES = NIN == 3 ? ((P == 3) ? 2 : 3)
                                  : NIN == 2 ? 2
@@ -136,6 +138,7 @@ enum BlockedBits { BLK_IN0 = 1, BLK_OUT = 8, BLK_PARTS = 16, BLK_A = 32 };
 struct TileCoord {
   int m0, n0, kb0, kb1, out_row0, nsub;
 };
+template <int BN>
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int w, int cta_rank) {
   const int n_blk = w % p.num_n_blocks;
   const int t = w / p.num_n_blocks;
@@ -143,11 +146,11 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int w, int
   const int z = t / p.num_m_blocks;
   TileCoord c;
   c.m0 = m_blk * PAIR_M + cta_rank * BLOCK_M;
-  c.n0 = n_blk * BLOCK_N;
+  c.n0 = n_blk * BN;
   c.kb0 = z * p.kb_per_split;
   c.kb1 = min(p.k_blocks, c.kb0 + p.kb_per_split);
   c.out_row0 = z * p.out_rows_per_split + c.m0;
-  const int ncols = min(BLOCK_N, p.N - c.n0);
+  const int ncols = min(BN, p.N - c.n0);
   c.nsub = (ncols + EPI_COLS - 1) / EPI_COLS;
   return c;
 }
@@ -196,9 +199,9 @@ __device__ __forceinline__ void soft_update16(const uint32_t (&v)[16], const flo
   }
 }
 
-template <int EPI, int P, int NIN>
+template <int EPI, int P, int NIN, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<P, NIN>;
+  using C = Cfg<P, NIN, BN>;
   constexpr int IN_STAGE_BYTES = C::IN_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // swizzled TMA / UMMA tiles need a 1024-byte aligned base; the offset is identical in both CTAs of the pair
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
   }
   __syncwarp();
   if (warp == 2) {
-    tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
     tmem_relinquish_pair();
   }
   tc_fence_before();
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     const bool a_blocked = (p.blocked_mask & BLK_A) != 0;
     uint32_t it = 0;
     for (int w = w_begin; w < w_end; w += w_step) {
-      const TileCoord c = decode_tile(p, w, cta_rank);
+      const TileCoord c = decode_tile<BN>(p, w, cta_rank);
       for (int kb = c.kb0; kb < c.kb1; ++kb, ++it) {
         const int s = it % C::OP_STAGES;
         const uint32_t ph = (it / C::OP_STAGES) & 1;
@@ -297,8 +300,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
           }
 #pragma unroll
           for (int q = 0; q < P; ++q)
-            tma_load_2d_pair(dst + (P + q) * C::TILE_BYTES, &p.tmB, full_bar(s), q * p.b_part_stride + kb * C::BK,
-                             c.n0 + cta_rank * HALF_N, kEvictLast);
+            tma_load_2d_pair(dst + P * C::TILE_BYTES + q * C::B_TILE_BYTES, &p.tmB, full_bar(s),
+                             q * p.b_part_stride + kb * C::BK, c.n0 + cta_rank * C::HALF_N, kEvictLast);
         }
         __syncwarp();
       }
@@ -306,15 +309,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA) ================================
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(PAIR_M, BLOCK_N);
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR_M, BN);
       uint32_t it = 0, tile_iter = 0;
       for (int w = w_begin; w < w_end; w += w_step, ++tile_iter) {
-        const TileCoord c = decode_tile(p, w, cta_rank);
+        const TileCoord c = decode_tile<BN>(p, w, cta_rank);
         const int acc = tile_iter & 1;
         const uint32_t acc_ph = (tile_iter >> 1) & 1;
         mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + acc * BN;
         uint32_t accumulate = 0;
         for (int kb = c.kb0; kb < c.kb1; ++kb, ++it) {
           const int s = it % C::OP_STAGES;
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
 #pragma unroll
             for (int pr = 0; pr < C::NPAIRS; ++pr) {
               const uint64_t adesc = make_kmajor_desc(stage + pair_a(P, pr) * C::TILE_BYTES, C::SPAN);
-              const uint64_t bdesc = make_kmajor_desc(stage + (P + pair_b(P, pr)) * C::TILE_BYTES, C::SPAN);
+              const uint64_t bdesc = make_kmajor_desc(stage + P * C::TILE_BYTES + pair_b(P, pr) * C::B_TILE_BYTES, C::SPAN);
 #pragma unroll
               for (int k = 0; k < C::BK / UMMA_K; ++k) {
                 // +32 bytes (16 bf16) per K step inside the swizzle span -> +2 in the (address >> 4) field
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     const uint32_t in_bytes = __popc(p.in_mask) * EPI_ARRAY_BYTES;
     uint32_t q = 0;
     for (int w = w_begin; w < w_end; w += w_step) {
-      const TileCoord c = decode_tile(p, w, cta_rank);
+      const TileCoord c = decode_tile<BN>(p, w, cta_rank);
       for (int j = 0; j < c.nsub; ++j, ++q) {
         const int e = q % C::IN_STAGES;
         const uint32_t ph = (q / C::IN_STAGES) & 1;
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     // ================================ epilogue storer ================================
     uint32_t q = 0;
     for (int w = w_begin; w < w_end; w += w_step) {
-      const TileCoord c = decode_tile(p, w, cta_rank);
+      const TileCoord c = decode_tile<BN>(p, w, cta_rank);
       for (int j = 0; j < c.nsub; ++j, ++q) {
         const int o = q % C::OUT_STAGES;
         const uint32_t ph = (q / C::OUT_STAGES) & 1;
@@ -422,12 +425,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     float stat_local = 0.f;
     uint32_t q = 0, tile_iter = 0;
     for (int w = w_begin; w < w_end; w += w_step, ++tile_iter) {
-      const TileCoord c = decode_tile(p, w, cta_rank);
+      const TileCoord c = decode_tile<BN>(p, w, cta_rank);
       const int acc = tile_iter & 1;
       const uint32_t acc_ph = (tile_iter >> 1) & 1;
       mbar_wait(tmem_full_bar(acc), acc_ph);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       // last sub-tile of this tile that belongs to this warp's group (-1: none)
       int j_last = -1;
       for (int j = c.nsub - 1; j >= 0 && j >= c.nsub - NUM_MATH_GROUPS; --j)
@@ -589,7 +592,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
   __syncwarp();
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  if (warp == 2) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
 }
 
 }  // namespace vtc

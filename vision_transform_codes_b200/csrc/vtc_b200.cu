@@ -137,7 +137,7 @@ struct F32Mat {
   bool blocked = false;  // tile-contiguous [ceil(cols/16)][rows][16] instead of row-major with pitch ld
 };
 
-int map_operand(CUtensorMap* m, const PartsMat& a, int block_k, const char* what) {
+int map_operand(CUtensorMap* m, const PartsMat& a, int block_k, const char* what, int box_rows = BLOCK_M) {
   if (a.block) {
     if (a.block != block_k) return fail(VTC_ERR_ARG, "%s: blocked operand of width %d read with K block %d", what, a.block, block_k);
     const uint64_t dims[3] = {static_cast<uint64_t>(a.block), static_cast<uint64_t>(a.rows),
@@ -149,7 +149,7 @@ int map_operand(CUtensorMap* m, const PartsMat& a, int block_k, const char* what
   }
   const uint64_t dims[2] = {static_cast<uint64_t>(a.pitch_elems()), static_cast<uint64_t>(a.rows)};
   const uint64_t str[1] = {static_cast<uint64_t>(a.pitch_elems()) * 2};
-  const uint32_t box[2] = {static_cast<uint32_t>(block_k), BLOCK_M};
+  const uint32_t box[2] = {static_cast<uint32_t>(block_k), static_cast<uint32_t>(box_rows)};
   return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.ptr, dims, str, box,
                 block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, what);
 }
@@ -234,13 +234,13 @@ struct GemmCall {
   int max_pairs = 0;     // cap on the SM pairs used (0 = all): concurrent chains share the chip
 };
 
-template <int EPI, int P, int NIN>
+template <int EPI, int P, int NIN, int BN>
 int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream) {
-  using Cf = Cfg<P, NIN>;
+  using Cf = Cfg<P, NIN, BN>;
   GemmParams p;
   memset(&p, 0, sizeof(p));
   TRY(map_operand(&p.tmA, c.A, Cf::BK, "A operand"));
-  TRY(map_operand(&p.tmB, c.B, Cf::BK, "B operand"));
+  TRY(map_operand(&p.tmB, c.B, Cf::BK, "B operand", Cf::HALF_N));
   for (int i = 0; i < 3; ++i)
     if (c.in_mask & (1 << i)) TRY(map_f32(&p.tmIn[i], c.in[i], "epilogue input"));
   if (c.store_out) TRY(map_f32(&p.tmOut, c.out, "fp32 output"));
@@ -248,7 +248,7 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   p.M = static_cast<int>(c.M);
   p.N = static_cast<int>(c.N);
   p.num_m_blocks = static_cast<int>(ceil_div(c.M, PAIR_M));
-  p.num_n_blocks = static_cast<int>(ceil_div(c.N, BLOCK_N));
+  p.num_n_blocks = static_cast<int>(ceil_div(c.N, BN));
   p.k_blocks = static_cast<int>(ceil_div(c.A.Kp, Cf::BK));  // Kp is a multiple of 64; the padding is zero
   p.a_part_stride = static_cast<int>(c.A.Kp);
   p.b_part_stride = static_cast<int>(c.B.Kp);
@@ -286,7 +286,7 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   CUDA_TRY(cudaGetDevice(&dev));
   bool& attr_set = attr_set_dev[dev & 63];
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(vtc_gemm_kernel<EPI, P, NIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
+    CUDA_TRY(cudaFuncSetAttribute(vtc_gemm_kernel<EPI, P, NIN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
     attr_set = true;
   }
   long long max_pairs = info.sm_count / 2;
@@ -307,7 +307,7 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (tune_flags() & TUNE_NO_PDL) ? 1 : 2;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_gemm_kernel<EPI, P, NIN>, p));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_gemm_kernel<EPI, P, NIN, BN>, p));
   COUNT_LAUNCH();
   return VTC_OK;
 }
@@ -326,23 +326,25 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
   const int nin = __builtin_popcount(c.in_mask);
   if (EPI == EPI_STORE) {
     if (nin > 1) return fail(VTC_ERR_ARG, "EPI_STORE takes at most one epilogue input");
+    // (a 128-wide tile variant, Cfg<.., 128>, fills the 74 SM pairs better for N = 256 -- 512 instead of 256 tiles --
+    //  but measured 10-15 % slower: the A panel is staged twice and the N = 128 MMA is shared-memory bound)
     switch (P) {
-      case 1: return launch_gemm_p<EPI_STORE, 1, 1>(c, info, stream);
-      case 2: return launch_gemm_p<EPI_STORE, 2, 1>(c, info, stream);
-      default: return launch_gemm_p<EPI_STORE, 3, 1>(c, info, stream);
+      case 1: return launch_gemm_p<EPI_STORE, 1, 1, 256>(c, info, stream);
+      case 2: return launch_gemm_p<EPI_STORE, 2, 1, 256>(c, info, stream);
+      default: return launch_gemm_p<EPI_STORE, 3, 1, 256>(c, info, stream);
     }
   }
   if (nin <= 2) {
     switch (P) {
-      case 1: return launch_gemm_p<EPI_FISTA, 1, 2>(c, info, stream);
-      case 2: return launch_gemm_p<EPI_FISTA, 2, 2>(c, info, stream);
-      default: return launch_gemm_p<EPI_FISTA, 3, 2>(c, info, stream);
+      case 1: return launch_gemm_p<EPI_FISTA, 1, 2, 256>(c, info, stream);
+      case 2: return launch_gemm_p<EPI_FISTA, 2, 2, 256>(c, info, stream);
+      default: return launch_gemm_p<EPI_FISTA, 3, 2, 256>(c, info, stream);
     }
   }
   switch (P) {
-    case 1: return launch_gemm_p<EPI_FISTA, 1, 3>(c, info, stream);
-    case 2: return launch_gemm_p<EPI_FISTA, 2, 3>(c, info, stream);
-    default: return launch_gemm_p<EPI_FISTA, 3, 3>(c, info, stream);
+    case 1: return launch_gemm_p<EPI_FISTA, 1, 3, 256>(c, info, stream);
+    case 2: return launch_gemm_p<EPI_FISTA, 2, 3, 256>(c, info, stream);
+    default: return launch_gemm_p<EPI_FISTA, 3, 3, 256>(c, info, stream);
   }
 }
 
