@@ -209,6 +209,7 @@ def main():
   nprod = pkg.PRECISIONS[args.precision]
   nparts = {1: 1, 3: 2, 6: 3}[nprod]
   form = {1: 'gram', 2: 'synthesis'}[lib.vtc_get_formulation(S, D)]
+  fused_iter = form == 'synthesis' and bool(lib.vtc_get_fused_iteration(S, D, nprod))
 
   def profile_call():
     lib.vtc_profile_enable(1)
@@ -230,6 +231,14 @@ def main():
     bytes_fused = Bn * S * (16 + 4 * nparts)
     flops_fused = gram_flops_iter
     bound = 'hbm' if nprod == 1 else 'tensor'
+  elif fused_iter:
+    # ONE launch per iteration (fista_iter_kernel.cuh): reads a_{k-1}, a_{k-2} (8 B) and writes a_k (4 B) per code
+    # element; per pixel reads x (4 B), reads r_{k-1} parts (2P B) and writes r_k parts (2P B). y_k stays on chip.
+    bytes_fused = Bn * S * 12 + Bn * D * (4 + 4 * nparts)
+    flops_fused = synth_flops_iter
+    hbm_ms = bytes_fused / (pk['hbm_gbs'] * 1e9) * 1e3
+    tensor_ms = nprod * flops_fused / (pk['bf16_sustained'] * 1e12) * 1e3
+    bound = 'hbm' if hbm_ms >= tensor_ms else 'tensor'
   else:
     # fused launch: acc = r Phi^T (K = D) + update. reads a_k, a_{k-1} (8 B) and r parts; writes a (4 B) + y parts (2P)
     bytes_fused = Bn * S * (12 + 2 * nparts) + Bn * D * 2 * nparts
@@ -249,10 +258,14 @@ def main():
   traffic = None  # DRAM bytes per launch of this kernel from the committed ncu --set full capture of the same shape
   tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
   if os.path.exists(tpath) and form == 'synthesis' and Bn == B_PER_GPU:
-    traffic = json.load(open(tpath)).get(args.precision, {}).get('fused_bytes')
+    traffic = json.load(open(tpath)).get(args.precision, {}).get('iter_bytes' if fused_iter else 'fused_bytes')
   roofline.update({
-      'kernel': 'vtc_gemm_kernel<EPI_FISTA,%d> (%s form)' % (nparts, form), 'traffic': traffic,
-      'launch_ms': fused_ms, 'first_launch_ms': first_ms if form == 'synthesis' else None,
+      'kernel': ('vtc_fista_iter_kernel<%d> (one launch per iteration, y_k on chip)' % nparts) if fused_iter else
+                'vtc_gemm_kernel<EPI_FISTA,%d> (%s form)' % (nparts, form), 'traffic': traffic,
+      'launch_ms': fused_ms, 'first_launch_ms': first_ms if (form == 'synthesis' and not fused_iter) else None,
+      'algorithmic_bytes_per_launch': bytes_fused, 'executed_mma_flops_per_launch': nprod * flops_fused,
+      'hbm_floor_ms': bytes_fused / (pk['hbm_gbs'] * 1e9) * 1e3,
+      'tensor_floor_ms': nprod * flops_fused / (pk['bf16_sustained'] * 1e12) * 1e3,
       'formulation': form, 'launches_per_iteration': n_launch // max(1, n_iter), 'ms_per_iteration': iter_ms_each,
       'setup_ms_per_step': setup_ms,
       # whole iteration loop against the tensor roofline, both flop conventions
@@ -285,7 +298,9 @@ def main():
       'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': args.precision + ' (bf16 products, fp32 accumulate)', 'data': 'synthetic',
       'config': {'workload': WORKLOAD, 'batch_per_gpu': Bn, 'atoms': S, 'pixels': D, 'iters': T,
-                 'precision': args.precision, 'formulation': form, 'parallelism': 'batch sharded over %d GPU(s), dictionary replicated, '
+                 'precision': args.precision, 'formulation': form,
+                 'schedule': 'one launch per iteration' if fused_iter else '%d launch(es) per iteration' % (n_launch // max(1, n_iter)),
+                 'parallelism': 'batch sharded over %d GPU(s), dictionary replicated, '
                  'no data-path collective' % world,
                  'l2': 'inputs larger than L2 (per-iteration state %.0f MB vs 126 MB L2)' % (Bn * S * 4 * 3 / 1e6)},
       'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'clocks': clocks,

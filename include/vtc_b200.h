@@ -62,6 +62,19 @@ int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches, int* i
 int vtc_set_formulation(int formulation);
 int vtc_get_formulation(int64_t S, int64_t D);
 
+/* Schedule of a synthesis-form iteration: 1 (default) = ONE launch per iteration that keeps the operand y_k on chip
+ * (panel-resident kernel: r_{k-1} Phi^T -> fused update -> y_k Phi - x accumulated in TMEM), used when D <= 256 and the
+ * precision is bf16 or bf16x3; 0 = the two-launch schedule (r = y Phi - x, then r Phi^T with the fused update), which
+ * is also what larger D and bf16x6 use. Both give identical iterates for identical arithmetic order per element up to
+ * the fp32 accumulation order of the synthesis contraction. Also VTC_B200_FUSED_ITER. vtc_get_fused_iteration reports
+ * whether a problem of this shape would run the one-launch schedule. */
+int vtc_set_fused_iteration(int on);
+int vtc_get_fused_iteration(int64_t S, int64_t D, int precision);
+/* Debug aid (tools/iter_trace.py): four threads of CTA 0 of the NEXT one-launch iteration kernel write a timeline into
+ * device_buffer (4 regions of 2048 uint64 words: [0] = event count, then event id << 48 | SM clock), zeroed by the
+ * caller. One shot: the pointer is dropped after that launch. */
+int vtc_debug_iter_trace(void* device_buffer);
+
 /* Number of concurrent half-batch chains vtc_fista_fc uses for this problem (1 unless VTC_B200_CHAINS=2 asks for two;
  * synthesis form and large batches only; measured neutral, hence opt-in). With 2, the tensor-bound and the HBM-bound launch of an iteration overlap across
  * the two halves of the batch, each on half of the SMs, on the caller's stream and an internal side stream that is

@@ -117,15 +117,21 @@ def formulation():
   lib = _lib.load()
 
   def choose(which):
-    _lib.check(lib.vtc_set_formulation({'auto': 0, 'gram': 1, 'synthesis': 2}[which]))
+    _lib.check(lib.vtc_set_formulation({'auto': 0, 'gram': 1, 'synthesis': 2, 'synthesis-two-launch': 2}[which]))
+    _lib.check(lib.vtc_set_fused_iteration(0 if which == 'synthesis-two-launch' else 1))
   yield choose
   lib.vtc_set_formulation(0)
+  lib.vtc_set_fused_iteration(1)
 
 
-@pytest.mark.parametrize('which', ['gram', 'synthesis'])
+SCHEDULES = ['gram', 'synthesis', 'synthesis-two-launch']
+
+
+@pytest.mark.parametrize('which', SCHEDULES)
 @pytest.mark.parametrize('name', ['inference_small', 'inference_config1', 'inference_overcomplete'])
 def test_both_formulations_against_reference_outputs(formulation, which, name):
-  """Gram form (y G - b) and synthesis form ((y Phi - x) Phi^T) are two contractions of the same iteration."""
+  """Gram form (y G - b) and synthesis form ((y Phi - x) Phi^T, as one panel-resident launch per iteration or as
+  two launches) are contractions of the same iteration."""
   ista_fista = modules()[0]
   formulation(which)
   g = load_golden(name)
@@ -134,11 +140,12 @@ def test_both_formulations_against_reference_outputs(formulation, which, name):
   check_codes(got, g['fista'], phi)
 
 
-@pytest.mark.parametrize('which', ['gram', 'synthesis'])
-def test_formulations_cover_variants_and_ragged_shapes(formulation, which):
+@pytest.mark.parametrize('shape', [(130, 200, 100), (700, 328, 72)])
+@pytest.mark.parametrize('which', SCHEDULES)
+def test_formulations_cover_variants_and_ragged_shapes(formulation, which, shape):
   ista_fista, subspace = modules()[:2]
   formulation(which)
-  B, S, D = 130, 200, 100
+  B, S, D = shape
   phi = oracle.synthetic_dictionary(S, D)
   x = oracle.synthetic_patches(B, D)
   for kw in ({'variant': 'ista'}, {'nonnegative_only': True}, {}):
@@ -302,3 +309,36 @@ def test_size_independent_properties_at_benchmark_shape():
   assert oracle.relative_l2(more.cpu(), a.cpu()) < 1e-4
   want = oracle.ista_fista(x[:384], phi, 0.1, T)
   check_codes(a[:384], want, phi)
+
+
+def test_one_launch_schedule_matches_two_launch_schedule(formulation):
+  """The panel-resident kernel accumulates the synthesis contraction in the same K order as the two-launch schedule,
+  so the two give the same iterates bit for bit: vanilla, hard / non-negative, subspace, warm start, plain bf16."""
+  import vision_transform_codes_b200 as pkg
+  from vision_transform_codes_b200 import _lib
+  ista_fista, subspace = modules()[:2]
+  B, S, D = 777, 1000, 256
+  assert _lib.load().vtc_get_fused_iteration(S, D, 3) in (0, 1)
+  phi = oracle.synthetic_dictionary(S, D).cuda()
+  x = oracle.synthetic_patches(B, D, kind='whitened').cuda()
+  warm = ista_fista.run(x, phi, 0.1, 3)
+  groups = [list(range(i, i + 2)) for i in range(0, S, 2)]
+  calls = [
+      lambda: ista_fista.run(x, phi, 0.1, 60),
+      lambda: ista_fista.run(x, phi, 0.1, 25, variant='ista', nonnegative_only=True),
+      lambda: ista_fista.run(x, phi, 0.1, 25, hard_threshold=True),
+      lambda: ista_fista.run(x, phi, 0.1, 25, initial_codes=warm),
+      lambda: subspace.run(x, phi, groups, 0.1, 25),
+      lambda: ista_fista.infer(x, phi, 0.1, 400, 'fista', None, 1e-3, False, False, 1),
+  ]
+  for precision in ('bf16x3', 'bf16'):
+    pkg.config.precision = precision
+    for call in calls:
+      formulation('synthesis')
+      one = call()
+      formulation('synthesis-two-launch')
+      two = call()
+      if isinstance(one, tuple):
+        assert one[1] == two[1], (one[1], two[1])
+        one, two = one[0], two[0]
+      assert torch.equal(one, two), (precision, oracle.relative_l2(one.cpu(), two.cpu()))

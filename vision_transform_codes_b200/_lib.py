@@ -22,6 +22,9 @@ SIGNATURES = {
                                 _c.POINTER(_f32), _c.POINTER(_f32)]),
     'vtc_set_formulation': (_int, [_int]),
     'vtc_get_formulation': (_int, [_i64, _i64]),
+    'vtc_set_fused_iteration': (_int, [_int]),
+    'vtc_get_fused_iteration': (_int, [_i64, _i64, _int]),
+    'vtc_debug_iter_trace': (_int, [_ptr]),
     'vtc_get_chains': (_int, [_i64, _i64, _i64]),
     'vtc_device_info': (_int, [_c.POINTER(_int)] * 3),
     'vtc_fista_workspace_bytes': (_size, [_i64, _i64, _i64, _int]),

@@ -1,0 +1,621 @@
+// Panel-resident ISTA/FISTA iteration (sm_100a): ONE launch per iteration of the synthesis form
+//
+//   grad = r_{k-1} Phi^T                       (analysis contraction,  K = D, N = S)        ista_fista.py:105-106
+//   a_k  = prox(y_{k-1} - eta * grad) ,  y_k = a_k + beta_k (a_k - a_{k-1})                 ista_fista.py:107-133
+//   r_k  = y_k Phi - x                         (synthesis contraction, K = S, N = D)
+//
+// with the next operand y_k never leaving the chip. A CTA pair (cluster of 2, cta_group::2) owns a 256-row panel of
+// patches for the whole launch and walks its atoms in tiles of 128:
+//
+//   tensor pipe   G(t): acc_g[t&1] (256 x 128, TMEM) = r_op[panel] * Phi[tile]^T           operands by TMA
+//                 R(t): acc_r (256 x 256, TMEM)     += y_k[panel, tile] * Phi[tile]         A operand written to shared
+//                                                                                            memory by the epilogue
+//   epilogue      per 16-atom sub-tile: tcgen05.ld acc_g, fused update (shared with gemm_kernel.cuh), a_k -> TMA store,
+//                 bf16 parts of y_k -> the y ring in the UMMA K-major SWIZZLE_64B layout -> R(t)
+//   panel end     acc_r - x -> bf16 parts -> r_op[panel] (in place: every G of the panel has completed), read by the
+//                 next launch
+//
+// Against the two-launch schedule (gemm_kernel.cuh: EPI_STORE then EPI_FISTA) this removes the HBM round trip of y_op
+// (2 P bytes written + 2 P bytes read per code element and iteration) and hides the synthesis MMAs under the state
+// stream. The MMA thread issues whichever of G(t+1) (K block by K block, as operands land) and R(t) (chunk by chunk, as
+// the epilogue of tile t writes y_k) has its inputs ready, so both run while the epilogue of tile t streams its state;
+// acc_g is double buffered (2 x 128 TMEM columns), acc_r takes the other 256.
+//
+// The fp32 inputs of a sub-tile (a_{k-1}, a_{k-2}: 2 x 8 KB) and its result share one ring: the math warps write a_k
+// over the a_{k-2} slot of the stage they just read and the TMA store leaves from there, so there is no separate
+// output ring to wait for and the whole budget goes into bytes in flight from HBM.
+//
+// Requirements (the host falls back to the two-launch schedule otherwise): D <= 256, P <= 2.
+//
+// Warp roles (4 + 4 * GROUPS + 1 warps):
+//   0        TMA producer of the G operand ring (r_op K blocks + Phi tile halves), both CTAs
+//   1        tcgen05.mma issuer (leader CTA)
+//   2        TMEM allocator, then TMA stores (a_k sub-tiles, r_op parts)
+//   3        TMA loader of the epilogue inputs (a_{k-1}, a_{k-2}; x at the panel end)
+//   4 ..     epilogue math, GROUPS groups of four warps on sub-tiles round-robin
+//   last     TMA producer of the Phi^T chunk ring (B operand of R), both CTAs
+#pragma once
+#include "gemm_kernel.cuh"
+
+namespace vtc {
+
+constexpr int IT_BN = 128;     // atoms per gradient tile (UMMA N of G)
+constexpr int IT_CHUNK = 32;   // atoms per y / Phi^T chunk = 2 sub-tiles (K extent of one group of R MMAs)
+constexpr int IT_RN = 256;     // UMMA N of R = padded pixel count
+constexpr int IT_VARIANTS = 2;  // tuning variants (stage counts / math warps), VTC_B200_ITER_VARIANT
+
+template <int P, int V>
+struct IterCfg {
+  static_assert(P == 1 || P == 2, "parts");
+  static_assert(V >= 0 && V < IT_VARIANTS, "variant");
+  // tuning variants (VTC_B200_ITER_VARIANT), measured on configs[1] (ms per iteration, bf16x3 / bf16):
+  //                     math groups   G   y   Phi^T   in/out stages
+  //   0 (default)           3         2   2   2       6                0.261 / 0.187
+  //   1                     2         4   2   2       4                0.261 / 0.234
+  // (3 groups with 4 G and 3 in/out stages: 0.350 / 0.324 -- the depth of the in/out ring, i.e. the state bytes in
+  //  flight per SM, is what bounds this kernel; deeper G, y or Phi^T rings measured neutral)
+  // epilogue math: GROUPS groups of four warps (one warp per TMEM lane quarter) on sub-tiles round-robin
+  static constexpr int GROUPS = (V == 1) ? 2 : 3;
+  static constexpr int MATH_WARPS = 4 * GROUPS;
+  static constexpr int PT_WARP = 4 + MATH_WARPS;           // Phi^T chunk producer: the last warp
+  static constexpr int THREADS = 32 * (PT_WARP + 1);
+  static constexpr int BK = (P == 1) ? 64 : 32;          // K extent of a G stage
+  static constexpr int SPAN = BK * 2;
+  static constexpr int A_TILE = BLOCK_M * SPAN;           // one part of this CTA's 128 rows of r_op
+  static constexpr int B_TILE = (IT_BN / 2) * SPAN;       // one part of this CTA's 64 atoms of the Phi tile
+  static constexpr int G_STAGE = P * (A_TILE + B_TILE);
+  static constexpr int Y_TILE = BLOCK_M * IT_CHUNK * 2;   // 8 KB: one part of y, 128 rows x 32 atoms, SWIZZLE_64B
+  static constexpr int Y_STAGE = P * Y_TILE;
+  static constexpr int PT_TILE = (IT_RN / 2) * IT_CHUNK * 2;  // 8 KB: one part of this CTA's 128 pixel rows of Phi^T
+  static constexpr int PT_STAGE = P * PT_TILE;
+  static constexpr int IN_STAGE = 2 * EPI_ARRAY_BYTES;
+  static constexpr int OUT_SLOT = EPI_ARRAY_BYTES;        // the result (a_k fp32, or P bf16 part sub-tiles of r) is written
+                                                          // over the second 8 KB of its input stage and stored from there
+  static constexpr int STORES_IN_FLIGHT = 1;              // TMA stores whose shared-memory reads may still be pending
+  // shared memory split between the rings (P = 2: G 24 KB, y 16 KB, Phi^T 16 KB, in/out 16 KB per stage)
+  static constexpr int G_STAGES = (V == 0) ? 2 : 4;
+  static constexpr int Y_STAGES = 2;
+  static constexpr int PT_STAGES = 2;
+  static constexpr int IN_STAGES = (V == 0) ? 6 : 4;      // a multiple of GROUPS: fixed owner group per stage
+  static constexpr int OFF_G = 0;
+  static constexpr int OFF_Y = OFF_G + G_STAGES * G_STAGE;
+  static constexpr int OFF_PT = OFF_Y + Y_STAGES * Y_STAGE;
+  static constexpr int OFF_IN = OFF_PT + PT_STAGES * PT_STAGE;
+  static constexpr int OFF_BAR = OFF_IN + IN_STAGES * IN_STAGE;
+  // barrier indices
+  static constexpr int B_G_FULL = 0;
+  static constexpr int B_G_EMPTY = B_G_FULL + G_STAGES;
+  static constexpr int B_PT_FULL = B_G_EMPTY + G_STAGES;
+  static constexpr int B_PT_EMPTY = B_PT_FULL + PT_STAGES;
+  static constexpr int B_Y_FULL = B_PT_EMPTY + PT_STAGES;
+  static constexpr int B_Y_EMPTY = B_Y_FULL + Y_STAGES;
+  static constexpr int B_ACCG_FULL = B_Y_EMPTY + Y_STAGES;
+  static constexpr int B_ACCG_EMPTY = B_ACCG_FULL + 2;
+  static constexpr int B_ACCR_FULL = B_ACCG_EMPTY + 2;
+  static constexpr int B_ACCR_EMPTY = B_ACCR_FULL + 1;
+  static constexpr int B_IN_FULL = B_ACCR_EMPTY + 1;
+  static constexpr int B_IN_FREE = B_IN_FULL + IN_STAGES;
+  static constexpr int B_OUT_FULL = B_IN_FREE + IN_STAGES;   // one per in/out stage
+  static constexpr int NUM_BARRIERS = B_OUT_FULL + IN_STAGES;
+  static constexpr int SMEM_TOTAL = OFF_BAR + NUM_BARRIERS * 8 + 16;
+  static constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
+  static constexpr int NPAIRS = (P == 1) ? 1 : 3;
+  static_assert(IN_STAGES % GROUPS == 0, "input stages must have a fixed owner group");
+  static_assert(P * EPI_PART_BYTES <= OUT_SLOT, "r parts must fit the output slot");
+  static_assert(SMEM_ALLOC <= 232448, "over the 227 KB shared memory limit");
+};
+
+struct IterParams {
+  CUtensorMap tmR;      // r_op (bf16 parts, tile-contiguous [part][Dp/BK][rows][BK]): box BK x 128, A operand of G
+  CUtensorMap tmPhi;    // phi_op (S x parts*Dp, row-major): box BK x 64, B operand of G
+  CUtensorMap tmPhiT;   // phiT_op (D x parts*Sp, row-major): box 32 x 128, SWIZZLE_64B, B operand of R
+  CUtensorMap tmIn[3];  // fp32 state: [0] = a_{k-1}, [2] = a_{k-2} (slot 1 unused), box 16 x 128
+  CUtensorMap tmX;      // images (B x D fp32, row-major), box 16 x 128
+  CUtensorMap tmOut;    // a_k
+  CUtensorMap tmROut;   // r_op as a store target: box 16 x 128, SWIZZLE_32B
+  int num_panels;       // ceil(B / 256)
+  int S;
+  int num_n_tiles;      // ceil(S / 128)
+  int kb_g;             // Dp / BK: K blocks of G (= column blocks per part of r_op)
+  int phi_part_stride;  // Dp
+  int phiT_part_stride; // Sp
+  int nsub_r;           // Dp / 16: sub-tiles of r written at the panel end
+  int r_block_w;        // BK of r_op's layout
+  int in_mask;          // bit 0: a_{k-1}; bit 2: a_{k-2}
+  int blocked_mask;     // BLK_IN0 << i, BLK_OUT
+  int do_r;             // produce r_k (0 on the last iteration: nothing consumes it)
+  int prox, group, use_momentum;
+  float beta_prev, beta_next;
+  const float* scalars;  // device: [0] = eta, [1] = theta
+  double* stat;          // optional: += sum |a_k - a_{k-1}|
+  unsigned long long* trace;  // optional (tools/iter_trace.py): 4 regions of 2048 words, [0] = event count, then
+                              // (event id << 48 | SM clock) words, written by four threads of CTA 0
+};
+
+// timeline events of CTA 0 for tools/iter_trace.py: id = kind << 8 | index
+enum TraceKind { TR_G_BEGIN = 1, TR_G_END = 2, TR_R_ISSUE = 3, TR_E_BEGIN = 4, TR_E_SUB = 5, TR_E_END = 6, TR_G_LOAD = 7,
+                 TR_START = 8, TR_STOP = 9, TR_E_IN = 10, TR_E_LD = 11, TR_E_CMP = 12, TR_E_YW = 13, TR_E_ARR = 14 };
+// Each tracing thread owns a region of 2048 words (role = 0 G producer, 1 issuer, 2 math warp 4, 3 thread 0) and a private
+// counter: plain stores, no atomics, so that the trace perturbs the timeline as little as possible.
+struct Tracer {
+  unsigned long long* base;
+  uint32_t n;
+  __device__ __forceinline__ Tracer(const IterParams& p, int role, bool mine)
+      : base((p.trace != nullptr && blockIdx.x == 0 && mine) ? p.trace + role * 2048 : nullptr), n(0) {}
+  __device__ __forceinline__ void operator()(int kind, int index) {
+    if (base != nullptr && n < 2047) {
+      base[++n] = (static_cast<unsigned long long>((kind << 8) | (index & 255)) << 48) |
+                  (static_cast<unsigned long long>(clock64()) & 0xFFFFFFFFFFFFull);
+      base[0] = n;
+    }
+  }
+};
+
+// non-blocking tests (the MMA issuer polls several barriers)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+template <int P, int V>
+__global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kernel(const __grid_constant__ IterParams p) {
+  using C = IterCfg<P, V>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sG = sbase + C::OFF_G, sY = sbase + C::OFF_Y, sPT = sbase + C::OFF_PT;
+  const uint32_t sIn = sbase + C::OFF_IN;
+  const uint32_t bar0 = sbase + C::OFF_BAR;
+  auto bar = [&](int idx) { return bar0 + 8 * idx; };
+  const uint32_t tmem_slot = bar0 + C::NUM_BARRIERS * 8;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = static_cast<int>(cluster_ctarank());
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int NT = p.num_n_tiles;
+  const int my_panels = (p.num_panels - cluster_id + num_clusters - 1) / num_clusters;  // panels cluster_id, +num_clusters, ...
+  const int my_tiles = my_panels * NT;
+  // sub-tiles of tile nt: an even number (whole chunks); columns at or beyond S are zero everywhere (TMA fill)
+  auto tile_chunks = [&](int nt) { return (min(IT_BN, p.S - nt * IT_BN) + IT_CHUNK - 1) / IT_CHUNK; };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmR);
+    tma_prefetch_desc(&p.tmPhi);
+    tma_prefetch_desc(&p.tmPhiT);
+    tma_prefetch_desc(&p.tmIn[0]);
+    if (p.in_mask & 4) tma_prefetch_desc(&p.tmIn[2]);
+    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&p.tmOut);
+    tma_prefetch_desc(&p.tmROut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::G_STAGES; ++s) {
+      mbar_init(bar(C::B_G_FULL + s), 2);    // one arrive per CTA's producer (leader's barrier is the one waited on)
+      mbar_init(bar(C::B_G_EMPTY + s), 1);   // multicast tcgen05.commit
+    }
+    for (int s = 0; s < C::PT_STAGES; ++s) {
+      mbar_init(bar(C::B_PT_FULL + s), 2);
+      mbar_init(bar(C::B_PT_EMPTY + s), 1);
+    }
+    for (int s = 0; s < C::Y_STAGES; ++s) {
+      mbar_init(bar(C::B_Y_FULL + s), 2 * 2 * 4);  // 2 CTAs x 2 sub-tiles x 4 warps (leader's barrier)
+      mbar_init(bar(C::B_Y_EMPTY + s), 1);         // multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar(C::B_ACCG_FULL + a), 1);
+      mbar_init(bar(C::B_ACCG_EMPTY + a), 2 * C::MATH_WARPS);
+    }
+    mbar_init(bar(C::B_ACCR_FULL), 1);
+    mbar_init(bar(C::B_ACCR_EMPTY), 2 * C::MATH_WARPS);
+    for (int e = 0; e < C::IN_STAGES; ++e) {
+      mbar_init(bar(C::B_IN_FULL + e), 1);
+      mbar_init(bar(C::B_IN_FREE + e), 1);    // the storer, once the TMA store of the stage's result has read it
+      mbar_init(bar(C::B_OUT_FULL + e), 4);   // the four math warps that wrote the result
+    }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
+  Tracer trace0(p, 3, threadIdx.x == 0);
+  trace0(TR_START, 0);
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================================ G operand producer (both CTAs) ================================
+    Tracer trace(p, 0, lane == 0);
+    uint32_t it = 0;
+    for (int pi = 0; pi < my_panels; ++pi) {
+      const int m0 = (cluster_id + pi * num_clusters) * PAIR_M + cta_rank * BLOCK_M;
+      for (int nt = 0; nt < NT; ++nt) {
+        const int n0 = nt * IT_BN;
+        for (int kb = 0; kb < p.kb_g; ++kb, ++it) {
+          const int s = it % C::G_STAGES;
+          const uint32_t ph = (it / C::G_STAGES) & 1;
+          mbar_wait(bar(C::B_G_EMPTY + s), ph ^ 1);
+          if (elect_one_sync()) {
+            const uint32_t full = bar(C::B_G_FULL + s);
+            if (leader) mbar_arrive_expect_tx(full, 2 * C::G_STAGE);
+            else mbar_arrive_remote(full, 0);
+            const uint32_t dst = sG + s * C::G_STAGE;
+            trace(TR_G_LOAD, nt * p.kb_g + kb);
+#pragma unroll
+            for (int q = 0; q < P; ++q)
+              tma_load_3d_pair(dst + q * C::A_TILE, &p.tmR, full, 0, m0, q * p.kb_g + kb, kEvictNormal);
+#pragma unroll
+            for (int q = 0; q < P; ++q)
+              tma_load_2d_pair(dst + P * C::A_TILE + q * C::B_TILE, &p.tmPhi, full, q * p.phi_part_stride + kb * C::BK,
+                               n0 + cta_rank * (IT_BN / 2), kEvictLast);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == C::PT_WARP) {
+    // ================================ Phi^T chunk producer (both CTAs) ================================
+    if (p.do_r) {
+      uint32_t it = 0;
+      for (int pi = 0; pi < my_panels; ++pi) {
+        for (int nt = 0; nt < NT; ++nt) {
+          const int nch = tile_chunks(nt);
+          for (int c = 0; c < nch; ++c, ++it) {
+            const int s = it % C::PT_STAGES;
+            const uint32_t ph = (it / C::PT_STAGES) & 1;
+            mbar_wait(bar(C::B_PT_EMPTY + s), ph ^ 1);
+            if (elect_one_sync()) {
+              const uint32_t full = bar(C::B_PT_FULL + s);
+              if (leader) mbar_arrive_expect_tx(full, 2 * C::PT_STAGE);
+              else mbar_arrive_remote(full, 0);
+#pragma unroll
+              for (int q = 0; q < P; ++q)
+                tma_load_2d_pair(sPT + s * C::PT_STAGE + q * C::PT_TILE, &p.tmPhiT, full,
+                                 q * p.phiT_part_stride + nt * IT_BN + c * IT_CHUNK, cta_rank * (IT_RN / 2), kEvictLast);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA) ================================
+    if (leader) {
+      constexpr uint32_t idesc_g = make_idesc_bf16(PAIR_M, IT_BN);
+      constexpr uint32_t idesc_r = make_idesc_bf16(PAIR_M, IT_RN);
+      const uint32_t acc_r = tmem_base + 2 * IT_BN;
+      Tracer trace(p, 1, lane == 0);
+      // Two instruction streams share the (in-order) tensor pipe: G(t), K block by K block as its operands land, and
+      // R(t), chunk by chunk as the epilogue of tile t writes y_k. Whichever has its inputs ready is issued next
+      // (non-blocking barrier tests), so a G waiting for an L2 round trip never holds up the R chunks that free the
+      // y ring, and vice versa. G runs at most two tiles ahead of the epilogue (acc_g is double buffered).
+      int g_tile = 0, g_kb = 0;
+      uint32_t g_it = 0, g_accumulate = 0;
+      int r_tile = 0, r_chunk = 0;
+      uint32_t r_it = 0;
+      uint32_t idle = 0;
+      while (g_tile < my_tiles || (p.do_r && r_tile < my_tiles)) {
+        bool progressed = false;
+        if (p.do_r && r_tile < my_tiles) {
+          const int pi = r_tile / NT, nt = r_tile % NT;
+          const bool first = (nt == 0 && r_chunk == 0);
+          const int ys = r_it % C::Y_STAGES, ps = r_it % C::PT_STAGES;
+          bool ready = mbar_test_wait(bar(C::B_Y_FULL + ys), (r_it / C::Y_STAGES) & 1) &&
+                       mbar_test_wait(bar(C::B_PT_FULL + ps), (r_it / C::PT_STAGES) & 1);
+          // the panel-end epilogue of the previous panel must have drained acc_r before it is overwritten
+          if (ready && first) ready = mbar_test_wait(bar(C::B_ACCR_EMPTY), (pi & 1) ^ 1);
+          if (ready) {
+            tc_fence_after();
+            const uint32_t ystage = sY + ys * C::Y_STAGE, pstage = sPT + ps * C::PT_STAGE;
+            const bool last = (nt == NT - 1) && (r_chunk == tile_chunks(nt) - 1);
+            if (elect_one_sync()) {
+              trace(TR_R_ISSUE, r_tile * 4 + r_chunk);
+              uint32_t accumulate = first ? 0u : 1u;
+#pragma unroll
+              for (int pr = 0; pr < C::NPAIRS; ++pr) {
+                const uint64_t adesc = make_kmajor_desc(ystage + pair_a(P, pr) * C::Y_TILE, IT_CHUNK * 2);
+                const uint64_t bdesc = make_kmajor_desc(pstage + pair_b(P, pr) * C::PT_TILE, IT_CHUNK * 2);
+#pragma unroll
+                for (int k = 0; k < IT_CHUNK / UMMA_K; ++k) {
+                  umma_bf16_pair(acc_r, adesc + 2 * k, bdesc + 2 * k, idesc_r, accumulate);
+                  accumulate = 1;
+                }
+              }
+              umma_commit_pair(bar(C::B_Y_EMPTY + ys), 3);
+              umma_commit_pair(bar(C::B_PT_EMPTY + ps), 3);
+              if (last) umma_commit_pair(bar(C::B_ACCR_FULL), 3);
+            }
+            __syncwarp();
+            ++r_it;
+            if (++r_chunk == tile_chunks(nt)) r_chunk = 0, ++r_tile;
+            progressed = true;
+          }
+        }
+        if (g_tile < my_tiles) {
+          const int acc = g_tile & 1;
+          const int s = g_it % C::G_STAGES;
+          bool ready = mbar_test_wait(bar(C::B_G_FULL + s), (g_it / C::G_STAGES) & 1);
+          if (ready && g_kb == 0) ready = mbar_test_wait(bar(C::B_ACCG_EMPTY + acc), ((g_tile >> 1) & 1) ^ 1);
+          if (ready) {
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * IT_BN;
+            const uint32_t stage = sG + s * C::G_STAGE;
+            if (g_kb == 0) g_accumulate = 0;
+            const bool last = (g_kb == p.kb_g - 1);
+            if (elect_one_sync()) {
+              if (g_kb == 0) trace(TR_G_BEGIN, g_tile);
+              if (last) trace(TR_G_END, g_tile);
+              uint32_t accumulate = g_accumulate;
+#pragma unroll
+              for (int pr = 0; pr < C::NPAIRS; ++pr) {
+                const uint64_t adesc = make_kmajor_desc(stage + pair_a(P, pr) * C::A_TILE, C::SPAN);
+                const uint64_t bdesc = make_kmajor_desc(stage + P * C::A_TILE + pair_b(P, pr) * C::B_TILE, C::SPAN);
+#pragma unroll
+                for (int k = 0; k < C::BK / UMMA_K; ++k) {
+                  umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_g, accumulate);
+                  accumulate = 1;
+                }
+              }
+              umma_commit_pair(bar(C::B_G_EMPTY + s), 3);
+              if (last) umma_commit_pair(bar(C::B_ACCG_FULL + acc), 3);
+            }
+            __syncwarp();
+            g_accumulate = 1;
+            ++g_it;
+            if (++g_kb == p.kb_g) g_kb = 0, ++g_tile;
+            progressed = true;
+          }
+        }
+        if (progressed) {
+          idle = 0;
+        } else {
+          // nothing ready: back off for a few tens of ns so the polling does not take issue slots from the math warps
+          asm volatile("nanosleep.u32 32;" ::: "memory");
+        }
+        if (!progressed && ++idle > (1u << 24)) {
+          if (lane == 0)
+            printf("vtc_b200: MMA issuer stalled (block %d, G tile %d kb %d, R tile %d chunk %d of %d tiles)\n",
+                   (int)blockIdx.x, g_tile, g_kb, r_tile, r_chunk, my_tiles);
+          __trap();
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ================================ epilogue input loader ================================
+    const uint32_t state_bytes = __popc(p.in_mask) * EPI_ARRAY_BYTES;
+    uint32_t q = 0;
+    for (int pi = 0; pi < my_panels; ++pi) {
+      const int m0 = (cluster_id + pi * num_clusters) * PAIR_M + cta_rank * BLOCK_M;
+      for (int nt = 0; nt <= NT; ++nt) {
+        const bool panel_end = (nt == NT);
+        if (panel_end && !p.do_r) break;
+        const int nsub = panel_end ? p.nsub_r : 2 * tile_chunks(nt);
+        for (int j = 0; j < nsub; ++j, ++q) {
+          const int e = q % C::IN_STAGES;
+          mbar_wait(bar(C::B_IN_FREE + e), ((q / C::IN_STAGES) & 1) ^ 1);
+          if (elect_one_sync()) {
+            const uint32_t full = bar(C::B_IN_FULL + e);
+            const uint32_t dst = sIn + e * C::IN_STAGE;
+            if (panel_end) {
+              mbar_arrive_expect_tx(full, EPI_ARRAY_BYTES);
+              tma_load_2d(dst, &p.tmX, full, j * EPI_COLS, m0, kEvictNormal);
+            } else {
+              mbar_arrive_expect_tx(full, state_bytes);
+              const int col = nt * IT_BN + j * EPI_COLS;
+              int slot = 0;
+              for (int i = 0; i < 3; i += 2) {
+                if (!(p.in_mask & (1 << i))) continue;
+                const uint32_t d = dst + slot * EPI_ARRAY_BYTES;
+                ++slot;
+                if (p.blocked_mask & (BLK_IN0 << i)) tma_load_3d(d, &p.tmIn[i], full, 0, m0, col / EPI_COLS, kEvictNormal);
+                else tma_load_2d(d, &p.tmIn[i], full, col, m0, kEvictNormal);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================ epilogue storer ================================
+    uint32_t q = 0;
+    for (int pi = 0; pi < my_panels; ++pi) {
+      const int m0 = (cluster_id + pi * num_clusters) * PAIR_M + cta_rank * BLOCK_M;
+      for (int nt = 0; nt <= NT; ++nt) {
+        const bool panel_end = (nt == NT);
+        if (panel_end && !p.do_r) break;
+        const int nsub = panel_end ? p.nsub_r : 2 * tile_chunks(nt);
+        for (int j = 0; j < nsub; ++j, ++q) {
+          const int e = q % C::IN_STAGES;
+          mbar_wait(bar(C::B_OUT_FULL + e), (q / C::IN_STAGES) & 1);
+          const uint32_t src = sIn + e * C::IN_STAGE + EPI_ARRAY_BYTES;
+          if (elect_one_sync()) {
+            if (panel_end) {
+              const int col = j * EPI_COLS;
+#pragma unroll
+              for (int part = 0; part < P; ++part)
+                tma_store_3d(&p.tmROut, src + part * EPI_PART_BYTES, col % p.r_block_w, m0,
+                             part * p.kb_g + col / p.r_block_w);
+            } else {
+              const int col = nt * IT_BN + j * EPI_COLS;
+              if (p.blocked_mask & BLK_OUT) tma_store_3d(&p.tmOut, src, 0, m0, col / EPI_COLS);
+              else tma_store_2d(&p.tmOut, src, col, m0);
+            }
+            bulk_commit();
+            if (q >= C::STORES_IN_FLIGHT) {
+              // all but the STORES_IN_FLIGHT most recent stores have read their stage: hand the oldest back to the loader
+              bulk_wait_read<C::STORES_IN_FLIGHT>();
+              mbar_arrive(bar(C::B_IN_FREE + (q - C::STORES_IN_FLIGHT) % C::IN_STAGES));
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (elect_one_sync()) bulk_wait<0>();
+    __syncwarp();
+  } else if (warp >= 4 && warp < 4 + C::MATH_WARPS) {
+    // ================================ epilogue math ================================
+    const uint32_t group = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t sw64 = (row >> 1) & 3;
+    const uint32_t sw32 = (row >> 2) & 1;
+    UpdateArgs ua;
+    ua.in_mask = p.in_mask, ua.prox = p.prox, ua.group = p.group, ua.use_momentum = p.use_momentum;
+    ua.beta_prev = p.beta_prev, ua.beta_next = p.beta_next;
+    ua.eta = __ldg(p.scalars + 0), ua.theta = __ldg(p.scalars + 1);
+    ua.want_stat = p.stat != nullptr;
+    const bool has_prev = (p.in_mask & 4) != 0;
+    Tracer trace(p, 2, warp == 4 && lane == 0);
+    float stat_local = 0.f;
+    uint32_t q = 0, yc = 0;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    int t = 0;
+    for (int pi = 0; pi < my_panels; ++pi) {
+      for (int nt = 0; nt <= NT; ++nt) {
+        const bool panel_end = (nt == NT);
+        if (panel_end && !p.do_r) break;
+        const int nsub = panel_end ? p.nsub_r : 2 * tile_chunks(nt);
+        uint32_t t_row, drained_bar;
+        if (panel_end) {
+          mbar_wait(bar(C::B_ACCR_FULL), pi & 1);
+          t_row = lane_base + 2 * IT_BN;
+          drained_bar = bar(C::B_ACCR_EMPTY);
+        } else {
+          const int acc = t & 1;
+          mbar_wait(bar(C::B_ACCG_FULL + acc), (t >> 1) & 1);
+          t_row = lane_base + acc * IT_BN;
+          drained_bar = bar(C::B_ACCG_EMPTY + acc);
+          ++t;
+        }
+        tc_fence_after();
+        trace(TR_E_BEGIN, pi * (NT + 1) + nt);
+        // last sub-tile of this tile that belongs to this warp's group (-1: none)
+        int j_last = -1;
+        for (int j = nsub - 1; j >= 0 && j >= nsub - C::GROUPS; --j)
+          if ((q + j) % C::GROUPS == group) {
+            j_last = j;
+            break;
+          }
+        if (j_last < 0) {
+          __syncwarp();
+          if (lane == 0) {
+            tc_fence_before();
+            mbar_arrive_remote(drained_bar, 0);
+          }
+        }
+        for (int j = 0; j < nsub; ++j, ++q) {
+          const uint32_t chunk = yc + (j >> 1);  // y chunk of this sub-tile (state tiles only)
+          if (q % C::GROUPS != group) continue;
+          const int e = q % C::IN_STAGES;
+          uint32_t v[16];
+          trace(TR_E_SUB, j);
+          tmem_ld16(t_row + j * EPI_COLS, v);
+          mbar_wait(bar(C::B_IN_FULL + e), (q / C::IN_STAGES) & 1);
+          trace(TR_E_IN, j);
+          tmem_ld_wait();
+          trace(TR_E_LD, j);
+          if (j == j_last) {
+            __syncwarp();
+            if (lane == 0) {
+              tc_fence_before();
+              mbar_arrive_remote(drained_bar, 0);
+            }
+          }
+          const uint32_t in_stage = sIn + e * C::IN_STAGE;
+          float in[3][16];
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const float4 a = lds128(in_stage + row * 64 + ((ch ^ sw64) << 4));
+            in[0][4 * ch + 0] = a.x, in[0][4 * ch + 1] = a.y, in[0][4 * ch + 2] = a.z, in[0][4 * ch + 3] = a.w;
+            in[1][4 * ch + 0] = 0.f, in[1][4 * ch + 1] = 0.f, in[1][4 * ch + 2] = 0.f, in[1][4 * ch + 3] = 0.f;
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_prev && !panel_end) b = lds128(in_stage + EPI_ARRAY_BYTES + row * 64 + ((ch ^ sw64) << 4));
+            in[2][4 * ch + 0] = b.x, in[2][4 * ch + 1] = b.y, in[2][4 * ch + 2] = b.z, in[2][4 * ch + 3] = b.w;
+          }
+          float outv[16], partv[16];
+          if (panel_end) {
+#pragma unroll
+            for (int x = 0; x < 16; ++x) partv[x] = __uint_as_float(v[x]) - in[0][x];  // r_k = y_k Phi - x
+          } else {
+            fista_update16(ua, v, in, outv, partv, stat_local);
+          }
+          trace(TR_E_CMP, j);
+          // the result goes over the second input slot of the same stage (every thread has read its own row of it):
+          // no output ring to wait for; the storer hands the stage back to the loader once the TMA store has read it
+          const uint32_t out_stage = in_stage + EPI_ARRAY_BYTES;
+          if (panel_end) {
+            split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
+              const uint32_t prow = out_stage + part * EPI_PART_BYTES + row * 32;
+              sts128u(prow + ((0 ^ sw32) << 4), w32[0], w32[1], w32[2], w32[3]);
+              sts128u(prow + ((1 ^ sw32) << 4), w32[4], w32[5], w32[6], w32[7]);
+            });
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(C::B_OUT_FULL + e));
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              sts128(out_stage + row * 64 + ((ch ^ sw64) << 4), outv[4 * ch], outv[4 * ch + 1], outv[4 * ch + 2],
+                     outv[4 * ch + 3]);
+            uint32_t yfull = 0;
+            if (p.do_r) {
+              // y_k parts straight into the A operand of R: [128 rows][64 B] per part, SWIZZLE_64B; this sub-tile is
+              // the 32-byte half (j & 1) of the row
+              const int ys = chunk % C::Y_STAGES;
+              mbar_wait(bar(C::B_Y_EMPTY + ys), ((chunk / C::Y_STAGES) & 1) ^ 1);
+              trace(TR_E_YW, j);
+              const uint32_t ystage = sY + ys * C::Y_STAGE + row * 64;
+              const uint32_t c0 = 2 * (j & 1);
+              split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
+                const uint32_t prow = ystage + part * C::Y_TILE;
+                sts128u(prow + (((c0 + 0) ^ sw64) << 4), w32[0], w32[1], w32[2], w32[3]);
+                sts128u(prow + (((c0 + 1) ^ sw64) << 4), w32[4], w32[5], w32[6], w32[7]);
+              });
+              yfull = bar(C::B_Y_FULL + ys);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(bar(C::B_OUT_FULL + e));
+              if (p.do_r) mbar_arrive_remote(yfull, 0);
+            }
+            trace(TR_E_ARR, j);
+          }
+        }
+        trace(TR_E_END, pi * (NT + 1) + nt);
+        if (!panel_end) yc += nsub >> 1;
+      }
+    }
+    if (p.stat) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) stat_local += __shfl_xor_sync(0xffffffffu, stat_local, o);
+      if (lane == 0) atomicAdd(p.stat, static_cast<double>(stat_local));
+    }
+  }
+
+  __syncwarp();
+  trace0(TR_STOP, 0);
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+}
+
+}  // namespace vtc

@@ -179,23 +179,127 @@ __device__ __forceinline__ void group_shrink(const float (&u)[16], float (&o)[16
 // Scalar soft-threshold update of 16 columns with the iteration's structure fixed at compile time (the common case):
 // no per-element selects on run-time flags. HASB: the drive b is an input (Gram form); PREV: a_{k-1} is an input
 // (momentum term non-zero); MOM: FISTA extrapolation of the new iterate.
+// The sums, differences and products run two columns at a time on the packed fp32x2 pipe (FADD2 / FMUL2 / FFMA2 of
+// sm_100): every packed operation rounds each half exactly like the scalar one it replaces (a - b is issued as
+// fma(b, -1, a): the product is exact, one rounding), so the result is bit-identical to the unpacked sequence and to
+// the reference's separate multiply and add; only the issue slots are halved.
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 template <bool HASB, bool PREV, bool MOM>
 __device__ __forceinline__ void soft_update16(const uint32_t (&v)[16], const float (&in)[3][16], float eta, float theta,
                                               float beta_prev, float beta_next, float (&outv)[16],
                                               float (&partv)[16], float& stat_local, bool want_stat) {
+  const float2 eta2 = make_float2(eta, eta), bp2 = make_float2(beta_prev, beta_prev);
+  const float2 bn2 = make_float2(beta_next, beta_next);
+#pragma unroll
+  for (int x = 0; x < 16; x += 2) {
+    const float2 ak = make_float2(in[0][x], in[0][x + 1]);
+    float2 y = ak;
+    if (PREV) y = __fadd2_rn(ak, __fmul2_rn(bp2, sub2(ak, make_float2(in[2][x], in[2][x + 1]))));
+    float2 g = make_float2(__uint_as_float(v[x]), __uint_as_float(v[x + 1]));
+    if (HASB) g = sub2(g, make_float2(in[1][x], in[1][x + 1]));
+    const float2 u = sub2(y, __fmul2_rn(eta2, g));
+    float2 a;
+    a.x = copysignf(fmaxf(__fsub_rn(fabsf(u.x), theta), 0.f), u.x);
+    a.y = copysignf(fmaxf(__fsub_rn(fabsf(u.y), theta), 0.f), u.y);
+    outv[x] = a.x;
+    outv[x + 1] = a.y;
+    const float2 d = sub2(a, ak);
+    const float2 yn = MOM ? __fadd2_rn(a, __fmul2_rn(bn2, d)) : a;
+    partv[x] = yn.x;
+    partv[x + 1] = yn.y;
+    if (want_stat) stat_local += fabsf(d.x) + fabsf(d.y);
+  }
+}
+
+// One ISTA/FISTA update of a 16-column sub-tile (shared by the GEMM epilogue below and the panel-resident iteration
+// kernel in fista_iter_kernel.cuh). v = accumulator (gradient, or y G in the Gram form), in[0] = a_{k-1}, in[1] = b (Gram
+// form only), in[2] = a_{k-2} (only when the momentum term is non-zero). outv = a_k, partv = y_k (next operand).
+struct UpdateArgs {
+  int in_mask, prox, group, use_momentum;
+  float beta_prev, beta_next, eta, theta;
+  bool want_stat;
+};
+__device__ __forceinline__ void fista_update16(const UpdateArgs& p, const uint32_t (&v)[16], const float (&in)[3][16],
+                                               float (&outv)[16], float (&partv)[16], float& stat_local) {
+  if (p.prox == 0 && p.group <= 1) {
+    // fast paths: scalar soft threshold (ista_fista.py:117-120) with the iteration structure known at compile time
+    const bool prev = (p.in_mask & 4) != 0;
+#define VTC_SOFT(HASB, PREV, MOM) \
+  soft_update16<HASB, PREV, MOM>(v, in, p.eta, p.theta, p.beta_prev, p.beta_next, outv, partv, stat_local, p.want_stat)
+    if (p.in_mask & 2) {  // Gram form: b is an input
+      if (!p.use_momentum) VTC_SOFT(true, false, false);
+      else if (!prev) VTC_SOFT(true, false, true);
+      else VTC_SOFT(true, true, true);
+    } else {              // synthesis form: the accumulator already is the whole gradient
+      if (!p.use_momentum) VTC_SOFT(false, false, false);
+      else if (!prev) VTC_SOFT(false, false, true);
+      else VTC_SOFT(false, true, true);
+    }
+#undef VTC_SOFT
+    return;
+  }
+  // general path. in[1] absent -> 0: the accumulator already is the full gradient
+  float u[16];
 #pragma unroll
   for (int x = 0; x < 16; ++x) {
     const float ak = in[0][x];
     float y = ak;
-    if (PREV) y = __fadd_rn(ak, __fmul_rn(beta_prev, __fsub_rn(ak, in[2][x])));
-    float g = __uint_as_float(v[x]);
-    if (HASB) g = __fsub_rn(g, in[1][x]);
-    const float u = __fsub_rn(y, __fmul_rn(eta, g));
-    const float a = copysignf(fmaxf(__fsub_rn(fabsf(u), theta), 0.f), u);
-    outv[x] = a;
-    const float d = __fsub_rn(a, ak);
-    partv[x] = MOM ? __fadd_rn(a, __fmul_rn(beta_next, d)) : a;
-    if (want_stat) stat_local += fabsf(d);
+    if (p.in_mask & 4) y = __fadd_rn(ak, __fmul_rn(p.beta_prev, __fsub_rn(ak, in[2][x])));
+    const float g = __fsub_rn(__uint_as_float(v[x]), in[1][x]);
+    u[x] = __fsub_rn(y, __fmul_rn(p.eta, g));
+  }
+  if (p.group <= 1) {
+#pragma unroll
+    for (int x = 0; x < 16; ++x) {
+      const float ux = u[x];
+      float a;
+      if (p.prox & PROX_HARD) {
+        const float mag = (p.prox & PROX_NONNEG) ? ux : fabsf(ux);
+        a = (mag < p.theta) ? 0.f : ux;
+      } else {
+        a = fmaxf(__fsub_rn(ux, p.theta), 0.f);
+      }
+      outv[x] = a;
+    }
+  } else {
+    switch (p.group) {
+      case 2: group_shrink<2>(u, outv, p.theta); break;
+      case 4: group_shrink<4>(u, outv, p.theta); break;
+      case 8: group_shrink<8>(u, outv, p.theta); break;
+      default: group_shrink<16>(u, outv, p.theta); break;
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < 16; ++x) {
+    const float a = outv[x];
+    const float d = __fsub_rn(a, in[0][x]);
+    partv[x] = p.use_momentum ? __fadd_rn(a, __fmul_rn(p.beta_next, d)) : a;
+    if (p.want_stat) stat_local += fabsf(d);
+  }
+}
+
+// bf16 split of 16 fp32 values into n_parts parts (hi, then the residual's hi, ...): emit(part, w32) receives the 16
+// bf16 of one part packed as 8 words (column 2x in the low half of word x).
+template <typename Emit>
+__device__ __forceinline__ void split_parts16(const float (&partv)[16], int n_parts, Emit emit) {
+  float r[16];
+#pragma unroll
+  for (int x = 0; x < 16; ++x) r[x] = partv[x];
+#pragma unroll
+  for (int part = 0; part < MAX_PARTS; ++part) {
+    if (part >= n_parts) break;
+    uint32_t w32[8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      // one cvt.rn.bf16x2.f32 packs two columns; the bf16 -> fp32 widening is a shift / mask of that word
+      const __nv_bfloat162 h = __floats2bfloat162_rn(r[2 * x], r[2 * x + 1]);
+      w32[x] = *reinterpret_cast<const uint32_t*>(&h);
+      if (part + 1 < n_parts) {
+        r[2 * x] = __fsub_rn(r[2 * x], __uint_as_float(w32[x] << 16));
+        r[2 * x + 1] = __fsub_rn(r[2 * x + 1], __uint_as_float(w32[x] & 0xffff0000u));
+      }
+    }
+    emit(part, w32);
   }
 }
 
@@ -486,62 +590,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
             outv[x] = __uint_as_float(v[x]) - in[0][x];
             partv[x] = outv[x];
           }
-        } else if (p.prox == 0 && p.group <= 1) {
-          // fast paths: scalar soft threshold (ista_fista.py:117-120) with the iteration structure known at compile time
-          const bool prev = (p.in_mask & 4) != 0;
-          const bool want_stat = p.stat != nullptr;
-#define VTC_SOFT(HASB, PREV, MOM) \
-  soft_update16<HASB, PREV, MOM>(v, in, eta, theta, p.beta_prev, p.beta_next, outv, partv, stat_local, want_stat)
-          if (p.in_mask & 2) {  // Gram form: b is an input
-            if (!p.use_momentum) VTC_SOFT(true, false, false);
-            else if (!prev) VTC_SOFT(true, false, true);
-            else VTC_SOFT(true, true, true);
-          } else {              // synthesis form: the accumulator already is the whole gradient
-            if (!p.use_momentum) VTC_SOFT(false, false, false);
-            else if (!prev) VTC_SOFT(false, false, true);
-            else VTC_SOFT(false, true, true);
-          }
-#undef VTC_SOFT
         } else {
-          // general path. in[0] = a_k, in[1] = b (absent -> 0: the accumulator already is the full gradient),
-          // in[2] = a_{k-1} (only loaded when the momentum term is non-zero)
-          float u[16];
-#pragma unroll
-          for (int x = 0; x < 16; ++x) {
-            const float ak = in[0][x];
-            float y = ak;
-            if (p.in_mask & 4) y = __fadd_rn(ak, __fmul_rn(p.beta_prev, __fsub_rn(ak, in[2][x])));
-            const float g = __fsub_rn(__uint_as_float(v[x]), in[1][x]);
-            u[x] = __fsub_rn(y, __fmul_rn(eta, g));
-          }
-          if (p.group <= 1) {
-#pragma unroll
-            for (int x = 0; x < 16; ++x) {
-              const float ux = u[x];
-              float a;
-              if (p.prox & PROX_HARD) {
-                const float mag = (p.prox & PROX_NONNEG) ? ux : fabsf(ux);
-                a = (mag < theta) ? 0.f : ux;
-              } else {
-                a = fmaxf(__fsub_rn(ux, theta), 0.f);
-              }
-              outv[x] = a;
-            }
-          } else {
-            switch (p.group) {
-              case 2: group_shrink<2>(u, outv, theta); break;
-              case 4: group_shrink<4>(u, outv, theta); break;
-              case 8: group_shrink<8>(u, outv, theta); break;
-              default: group_shrink<16>(u, outv, theta); break;
-            }
-          }
-#pragma unroll
-          for (int x = 0; x < 16; ++x) {
-            const float a = outv[x];
-            const float d = __fsub_rn(a, in[0][x]);
-            partv[x] = p.use_momentum ? __fadd_rn(a, __fmul_rn(p.beta_next, d)) : a;
-            if (p.stat) stat_local += fabsf(d);
-          }
+          UpdateArgs ua;
+          ua.in_mask = p.in_mask, ua.prox = p.prox, ua.group = p.group, ua.use_momentum = p.use_momentum;
+          ua.beta_prev = p.beta_prev, ua.beta_next = p.beta_next, ua.eta = eta, ua.theta = theta;
+          ua.want_stat = p.stat != nullptr;
+          fista_update16(ua, v, in, outv, partv, stat_local);
         }
         // every lane has consumed its inputs: hand the in stage back to the loader
         __syncwarp();
@@ -555,27 +609,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
                    outv[4 * ch + 3]);
         }
         if (p.n_parts) {
-          float r[16];
-#pragma unroll
-          for (int x = 0; x < 16; ++x) r[x] = partv[x];
-#pragma unroll
-          for (int part = 0; part < MAX_PARTS; ++part) {
-            if (part >= p.n_parts) break;
-            uint32_t w32[8];
-#pragma unroll
-            for (int x = 0; x < 8; ++x) {
-              // one cvt.rn.bf16x2.f32 packs two columns; the bf16 -> fp32 widening is a shift / mask of that word
-              const __nv_bfloat162 h = __floats2bfloat162_rn(r[2 * x], r[2 * x + 1]);
-              w32[x] = *reinterpret_cast<const uint32_t*>(&h);
-              if (part + 1 < p.n_parts) {
-                r[2 * x] = __fsub_rn(r[2 * x], __uint_as_float(w32[x] << 16));
-                r[2 * x + 1] = __fsub_rn(r[2 * x + 1], __uint_as_float(w32[x] & 0xffff0000u));
-              }
-            }
+          split_parts16(partv, p.n_parts, [&](int part, const uint32_t (&w32)[8]) {
             const uint32_t prow = out_stage + EPI_ARRAY_BYTES + part * EPI_PART_BYTES + row * 32;
             sts128u(prow + ((0 ^ sw32) << 4), w32[0], w32[1], w32[2], w32[3]);
             sts128u(prow + ((1 ^ sw32) << 4), w32[4], w32[5], w32[6], w32[7]);
-          }
+          });
         }
         fence_proxy_async_smem();
         __syncwarp();

@@ -13,6 +13,7 @@
 
 #include "aux_kernels.cuh"
 #include "gemm_kernel.cuh"
+#include "fista_iter_kernel.cuh"
 
 namespace {
 
@@ -348,6 +349,121 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------- fused iteration
+// One launch = one ISTA/FISTA iteration of the synthesis form with the operand y_k kept on chip (fista_iter_kernel.cuh).
+struct IterCall {
+  PartsMat r_op, phi_op, phiT_op;
+  int precision = VTC_PRECISION_BF16X3;
+  int64_t B = 0, S = 0, D = 0;
+  F32Mat a_prev, a_prev2, x, out;
+  bool has_prev2 = false, do_r = true;
+  int prox = 0, group = 1, use_momentum = 0;
+  float beta_prev = 0.f, beta_next = 0.f;
+  const float* scalars = nullptr;
+  double* stat = nullptr;
+  int max_pairs = 0;
+};
+
+unsigned long long* g_iter_trace = nullptr;  // vtc_debug_iter_trace
+
+// VTC_B200_FUSED_ITER=0 keeps the two-launch schedule (for comparison and as the reference of the parity tests)
+int g_fused_iter = -1;
+bool fused_iter_enabled() {
+  if (g_fused_iter < 0) {
+    const char* e = getenv("VTC_B200_FUSED_ITER");
+    g_fused_iter = e ? (atoi(e) != 0) : 1;
+  }
+  return g_fused_iter != 0;
+}
+bool fused_iter_ok(int64_t S, int64_t D, int precision) {
+  return fused_iter_enabled() && formulation_for(S, D) == FORM_SYNTHESIS && D <= IT_RN && parts_for(precision) <= 2;
+}
+
+// tuning variant of the fused iteration kernel (stage counts / math warps); VTC_B200_ITER_VARIANT overrides
+int iter_variant() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("VTC_B200_ITER_VARIANT");
+    cached = e ? atoi(e) : 0;
+    if (cached < 0 || cached >= IT_VARIANTS) cached = 0;
+  }
+  return cached;
+}
+
+template <int P, int V>
+int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream) {
+  using Cf = IterCfg<P, V>;
+  IterParams p;
+  memset(&p, 0, sizeof(p));
+  if (c.r_op.block != Cf::BK) return fail(VTC_ERR_ARG, "fused iteration: r_op must be tile-contiguous with block %d", Cf::BK);
+  TRY(map_operand(&p.tmR, c.r_op, Cf::BK, "r operand"));
+  TRY(map_operand(&p.tmPhi, c.phi_op, Cf::BK, "dictionary operand", IT_BN / 2));
+  TRY(map_operand(&p.tmPhiT, c.phiT_op, IT_CHUNK, "transposed dictionary operand", IT_RN / 2));
+  TRY(map_f32(&p.tmIn[0], c.a_prev, "a_{k-1}"));
+  if (c.has_prev2) TRY(map_f32(&p.tmIn[2], c.a_prev2, "a_{k-2}"));
+  TRY(map_f32(&p.tmX, c.x, "images"));
+  TRY(map_f32(&p.tmOut, c.out, "a_k"));
+  TRY(map_parts_out(&p.tmROut, c.r_op, "r parts output"));
+  p.num_panels = static_cast<int>(ceil_div(c.B, PAIR_M));
+  p.S = static_cast<int>(c.S);
+  p.num_n_tiles = static_cast<int>(ceil_div(c.S, IT_BN));
+  p.kb_g = static_cast<int>(c.r_op.Kp / Cf::BK);
+  p.phi_part_stride = static_cast<int>(c.phi_op.Kp);
+  p.phiT_part_stride = static_cast<int>(c.phiT_op.Kp);
+  p.nsub_r = static_cast<int>(c.r_op.Kp / EPI_COLS);
+  p.r_block_w = Cf::BK;
+  p.in_mask = 1 | (c.has_prev2 ? 4 : 0);
+  if (c.a_prev.blocked) p.blocked_mask |= BLK_IN0;
+  if (c.has_prev2 && c.a_prev2.blocked) p.blocked_mask |= (BLK_IN0 << 2);
+  if (c.out.blocked) p.blocked_mask |= BLK_OUT;
+  p.do_r = c.do_r ? 1 : 0;
+  p.prox = c.prox, p.group = c.group, p.use_momentum = c.use_momentum;
+  p.beta_prev = c.beta_prev, p.beta_next = c.beta_next;
+  p.scalars = c.scalars;
+  p.stat = c.stat;
+  p.trace = g_iter_trace;
+  g_iter_trace = nullptr;  // one shot: only the next launch is traced
+  static bool attr_set_dev[64] = {};
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  bool& attr_set = attr_set_dev[dev & 63];
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(vtc_fista_iter_kernel<P, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
+    attr_set = true;
+  }
+  long long max_pairs = info.sm_count / 2;
+  if (c.max_pairs > 0 && c.max_pairs < max_pairs) max_pairs = c.max_pairs;
+  const int pairs = static_cast<int>(p.num_panels < max_pairs ? p.num_panels : max_pairs);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(Cf::THREADS);
+  cfg.dynamicSmemBytes = Cf::SMEM_ALLOC;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (tune_flags() & TUNE_NO_PDL) ? 1 : 2;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_fista_iter_kernel<P, V>, p));
+  COUNT_LAUNCH();
+  return VTC_OK;
+}
+int launch_iter(const IterCall& c, cudaStream_t stream) {
+  DeviceInfo info;
+  TRY(require_sm100(&info));
+  if (c.D > IT_RN) return fail(VTC_ERR_ARG, "fused iteration needs D <= %d", IT_RN);
+  const bool one = parts_for(c.precision) == 1;
+  switch (iter_variant()) {
+    case 1: return one ? launch_iter_p<1, 1>(c, info, stream) : launch_iter_p<2, 1>(c, info, stream);
+    default: return one ? launch_iter_p<1, 0>(c, info, stream) : launch_iter_p<2, 0>(c, info, stream);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- small launches
 int grid_for(int64_t work, int threads, int sm_count) {
   int64_t g = ceil_div(work, threads);
@@ -510,6 +626,17 @@ int vtc_set_formulation(int formulation) {
   return VTC_OK;
 }
 int vtc_get_formulation(int64_t S, int64_t D) { return formulation_for(S, D); }
+int vtc_set_fused_iteration(int on) {
+  g_fused_iter = on != 0;
+  return VTC_OK;
+}
+int vtc_debug_iter_trace(void* device_buffer) {
+  g_iter_trace = static_cast<unsigned long long*>(device_buffer);
+  return VTC_OK;
+}
+int vtc_get_fused_iteration(int64_t S, int64_t D, int precision) {
+  return valid_precision(precision) && fused_iter_ok(S, D, precision) ? 1 : 0;
+}
 int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches, int* iters, float* fused_launch_ms,
                      float* first_launch_ms) {
   if (!g_prof.valid) return fail(VTC_ERR_ARG, "vtc_profile_last: no profiled vtc_fista_fc call");
@@ -576,6 +703,7 @@ struct FistaCommon {
   float sparsity_weight;
   int num_iters, variant, prox, group_size, precision, P;
   bool gram, early;
+  bool fused_iter;  // one launch per iteration (fista_iter_kernel.cuh) instead of two
 };
 
 struct FistaChain {
@@ -655,7 +783,7 @@ int chain_setup(const FistaCommon& cm, FistaChain& ch) {
   ch.X2 = F32Mat{w.X2, B, S, 0, true};
   ch.final_out = tma_ok(ch.codes_out, ch.ld_codes) ? F32Mat{ch.codes_out, B, S, ch.ld_codes, false}
                                                     : F32Mat{w.out_pad, B, S, w.ldS, false};
-  CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[1].ptr), 0, w.yop[1].bytes(), st));
+  if (!cm.fused_iter) CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[1].ptr), 0, w.yop[1].bytes(), st));
   if (ch.initial_codes) {
     if (tma_ok(ch.initial_codes, ch.ld_codes)) {
       ch.init = F32Mat{ch.initial_codes, B, S, ch.ld_codes, false};
@@ -671,6 +799,17 @@ int chain_setup(const FistaCommon& cm, FistaChain& ch) {
     ch.init = ch.X2;
   }
   if (cm.early) CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * cm.num_iters, st));
+  if (cm.fused_iter) {
+    // the fused schedule carries r_{k-1} = y_{k-1} Phi - x between launches: r_0 from the starting point, once
+    GemmCall r;
+    r.precision = cm.precision;
+    r.max_pairs = ch.max_pairs;
+    r.A = w.yop[0], r.B = w.phiT_op;
+    r.M = B, r.N = D, r.K = S;
+    r.in[0] = F32Mat{ch.x_in, B, D, ch.ld_x}, r.in_mask = 1;
+    r.parts_out = w.r_op, r.n_parts = cm.P;
+    TRY(launch_gemm<EPI_STORE>(r, st));
+  }
   return VTC_OK;
 }
 
@@ -685,6 +824,29 @@ int chain_iterate(const FistaCommon& cm, FistaChain& ch, int k, float beta_prev,
   // stopping goes straight to the caller's row-major buffer
   const F32Mat& a_out = (k == cm.num_iters && !cm.early) ? ch.final_out : (k & 1) ? ch.X1 : ch.X2;
   if (sample >= 0) CUDA_TRY(cudaEventRecord(g_prof.k1_begin[sample], st));
+  if (cm.fused_iter) {
+    IterCall c;
+    c.r_op = w.r_op, c.phi_op = w.phi_op, c.phiT_op = w.phiT_op;
+    c.precision = cm.precision;
+    c.B = B, c.S = S, c.D = D;
+    c.a_prev = a_prev;
+    c.has_prev2 = (cm.variant == VTC_VARIANT_FISTA && beta_prev != 0.f);
+    c.a_prev2 = a_prev2;
+    c.x = F32Mat{ch.x_in, B, D, ch.ld_x};
+    c.out = a_out;
+    c.do_r = k < cm.num_iters;
+    c.prox = cm.prox, c.group = cm.group_size, c.use_momentum = (cm.variant == VTC_VARIANT_FISTA);
+    c.beta_prev = beta_prev, c.beta_next = beta_k;
+    c.scalars = w.scalars;
+    c.stat = cm.early ? w.stats + (k - 1) : nullptr;
+    c.max_pairs = ch.max_pairs;
+    TRY(launch_iter(c, st));
+    if (sample >= 0) {
+      CUDA_TRY(cudaEventRecord(g_prof.k1_end[sample], st));
+      CUDA_TRY(cudaEventRecord(g_prof.k2_end[sample], st));
+    }
+    return VTC_OK;
+  }
   GemmCall g;
   g.precision = cm.precision;
   g.max_pairs = ch.max_pairs;
@@ -812,6 +974,7 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   cm.group_size = group_size;
   cm.precision = precision, cm.P = parts_for(precision);
   cm.gram = formulation_for(S, D) == FORM_GRAM;
+  cm.fused_iter = fused_iter_ok(S, D, precision);
   cm.early = early_stopping_epsilon >= 0.f;
   if (cm.early && num_iters > 4096) return fail(VTC_ERR_UNSUPPORTED, "early stopping supports at most 4096 iterations");
 
@@ -882,7 +1045,7 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
     for (int c = 0; c < chains; ++c) TRY(chain_iterate(cm, ch[c], k, beta_prev, beta_k, c == 0 ? sample : -1));
     if (sample >= 0) {
       g_prof.samples = sample + 1;
-      g_prof.two_launches = !cm.gram;
+      g_prof.two_launches = !cm.gram && !cm.fused_iter;
     }
     beta_prev = beta_k;
     k_done = k;
@@ -901,7 +1064,7 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   }
   if (g_prof.on) {
     CUDA_TRY(cudaEventRecord(g_prof.iter_end, st));
-    g_prof.iter_launches = k_done * (cm.gram ? 1 : 2) * chains;
+    g_prof.iter_launches = k_done * ((cm.gram || cm.fused_iter) ? 1 : 2) * chains;
     g_prof.iters = k_done;
     g_prof.valid = true;
   }
