@@ -31,7 +31,7 @@ B_PER_GPU, S, D, T, LAM = 65536, 1024, 256, 300, 0.1
 TRAIN_GLOBAL_BATCH = 524288
 WORKLOAD = ('configs[1]: fully-connected FISTA, 16x16 whitened patches (D=256), 1024 atoms, '
             'batch 65536 per GPU, 300 iters, lambda 0.1')
-CPU_SAMPLE = 2048
+CPU_SAMPLE = 32768
 
 
 def peaks():

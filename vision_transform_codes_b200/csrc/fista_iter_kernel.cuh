@@ -40,20 +40,18 @@
 namespace vtc {
 
 constexpr int IT_BN = 128;     // atoms per gradient tile (UMMA N of G)
-constexpr int IT_CHUNK = 32;   // atoms per y / Phi^T chunk = 2 sub-tiles (K extent of one group of R MMAs)
 constexpr int IT_RN = 256;     // UMMA N of R = padded pixel count
-constexpr int IT_VARIANTS = 2;  // tuning variants (stage counts / math warps), VTC_B200_ITER_VARIANT
+constexpr int IT_VARIANTS = 3;  // tuning variants (stage counts / math warps), VTC_B200_ITER_VARIANT
 
 template <int P, int V>
 struct IterCfg {
   static_assert(P == 1 || P == 2, "parts");
   static_assert(V >= 0 && V < IT_VARIANTS, "variant");
-  // tuning variants (VTC_B200_ITER_VARIANT), measured on configs[1] (ms per iteration, bf16x3 / bf16):
-  //                     math groups   G   y   Phi^T   in/out stages
-  //   0 (default)           3         2   2   2       6                0.261 / 0.187
-  //   1                     2         4   2   2       4                0.261 / 0.234
-  // (3 groups with 4 G and 3 in/out stages: 0.350 / 0.324 -- the depth of the in/out ring, i.e. the state bytes in
-  //  flight per SM, is what bounds this kernel; deeper G, y or Phi^T rings measured neutral)
+  // tuning variants (VTC_B200_ITER_VARIANT); see profiles/README.md for what each measured
+  //                     math groups   chunk   G (P=2 / P=1)   y   Phi^T   in/out stages
+  //   0                     3          32       2 / 3          3   2       6
+  //   1                     2          32       4 / 4          2   2       4
+  //   2                     3          16       3 / 4          3   3       6
   // epilogue math: GROUPS groups of four warps (one warp per TMEM lane quarter) on sub-tiles round-robin
   static constexpr int GROUPS = (V == 1) ? 2 : 3;
   static constexpr int MATH_WARPS = 4 * GROUPS;
@@ -64,19 +62,25 @@ struct IterCfg {
   static constexpr int A_TILE = BLOCK_M * SPAN;           // one part of this CTA's 128 rows of r_op
   static constexpr int B_TILE = (IT_BN / 2) * SPAN;       // one part of this CTA's 64 atoms of the Phi tile
   static constexpr int G_STAGE = P * (A_TILE + B_TILE);
-  static constexpr int Y_TILE = BLOCK_M * IT_CHUNK * 2;   // 8 KB: one part of y, 128 rows x 32 atoms, SWIZZLE_64B
+  // atoms per y / Phi^T chunk (K extent of one group of R MMAs): 32 = two sub-tiles (64-byte rows, SWIZZLE_64B) or
+  // 16 = one sub-tile (32-byte rows, SWIZZLE_32B: half the ring bytes, twice the handshakes)
+  static constexpr int CHUNK = (V == 2) ? 16 : 32;
+  static constexpr int SUBS = CHUNK / EPI_COLS;           // sub-tiles per chunk
+  static constexpr int Y_TILE = BLOCK_M * CHUNK * 2;      // one part of y: 128 rows x CHUNK atoms
   static constexpr int Y_STAGE = P * Y_TILE;
-  static constexpr int PT_TILE = (IT_RN / 2) * IT_CHUNK * 2;  // 8 KB: one part of this CTA's 128 pixel rows of Phi^T
+  static constexpr int PT_TILE = (IT_RN / 2) * CHUNK * 2;  // one part of this CTA's 128 pixel rows of Phi^T
   static constexpr int PT_STAGE = P * PT_TILE;
   static constexpr int IN_STAGE = 2 * EPI_ARRAY_BYTES;
   static constexpr int OUT_SLOT = EPI_ARRAY_BYTES;        // the result (a_k fp32, or P bf16 part sub-tiles of r) is written
                                                           // over the second 8 KB of its input stage and stored from there
   static constexpr int STORES_IN_FLIGHT = 1;              // TMA stores whose shared-memory reads may still be pending
   // shared memory split between the rings (P = 2: G 24 KB, y 16 KB, Phi^T 16 KB, in/out 16 KB per stage)
-  static constexpr int G_STAGES = (V == 0) ? 2 : 4;
-  static constexpr int Y_STAGES = 2;
-  static constexpr int PT_STAGES = 2;
-  static constexpr int IN_STAGES = (V == 0) ? 6 : 4;      // a multiple of GROUPS: fixed owner group per stage
+  static constexpr int G_STAGES = (V == 0) ? (P == 2 ? 2 : 3) : (V == 2 && P == 2) ? 3 : 4;
+  // every y stage must always be written by the same math groups (a group then sees the phases of the stage's
+  // barrier strictly in order, like the in/out stages): Y_STAGES * SUBS is a multiple of GROUPS
+  static constexpr int Y_STAGES = (V == 1) ? 2 : 3;
+  static constexpr int PT_STAGES = (V == 2) ? 3 : 2;
+  static constexpr int IN_STAGES = (V == 1) ? 4 : 6;      // a multiple of GROUPS: fixed owner group per stage
   static constexpr int OFF_G = 0;
   static constexpr int OFF_Y = OFF_G + G_STAGES * G_STAGE;
   static constexpr int OFF_PT = OFF_Y + Y_STAGES * Y_STAGE;
@@ -101,6 +105,11 @@ struct IterCfg {
   static constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
   static constexpr int NPAIRS = (P == 1) ? 1 : 3;
   static_assert(IN_STAGES % GROUPS == 0, "input stages must have a fixed owner group");
+  static_assert((Y_STAGES * SUBS) % GROUPS == 0, "y stages must have fixed writer groups");
+  // the panel-end sub-tiles are padded to a multiple of this with empty ones, so that the running sub-tile index (which
+  // selects the math group and the in/out stage) and the running y chunk index stay congruent from panel to panel
+  static constexpr int PANEL_END_PAD = 6;
+  static_assert(PANEL_END_PAD % GROUPS == 0, "padding must keep the group assignment aligned");
   static_assert(P * EPI_PART_BYTES <= OUT_SLOT, "r parts must fit the output slot");
   static_assert(SMEM_ALLOC <= 232448, "over the 227 KB shared memory limit");
 };
@@ -128,6 +137,11 @@ struct IterParams {
   float beta_prev, beta_next;
   const float* scalars;  // device: [0] = eta, [1] = theta
   double* stat;          // optional: += sum |a_k - a_{k-1}|
+  // L2 prefetch of the state stream (tile-contiguous inputs only): a sub-tile is one contiguous span of rows * 64 bytes
+  const char* pf_base[2];          // a_{k-1}, a_{k-2} (nullptr: not prefetched)
+  unsigned long long pf_block_bytes;  // bytes between column blocks = rows * 64
+  int rows;                        // B
+  int pf_distance;                 // sub-tiles ahead of the shared-memory loads (0 = off)
   unsigned long long* trace;  // optional (tools/iter_trace.py): 4 regions of 2048 words, [0] = event count, then
                               // (event id << 48 | SM clock) words, written by four threads of CTA 0
 };
@@ -150,6 +164,11 @@ struct Tracer {
     }
   }
 };
+
+// bring `bytes` (a multiple of 16) at a 16-byte aligned global address into L2; no shared memory, no barrier
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 
 // non-blocking tests (the MMA issuer polls several barriers)
 __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
@@ -185,8 +204,9 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
   const int NT = p.num_n_tiles;
   const int my_panels = (p.num_panels - cluster_id + num_clusters - 1) / num_clusters;  // panels cluster_id, +num_clusters, ...
   const int my_tiles = my_panels * NT;
+  const int nsub_r_pad = (p.nsub_r + C::PANEL_END_PAD - 1) / C::PANEL_END_PAD * C::PANEL_END_PAD;
   // sub-tiles of tile nt: an even number (whole chunks); columns at or beyond S are zero everywhere (TMA fill)
-  auto tile_chunks = [&](int nt) { return (min(IT_BN, p.S - nt * IT_BN) + IT_CHUNK - 1) / IT_CHUNK; };
+  auto tile_chunks = [&](int nt) { return (min(IT_BN, p.S - nt * IT_BN) + C::CHUNK - 1) / C::CHUNK; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmR);
@@ -208,7 +228,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
       mbar_init(bar(C::B_PT_EMPTY + s), 1);
     }
     for (int s = 0; s < C::Y_STAGES; ++s) {
-      mbar_init(bar(C::B_Y_FULL + s), 2 * 2 * 4);  // 2 CTAs x 2 sub-tiles x 4 warps (leader's barrier)
+      mbar_init(bar(C::B_Y_FULL + s), 2 * C::SUBS * 4);  // 2 CTAs x sub-tiles of a chunk x 4 warps (leader's barrier)
       mbar_init(bar(C::B_Y_EMPTY + s), 1);         // multicast tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -287,7 +307,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
 #pragma unroll
               for (int q = 0; q < P; ++q)
                 tma_load_2d_pair(sPT + s * C::PT_STAGE + q * C::PT_TILE, &p.tmPhiT, full,
-                                 q * p.phiT_part_stride + nt * IT_BN + c * IT_CHUNK, cta_rank * (IT_RN / 2), kEvictLast);
+                                 q * p.phiT_part_stride + nt * IT_BN + c * C::CHUNK, cta_rank * (IT_RN / 2), kEvictLast);
             }
             __syncwarp();
           }
@@ -329,10 +349,10 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
               uint32_t accumulate = first ? 0u : 1u;
 #pragma unroll
               for (int pr = 0; pr < C::NPAIRS; ++pr) {
-                const uint64_t adesc = make_kmajor_desc(ystage + pair_a(P, pr) * C::Y_TILE, IT_CHUNK * 2);
-                const uint64_t bdesc = make_kmajor_desc(pstage + pair_b(P, pr) * C::PT_TILE, IT_CHUNK * 2);
+                const uint64_t adesc = make_kmajor_desc(ystage + pair_a(P, pr) * C::Y_TILE, C::CHUNK * 2);
+                const uint64_t bdesc = make_kmajor_desc(pstage + pair_b(P, pr) * C::PT_TILE, C::CHUNK * 2);
 #pragma unroll
-                for (int k = 0; k < IT_CHUNK / UMMA_K; ++k) {
+                for (int k = 0; k < C::CHUNK / UMMA_K; ++k) {
                   umma_bf16_pair(acc_r, adesc + 2 * k, bdesc + 2 * k, idesc_r, accumulate);
                   accumulate = 1;
                 }
@@ -399,20 +419,52 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
   } else if (warp == 3) {
     // ================================ epilogue input loader ================================
     const uint32_t state_bytes = __popc(p.in_mask) * EPI_ARRAY_BYTES;
+    // L2 prefetch cursor: runs pf_distance state sub-tiles ahead of the shared-memory loads, so that those find their
+    // data in L2 (a fraction of the HBM latency) and the few stages of the in/out ring are enough bytes in flight
+    int ppi = 0, pnt = 0, pj = 0;
+    const int s_blocks = (p.S + EPI_COLS - 1) / EPI_COLS;
+    auto prefetch_next = [&](bool issue) {
+      if (ppi >= my_panels) return;
+      if (issue) {
+        const int pm0 = (cluster_id + ppi * num_clusters) * PAIR_M + cta_rank * BLOCK_M;
+        const int blk = pnt * (IT_BN / EPI_COLS) + pj;
+        const int nrows = min(BLOCK_M, p.rows - pm0);
+        if (nrows > 0 && blk < s_blocks) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (p.pf_base[i] != nullptr)
+              bulk_prefetch_l2(p.pf_base[i] + blk * p.pf_block_bytes + static_cast<unsigned long long>(pm0) * 64,
+                               static_cast<uint32_t>(nrows) * 64);
+        }
+      }
+      if (++pj == C::SUBS * tile_chunks(pnt)) {
+        pj = 0;
+        if (++pnt == NT) pnt = 0, ++ppi;
+      }
+    };
+    const bool pf_on = p.pf_distance > 0 && (p.pf_base[0] != nullptr || p.pf_base[1] != nullptr);
+    if (pf_on && elect_one_sync()) {
+      for (int i = 0; i < C::IN_STAGES; ++i) prefetch_next(false);   // these are loaded straight away
+      for (int i = C::IN_STAGES; i < p.pf_distance; ++i) prefetch_next(true);
+    }
+    __syncwarp();
     uint32_t q = 0;
     for (int pi = 0; pi < my_panels; ++pi) {
       const int m0 = (cluster_id + pi * num_clusters) * PAIR_M + cta_rank * BLOCK_M;
       for (int nt = 0; nt <= NT; ++nt) {
         const bool panel_end = (nt == NT);
         if (panel_end && !p.do_r) break;
-        const int nsub = panel_end ? p.nsub_r : 2 * tile_chunks(nt);
+        const int nsub = panel_end ? nsub_r_pad : C::SUBS * tile_chunks(nt);
         for (int j = 0; j < nsub; ++j, ++q) {
           const int e = q % C::IN_STAGES;
           mbar_wait(bar(C::B_IN_FREE + e), ((q / C::IN_STAGES) & 1) ^ 1);
           if (elect_one_sync()) {
+            if (pf_on && !panel_end) prefetch_next(true);
             const uint32_t full = bar(C::B_IN_FULL + e);
             const uint32_t dst = sIn + e * C::IN_STAGE;
-            if (panel_end) {
+            if (panel_end && j >= p.nsub_r) {
+              mbar_arrive(full);  // padding sub-tile: nothing to load
+            } else if (panel_end) {
               mbar_arrive_expect_tx(full, EPI_ARRAY_BYTES);
               tma_load_2d(dst, &p.tmX, full, j * EPI_COLS, m0, kEvictNormal);
             } else {
@@ -440,13 +492,15 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
       for (int nt = 0; nt <= NT; ++nt) {
         const bool panel_end = (nt == NT);
         if (panel_end && !p.do_r) break;
-        const int nsub = panel_end ? p.nsub_r : 2 * tile_chunks(nt);
+        const int nsub = panel_end ? nsub_r_pad : C::SUBS * tile_chunks(nt);
         for (int j = 0; j < nsub; ++j, ++q) {
           const int e = q % C::IN_STAGES;
           mbar_wait(bar(C::B_OUT_FULL + e), (q / C::IN_STAGES) & 1);
           const uint32_t src = sIn + e * C::IN_STAGE + EPI_ARRAY_BYTES;
           if (elect_one_sync()) {
-            if (panel_end) {
+            if (panel_end && j >= p.nsub_r) {
+              // padding sub-tile: nothing to store (the empty bulk group below keeps the recycling uniform)
+            } else if (panel_end) {
               const int col = j * EPI_COLS;
 #pragma unroll
               for (int part = 0; part < P; ++part)
@@ -492,7 +546,8 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
       for (int nt = 0; nt <= NT; ++nt) {
         const bool panel_end = (nt == NT);
         if (panel_end && !p.do_r) break;
-        const int nsub = panel_end ? p.nsub_r : 2 * tile_chunks(nt);
+        const int nsub = panel_end ? p.nsub_r : C::SUBS * tile_chunks(nt);   // real sub-tiles
+        const int nsub_all = panel_end ? nsub_r_pad : nsub;                  // + padding at the panel end
         uint32_t t_row, drained_bar;
         if (panel_end) {
           mbar_wait(bar(C::B_ACCR_FULL), pi & 1);
@@ -521,10 +576,16 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
             mbar_arrive_remote(drained_bar, 0);
           }
         }
-        for (int j = 0; j < nsub; ++j, ++q) {
-          const uint32_t chunk = yc + (j >> 1);  // y chunk of this sub-tile (state tiles only)
+        for (int j = 0; j < nsub_all; ++j, ++q) {
+          const uint32_t chunk = yc + j / C::SUBS;  // y chunk of this sub-tile (state tiles only)
           if (q % C::GROUPS != group) continue;
           const int e = q % C::IN_STAGES;
+          if (j >= nsub) {  // padding sub-tile of the panel end: pass the stage on
+            mbar_wait(bar(C::B_IN_FULL + e), (q / C::IN_STAGES) & 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(C::B_OUT_FULL + e));
+            continue;
+          }
           uint32_t v[16];
           trace(TR_E_SUB, j);
           tmem_ld16(t_row + j * EPI_COLS, v);
@@ -577,17 +638,18 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
                      outv[4 * ch + 3]);
             uint32_t yfull = 0;
             if (p.do_r) {
-              // y_k parts straight into the A operand of R: [128 rows][64 B] per part, SWIZZLE_64B; this sub-tile is
-              // the 32-byte half (j & 1) of the row
+              // y_k parts straight into the A operand of R, K-major with rows of CHUNK * 2 bytes in the matching TMA /
+              // UMMA swizzle: 64-byte rows (this sub-tile is the 32-byte half j % 2 of the row) or 32-byte rows
               const int ys = chunk % C::Y_STAGES;
               mbar_wait(bar(C::B_Y_EMPTY + ys), ((chunk / C::Y_STAGES) & 1) ^ 1);
               trace(TR_E_YW, j);
-              const uint32_t ystage = sY + ys * C::Y_STAGE + row * 64;
-              const uint32_t c0 = 2 * (j & 1);
+              const uint32_t ystage = sY + ys * C::Y_STAGE + row * (C::CHUNK * 2);
+              const uint32_t c0 = 2 * (j % C::SUBS);
+              const uint32_t sw = (C::CHUNK == 32) ? sw64 : sw32;
               split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
                 const uint32_t prow = ystage + part * C::Y_TILE;
-                sts128u(prow + (((c0 + 0) ^ sw64) << 4), w32[0], w32[1], w32[2], w32[3]);
-                sts128u(prow + (((c0 + 1) ^ sw64) << 4), w32[4], w32[5], w32[6], w32[7]);
+                sts128u(prow + (((c0 + 0) ^ sw) << 4), w32[0], w32[1], w32[2], w32[3]);
+                sts128u(prow + (((c0 + 1) ^ sw) << 4), w32[4], w32[5], w32[6], w32[7]);
               });
               yfull = bar(C::B_Y_FULL + ys);
             }
@@ -601,7 +663,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
           }
         }
         trace(TR_E_END, pi * (NT + 1) + nt);
-        if (!panel_end) yc += nsub >> 1;
+        if (!panel_end) yc += nsub / C::SUBS;
       }
     }
     if (p.stat) {

@@ -283,10 +283,11 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
                ::"r"(bar), "h"(mask)
                : "memory");
 }
-// K-major operand tile whose rows are one swizzle span of `span_bytes` (128 or 64): 8-row groups are
-// 8 * span_bytes apart (SBO); layout_type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
+// K-major operand tile whose rows are one swizzle span of `span_bytes` (128, 64 or 32): 8-row groups are
+// 8 * span_bytes apart (SBO); layout_type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B.
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t span_bytes) {
-  const uint32_t hi = (((8 * span_bytes) >> 4) & 0x3FFF) | (1u << 14) | ((span_bytes == 128 ? 2u : 4u) << 29);
+  const uint32_t hi = (((8 * span_bytes) >> 4) & 0x3FFF) | (1u << 14) |
+                      ((span_bytes == 128 ? 2u : span_bytes == 64 ? 4u : 6u) << 29);
   const uint32_t lo = (smem_addr >> 4) & 0x3FFF;
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }

@@ -152,7 +152,8 @@ int map_operand(CUtensorMap* m, const PartsMat& a, int block_k, const char* what
   const uint64_t str[1] = {static_cast<uint64_t>(a.pitch_elems()) * 2};
   const uint32_t box[2] = {static_cast<uint32_t>(block_k), static_cast<uint32_t>(box_rows)};
   return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.ptr, dims, str, box,
-                block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, what);
+                block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, what);
 }
 int map_f32(CUtensorMap* m, const F32Mat& a, const char* what) {
   if (a.blocked) {
@@ -398,7 +399,7 @@ int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream
   if (c.r_op.block != Cf::BK) return fail(VTC_ERR_ARG, "fused iteration: r_op must be tile-contiguous with block %d", Cf::BK);
   TRY(map_operand(&p.tmR, c.r_op, Cf::BK, "r operand"));
   TRY(map_operand(&p.tmPhi, c.phi_op, Cf::BK, "dictionary operand", IT_BN / 2));
-  TRY(map_operand(&p.tmPhiT, c.phiT_op, IT_CHUNK, "transposed dictionary operand", IT_RN / 2));
+  TRY(map_operand(&p.tmPhiT, c.phiT_op, Cf::CHUNK, "transposed dictionary operand", IT_RN / 2));
   TRY(map_f32(&p.tmIn[0], c.a_prev, "a_{k-1}"));
   if (c.has_prev2) TRY(map_f32(&p.tmIn[2], c.a_prev2, "a_{k-2}"));
   TRY(map_f32(&p.tmX, c.x, "images"));
@@ -421,6 +422,18 @@ int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream
   p.beta_prev = c.beta_prev, p.beta_next = c.beta_next;
   p.scalars = c.scalars;
   p.stat = c.stat;
+  // L2 prefetch of the tile-contiguous state inputs, VTC_B200_ITER_PREFETCH sub-tiles ahead (0 = off)
+  static int pf_distance = -1;
+  if (pf_distance < 0) {
+    const char* e = getenv("VTC_B200_ITER_PREFETCH");
+    pf_distance = e ? atoi(e) : 0;  // measured slower at every distance (profiles/README.md): off
+    if (pf_distance > 0 && pf_distance < Cf::IN_STAGES) pf_distance = Cf::IN_STAGES;
+  }
+  p.pf_distance = pf_distance;
+  p.rows = static_cast<int>(c.B);
+  p.pf_block_bytes = static_cast<unsigned long long>(c.B) * EPI_COLS * 4;
+  p.pf_base[0] = c.a_prev.blocked ? static_cast<const char*>(c.a_prev.ptr) : nullptr;
+  p.pf_base[1] = (c.has_prev2 && c.a_prev2.blocked) ? static_cast<const char*>(c.a_prev2.ptr) : nullptr;
   p.trace = g_iter_trace;
   g_iter_trace = nullptr;  // one shot: only the next launch is traced
   static bool attr_set_dev[64] = {};
@@ -460,6 +473,7 @@ int launch_iter(const IterCall& c, cudaStream_t stream) {
   const bool one = parts_for(c.precision) == 1;
   switch (iter_variant()) {
     case 1: return one ? launch_iter_p<1, 1>(c, info, stream) : launch_iter_p<2, 1>(c, info, stream);
+    case 2: return one ? launch_iter_p<1, 2>(c, info, stream) : launch_iter_p<2, 2>(c, info, stream);
     default: return one ? launch_iter_p<1, 0>(c, info, stream) : launch_iter_p<2, 0>(c, info, stream);
   }
 }
