@@ -21,6 +21,9 @@ Reference lines followed (paths relative to vision_transform_codes/):
   dictionary update    dict_update_rules/fully_connected/sc_cheap_quadratic_descent.py:42-48, sc_steepest_descent.py:37-41
   Hessian running mean training/sparse_coding.py:154
   train step           training/sparse_coding.py:513-515
+  convolutional ISTA/FISTA   analysis_transforms/convolutional/ista_fista.py:104-197, utils/convolutions.py:7-24
+  convolutional dict update  dict_update_rules/convolutional/sc_cheap_quadratic_descent.py:59-79,
+                             sc_steepest_descent.py:55-72; Hessian running mean training/sparse_coding.py:158-161
 """
 import torch
 
@@ -206,6 +209,142 @@ def train_steps(batches, dictionary, sparsity_weight, num_iters, stepsize, varia
     else:
       phi = sc_dictionary_update(x, phi, codes, None, stepsize=stepsize)
   return phi, h, codes
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Convolutional sparse coding: images (b, c, h, w) already padded, dictionary (s, c, kh, kw),
+# codes (b, s, sh, sw); synthesis = conv_transpose2d, analysis = conv2d, both with stride kernel_stride.
+def get_padding_amt(image_dim, kernel_dim, dim_stride):
+  """utils/convolutions.py:7-12."""
+  leading = kernel_dim - dim_stride
+  trailing = kernel_dim - dim_stride
+  if image_dim % dim_stride != 0:
+    trailing += dim_stride - (image_dim % dim_stride)
+  return leading, trailing
+
+
+def code_dim_from_padded_img_dim(padded_image_dim, kernel_dim, dim_stride):
+  """utils/convolutions.py:14-15."""
+  import math
+  return 1 + int(math.ceil((padded_image_dim - kernel_dim) / dim_stride))
+
+
+def create_mask(images_with_padding, padding):
+  """utils/convolutions.py:17-24: ones, zero on the padded border."""
+  mask = torch.ones_like(images_with_padding)
+  if padding is not None:
+    mask[:, :, 0:padding[0][0], :] = 0.0
+    mask[:, :, -padding[0][1]:, :] = 0.0
+    mask[:, :, :, 0:padding[1][0]] = 0.0
+    mask[:, :, :, -padding[1][1]:] = 0.0
+  return mask
+
+
+def conv_ista_fista(images_padded, dictionary, kernel_stride, padding_dims, sparsity_weight, num_iters,
+                    variant='fista', initial_codes=None, early_stopping_epsilon=None, nonnegative_only=False,
+                    hard_threshold=False, return_iters=False):
+  """analysis_transforms/convolutional/ista_fista.py:104-197."""
+  assert variant in ['ista', 'fista']
+  F = torch.nn.functional
+  flat = torch.flatten(dictionary, start_dim=1)
+  stepsize = 1. / torch.linalg.eigvalsh(torch.mm(flat, flat.t()))[-1]
+  cutoff = sparsity_weight * stepsize
+  sh = code_dim_from_padded_img_dim(images_padded.shape[2], dictionary.shape[2], kernel_stride[0])
+  sw = code_dim_from_padded_img_dim(images_padded.shape[3], dictionary.shape[3], kernel_stride[1])
+  if initial_codes is None:
+    eval_pt = images_padded.new_zeros((images_padded.shape[0], dictionary.shape[0], sh, sw))
+  else:
+    assert tuple(initial_codes.shape) == (images_padded.shape[0], dictionary.shape[0], sh, sw)
+    eval_pt = initial_codes
+  previous = eval_pt.clone()
+  mask = create_mask(images_padded, padding_dims)
+  betas = momentum_coefficients(num_iters)
+  codes, done = None, 0
+  for k in range(num_iters):
+    residual = mask * (F.conv_transpose2d(eval_pt, dictionary, stride=kernel_stride) - images_padded)
+    codes = threshold(eval_pt - stepsize * F.conv2d(residual, dictionary, stride=kernel_stride), cutoff,
+                      nonnegative_only, hard_threshold)
+    change = codes - previous
+    eval_pt = codes + betas[k] * change if variant == 'fista' else codes
+    previous = codes
+    done = k + 1
+    if early_stopping_epsilon is not None:
+      if bool(torch.mean(torch.abs(change) / stepsize) < early_stopping_epsilon) and k > 0:
+        break
+  return (codes, done) if return_iters else codes
+
+
+def conv_dictionary_gradient(images_padded, dictionary, codes, kernel_stride, padding_dims):
+  """The data-term gradient, summed over the batch (NOT divided by it):
+  dict_update_rules/convolutional/sc_cheap_quadratic_descent.py:65-71 without the division."""
+  F = torch.nn.functional
+  mask = create_mask(images_padded, padding_dims)
+  residual = mask * (F.conv_transpose2d(codes, dictionary, stride=kernel_stride) - images_padded)
+  return F.conv2d(residual.transpose(dim0=1, dim1=0), codes.transpose(dim0=1, dim1=0),
+                  dilation=kernel_stride).transpose(dim0=1, dim1=0)
+
+
+def conv_sc_dictionary_update(images_padded, dictionary, codes, kernel_stride, padding_dims, hessian_diagonal=None,
+                              stepsize=0.001, num_iters=1, lowest_code_val=0.001, normalize_dictionary=True,
+                              batch_size=None, extra_gradient=None):
+  """convolutional/sc_cheap_quadratic_descent.py:59-79 (hessian_diagonal given) / sc_steepest_descent.py:55-72 (None).
+  Functional: returns the updated dictionary. batch_size / extra_gradient as in sc_dictionary_update."""
+  phi = dictionary.clone()
+  divisor = images_padded.shape[0] if batch_size is None else batch_size
+  for it in range(num_iters):
+    gradient = conv_dictionary_gradient(images_padded, phi, codes, kernel_stride, padding_dims)
+    if extra_gradient is not None and it == 0:
+      gradient = gradient + extra_gradient
+    gradient = gradient / divisor
+    if hessian_diagonal is not None:
+      gradient = gradient / (hessian_diagonal[:, None, None, None] + lowest_code_val)
+    gradient = gradient * (phi.norm(p=2) / gradient.norm(p=2))
+    phi = phi - stepsize * gradient
+    if normalize_dictionary:
+      phi = phi / torch.squeeze(phi.norm(p=2, dim=(1, 2, 3)))[:, None, None, None]
+  return phi
+
+
+def conv_hessian_running_mean(hessian_diagonal, codes):
+  """training/sparse_coding.py:158-161 (functional)."""
+  return hessian_diagonal * 0.99 + torch.mean(torch.sum(codes**2, dim=(2, 3)), dim=0) / 100
+
+
+def synthetic_conv_dictionary(num_kernels, channels, kh, kw, seed=1, window=0.18):
+  """Unit-norm random kernels as every conv example / test initialises (examples/train_convolutional_sparse_coding.py:
+  95-99), by default under a Gaussian window of width `window` (in units of the kernel size). The reference's step size
+  comes from the Gram matrix of the flattened kernels, which under-estimates the Lipschitz constant of the overlapping
+  strided synthesis; with plain random kernels FISTA diverges (window=0 reproduces that), windowed kernels overlap
+  little and converge -- the well-posed case for parity and benchmarks."""
+  g = torch.Generator().manual_seed(seed)
+  phi = torch.randn(num_kernels, channels, kh, kw, generator=g)
+  if window:
+    yy = (torch.arange(kh) - (kh - 1) / 2)[:, None] / (window * kh)
+    xx = (torch.arange(kw) - (kw - 1) / 2)[None, :] / (window * kw)
+    phi = phi * torch.exp(-0.5 * (yy**2 + xx**2))
+  return phi / torch.squeeze(phi.norm(p=2, dim=(1, 2, 3)))[:, None, None, None]
+
+
+def synthetic_padded_images(batch, channels, height, width, kernel, stride, seed=0, std=0.3):
+  """Whitened 1/f-noise images of (height, width) zero-padded by get_padding_amt on every side; returns
+  (images_padded, padding_dims)."""
+  g = torch.Generator().manual_seed(seed)
+  fy = torch.fft.fftfreq(height)[:, None]
+  fx = torch.fft.fftfreq(width)[None, :]
+  rad = torch.sqrt(fy**2 + fx**2)
+  amp = 1.0 / torch.clamp(rad, min=1.0 / max(height, width))
+  whiten = torch.clamp(rad, min=1e-3) * torch.exp(-(rad / (0.5 * 0.9))**8)
+  phase = torch.rand(batch, channels, height, width, generator=g) * 2 * torch.pi
+  img = torch.fft.ifft2(amp * torch.exp(1j * phase)).real
+  lo = img.amin(dim=(2, 3), keepdim=True)
+  hi = img.amax(dim=(2, 3), keepdim=True)
+  img = (img - lo) / (hi - lo)
+  img = torch.fft.ifft2(torch.fft.fft2(img) * whiten).real
+  img = (img * (std / img.std())).float()
+  pv = get_padding_amt(height, kernel[0], stride[0])
+  ph = get_padding_amt(width, kernel[1], stride[1])
+  padded = torch.nn.functional.pad(img, (ph[0], ph[1], pv[0], pv[1]))
+  return padded.contiguous(), (pv, ph)
 
 
 # ---------------------------------------------------------------------------------------------------------------

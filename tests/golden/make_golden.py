@@ -153,10 +153,92 @@ def make_training():
        subspace_cheap_aligned=phi_d)
 
 
+def conv_inputs(b, c, hw, k, stride, s, seed=0, std=0.3, window=0.18):
+  """Seeded padded images + unit-norm kernels, padded as utils.convolutions.get_padding_amt prescribes.
+  window > 0 multiplies the random kernels by a Gaussian of that width (in units of the kernel size): the reference
+  takes its step size from the Gram matrix of the FLATTENED kernels, which under-estimates the Lipschitz constant of the
+  strided, overlapping synthesis (2.58 against 1.59 for 24 plain random 16x16 kernels at stride 8) -- FISTA then
+  diverges and amplifies rounding noise without bound, which makes a useless parity case. Windowed kernels overlap
+  little (ratio 1.05), the iteration converges; ISTA is stable either way and is also pinned on plain kernels."""
+  from utils.convolutions import get_padding_amt
+  g = torch.Generator().manual_seed(seed)
+  img = std * torch.randn(b, c, hw[0], hw[1], generator=g)
+  pv = get_padding_amt(hw[0], k[0], stride[0])
+  ph = get_padding_amt(hw[1], k[1], stride[1])
+  x = torch.nn.functional.pad(img, (ph[0], ph[1], pv[0], pv[1])).contiguous()
+  g2 = torch.Generator().manual_seed(seed + 1)
+  phi = torch.randn(s, c, k[0], k[1], generator=g2)
+  if window:
+    yy = (torch.arange(k[0]) - (k[0] - 1) / 2)[:, None] / (window * k[0])
+    xx = (torch.arange(k[1]) - (k[1] - 1) / 2)[None, :] / (window * k[1])
+    phi = phi * torch.exp(-0.5 * (yy**2 + xx**2))
+  phi = phi / torch.squeeze(phi.norm(p=2, dim=(1, 2, 3)))[:, None, None, None]
+  return x, phi, (pv, ph)
+
+
+def make_conv():
+  """Convolutional path: the call matrix of the reference's tests/ista_fista_2.py, the two conv dictionary updates
+  and a short conv training run (tests/sparse_coding_4.py), on small seeded inputs."""
+  from analysis_transforms.convolutional import ista_fista as conv_ista_fista
+  from dict_update_rules.convolutional import sc_cheap_quadratic_descent as conv_cheap
+  from dict_update_rules.convolutional import sc_steepest_descent as conv_steepest
+  lam, T = 0.05, 40
+  # (a) the shape family of BASELINE configs[4]: 1 channel, 16x16 kernels, stride 8 (here 24 kernels on 48x40 images)
+  x, phi, pad = conv_inputs(3, 1, (48, 40), (16, 16), (8, 8), 24)
+  st = (8, 8)
+  warm = conv_ista_fista.run(x, phi, st, pad, lam, 4, variant='fista')
+  codes = conv_ista_fista.run(x, phi, st, pad, lam, T, variant='fista')
+  h = torch.mean(torch.sum(codes**2, dim=(2, 3)), dim=0) / 100
+
+  def updated(mod, *args, **kw):
+    d = phi.clone()
+    mod.run(x, d, codes, *args, **kw)
+    return d
+
+  save('conv_small', images_padded=x, dictionary=phi, stride=np.array(st), padding=np.array(pad), sparsity_weight=lam,
+       num_iters=T, warm_start=warm, fista=codes,
+       ista=conv_ista_fista.run(x, phi, st, pad, lam, T, variant='ista'),
+       plain_dictionary=conv_inputs(3, 1, (48, 40), (16, 16), (8, 8), 24, window=0)[1],
+       ista_plain=conv_ista_fista.run(x, conv_inputs(3, 1, (48, 40), (16, 16), (8, 8), 24, window=0)[1], st, pad, lam, T,
+                                      variant='ista'),
+       ista_early=conv_ista_fista.run(x, phi, st, pad, lam, 500, variant='ista', early_stopping_epsilon=1e-3),
+       fista_nonneg=conv_ista_fista.run(x, phi, st, pad, lam, T, variant='fista', nonnegative_only=True),
+       ista_hard_nonneg=conv_ista_fista.run(x, phi, st, pad, lam, T, variant='ista', nonnegative_only=True,
+                                            hard_threshold=True),
+       fista_warm=conv_ista_fista.run(x, phi, st, pad, lam, T, variant='fista', initial_codes=warm),
+       hessian_diagonal=h,
+       cheap_1=updated(conv_cheap, h, st, pad, stepsize=0.05),
+       cheap_2=updated(conv_cheap, h, st, pad, stepsize=0.02, num_iters=2),
+       steepest_1=updated(conv_steepest, st, pad, stepsize=0.05),
+       steepest_unnormalized=updated(conv_steepest, st, pad, stepsize=0.05, normalize_dictionary=False))
+  # (b) two channels, rectangular kernels and strides, image size not a multiple of the stride
+  x2, phi2, pad2 = conv_inputs(2, 2, (21, 30), (8, 12), (4, 6), 10, seed=5)
+  st2 = (4, 6)
+  codes2 = conv_ista_fista.run(x2, phi2, st2, pad2, lam, T, variant='fista')
+  h2 = torch.mean(torch.sum(codes2**2, dim=(2, 3)), dim=0) / 100
+  d2 = phi2.clone()
+  conv_cheap.run(x2, d2, codes2, h2, st2, pad2, stepsize=0.05)
+  save('conv_two_channel', images_padded=x2, dictionary=phi2, stride=np.array(st2), padding=np.array(pad2),
+       sparsity_weight=lam, num_iters=T, fista=codes2, hessian_diagonal=h2, cheap_1=d2)
+  # (c) the unmodified trainer in convolutional mode (tests/sparse_coding_4.py): ista + cheap quadratic descent
+  nb, b = 3, 2
+  xb, phi0, padb = conv_inputs(nb * b, 1, (32, 32), (16, 16), (8, 8), 16, seed=9)
+  xb = xb.view(nb, b, *xb.shape[1:])
+  params = {
+      'mode': 'convolutional', 'num_epochs': 1, 'strides': (8, 8), 'padding': padb,
+      'code_inference_algorithm': 'ista',
+      'inference_param_schedule': {0: {'sparsity_weight': 0.05, 'num_iters': 15}},
+      'dictionary_update_algorithm': 'sc_cheap_quadratic_descent',
+      'dict_update_param_schedule': {0: {'stepsize': 0.05, 'num_iters': 1}}}
+  d = phi0.clone()
+  sparse_coding.train_dictionary(xb, xb[:1], d, params)
+  d_b = phi0.clone()
+  sparse_coding.train_dictionary(xb, xb[:1], d_b, dict(params, code_inference_algorithm='fista',
+                                                        dictionary_update_algorithm='sc_steepest_descent'))
+  save('conv_training_small', batches=xb, dictionary=phi0, padding=np.array(padb), ista_cheap=d, fista_steepest=d_b)
+
+
 if __name__ == '__main__':
-  make_inference()
-  make_config1()
-  make_overcomplete()
-  make_subspace()
-  make_dict_update()
-  make_training()
+  which = sys.argv[1:] or ['inference', 'config1', 'overcomplete', 'subspace', 'dict_update', 'training', 'conv']
+  for name in which:
+    globals()['make_' + name]()

@@ -127,3 +127,68 @@ def test_whitened_generator_statistics():
   x = oracle.synthetic_patches(2048, 256, kind='whitened')
   assert x.shape == (2048, 256)
   assert abs(float(x.std()) - 0.3) < 1e-3
+
+
+def conv_args(g):
+  stride = tuple(int(v) for v in g['stride'])
+  padding = tuple(tuple(int(v) for v in row) for row in g['padding'])
+  return g['images_padded'], g['dictionary'], stride, padding, g['sparsity_weight'], g['num_iters']
+
+
+def test_conv_inference_matches_reference_outputs():
+  """Call matrix of the reference's tests/ista_fista_2.py on outputs of the reference's convolutional path."""
+  g = load_golden('conv_small')
+  x, phi, st, pad, lam, T = conv_args(g)
+  close(oracle.conv_ista_fista(x, phi, st, pad, lam, T, variant='fista'), g['fista'])
+  close(oracle.conv_ista_fista(x, phi, st, pad, lam, T, variant='ista'), g['ista'])
+  close(oracle.conv_ista_fista(x, g['plain_dictionary'], st, pad, lam, T, variant='ista'), g['ista_plain'])
+  close(oracle.conv_ista_fista(x, phi, st, pad, lam, 500, variant='ista', early_stopping_epsilon=1e-3), g['ista_early'])
+  close(oracle.conv_ista_fista(x, phi, st, pad, lam, T, nonnegative_only=True), g['fista_nonneg'])
+  close(oracle.conv_ista_fista(x, phi, st, pad, lam, T, variant='ista', nonnegative_only=True, hard_threshold=True),
+        g['ista_hard_nonneg'], 1e-5)
+  close(oracle.conv_ista_fista(x, phi, st, pad, lam, T, initial_codes=g['warm_start']), g['fista_warm'])
+  g2 = load_golden('conv_two_channel')
+  x, phi, st, pad, lam, T = conv_args(g2)
+  close(oracle.conv_ista_fista(x, phi, st, pad, lam, T), g2['fista'])
+
+
+def test_conv_dictionary_update_matches_reference_outputs():
+  g = load_golden('conv_small')
+  x, phi, st, pad, _, _ = conv_args(g)
+  a, h = g['fista'], g['hessian_diagonal']
+  close(oracle.conv_hessian_running_mean(torch.zeros_like(h), a), h)
+  close(oracle.conv_sc_dictionary_update(x, phi, a, st, pad, h, stepsize=0.05), g['cheap_1'])
+  close(oracle.conv_sc_dictionary_update(x, phi, a, st, pad, h, stepsize=0.02, num_iters=2), g['cheap_2'])
+  close(oracle.conv_sc_dictionary_update(x, phi, a, st, pad, None, stepsize=0.05), g['steepest_1'])
+  close(oracle.conv_sc_dictionary_update(x, phi, a, st, pad, None, stepsize=0.05, normalize_dictionary=False),
+        g['steepest_unnormalized'])
+  g2 = load_golden('conv_two_channel')
+  x, phi, st, pad, _, _ = conv_args(g2)
+  close(oracle.conv_sc_dictionary_update(x, phi, g2['fista'], st, pad, g2['hessian_diagonal'], stepsize=0.05),
+        g2['cheap_1'])
+
+
+def test_conv_training_matches_reference_trainer():
+  """Three batches of the unmodified train_dictionary in convolutional mode (reference tests/sparse_coding_4.py)."""
+  g = load_golden('conv_training_small')
+  pad = tuple(tuple(int(v) for v in row) for row in g['padding'])
+  for variant, rule, key in (('ista', 'cheap', 'ista_cheap'), ('fista', 'steepest', 'fista_steepest')):
+    phi = g['dictionary'].clone()
+    h = torch.zeros(phi.size(0))
+    for x in g['batches']:
+      codes = oracle.conv_ista_fista(x, phi, (8, 8), pad, 0.05, 15, variant=variant)
+      if rule == 'cheap':
+        h = oracle.conv_hessian_running_mean(h, codes)
+        phi = oracle.conv_sc_dictionary_update(x, phi, codes, (8, 8), pad, h, stepsize=0.05)
+      else:
+        phi = oracle.conv_sc_dictionary_update(x, phi, codes, (8, 8), pad, None, stepsize=0.05)
+    close(phi, g[key], 1e-5)
+
+
+def test_conv_padding_helpers():
+  assert oracle.get_padding_amt(512, 16, 8) == (8, 8)
+  assert oracle.get_padding_amt(21, 8, 4) == (4, 7)
+  assert oracle.code_dim_from_padded_img_dim(528, 16, 8) == 65
+  x, pad = oracle.synthetic_padded_images(2, 1, 40, 48, (16, 16), (8, 8))
+  assert tuple(x.shape) == (2, 1, 56, 64) and pad == ((8, 8), (8, 8))
+  assert float(x[:, :, :8].abs().max()) == 0.0 and float(x[:, :, :, -8:].abs().max()) == 0.0
