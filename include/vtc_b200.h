@@ -174,6 +174,62 @@ int vtc_gather_cols(const float* src, int64_t ld_src, const int32_t* index, int6
 int vtc_scatter_add_cols(const float* src, int64_t ld_src, const int32_t* index, int64_t B, int64_t n_slots,
                          float* dst, int64_t ld_dst, int64_t S, vtc_stream_t stream);
 
+/*
+ * ---- Convolutional sparse coding (BASELINE.json configs[4]) ----
+ *
+ * ISTA / FISTA code inference with strided convolutional synthesis. Replaces
+ * analysis_transforms/convolutional/ista_fista.py:17-197 (run):
+ *   codes <- prox(y - eta * conv2d(mask * (conv_transpose2d(y, dictionary, stride) - images_padded), dictionary, stride))
+ * with eta = 1 / lambda_max of the Gram matrix of the flattened kernels (:104-113) and mask = create_mask
+ * (utils/convolutions.py:17-24). The strided convolutions run as tcgen05 GEMMs over stride-sized image blocks (the
+ * (KH/SY)*(KW/SX) kernel taps are row shifts of the same operand), the fused epilogues are those of vtc_fista_fc.
+ *
+ *   images_padded (B, C, H, W) float32 dense  -- never written; H - KH and W - KW must be multiples of the stride
+ *   dictionary    (S, C, KH, KW) float32 dense -- never written; KH % SY == 0 and KW % SX == 0 (else VTC_ERR_UNSUPPORTED)
+ *   initial_codes (B, S, SH, SW) or NULL, codes_out (B, S, SH, SW), SH = (H - KH) / SY + 1, SW = (W - KW) / SX + 1
+ *   pad_*: rows / columns of the padded border whose reconstruction error is ignored (padding_dims of the reference)
+ *   early_stopping_epsilon, iters_run, lipschitz_out: as vtc_fista_fc.
+ */
+size_t vtc_fista_conv_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t S, int64_t KH, int64_t KW,
+                                      int64_t SY, int64_t SX, int precision);
+int vtc_fista_conv(const float* images_padded, const float* dictionary, const float* initial_codes, float* codes_out,
+                   int64_t B, int64_t C, int64_t H, int64_t W, int64_t S, int64_t KH, int64_t KW, int64_t SY,
+                   int64_t SX, int pad_top, int pad_bottom, int pad_left, int pad_right, float sparsity_weight,
+                   int num_iters, int variant, int nonnegative_only, int hard_threshold,
+                   float early_stopping_epsilon, int precision, void* workspace, size_t workspace_bytes,
+                   int* iters_run, float* lipschitz_out, vtc_stream_t stream);
+
+/*
+ * Convolutional dictionary gradient, summed over the batch and NOT divided by it, in dictionary layout (S, C, KH, KW):
+ *   conv2d((mask * (conv_transpose2d(codes, dictionary) - images_padded))^T, codes^T, dilation = stride)^T
+ * (dict_update_rules/convolutional/sc_cheap_quadratic_descent.py:65-71, sc_steepest_descent.py:59-65). Separate from
+ * the apply step so that a data-parallel caller can all-reduce grad_sum in between.
+ */
+size_t vtc_conv_dict_grad_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t S, int64_t KH,
+                                          int64_t KW, int64_t SY, int64_t SX, int precision);
+int vtc_sc_conv_dict_grad(const float* images_padded, const float* dictionary, const float* codes, float* grad_sum,
+                          int64_t B, int64_t C, int64_t H, int64_t W, int64_t S, int64_t KH, int64_t KW, int64_t SY,
+                          int64_t SX, int pad_top, int pad_bottom, int pad_left, int pad_right, int precision,
+                          void* workspace, size_t workspace_bytes, vtc_stream_t stream);
+
+/*
+ * Apply step, in place on `dictionary` (S, per_kernel = C*KH*KW):
+ *   U = grad_sum / batch_global; if hessian_diagonal: U /= (h + lowest_code_val); U *= ||dictionary|| / ||U||;
+ *   dictionary -= stepsize * U; if normalize: every kernel divided by its L2 norm.
+ * convolutional/sc_cheap_quadratic_descent.py:72-79; hessian_diagonal == NULL gives sc_steepest_descent.py:66-72.
+ */
+int vtc_sc_conv_dict_apply(float* dictionary, const float* grad_sum, const float* hessian_diagonal, int64_t S,
+                           int64_t per_kernel, int64_t batch_global, float stepsize, float lowest_code_val,
+                           int normalize, vtc_stream_t stream);
+
+/*
+ * Hessian-diagonal running average of the convolutional trainer (training/sparse_coding.py:158-161):
+ *   h <- 0.99 * h + mean_over_images(sum_over_positions(codes^2)) / 100.
+ * codes (B, S, positions); code_sq_sum (S,) receives the sum over this shard's images and positions.
+ */
+int vtc_conv_hessian_diag_update(const float* codes, int64_t B, int64_t S, int64_t positions, int64_t batch_global,
+                                 float* code_sq_sum, float* hessian_diagonal, int apply_ema, vtc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

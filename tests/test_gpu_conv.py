@@ -1,0 +1,209 @@
+"""
+Parity of the convolutional CUDA path (drop-in modules -> ctypes -> C ABI) with outputs of the reference
+(tests/golden/conv_*.npz, made by make_golden.py from /root/reference) and with the CPU oracle on seeded inputs.
+Same tolerances as the fully-connected path: relative L2 <= 1e-4 on codes (bf16x3 arithmetic), 1e-5 on dictionaries.
+"""
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import vtc_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+CODE_TOL = 1e-4
+DICT_TOL = 1e-5
+
+
+@pytest.fixture(autouse=True)
+def default_precision():
+  import vision_transform_codes_b200 as pkg
+  saved = (pkg.config.precision, pkg.config.update_precision)
+  pkg.config.precision, pkg.config.update_precision = 'bf16x3', 'bf16x6'
+  yield
+  pkg.config.precision, pkg.config.update_precision = saved
+
+
+def modules():
+  from vision_transform_codes_b200.analysis_transforms.convolutional import ista_fista
+  from vision_transform_codes_b200.dict_update_rules.convolutional import sc_cheap_quadratic_descent, sc_steepest_descent
+  return ista_fista, sc_cheap_quadratic_descent, sc_steepest_descent
+
+
+def conv_args(g):
+  stride = tuple(int(v) for v in g['stride'])
+  padding = tuple(tuple(int(v) for v in row) for row in g['padding'])
+  return g['images_padded'], g['dictionary'], stride, padding, g['sparsity_weight'], g['num_iters']
+
+
+def check(got, want, tol=CODE_TOL, band=1e-4):
+  got = got.cpu()
+  assert got.shape == want.shape and got.dtype == torch.float32
+  assert torch.isfinite(got).all()
+  err = oracle.relative_l2(got, want)
+  assert err <= tol, err
+  if band is not None:
+    flips, outside = oracle.support_mismatches(got, want, band=band)
+    assert outside == 0, (flips, outside)
+  return err
+
+
+def test_conv_inference_call_matrix_against_reference_outputs():
+  """The call matrix of the reference's tests/ista_fista_2.py."""
+  ista_fista = modules()[0]
+  g = load_golden('conv_small')
+  x, phi, st, pad, lam, T = conv_args(g)
+  xd, pd = x.cuda(), phi.cuda()
+  keep_x, keep_p = xd.clone(), pd.clone()
+  check(ista_fista.run(xd, pd, st, pad, lam, T, variant='fista'), g['fista'])
+  check(ista_fista.run(xd, pd, st, pad, lam, T, variant='ista'), g['ista'])
+  check(ista_fista.run(xd, g['plain_dictionary'].cuda(), st, pad, lam, T, variant='ista'), g['ista_plain'])
+  check(ista_fista.run(xd, pd, st, pad, lam, T, nonnegative_only=True), g['fista_nonneg'])
+  got = ista_fista.run(xd, pd, st, pad, lam, T, variant='ista', nonnegative_only=True, hard_threshold=True)
+  err = check(got, g['ista_hard_nonneg'], tol=8e-2, band=None)  # discontinuous prox: ties move whole coefficients
+  flips, _ = oracle.support_mismatches(got.cpu(), g['ista_hard_nonneg'])
+  assert flips <= 0.005 * got.numel(), (flips, err)
+  check(ista_fista.run(xd, pd, st, pad, lam, 500, variant='ista', early_stopping_epsilon=1e-3), g['ista_early'],
+        tol=2e-3, band=None)
+  warm = g['warm_start'].cuda()
+  keep_w = warm.clone()
+  out = ista_fista.run(xd, pd, st, pad, lam, T, initial_codes=warm)
+  check(out, g['fista_warm'])
+  # the reference's own assertions (tests/ista_fista_2.py:56-68): nothing passed in is mutated
+  assert torch.equal(xd, keep_x) and torch.equal(pd, keep_p) and torch.equal(warm, keep_w)
+  assert not torch.allclose(out, warm)
+
+
+def test_conv_two_channels_rectangular_kernels():
+  ista_fista, cheap, _ = modules()
+  g = load_golden('conv_two_channel')
+  x, phi, st, pad, lam, T = conv_args(g)
+  check(ista_fista.run(x.cuda(), phi.cuda(), st, pad, lam, T), g['fista'])
+  d = phi.cuda()
+  cheap.run(x.cuda(), d, g['fista'].cuda(), g['hessian_diagonal'].cuda(), st, pad, stepsize=0.05)
+  assert oracle.relative_l2(d.cpu(), g['cheap_1']) < DICT_TOL
+
+
+def test_conv_dictionary_updates_against_reference_outputs():
+  _, cheap, steepest = modules()
+  g = load_golden('conv_small')
+  x, phi, st, pad, _, _ = conv_args(g)
+  xd, a, h = x.cuda(), g['fista'].cuda(), g['hessian_diagonal'].cuda()
+  keep = (xd.clone(), a.clone(), h.clone())
+
+  def updated(fn, *args, **kw):
+    d = phi.cuda()
+    assert fn(xd, d, a, *args, **kw) is None  # in place, returns None
+    return d.cpu()
+
+  assert oracle.relative_l2(updated(cheap.run, h, st, pad, stepsize=0.05), g['cheap_1']) < DICT_TOL
+  assert oracle.relative_l2(updated(cheap.run, h, st, pad, stepsize=0.02, num_iters=2), g['cheap_2']) < 2 * DICT_TOL
+  assert oracle.relative_l2(updated(steepest.run, st, pad, stepsize=0.05), g['steepest_1']) < DICT_TOL
+  assert oracle.relative_l2(updated(steepest.run, st, pad, stepsize=0.05, normalize_dictionary=False),
+                            g['steepest_unnormalized']) < DICT_TOL
+  assert torch.equal(xd, keep[0]) and torch.equal(a, keep[1]) and torch.equal(h, keep[2])
+
+
+def test_conv_hessian_running_mean():
+  from vision_transform_codes_b200.dict_update_rules.convolutional import _common
+  g = load_golden('conv_small')
+  h = torch.zeros(g['fista'].size(1), device='cuda')
+  _common.hessian_running_mean(h, g['fista'].cuda())
+  assert oracle.relative_l2(h.cpu(), g['hessian_diagonal']) < 1e-6
+  h2 = oracle.conv_hessian_running_mean(g['hessian_diagonal'], g['ista'])
+  _common.hessian_running_mean(h, g['ista'].cuda())
+  assert oracle.relative_l2(h.cpu(), h2) < 1e-6
+
+
+def test_conv_training_matches_reference_trainer():
+  """Three batches of train_dictionary in convolutional mode (reference tests/sparse_coding_4.py) through the drop-ins."""
+  from vision_transform_codes_b200.dict_update_rules.convolutional import _common
+  ista_fista, cheap, steepest = modules()
+  g = load_golden('conv_training_small')
+  pad = tuple(tuple(int(v) for v in row) for row in g['padding'])
+  for variant, rule, key in (('ista', 'cheap', 'ista_cheap'), ('fista', 'steepest', 'fista_steepest')):
+    phi = g['dictionary'].cuda()
+    h = torch.zeros(phi.size(0), device='cuda')
+    for x in g['batches']:
+      x = x.cuda()
+      codes = ista_fista.run(x, phi, (8, 8), pad, 0.05, 15, variant=variant)
+      if rule == 'cheap':
+        _common.hessian_running_mean(h, codes)
+        cheap.run(x, phi, codes, h, (8, 8), pad, stepsize=0.05)
+      else:
+        steepest.run(x, phi, codes, (8, 8), pad, stepsize=0.05)
+    assert oracle.relative_l2(phi.cpu(), g[key]) < 5e-5, key
+
+
+@pytest.mark.parametrize('shape', [
+    # (images, channels, height, width, kernels, kernel, stride)
+    (2, 1, 64, 64, 64, (16, 16), (8, 8)),      # BASELINE configs[4] family: 64 filters of 16x16 at stride 8
+    (3, 3, 30, 44, 20, (12, 8), (4, 4)),       # colour, 3x2 taps
+    (1, 1, 40, 40, 16, (8, 8), (8, 8)),        # stride = kernel: no overlap (a single tap)
+    (5, 2, 17, 23, 33, (6, 9), (2, 3)),        # 3x3 taps, sizes that need trailing padding
+])
+def test_conv_against_oracle_on_seeded_images(shape):
+  ista_fista, cheap, _ = modules()
+  b, c, h, w, s, k, st = shape
+  x, pad = oracle.synthetic_padded_images(b, c, h, w, k, st)
+  phi = oracle.synthetic_conv_dictionary(s, c, k[0], k[1])
+  if pad[0][1] == 0 or pad[1][1] == 0:
+    # a trailing padding of 0 makes the reference's create_mask zero everywhere (``mask[..., -0:] = 0``): all codes
+    # stay zero, here as there; "no padding" is padding_dims=None
+    assert float(oracle.conv_ista_fista(x, phi, st, pad, 0.05, 5).abs().max()) == 0.0
+    assert float(ista_fista.run(x.cuda(), phi.cuda(), st, pad, 0.05, 5).abs().max()) == 0.0
+    pad = None
+  want = oracle.conv_ista_fista(x, phi, st, pad, 0.05, 30)
+  got = ista_fista.run(x.cuda(), phi.cuda(), st, pad, 0.05, 30)
+  check(got, want)
+  hd = oracle.conv_hessian_running_mean(torch.zeros(s), want)
+  want_phi = oracle.conv_sc_dictionary_update(x, phi, want, st, pad, hd, stepsize=0.05)
+  d = phi.cuda()
+  cheap.run(x.cuda(), d, want.cuda(), hd.cuda(), st, pad, stepsize=0.05)
+  assert oracle.relative_l2(d.cpu(), want_phi) < DICT_TOL
+
+
+def test_conv_known_answer_without_overlap():
+  """stride = kernel size and orthonormal kernels: the convolutional code is the fully-connected code of every block,
+  a = soft(<block, kernel>, lambda) after any number of iterations (step size 1)."""
+  ista_fista = modules()[0]
+  torch.manual_seed(4)
+  q, _ = torch.linalg.qr(torch.randn(16, 16))
+  phi = q.reshape(16, 1, 4, 4).contiguous()
+  x = 0.5 * torch.randn(3, 1, 12, 20)
+  blocks = x.unfold(2, 4, 4).unfold(3, 4, 4).reshape(3, 3, 5, 16)          # (b, i, j, pixels)
+  want = oracle.threshold(torch.einsum('bijp,sp->bsij', blocks, q), 0.1)
+  for variant in ('ista', 'fista'):
+    got = ista_fista.run(x.cuda(), phi.cuda(), (4, 4), None, 0.1, 4, variant=variant).cpu()
+    assert (got - want).abs().max() < 3e-5
+
+
+def test_conv_error_behaviour():
+  ista_fista = modules()[0]
+  x = torch.zeros(1, 1, 32, 32).cuda()
+  phi = oracle.synthetic_conv_dictionary(8, 1, 16, 16).cuda()
+  pad = ((8, 8), (8, 8))
+  with pytest.raises(AssertionError):
+    ista_fista.run(x, phi, (8, 8), pad, 0.1, 3, variant='lista')
+  with pytest.raises(UnboundLocalError):
+    ista_fista.run(x, phi, (8, 8), pad, 0.1, 0)
+  with pytest.raises(NotImplementedError):
+    # kernel not a multiple of the stride: not on the GEMM path
+    ista_fista.run(torch.zeros(1, 1, 31, 31).cuda(), phi, (5, 5), pad, 0.1, 3)
+  with pytest.raises(RuntimeError):
+    ista_fista.run(torch.zeros(1, 1, 35, 32).cuda(), phi, (8, 8), pad, 0.1, 3)
+  bad = phi.clone()
+  bad[2, 0, 3, 3] = float('inf')
+  with pytest.raises(RuntimeError):
+    ista_fista.run(x, bad, (8, 8), pad, 0.1, 3)
+
+
+def test_conv_determinism_and_image_shard_independence():
+  """What sharding a batch of images over GPUs relies on: every image's code depends on that image only."""
+  ista_fista = modules()[0]
+  x, pad = oracle.synthetic_padded_images(6, 1, 96, 96, (16, 16), (8, 8))
+  phi = oracle.synthetic_conv_dictionary(64, 1, 16, 16).cuda()
+  xd = x.cuda()
+  a = ista_fista.run(xd, phi, (8, 8), pad, 0.05, 40)
+  assert torch.equal(a, ista_fista.run(xd, phi, (8, 8), pad, 0.05, 40))
+  assert torch.equal(a[3:], ista_fista.run(xd[3:], phi, (8, 8), pad, 0.05, 40))

@@ -43,6 +43,13 @@ SIGNATURES = {
     'vtc_gather_rows': (_int, [_ptr, _i64, _ptr, _i64, _i64, _ptr, _ptr]),
     'vtc_gather_cols': (_int, [_ptr, _i64, _ptr, _i64, _i64, _ptr, _i64, _ptr]),
     'vtc_scatter_add_cols': (_int, [_ptr, _i64, _ptr, _i64, _i64, _ptr, _i64, _i64, _ptr]),
+    'vtc_fista_conv_workspace_bytes': (_size, [_i64] * 9 + [_int]),
+    'vtc_fista_conv': (_int, [_ptr, _ptr, _ptr, _ptr] + [_i64] * 9 + [_int] * 4 + [_f32, _int, _int, _int, _int, _f32,
+                              _int, _ptr, _size, _c.POINTER(_int), _c.POINTER(_f32), _ptr]),
+    'vtc_conv_dict_grad_workspace_bytes': (_size, [_i64] * 9 + [_int]),
+    'vtc_sc_conv_dict_grad': (_int, [_ptr, _ptr, _ptr, _ptr] + [_i64] * 9 + [_int] * 4 + [_int, _ptr, _size, _ptr]),
+    'vtc_sc_conv_dict_apply': (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _f32, _f32, _int, _ptr]),
+    'vtc_conv_hessian_diag_update': (_int, [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _int, _ptr]),
 }
 
 _lib = None

@@ -339,4 +339,183 @@ __global__ void scatter_add_cols_kernel(const float* __restrict__ src, int64_t l
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Convolutional path (vtc_fista_conv): a strided convolution whose kernel is (ty x tx) strides large is a GEMM over
+// "image blocks". Rows of every internal matrix are (image, i, j) on a grid of gh x gw stride-sized blocks; columns are
+// either the S code channels or the db = c * sy * sx pixels (channel, dy, dx) of one block.
+struct ConvGeom {
+  int b, c, h, w;        // padded images
+  int s, kh, kw;         // kernels
+  int sy, sx, ty, tx;    // stride; kernel extent in strides (kh / sy, kw / sx)
+  int gh, gw;            // grid of blocks: h / sy, w / sx
+  int ch, cw;            // code grid: gh - ty + 1, gw - tx + 1
+  int db;                // pixels per block: c * sy * sx
+};
+
+// images (b, c, h, w) -> blocks (b*gh*gw x db, pitch ld)
+__global__ void conv_image_to_blocks_kernel(const float* __restrict__ img, ConvGeom g, float* __restrict__ out,
+                                            int64_t ld) {
+  const int64_t rows = static_cast<int64_t>(g.b) * g.gh * g.gw;
+  const int64_t total = rows * g.db;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / g.db;
+    const int pix = static_cast<int>(i - row * g.db);
+    const int dx = pix % g.sx, dy = (pix / g.sx) % g.sy, ch = pix / (g.sx * g.sy);
+    const int gj = static_cast<int>(row % g.gw), gi = static_cast<int>((row / g.gw) % g.gh);
+    const int64_t bi = row / (static_cast<int64_t>(g.gw) * g.gh);
+    out[row * ld + pix] = img[((bi * g.c + ch) * g.h + gi * g.sy + dy) * g.w + gj * g.sx + dx];
+  }
+}
+
+// codes (b, s, ch, cw) -> grid layout (b*gh*gw x s, pitch ld); rows outside the code grid are zero
+__global__ void conv_codes_to_grid_kernel(const float* __restrict__ codes, ConvGeom g, float* __restrict__ out,
+                                          int64_t ld) {
+  const int64_t rows = static_cast<int64_t>(g.b) * g.gh * g.gw;
+  const int64_t total = rows * g.s;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    // consecutive threads walk the source's fastest axis (j) so that the read is coalesced
+    const int gj = static_cast<int>(i % g.gw);
+    const int gi = static_cast<int>((i / g.gw) % g.gh);
+    const int sc = static_cast<int>((i / (static_cast<int64_t>(g.gw) * g.gh)) % g.s);
+    const int64_t bi = i / (static_cast<int64_t>(g.gw) * g.gh * g.s);
+    const int64_t row = (bi * g.gh + gi) * g.gw + gj;
+    float v = 0.f;
+    if (gi < g.ch && gj < g.cw) v = codes[((bi * g.s + sc) * g.ch + gi) * g.cw + gj];
+    out[row * ld + sc] = v;
+  }
+}
+
+// grid layout (row-major, pitch ld) -> codes (b, s, ch, cw)
+__global__ void conv_grid_to_codes_kernel(const float* __restrict__ grid, int64_t ld, ConvGeom g,
+                                          float* __restrict__ codes) {
+  const int64_t total = static_cast<int64_t>(g.b) * g.s * g.ch * g.cw;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cj = static_cast<int>(i % g.cw);
+    const int ci = static_cast<int>((i / g.cw) % g.ch);
+    const int sc = static_cast<int>((i / (static_cast<int64_t>(g.cw) * g.ch)) % g.s);
+    const int64_t bi = i / (static_cast<int64_t>(g.cw) * g.ch * g.s);
+    codes[i] = grid[((bi * g.gh + ci) * g.gw + cj) * ld + sc];
+  }
+}
+
+// dictionary (s, c, kh, kw) -> the two B operands, each as bf16 parts with the taps q = (qy, qx) side by side along K:
+//   analysis  (s  x nparts * nq*dbp):  [sc][part][q * dbp + pix] = Phi[sc, ch, qy*sy+dy, qx*sx+dx]
+//   synthesis (db x nparts * nq*sp ):  [pix][part][q * sp + sc]  = the same value
+// (pix = (ch*sy + dy)*sx + dx). Both buffers are zeroed by the caller (padding columns stay zero).
+__global__ void conv_dict_operands_kernel(const float* __restrict__ dict, ConvGeom g, int nparts, int64_t dbp, int64_t sp,
+                                          __nv_bfloat16* __restrict__ analysis, __nv_bfloat16* __restrict__ synthesis) {
+  const int64_t per_kernel = static_cast<int64_t>(g.c) * g.kh * g.kw;
+  const int64_t total = g.s * per_kernel;
+  const int nq = g.ty * g.tx;
+  const int64_t ka = nq * dbp, ks = nq * sp;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t sc = i / per_kernel;
+    const int e = static_cast<int>(i - sc * per_kernel);
+    const int v_ = e % g.kw, u_ = (e / g.kw) % g.kh, ch = e / (g.kw * g.kh);
+    const int q = (u_ / g.sy) * g.tx + v_ / g.sx;
+    const int pix = (ch * g.sy + u_ % g.sy) * g.sx + v_ % g.sx;
+    float v = dict[i];
+    for (int p = 0; p < nparts; ++p) {
+      const __nv_bfloat16 hpart = __float2bfloat16_rn(v);
+      v = __fsub_rn(v, __bfloat162float(hpart));
+      analysis[sc * (nparts * ka) + p * ka + q * dbp + pix] = hpart;
+      synthesis[static_cast<int64_t>(pix) * (nparts * ks) + p * ks + q * sp + sc] = hpart;
+    }
+  }
+}
+
+// per-tap gradient blocks (nq matrices of s x ld, tap q = rows of codes^T against blocks shifted by tap q)
+//   -> gradient in dictionary layout (s, c, kh, kw)
+__global__ void conv_grad_to_dict_layout_kernel(const float* __restrict__ taps, int64_t tap_stride, int64_t ld,
+                                                ConvGeom g, float* __restrict__ grad) {
+  const int64_t per_kernel = static_cast<int64_t>(g.c) * g.kh * g.kw;
+  const int64_t total = g.s * per_kernel;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t sc = i / per_kernel;
+    const int e = static_cast<int>(i - sc * per_kernel);
+    const int v_ = e % g.kw, u_ = (e / g.kw) % g.kh, ch = e / (g.kw * g.kh);
+    const int q = (u_ / g.sy) * g.tx + v_ / g.sx;
+    const int pix = (ch * g.sy + u_ % g.sy) * g.sx + v_ % g.sx;
+    grad[i] = taps[q * tap_stride + sc * ld + pix];
+  }
+}
+
+// sum over images and positions of codes^2 per channel: codes (b, s, n) -> out (s,)   (training/sparse_coding.py:158-161)
+__global__ void conv_channel_sq_sum_kernel(const float* __restrict__ codes, int64_t b, int64_t s, int64_t n,
+                                           float* __restrict__ out) {
+  __shared__ double red[256];
+  const int64_t sc = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t bi = 0; bi < b; ++bi) {
+    const float* src = codes + (bi * s + sc) * n;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += static_cast<double>(src[i]) * src[i];
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[sc] = static_cast<float>(red[0]);
+}
+
+// Convolutional dictionary apply step, in place (dict_update_rules/convolutional/sc_cheap_quadratic_descent.py:72-79,
+// sc_steepest_descent.py:66-72):  U = grad_sum / batch;  U /= (h + lowest) if h;  U *= ||Phi|| / ||U||  (Frobenius norms
+// over the whole dictionary);  Phi -= stepsize * U;  every kernel divided by its own norm if normalize.
+// One block (the dictionary is a few thousand to a few hundred thousand floats); reductions in double, fixed order.
+__global__ void conv_dict_apply_kernel(float* __restrict__ dict, const float* __restrict__ grad_sum,
+                                       const float* __restrict__ hessian, int64_t s, int64_t per_kernel, float batch,
+                                       float stepsize, float lowest, int normalize) {
+  __shared__ double red[1024];
+  __shared__ double total_phi, total_u;
+  const int64_t total = s * per_kernel;
+  auto block_sum = [&](double v) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+  };
+  auto update_of = [&](int64_t i) {
+    float u = grad_sum[i] / batch;
+    if (hessian != nullptr) u = u / (hessian[i / per_kernel] + lowest);
+    return u;
+  };
+  double a = 0.0, b = 0.0;
+  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const float u = update_of(i);
+    a += static_cast<double>(dict[i]) * dict[i];
+    b += static_cast<double>(u) * u;
+  }
+  const double sp = block_sum(a), su = block_sum(b);
+  if (threadIdx.x == 0) total_phi = sp, total_u = su;
+  __syncthreads();
+  const float scale = static_cast<float>(sqrt(total_phi)) / static_cast<float>(sqrt(total_u));
+  for (int64_t i = threadIdx.x; i < total; i += blockDim.x)
+    dict[i] = __fsub_rn(dict[i], __fmul_rn(stepsize, __fmul_rn(update_of(i), scale)));
+  __syncthreads();
+  if (normalize) {
+    // one warp per kernel at a time
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int64_t sc = warp; sc < s; sc += nwarps) {
+      float* row = dict + sc * per_kernel;
+      double acc = 0.0;
+      for (int64_t i = lane; i < per_kernel; i += 32) acc += static_cast<double>(row[i]) * row[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const float nrm = static_cast<float>(sqrt(acc));
+      for (int64_t i = lane; i < per_kernel; i += 32) row[i] = row[i] / nrm;
+    }
+  }
+}
+
 }  // namespace vtc

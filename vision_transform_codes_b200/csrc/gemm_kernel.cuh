@@ -40,6 +40,7 @@ constexpr int BLOCK_N = 256;        // default UMMA N (a kernel template paramet
 constexpr int UMMA_K = 16;
 constexpr int EPI_COLS = 16;        // epilogue sub-tile width (fp32 columns)
 constexpr int MAX_PARTS = 3;
+constexpr int MAX_SEGMENTS = 16;     // kernel taps per image in units of the stride (e.g. 16x16 kernel, stride 8: 4)
 constexpr int NUM_MATH_GROUPS = 2;   // groups of four warps (one per TMEM lane quarter) taking sub-tiles round-robin
                                     // (three groups measured no faster: the fused launch is not issue-bound)
 constexpr int NUM_MATH_WARPS = 4 * NUM_MATH_GROUPS;
@@ -132,6 +133,17 @@ struct GemmParams {
   int a_blocks_per_part;      // blocked A: column blocks per part
   int parts_block_w;          // blocked parts output: block width (the consumer's BK) ...
   int parts_blocks_per_part;  // ... and column blocks per part
+  // Segmented K (strided convolutions as GEMMs over image blocks, see vtc_fista_conv): K is nseg segments of seg_kb
+  // K blocks; segment q reads the SAME A matrix (columns (kb % seg_kb) * BK) with its rows shifted by seg_shift[q],
+  // against B columns kb * BK as usual. Rows shifted outside the matrix read as zero (TMA fill). seg_kb = 0: off.
+  int seg_kb;
+  int seg_shift[MAX_SEGMENTS];
+  // Rows are (image, i, j) on a grid_h x grid_w grid of stride-sized image blocks (grid_w = 0: no grid).
+  //   EPI_FISTA: code positions exist for i < code_h, j < code_w; the other rows are padding and stay exactly zero.
+  //   EPI_STORE: columns are (channel, dy, dx) of a blk_sy x blk_sx block; outputs whose pixel (i*sy+dy, j*sx+dx) lies
+  //              outside [pix_y0, pix_y1) x [pix_x0, pix_x1) are forced to zero (utils/convolutions.py:17-24 create_mask).
+  int grid_h, grid_w, code_h, code_w;
+  int blk_sy, blk_sx, pix_y0, pix_y1, pix_x0, pix_x1;
 };
 enum BlockedBits { BLK_IN0 = 1, BLK_OUT = 8, BLK_PARTS = 16, BLK_A = 32 };
 
@@ -393,13 +405,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
           if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
           else mbar_arrive_remote(full_bar(s), 0);
           const uint32_t dst = sOp + s * C::STAGE_BYTES;
+          // segmented K: this K block of A = column block (kb % seg_kb) of the rows shifted by the segment's offset
+          const int kba = p.seg_kb ? kb % p.seg_kb : kb;
+          const int arow = p.seg_kb ? c.m0 + p.seg_shift[kb / p.seg_kb] : c.m0;
 #pragma unroll
           for (int q = 0; q < P; ++q) {
             if (a_blocked)
-              tma_load_3d_pair(dst + q * C::TILE_BYTES, &p.tmA, full_bar(s), 0, c.m0, q * p.a_blocks_per_part + kb,
+              tma_load_3d_pair(dst + q * C::TILE_BYTES, &p.tmA, full_bar(s), 0, arow, q * p.a_blocks_per_part + kba,
                                kEvictNormal);
             else
-              tma_load_2d_pair(dst + q * C::TILE_BYTES, &p.tmA, full_bar(s), q * p.a_part_stride + kb * C::BK, c.m0,
+              tma_load_2d_pair(dst + q * C::TILE_BYTES, &p.tmA, full_bar(s), q * p.a_part_stride + kba * C::BK, arow,
                                kEvictNormal);
           }
 #pragma unroll
@@ -584,11 +599,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
         }
         float outv[16];   // fp32 result
         float partv[16];  // value whose bf16 split is emitted as parts
+        int gi = 0, gj = 0;  // grid position of this thread's row
+        if (p.grid_w > 0) {
+          const int cell = (c.m0 + row) % (p.grid_h * p.grid_w);
+          gi = cell / p.grid_w;
+          gj = cell - gi * p.grid_w;
+          if (EPI == EPI_FISTA && (gi >= p.code_h || gj >= p.code_w)) {
+            // padding row of the code grid: its inputs are zero and stay zero (prox(0) = 0 for every variant)
+#pragma unroll
+            for (int x = 0; x < 16; ++x) v[x] = 0u;
+          }
+        }
         if (EPI == EPI_STORE) {
 #pragma unroll
           for (int x = 0; x < 16; ++x) {
             outv[x] = __uint_as_float(v[x]) - in[0][x];
             partv[x] = outv[x];
+          }
+          if (p.grid_w > 0) {
+            // reconstruction mask: zero outside the un-padded image; column -> (dy, dx) walks incrementally
+            const int col0 = c.n0 + j * EPI_COLS;
+            int dx = col0 % p.blk_sx;
+            int dy = (col0 / p.blk_sx) % p.blk_sy;
+            const int py0 = gi * p.blk_sy, px0 = gj * p.blk_sx;
+#pragma unroll
+            for (int x = 0; x < 16; ++x) {
+              const int py = py0 + dy, px = px0 + dx;
+              if (py < p.pix_y0 || py >= p.pix_y1 || px < p.pix_x0 || px >= p.pix_x1) outv[x] = 0.f, partv[x] = 0.f;
+              if (++dx == p.blk_sx) {
+                dx = 0;
+                if (++dy == p.blk_sy) dy = 0;
+              }
+            }
           }
         } else {
           UpdateArgs ua;

@@ -234,6 +234,11 @@ struct GemmCall {
   const float* scalars = nullptr;
   double* stat = nullptr;
   int max_pairs = 0;     // cap on the SM pairs used (0 = all): concurrent chains share the chip
+  // segmented K and grid masks of the convolutional path (GemmParams has the semantics)
+  int seg_kb = 0, nseg = 0;
+  int seg_shift[MAX_SEGMENTS] = {};
+  int grid_h = 0, grid_w = 0, code_h = 0, code_w = 0;
+  int blk_sy = 1, blk_sx = 1, pix_y0 = 0, pix_y1 = 0, pix_x0 = 0, pix_x1 = 0;
 };
 
 template <int EPI, int P, int NIN, int BN>
@@ -251,7 +256,16 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   p.N = static_cast<int>(c.N);
   p.num_m_blocks = static_cast<int>(ceil_div(c.M, PAIR_M));
   p.num_n_blocks = static_cast<int>(ceil_div(c.N, BN));
-  p.k_blocks = static_cast<int>(ceil_div(c.A.Kp, Cf::BK));  // Kp is a multiple of 64; the padding is zero
+  p.k_blocks = static_cast<int>(ceil_div(c.B.Kp, Cf::BK));  // Kp is a multiple of 64; the padding is zero
+  if (c.nseg > 0) {
+    // A holds one segment's columns; B holds all nseg segments side by side
+    p.seg_kb = static_cast<int>(c.A.Kp / Cf::BK);
+    if (c.nseg > MAX_SEGMENTS || c.B.Kp != c.A.Kp * c.nseg) return fail(VTC_ERR_ARG, "bad K segmentation");
+    for (int i = 0; i < c.nseg; ++i) p.seg_shift[i] = c.seg_shift[i];
+  }
+  p.grid_h = c.grid_h, p.grid_w = c.grid_w, p.code_h = c.code_h, p.code_w = c.code_w;
+  p.blk_sy = c.blk_sy, p.blk_sx = c.blk_sx;
+  p.pix_y0 = c.pix_y0, p.pix_y1 = c.pix_y1, p.pix_x0 = c.pix_x0, p.pix_x1 = c.pix_x1;
   p.a_part_stride = static_cast<int>(c.A.Kp);
   p.b_part_stride = static_cast<int>(c.B.Kp);
   p.out_part_stride = static_cast<int>(c.parts_out.Kp);
@@ -319,7 +333,7 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
   DeviceInfo info;
   TRY(require_sm100(&info));
   if (c.M <= 0 || c.N <= 0 || c.K <= 0) return fail(VTC_ERR_ARG, "empty GEMM %lld x %lld x %lld", (long long)c.M, (long long)c.N, (long long)c.K);
-  if (c.A.K != c.K || c.B.K != c.K || c.A.Kp != c.B.Kp) return fail(VTC_ERR_ARG, "operand K mismatch");
+  if (c.nseg == 0 && (c.A.K != c.K || c.B.K != c.K || c.A.Kp != c.B.Kp)) return fail(VTC_ERR_ARG, "operand K mismatch");
   const int P = parts_for(c.precision);
   if (c.A.parts < P || c.B.parts < P) return fail(VTC_ERR_ARG, "operand has too few bf16 parts for precision %d", c.precision);
   if (c.n_parts > MAX_PARTS || (c.n_parts && c.parts_out.parts < c.n_parts)) return fail(VTC_ERR_ARG, "bad parts output");
@@ -330,6 +344,15 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     if (nin > 1) return fail(VTC_ERR_ARG, "EPI_STORE takes at most one epilogue input");
     // (a 128-wide tile variant, Cfg<.., 128>, fills the 74 SM pairs better for N = 256 -- 512 instead of 256 tiles --
     //  but measured 10-15 % slower: the A panel is staged twice and the N = 128 MMA is shared-memory bound)
+    // narrow outputs (the convolutional path: N = code channels or pixels per block) take the 128-wide tile so that
+    // fewer MMA columns are spent on zero padding
+    if (c.N <= 128 && c.nseg > 0) {
+      switch (P) {
+        case 1: return launch_gemm_p<EPI_STORE, 1, 1, 128>(c, info, stream);
+        case 2: return launch_gemm_p<EPI_STORE, 2, 1, 128>(c, info, stream);
+        default: return launch_gemm_p<EPI_STORE, 3, 1, 128>(c, info, stream);
+      }
+    }
     switch (P) {
       case 1: return launch_gemm_p<EPI_STORE, 1, 1, 256>(c, info, stream);
       case 2: return launch_gemm_p<EPI_STORE, 2, 1, 256>(c, info, stream);
@@ -337,6 +360,13 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     }
   }
   if (nin <= 2) {
+    if (c.N <= 128 && c.nseg > 0) {
+      switch (P) {
+        case 1: return launch_gemm_p<EPI_FISTA, 1, 2, 128>(c, info, stream);
+        case 2: return launch_gemm_p<EPI_FISTA, 2, 2, 128>(c, info, stream);
+        default: return launch_gemm_p<EPI_FISTA, 3, 2, 128>(c, info, stream);
+      }
+    }
     switch (P) {
       case 1: return launch_gemm_p<EPI_FISTA, 1, 2, 256>(c, info, stream);
       case 2: return launch_gemm_p<EPI_FISTA, 2, 2, 256>(c, info, stream);
@@ -1321,6 +1351,371 @@ int vtc_scatter_add_cols(const float* src, int64_t ld_src, const int32_t* index,
   scatter_add_cols_kernel<<<grid_for(B * n_slots, 256, info.sm_count), 256, 0, st>>>(src, ld_src, index, B, n_slots,
                                                                                       dst, ld_dst);
   COUNT_LAUNCH();
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+}  // extern "C"
+
+// ================================================================================================ convolutional path
+namespace {
+
+struct ConvShape {
+  ConvGeom g;
+  int64_t rows;          // b * gh * gw
+  int nq;                // kernel taps in units of the stride: ty * tx
+  int pad_t, pad_b, pad_l, pad_r;
+  int64_t per_kernel;    // c * kh * kw
+};
+
+int conv_shape(int64_t B, int64_t C, int64_t H, int64_t W, int64_t S, int64_t KH, int64_t KW, int64_t SY, int64_t SX,
+               int pad_t, int pad_b, int pad_l, int pad_r, ConvShape* out) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || S <= 0 || KH <= 0 || KW <= 0 || SY <= 0 || SX <= 0)
+    return fail(VTC_ERR_ARG, "convolutional path: bad shape");
+  if (KH % SY != 0 || KW % SX != 0)
+    return fail(VTC_ERR_UNSUPPORTED, "convolutional path: the kernel size (%lld x %lld) must be a multiple of the stride (%lld x %lld)",
+                (long long)KH, (long long)KW, (long long)SY, (long long)SX);
+  if (H < KH || W < KW || (H - KH) % SY != 0 || (W - KW) % SX != 0)
+    return fail(VTC_ERR_ARG, "convolutional path: padded image (%lld x %lld) is not kernel + a whole number of strides "
+                "(pad it with utils.convolutions.get_padding_amt)", (long long)H, (long long)W);
+  if (pad_t < 0 || pad_b < 0 || pad_l < 0 || pad_r < 0 || pad_t + pad_b > H || pad_l + pad_r > W)
+    return fail(VTC_ERR_ARG, "convolutional path: bad padding");
+  ConvShape& cs = *out;
+  ConvGeom& g = cs.g;
+  g.b = (int)B, g.c = (int)C, g.h = (int)H, g.w = (int)W, g.s = (int)S, g.kh = (int)KH, g.kw = (int)KW;
+  g.sy = (int)SY, g.sx = (int)SX, g.ty = (int)(KH / SY), g.tx = (int)(KW / SX);
+  g.gh = (int)(H / SY), g.gw = (int)(W / SX);
+  g.ch = g.gh - g.ty + 1, g.cw = g.gw - g.tx + 1;
+  g.db = (int)(C * SY * SX);
+  cs.nq = g.ty * g.tx;
+  if (cs.nq > MAX_SEGMENTS) return fail(VTC_ERR_UNSUPPORTED, "convolutional path: at most %d kernel taps per stride cell (kernel / stride), got %d", MAX_SEGMENTS, cs.nq);
+  cs.rows = B * g.gh * g.gw;
+  if (cs.rows > (1ll << 31) - 4096) return fail(VTC_ERR_ARG, "convolutional path: too many grid rows for 32-bit tile coordinates");
+  cs.pad_t = pad_t, cs.pad_b = pad_b, cs.pad_l = pad_l, cs.pad_r = pad_r;
+  cs.per_kernel = C * KH * KW;
+  return VTC_OK;
+}
+
+struct ConvWs {
+  float* scalars;
+  double* stats;
+  LipschitzWs lip;
+  PartsMat phiA_op, phiS_op, yop[2], r_op;
+  float *xblk, *X1, *X2, *init_pad, *out_pad;
+  int64_t ldS, ldD;
+};
+ConvWs carve_conv(Carver& cv, const ConvShape& cs, int precision) {
+  ConvWs w;
+  const ConvGeom& g = cs.g;
+  const int P = parts_for(precision);
+  const int bk = (P == 1) ? 64 : 32;
+  const int64_t Sp = round_up(g.s, 64), Dbp = round_up(g.db, 64);
+  w.scalars = static_cast<float*>(cv.take(64));
+  w.stats = static_cast<double*>(cv.take(8 * 4096));
+  w.lip = carve_lipschitz(cv, cs.per_kernel);
+  w.phiA_op = carve_parts(cv, g.s, cs.nq * Dbp, 3);
+  w.phiS_op = carve_parts(cv, g.db, cs.nq * Sp, 3);
+  w.ldS = round_up(g.s, 4);
+  w.ldD = round_up(g.db, 4);
+  w.xblk = static_cast<float*>(cv.take(static_cast<size_t>(cs.rows) * w.ldD * 4));
+  w.yop[0] = carve_parts(cv, cs.rows, g.s, P, bk);
+  w.yop[1] = carve_parts(cv, cs.rows, g.s, P, bk);
+  w.r_op = carve_parts(cv, cs.rows, g.db, P, bk);
+  const size_t state_blk = static_cast<size_t>(cs.rows) * round_up(g.s, EPI_COLS) * 4;
+  w.X1 = static_cast<float*>(cv.take(state_blk));
+  w.X2 = static_cast<float*>(cv.take(state_blk));
+  w.init_pad = static_cast<float*>(cv.take(static_cast<size_t>(cs.rows) * w.ldS * 4));
+  w.out_pad = static_cast<float*>(cv.take(static_cast<size_t>(cs.rows) * w.ldS * 4));
+  return w;
+}
+
+// the two dictionary operands (analysis: N = code channels, synthesis: N = pixels of a block; taps along K)
+int conv_dictionary_operands(const float* dictionary, const ConvShape& cs, const ConvWs& w, cudaStream_t st) {
+  DeviceInfo info;
+  TRY(device_info(&info));
+  CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.phiA_op.ptr), 0, w.phiA_op.bytes(), st));
+  CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.phiS_op.ptr), 0, w.phiS_op.bytes(), st));
+  conv_dict_operands_kernel<<<grid_for(cs.g.s * cs.per_kernel, 256, info.sm_count), 256, 0, st>>>(
+      dictionary, cs.g, 3, round_up(cs.g.db, 64), round_up(cs.g.s, 64),
+      reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(w.phiA_op.ptr)),
+      reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(w.phiS_op.ptr)));
+  COUNT_LAUNCH();
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+// r = mask * (conv_transpose(y) - x) on the block grid: synthesis contraction over (tap, channel), taps = row shifts
+void conv_synthesis_call(GemmCall& r, const ConvShape& cs, const ConvWs& w, const PartsMat& y, int precision) {
+  const ConvGeom& g = cs.g;
+  r.precision = precision;
+  r.A = y, r.B = w.phiS_op;
+  r.M = cs.rows, r.N = g.db, r.K = static_cast<int64_t>(cs.nq) * g.s;
+  r.nseg = cs.nq;
+  for (int qy = 0; qy < g.ty; ++qy)
+    for (int qx = 0; qx < g.tx; ++qx) r.seg_shift[qy * g.tx + qx] = -(qy * g.gw + qx);
+  r.in[0] = F32Mat{w.xblk, cs.rows, g.db, w.ldD}, r.in_mask = 1;
+  r.grid_h = g.gh, r.grid_w = g.gw;
+  r.blk_sy = g.sy, r.blk_sx = g.sx;
+  r.pix_y0 = cs.pad_t, r.pix_y1 = g.h - cs.pad_b, r.pix_x0 = cs.pad_l, r.pix_x1 = g.w - cs.pad_r;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t vtc_fista_conv_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t S, int64_t KH, int64_t KW,
+                                      int64_t SY, int64_t SX, int precision) {
+  ConvShape cs;
+  if (!valid_precision(precision) || conv_shape(B, C, H, W, S, KH, KW, SY, SX, 0, 0, 0, 0, &cs) != VTC_OK) return 0;
+  Carver cv(nullptr, 0);
+  carve_conv(cv, cs, precision);
+  return cv.off + 2048;
+}
+
+int vtc_fista_conv(const float* images_padded, const float* dictionary, const float* initial_codes, float* codes_out,
+                   int64_t B, int64_t C, int64_t H, int64_t W, int64_t S, int64_t KH, int64_t KW, int64_t SY,
+                   int64_t SX, int pad_top, int pad_bottom, int pad_left, int pad_right, float sparsity_weight,
+                   int num_iters, int variant, int nonnegative_only, int hard_threshold,
+                   float early_stopping_epsilon, int precision, void* workspace, size_t workspace_bytes,
+                   int* iters_run, float* lipschitz_out, vtc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!images_padded || !dictionary || !codes_out) return fail(VTC_ERR_ARG, "vtc_fista_conv: null pointer");
+  if (variant != VTC_VARIANT_ISTA && variant != VTC_VARIANT_FISTA) return fail(VTC_ERR_ARG, "variant must be ista or fista");
+  if (!valid_precision(precision)) return fail(VTC_ERR_ARG, "precision must be 1, 3 or 6");
+  if (num_iters < 1) return fail(VTC_ERR_ARG, "num_iters must be >= 1");
+  ConvShape cs;
+  TRY(conv_shape(B, C, H, W, S, KH, KW, SY, SX, pad_top, pad_bottom, pad_left, pad_right, &cs));
+  const ConvGeom& g = cs.g;
+  DeviceInfo info;
+  TRY(require_sm100(&info));
+  const bool early = early_stopping_epsilon >= 0.f;
+  if (early && num_iters > 4096) return fail(VTC_ERR_UNSUPPORTED, "early stopping supports at most 4096 iterations");
+  Carver cv(workspace, workspace_bytes);
+  ConvWs w = carve_conv(cv, cs, precision);
+  if (!workspace || !cv.fits()) return fail(VTC_ERR_WORKSPACE, "vtc_fista_conv: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
+  const int P = parts_for(precision);
+  const int64_t R = cs.rows;
+
+  // ---- setup: step size from the Gram matrix of the flattened kernels (convolutional/ista_fista.py:104-113),
+  //      dictionary operands, images as blocks, starting point
+  TRY(run_lipschitz(dictionary, S, cs.per_kernel, w.lip, sparsity_weight, w.scalars, nullptr, st));
+  TRY(conv_dictionary_operands(dictionary, cs, w, st));
+  conv_image_to_blocks_kernel<<<grid_for(R * g.db, 256, info.sm_count), 256, 0, st>>>(images_padded, g, w.xblk, w.ldD);
+  COUNT_LAUNCH();
+  CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.r_op.ptr), 0, w.r_op.bytes(), st));
+  CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[1].ptr), 0, w.yop[1].bytes(), st));
+  F32Mat X1{w.X1, R, S, 0, true}, X2{w.X2, R, S, 0, true}, init, final_out{w.out_pad, R, S, w.ldS, false};
+  if (initial_codes) {
+    conv_codes_to_grid_kernel<<<grid_for(R * S, 256, info.sm_count), 256, 0, st>>>(initial_codes, g, w.init_pad, w.ldS);
+    COUNT_LAUNCH();
+    init = F32Mat{w.init_pad, R, S, w.ldS, false};
+    TRY(split_rows(w.init_pad, w.ldS, R, S, w.yop[0], st));
+  } else {
+    CUDA_TRY(cudaMemsetAsync(w.X2, 0, static_cast<size_t>(R) * round_up(S, EPI_COLS) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[0].ptr), 0, w.yop[0].bytes(), st));
+    init = X2;
+  }
+  if (early) CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * num_iters, st));
+  CUDA_TRY(cudaGetLastError());
+
+  float eta_host = 0.f;
+  float sc_host[4] = {0, 0, 0, 0};
+  if (early || lipschitz_out) {
+    CUDA_TRY(cudaMemcpyAsync(sc_host, w.scalars, sizeof(sc_host), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    eta_host = sc_host[0];
+    if (lipschitz_out) *lipschitz_out = sc_host[2];
+    if (sc_host[3] != 0.f || !isfinite(sc_host[2]))
+      return fail(VTC_ERR_NONFINITE, "largest eigenvalue of the kernel Gram matrix is %g: a dictionary element overflowed", sc_host[2]);
+  }
+
+  // ---- iterations (convolutional/ista_fista.py:141-190): two launches each
+  double t_k = 1.0;
+  float beta_prev = 0.f;
+  int k_done = 0;
+  for (int k = 1; k <= num_iters; ++k) {
+    const double t_next = (1.0 + sqrt(1.0 + 4.0 * t_k * t_k)) / 2.0;
+    const float beta_k = (variant == VTC_VARIANT_FISTA) ? static_cast<float>((t_k - 1.0) / t_next) : 0.f;
+    t_k = t_next;
+    const F32Mat& a_prev = (k == 1) ? init : ((k - 1) & 1) ? X1 : X2;
+    const F32Mat& a_prev2 = (k <= 2) ? init : (k & 1) ? X1 : X2;
+    const F32Mat& a_out = (k == num_iters && !early) ? final_out : (k & 1) ? X1 : X2;
+    {
+      GemmCall r;
+      conv_synthesis_call(r, cs, w, w.yop[(k - 1) & 1], precision);
+      r.parts_out = w.r_op, r.n_parts = P;
+      TRY(launch_gemm<EPI_STORE>(r, st));
+    }
+    GemmCall c;
+    c.precision = precision;
+    c.A = w.r_op, c.B = w.phiA_op;
+    c.M = R, c.N = S, c.K = static_cast<int64_t>(cs.nq) * g.db;
+    c.nseg = cs.nq;
+    for (int qy = 0; qy < g.ty; ++qy)
+      for (int qx = 0; qx < g.tx; ++qx) c.seg_shift[qy * g.tx + qx] = qy * g.gw + qx;
+    c.grid_h = g.gh, c.grid_w = g.gw, c.code_h = g.ch, c.code_w = g.cw;
+    c.in[0] = a_prev, c.in_mask = 1;
+    if (variant == VTC_VARIANT_FISTA && beta_prev != 0.f) c.in[2] = a_prev2, c.in_mask |= 4;
+    c.out = a_out, c.store_out = true;
+    if (k < num_iters) c.parts_out = w.yop[k & 1], c.n_parts = P;
+    c.prox = (hard_threshold ? PROX_HARD : 0) | (nonnegative_only ? PROX_NONNEG : 0);
+    c.group = 1;
+    c.use_momentum = (variant == VTC_VARIANT_FISTA);
+    c.beta_prev = beta_prev, c.beta_next = beta_k;
+    c.scalars = w.scalars;
+    c.stat = early ? w.stats + (k - 1) : nullptr;
+    TRY(launch_gemm<EPI_FISTA>(c, st));
+    beta_prev = beta_k;
+    k_done = k;
+    if (early) {
+      double sum_abs = 0.0;
+      CUDA_TRY(cudaMemcpyAsync(&sum_abs, w.stats + (k - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      const double count = static_cast<double>(B) * S * g.ch * g.cw;
+      if (sum_abs / count / static_cast<double>(eta_host) < static_cast<double>(early_stopping_epsilon) && k > 1) break;
+    }
+  }
+  if (early) {
+    const F32Mat& res = (k_done & 1) ? X1 : X2;
+    unblock_f32_kernel<<<grid_for(R * S, 256, info.sm_count), 256, 0, st>>>(static_cast<const float*>(res.ptr), R, S,
+                                                                            w.out_pad, w.ldS);
+    COUNT_LAUNCH();
+  }
+  conv_grid_to_codes_kernel<<<grid_for(B * S * g.ch * g.cw, 256, info.sm_count), 256, 0, st>>>(w.out_pad, w.ldS, g, codes_out);
+  COUNT_LAUNCH();
+  CUDA_TRY(cudaGetLastError());
+  if (iters_run) *iters_run = k_done;
+  return VTC_OK;
+}
+
+// ---- convolutional dictionary update ------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+struct ConvGradWs {
+  ConvWs fw;             // reuses the inference carving for the operands, the image blocks and one y operand
+  float* rblk;           // masked residual on the block grid (rows x ldD)
+  PartsMat aT_op, RT_op; // codes^T and (tap-shifted) residual^T with the grid rows along K
+  float* partial;
+  int ksplits;
+  int64_t rows_per_split, ldTap;
+  float* taps;           // nq gradient blocks (s x ldTap each)
+};
+ConvGradWs carve_conv_grad(Carver& cv, const ConvShape& cs, int precision, int sm_count) {
+  ConvGradWs w;
+  const ConvGeom& g = cs.g;
+  const int P = parts_for(precision);
+  w.fw = carve_conv(cv, cs, precision);
+  w.rblk = static_cast<float*>(cv.take(static_cast<size_t>(cs.rows) * w.fw.ldD * 4));
+  w.aT_op = carve_parts(cv, g.s, cs.rows, P);
+  w.RT_op = carve_parts(cv, g.db, cs.rows, P);
+  const int64_t tiles_mn = ceil_div(g.s, PAIR_M) * ceil_div(g.db, BLOCK_N);
+  const int64_t kb = k_blocks_for(w.aT_op.Kp, precision);
+  int64_t ks = (sm_count / 2) / tiles_mn;
+  if (ks < 1) ks = 1;
+  if (ks > kb) ks = kb;
+  w.ksplits = static_cast<int>(ks);
+  w.rows_per_split = ceil_div(g.s, PAIR_M) * PAIR_M;
+  w.ldTap = round_up(g.db, 4);
+  w.partial = static_cast<float*>(cv.take(static_cast<size_t>(w.ksplits) * w.rows_per_split * w.ldTap * 4));
+  w.taps = static_cast<float*>(cv.take(static_cast<size_t>(cs.nq) * g.s * w.ldTap * 4));
+  return w;
+}
+}  // namespace
+extern "C" {
+
+size_t vtc_conv_dict_grad_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t S, int64_t KH,
+                                          int64_t KW, int64_t SY, int64_t SX, int precision) {
+  ConvShape cs;
+  if (!valid_precision(precision) || conv_shape(B, C, H, W, S, KH, KW, SY, SX, 0, 0, 0, 0, &cs) != VTC_OK) return 0;
+  Carver cv(nullptr, 0);
+  carve_conv_grad(cv, cs, precision, 148);
+  return cv.off + 2048;
+}
+
+int vtc_sc_conv_dict_grad(const float* images_padded, const float* dictionary, const float* codes, float* grad_sum,
+                          int64_t B, int64_t C, int64_t H, int64_t W, int64_t S, int64_t KH, int64_t KW, int64_t SY,
+                          int64_t SX, int pad_top, int pad_bottom, int pad_left, int pad_right, int precision,
+                          void* workspace, size_t workspace_bytes, vtc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!images_padded || !dictionary || !codes || !grad_sum) return fail(VTC_ERR_ARG, "vtc_sc_conv_dict_grad: null pointer");
+  if (!valid_precision(precision)) return fail(VTC_ERR_ARG, "precision must be 1, 3 or 6");
+  ConvShape cs;
+  TRY(conv_shape(B, C, H, W, S, KH, KW, SY, SX, pad_top, pad_bottom, pad_left, pad_right, &cs));
+  const ConvGeom& g = cs.g;
+  DeviceInfo info;
+  TRY(require_sm100(&info));
+  Carver cv(workspace, workspace_bytes);
+  ConvGradWs w = carve_conv_grad(cv, cs, precision, info.sm_count < 148 ? info.sm_count : 148);
+  if (!workspace || !cv.fits()) return fail(VTC_ERR_WORKSPACE, "vtc_sc_conv_dict_grad: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
+  const int64_t R = cs.rows;
+  // codes on the block grid (a^T as the operand of the gradient contraction; a as the operand of the synthesis)
+  conv_codes_to_grid_kernel<<<grid_for(R * S, 256, info.sm_count), 256, 0, st>>>(codes, g, w.fw.init_pad, w.fw.ldS);
+  COUNT_LAUNCH();
+  TRY(split_rows(w.fw.init_pad, w.fw.ldS, R, S, w.fw.yop[0], st));
+  TRY(transpose_split(w.fw.init_pad, w.fw.ldS, R, S, w.aT_op, st));
+  TRY(conv_dictionary_operands(dictionary, cs, w.fw, st));
+  conv_image_to_blocks_kernel<<<grid_for(R * g.db, 256, info.sm_count), 256, 0, st>>>(images_padded, g, w.fw.xblk, w.fw.ldD);
+  COUNT_LAUNCH();
+  // masked residual (convolutional/sc_cheap_quadratic_descent.py:65-69), fp32, then transposed into operand parts
+  {
+    GemmCall r;
+    conv_synthesis_call(r, cs, w.fw, w.fw.yop[0], precision);
+    r.out = F32Mat{w.rblk, R, g.db, w.fw.ldD}, r.store_out = true;
+    TRY(launch_gemm<EPI_STORE>(r, st));
+  }
+  // one contraction over the grid rows per kernel tap: grad[s, tap, pix] = sum_m a[m, s] * r[m + shift(tap), pix];
+  // the shift is taken while transposing the residual into its operand parts (rows past the end read as zero)
+  const int64_t kb = k_blocks_for(w.aT_op.Kp, precision);
+  const int64_t per = ceil_div(kb, w.ksplits);
+  const int nsplit = static_cast<int>(ceil_div(kb, per));
+  for (int qy = 0; qy < g.ty; ++qy)
+    for (int qx = 0; qx < g.tx; ++qx) {
+      const int q = qy * g.tx + qx;
+      GemmCall c;
+      c.A = w.aT_op, c.B = w.RT_op;
+      c.precision = precision;
+      c.M = S, c.N = g.db, c.K = w.aT_op.K;
+      const int64_t shift = static_cast<int64_t>(qy) * g.gw + qx;
+      TRY(transpose_split(w.rblk + shift * w.fw.ldD, w.fw.ldD, R - shift, g.db, w.RT_op, st));
+      c.ksplits = w.ksplits;
+      c.out_rows_per_split = w.rows_per_split;
+      c.out = F32Mat{w.partial, static_cast<int64_t>(w.ksplits) * w.rows_per_split, g.db, w.ldTap}, c.store_out = true;
+      TRY(launch_gemm<EPI_STORE>(c, st));
+      reduce_partials_kernel<<<grid_for(S * g.db, 256, info.sm_count), 256, 0, st>>>(
+          w.partial, nsplit, w.rows_per_split, w.ldTap, S, g.db, w.taps + static_cast<size_t>(q) * S * w.ldTap);
+      COUNT_LAUNCH();
+    }
+  conv_grad_to_dict_layout_kernel<<<grid_for(S * cs.per_kernel, 256, info.sm_count), 256, 0, st>>>(
+      w.taps, S * w.ldTap, w.ldTap, g, grad_sum);
+  COUNT_LAUNCH();
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+int vtc_sc_conv_dict_apply(float* dictionary, const float* grad_sum, const float* hessian_diagonal, int64_t S,
+                           int64_t per_kernel, int64_t batch_global, float stepsize, float lowest_code_val,
+                           int normalize, vtc_stream_t stream) {
+  if (!dictionary || !grad_sum || S <= 0 || per_kernel <= 0 || batch_global <= 0) return fail(VTC_ERR_ARG, "vtc_sc_conv_dict_apply: bad argument");
+  conv_dict_apply_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      dictionary, grad_sum, hessian_diagonal, S, per_kernel, static_cast<float>(batch_global), stepsize,
+      lowest_code_val, normalize);
+  COUNT_LAUNCH();
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+int vtc_conv_hessian_diag_update(const float* codes, int64_t B, int64_t S, int64_t positions, int64_t batch_global,
+                                 float* code_sq_sum, float* hessian_diagonal, int apply_ema, vtc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!codes || !code_sq_sum || B <= 0 || S <= 0 || positions <= 0 || batch_global <= 0) return fail(VTC_ERR_ARG, "vtc_conv_hessian_diag_update: bad argument");
+  if (apply_ema && !hessian_diagonal) return fail(VTC_ERR_ARG, "vtc_conv_hessian_diag_update: hessian_diagonal required");
+  conv_channel_sq_sum_kernel<<<static_cast<unsigned>(S), 256, 0, st>>>(codes, B, S, positions, code_sq_sum);
+  COUNT_LAUNCH();
+  if (apply_ema) {
+    hessian_ema_kernel<<<static_cast<unsigned>(ceil_div(S, 256)), 256, 0, st>>>(hessian_diagonal, code_sq_sum, S,
+                                                                              static_cast<float>(batch_global));
+    COUNT_LAUNCH();
+  }
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
 }
