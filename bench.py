@@ -32,6 +32,7 @@ TRAIN_GLOBAL_BATCH = 524288
 WORKLOAD = ('configs[1]: fully-connected FISTA, 16x16 whitened patches (D=256), 1024 atoms, '
             'batch 65536 per GPU, 300 iters, lambda 0.1')
 CPU_SAMPLE = 32768
+CONV_IMAGES_PER_GPU, CONV_LAM = 128, 0.05
 
 
 def peaks():
@@ -100,6 +101,51 @@ def cpu_reference_patches_per_sec(sample, repeats=1):
     oracle.ista_fista(x, phi, LAM, T)
     best = min(best, time.perf_counter() - t0)
   return sample / best, cores, best
+
+
+def conv_benchmark(world, rank, dev, timed, pk, precision, images_per_gpu=CONV_IMAGES_PER_GPU):
+  """BASELINE.json configs[4]: convolutional FISTA, 64 filters of 16x16 at stride 8 on 512x512 whitened images,
+  sharded by image (no data-path collective), plus one conv dictionary update on the same batch."""
+  import vision_transform_codes_b200 as pkg
+  from oracle import vtc_oracle as oracle  # seeded input generators only
+  from vision_transform_codes_b200.analysis_transforms.convolutional import ista_fista as conv_ista_fista
+  from vision_transform_codes_b200.dict_update_rules.convolutional import sc_cheap_quadratic_descent as conv_update
+  from vision_transform_codes_b200.dict_update_rules.convolutional import _common as conv_common
+  nk, k, st, side = 64, (16, 16), (8, 8), 512
+  few, pad = oracle.synthetic_padded_images(8, 1, side, side, k, st, seed=100 + rank)
+  x = few.repeat((images_per_gpu + 7) // 8, 1, 1, 1)[:images_per_gpu].contiguous().to(dev)
+  phi = oracle.synthetic_conv_dictionary(nk, 1, k[0], k[1]).to(dev)
+  saved = pkg.config.precision
+  pkg.config.precision = precision
+  ms, launches = timed(lambda: conv_ista_fista.run(x, phi, st, pad, CONV_LAM, T), 2, 1)
+  ms /= 2
+  codes = conv_ista_fista.run(x, phi, st, pad, CONV_LAM, T)
+  h = torch.zeros(nk, device=dev)
+
+  def update():
+    conv_common.hessian_running_mean(h, codes)
+    conv_update.run(x, phi.clone(), codes, h, st, pad, stepsize=0.001)
+
+  ums, _ = timed(update, 2, 1)
+  ums /= 2
+  pkg.config.precision = saved
+  sh = (x.shape[2] - k[0]) // st[0] + 1
+  rows = images_per_gpu * (x.shape[2] // st[0]) * (x.shape[3] // st[1])
+  nparts = {'bf16': 1, 'bf16x3': 2, 'bf16x6': 3}[precision]
+  # per grid row and iteration (64 code channels / 64 pixels per block): state 12 B x 64, image 4 B x 64, y and r parts
+  # written once and read once each (2 P B x 64 x 2 x 2)
+  bytes_iter = rows * 64 * (12 + 4 + 8 * nparts)
+  flops_iter = 4.0 * images_per_gpu * nk * 256 * sh * sh
+  return {
+      'workload': 'configs[4]: convolutional FISTA, 64 filters 16x16, stride 8, %d whitened 512x512 images per GPU '
+                  '(padded 528x528, codes 64x65x65), %d iters, lambda %g, sharded by image' % (images_per_gpu, T, CONV_LAM),
+      'value': world * images_per_gpu / (ms * 1e-3), 'unit': 'images/s', 'ms_per_step': ms, 'precision': precision,
+      'ms_per_iteration': ms / T, 'launches_per_step': int(launches // 2),
+      'algorithmic_bytes_per_iteration': bytes_iter,
+      'hbm_gbs_achieved': bytes_iter / (ms / T * 1e-3) / 1e9, 'hbm_frac': bytes_iter / (ms / T * 1e-3) / 1e9 / pk['hbm_gbs'],
+      'algorithmic_tflops': flops_iter / (ms / T * 1e-3) / 1e12,
+      'dictionary_update_ms': ums,
+  }
 
 
 def run_reference(args, rank):
@@ -323,6 +369,7 @@ def main():
       line['train_step'] = trainer.benchmark_train_step(TRAIN_GLOBAL_BATCH, S, D, T, LAM, world, rank, dev, timed)
     except ImportError:
       pass
+    line['conv_path'] = conv_benchmark(world, rank, dev, timed, pk, args.precision)
     if rank == 0 and world == 1:
       v, cores, secs = cpu_reference_patches_per_sec(CPU_SAMPLE)
       line['cpu_baseline'] = {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': 'port',
