@@ -204,6 +204,8 @@ def main():
   dev = torch.device('cuda', local_rank)
   torch.cuda.set_device(dev)
   if world > 1:
+    # NCCL writes its version banner / debug lines to stdout by default; stdout carries the one JSON line only
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     dist.init_process_group('nccl', device_id=dev)
   lib = _lib.load()
   pkg.config.precision = args.precision

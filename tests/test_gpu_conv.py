@@ -207,3 +207,29 @@ def test_conv_determinism_and_image_shard_independence():
   a = ista_fista.run(xd, phi, (8, 8), pad, 0.05, 40)
   assert torch.equal(a, ista_fista.run(xd, phi, (8, 8), pad, 0.05, 40))
   assert torch.equal(a[3:], ista_fista.run(xd[3:], phi, (8, 8), pad, 0.05, 40))
+
+
+def test_conv_lean_trainer_matches_reference_trainer(tmp_path):
+  """The package's own train_dictionary in convolutional mode, with the reference's parameter dictionary
+  (tests/sparse_coding_4.py), against the unmodified reference trainer's result; checkpoints in its pickle format."""
+  import numpy as np
+  from vision_transform_codes_b200.training import sparse_coding as trainer
+  g = load_golden('conv_training_small')
+  pad = tuple(tuple(int(v) for v in row) for row in g['padding'])
+  params = {
+      'mode': 'convolutional', 'num_epochs': 1, 'strides': (8, 8), 'padding': pad,
+      'code_inference_algorithm': 'ista',
+      'inference_param_schedule': {0: {'sparsity_weight': 0.05, 'num_iters': 15}},
+      'dictionary_update_algorithm': 'sc_cheap_quadratic_descent',
+      'dict_update_param_schedule': {0: {'stepsize': 0.05, 'num_iters': 1}},
+      'checkpoint_schedule': {2}, 'logging_folder_fullpath': tmp_path}
+  phi = g['dictionary'].cuda()
+  trainer.train_dictionary([x.cuda() for x in g['batches']], None, phi, params)
+  assert oracle.relative_l2(phi.cpu(), g['ista_cheap']) < 5e-5
+  ckpt = trainer.load_newest_dictionary_checkpoint(tmp_path)
+  assert isinstance(ckpt, np.ndarray) and ckpt.dtype == np.float32 and ckpt.shape == tuple(phi.shape)
+  phi2 = g['dictionary'].cuda()
+  trainer.train_dictionary([x.cuda() for x in g['batches']], None, phi2,
+                           dict(params, code_inference_algorithm='fista',
+                                dictionary_update_algorithm='sc_steepest_descent', checkpoint_schedule=None))
+  assert oracle.relative_l2(phi2.cpu(), g['fista_steepest']) < 5e-5

@@ -20,6 +20,8 @@ import torch
 
 from vision_transform_codes_b200 import _lib, config
 from vision_transform_codes_b200.analysis_transforms.fully_connected import ista_fista, subspace_ista_fista
+from vision_transform_codes_b200.analysis_transforms.convolutional import ista_fista as conv_ista_fista
+from vision_transform_codes_b200.dict_update_rules.convolutional import _common as _conv_common
 from vision_transform_codes_b200.dict_update_rules.fully_connected import _common
 
 CHEAP_QUADRATIC = ('sc_cheap_quadratic_descent', 'subspace_sc_cheap_quadratic_descent')
@@ -28,8 +30,12 @@ UPDATE_RULES = ('sc_steepest_descent', 'sc_cheap_quadratic_descent', 'subspace_s
 
 
 def infer_codes(images, dictionary, code_inf_alg, sparsity_weight, num_iters, nonnegative_only=False,
-                hard_threshold=False, group_assignments=None):
-  """training/sparse_coding.py:124-140."""
+                hard_threshold=False, group_assignments=None, kernel_strides=None, image_padding=None):
+  """training/sparse_coding.py:124-140 (kernel_strides given: the convolutional branch, :132-134)."""
+  if kernel_strides is not None:
+    return conv_ista_fista.run(images, dictionary, kernel_strides, image_padding, sparsity_weight, num_iters,
+                               variant=code_inf_alg, nonnegative_only=nonnegative_only,
+                               hard_threshold=hard_threshold)
   if code_inf_alg in ('subspace_ista', 'subspace_fista'):
     return subspace_ista_fista.run(images, dictionary, group_assignments, sparsity_weight, num_iters,
                                    variant=code_inf_alg[9:], hard_threshold=hard_threshold)
@@ -97,9 +103,30 @@ def update_dictionary(images, dictionary, codes, hessian_diag, stepsize, num_ite
                                        float(stepsize), float(lowest_code_val), int(bool(normalize_dictionary)), st))
 
 
+def update_dictionary_convolutional(images_padded, dictionary, codes, hessian_diag, kernel_strides, image_padding,
+                                    stepsize, num_iters, lowest_code_val=0.001, normalize_dictionary=True):
+  """training/sparse_coding.py:142-168, convolutional branch: Hessian running mean (:158-161, when hessian_diag is
+  given) then num_iters descent steps; data parallel: the squared-code sums and every gradient are all-reduced."""
+  if hessian_diag is not None:
+    _conv_common.hessian_running_mean(hessian_diag, codes)
+  _conv_common.descend(images_padded, dictionary, codes, hessian_diag, kernel_strides, image_padding, stepsize,
+                       num_iters, lowest_code_val, normalize_dictionary)
+
+
+def load_newest_dictionary_checkpoint(checkpoint_dir):
+  """The dictionary (ndarray) of the highest checkpoint iteration in a logging folder: files are raw pickles of the
+  float32 ndarray named checkpoint_dictionary_iter_<k>, as the reference writes them (training/sparse_coding.py:
+  170-175) and reads them back (utils/misc.py:9-21)."""
+  import os
+  iter_nums = [int(f[27:]) for f in os.listdir(checkpoint_dir) if f[:27] == 'checkpoint_dictionary_iter_']
+  newest = max(iter_nums)
+  with open(os.path.join(str(checkpoint_dir), 'checkpoint_dictionary_iter_' + str(newest)), 'rb') as f:
+    return pickle.load(f)
+
+
 def train_dictionary(training_image_dataset, validation_image_dataset, init_dictionary, all_params):
   """
-  Train a sparse coding dictionary (fully-connected mode), in place on ``init_dictionary``.
+  Train a sparse coding dictionary (fully-connected or convolutional mode), in place on ``init_dictionary``.
 
   Same arguments as the reference's train_dictionary (training/sparse_coding.py:9-117). Under data parallelism
   ``training_image_dataset`` yields THIS rank's shard of every batch.
@@ -115,8 +142,16 @@ def train_dictionary(training_image_dataset, validation_image_dataset, init_dict
   assert coding_mode in ['fully-connected', 'convolutional']
   assert code_inf_alg in ['ista', 'fista', 'subspace_ista', 'subspace_fista']
   assert dict_update_alg in UPDATE_RULES
-  if coding_mode != 'fully-connected':
-    raise NotImplementedError('the B200 path covers fully-connected sparse coding')
+  convolutional = coding_mode == 'convolutional'
+  kernel_strides = image_padding = None
+  if convolutional:
+    # training/sparse_coding.py:295-299, :394-419: plain ISTA/FISTA and the two non-subspace update rules only
+    kernel_strides = all_params['strides']
+    image_padding = all_params['padding']
+    if code_inf_alg not in ('ista', 'fista'):
+      raise KeyError('Havent implemented subspace ISTA for convolutional yet')
+    if dict_update_alg not in ('sc_steepest_descent', 'sc_cheap_quadratic_descent'):
+      raise KeyError('Not implemented for convolutional')
   for key in ('training_visualization_schedule', 'dict_element_rp_schedule'):
     if key in all_params:
       raise NotImplementedError('%s is host-side orchestration outside the B200 hot path; run the reference '
@@ -137,7 +172,7 @@ def train_dictionary(training_image_dataset, validation_image_dataset, init_dict
     assert group_assignments is not None
     alignment_penalty = all_params['subspace_alignment_penalty']
   if all_params.get('renormalize_dictionary', True):
-    norms = init_dictionary.norm(p=2, dim=1)
+    norms = init_dictionary.flatten(1).norm(p=2, dim=1)
     assert torch.allclose(norms, torch.ones_like(norms)), 'Please ensure the initial dictionary is already normalized'
   ckpt_sched = all_params.get('checkpoint_schedule')
   logging_path = all_params.get('logging_folder_fullpath')
@@ -150,7 +185,7 @@ def train_dictionary(training_image_dataset, validation_image_dataset, init_dict
   hessian_diag = None
   if dict_update_alg in CHEAP_QUADRATIC:
     hessian_diag = init_dictionary.new_zeros(init_dictionary.shape[0])
-  state = _UpdateState(dictionary)
+  state = None if convolutional else _UpdateState(dictionary)
   rank0 = (not config.data_parallel) or torch.distributed.get_rank(config.process_group) == 0
 
   starttime = time.time()
@@ -173,9 +208,13 @@ def train_dictionary(training_image_dataset, validation_image_dataset, init_dict
       if dictionary.device != t_batch_images.device:
         t_batch_images = t_batch_images.to(dictionary.device)
       t_codes = infer_codes(t_batch_images, dictionary, code_inf_alg, sparsity_weight, inf_num_iters, nonneg_only,
-                            hard_threshold, group_assignments)
-      update_dictionary(t_batch_images, dictionary, t_codes, hessian_diag, d_upd_stp, d_upd_niters, state,
-                        group_assignments=group_assignments, alignment_penalty=alignment_penalty)
+                            hard_threshold, group_assignments, kernel_strides, image_padding)
+      if convolutional:
+        update_dictionary_convolutional(t_batch_images, dictionary, t_codes, hessian_diag, kernel_strides,
+                                        image_padding, d_upd_stp, d_upd_niters)
+      else:
+        update_dictionary(t_batch_images, dictionary, t_codes, hessian_diag, d_upd_stp, d_upd_niters, state,
+                          group_assignments=group_assignments, alignment_penalty=alignment_penalty)
       total_iter_idx += 1
     if rank0:
       print("Epoch", epoch_idx + 1, "finished")
