@@ -57,6 +57,21 @@ def _worker(rank, world, port, result_path):
   dist.all_gather(gathered, new_phi)
   ok = ok and all(torch.equal(g, gathered[0]) for g in gathered)
   ok = ok and trainer._common.global_batch_size(B // world, torch.device('cpu')) == B
+  # convolutional mode shards by image: the gradient sums of the shards add up to the full-batch gradient, and the
+  # update applied with the global image count (what dict_update_rules.convolutional._common.descend does around its
+  # all-reduce) is the single-process update of the reference
+  xi, pad = oracle.synthetic_padded_images(4, 1, 24, 24, (8, 8), (4, 4))
+  kern = oracle.synthetic_conv_dictionary(6, 1, 8, 8)
+  ci = oracle.conv_ista_fista(xi, kern, (4, 4), pad, 0.05, 10)
+  half = slice(rank * 2, rank * 2 + 2)
+  g_local = oracle.conv_dictionary_gradient(xi[half], kern, ci[half], (4, 4), pad)
+  g_sum = g_local.clone()
+  dist.all_reduce(g_sum, op=dist.ReduceOp.SUM)
+  hc = oracle.conv_hessian_running_mean(torch.zeros(6), ci)
+  got = oracle.conv_sc_dictionary_update(xi[half], kern, ci[half], (4, 4), pad, hc, stepsize=0.05, batch_size=4,
+                                         extra_gradient=g_sum - g_local)
+  want = oracle.conv_sc_dictionary_update(xi, kern, ci, (4, 4), pad, hc, stepsize=0.05)
+  ok = ok and oracle.relative_l2(got, want) < 1e-6
   with open(result_path + str(rank), 'w') as f:
     f.write('ok' if ok else 'fail')
   dist.destroy_process_group()
