@@ -52,18 +52,24 @@ constexpr int EPI_PART_BYTES = BLOCK_M * EPI_COLS * 2;   // 4 KB: one bf16 [128 
 // (227 KB) is split between the operand ring and the epilogue's input ring according to what bounds the launch:
 // NIN = 1 (plain GEMMs, K large): deep operand ring; NIN = 2 (fused update after the short K = D contraction of the
 // synthesis form, HBM-bound): shallow operand ring, 5-8 input stages in flight; NIN = 3 (Gram-form fused update).
-template <int P, int NIN, int BN>
+// RES > 0: "resident B" -- the launch has a single column of tiles (N <= BN) and at most RES K blocks, so this CTA's half
+// of B is the same for every tile: it is loaded once into its own region and the ring carries A only (the
+// convolutional launches: B is the 16-64 KB dictionary operand, re-fetching it per tile was a third of the L2->SM bytes).
+template <int P, int NIN, int BN, int RES = 0>
 struct Cfg {
-  static_assert(BN == 256 || BN == 128, "tile width");
+  static_assert(BN == 256 || BN == 128 || BN == 64, "tile width");
   static constexpr int HALF_N = BN / 2;                         // B rows staged by each CTA of the pair
   static constexpr int TMEM_COLS = 2 * BN;                      // two accumulators
   static constexpr int BK = (P == 1) ? 64 : 32;                 // K extent of a stage
   static constexpr int SPAN = BK * 2;                           // bytes per operand row = swizzle span (128 / 64)
   static constexpr int TILE_BYTES = BLOCK_M * SPAN;             // one part tile of A
   static constexpr int B_TILE_BYTES = HALF_N * SPAN;            // one part tile of this CTA's half of B
-  static constexpr int STAGE_BYTES = P * (TILE_BYTES + B_TILE_BYTES);
+  static constexpr int STAGE_BYTES = RES > 0 ? P * TILE_BYTES : P * (TILE_BYTES + B_TILE_BYTES);
+  static constexpr int BRES_KB_BYTES = P * B_TILE_BYTES;        // one K block of the resident B
+  static constexpr int BRES_BYTES = RES * BRES_KB_BYTES;
   static constexpr int IN_STAGE_BYTES = NIN * EPI_ARRAY_BYTES;
-  static constexpr int OP_STAGES = NIN == 3 ? ((P == 3) ? 2 : 3)
+  static constexpr int OP_STAGES = RES > 0 ? (NIN == 1 ? 6 : (P == 3 ? 2 : 3))
+                                 : NIN == 3 ? ((P == 3) ? 2 : 3)
                                  : NIN == 2 ? 2
                                             : ((P == 3) ? 3 : 4);
   // IN_STAGES is a multiple of NUM_MATH_GROUPS: every input stage is always consumed by the same math group, so a
@@ -76,10 +82,11 @@ struct Cfg {
   static constexpr int OUT_STAGE_BYTES = EPI_ARRAY_BYTES + P * EPI_PART_BYTES;
   static constexpr int NPAIRS = (P == 1) ? 1 : (P == 2) ? 3 : 6;
   static constexpr int OFF_OP = 0;
-  static constexpr int OFF_IN = OFF_OP + OP_STAGES * STAGE_BYTES;
+  static constexpr int OFF_BRES = OFF_OP + OP_STAGES * STAGE_BYTES;
+  static constexpr int OFF_IN = OFF_BRES + BRES_BYTES;
   static constexpr int OFF_OUT = OFF_IN + IN_STAGES * IN_STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_OUT + OUT_STAGES * OUT_STAGE_BYTES;
-  static constexpr int NUM_BARRIERS = 2 * OP_STAGES + 4 + 2 * IN_STAGES + 2 * OUT_STAGES;
+  static constexpr int NUM_BARRIERS = 2 * OP_STAGES + 4 + 2 * IN_STAGES + 2 * OUT_STAGES + 1;  // + resident B full
   static constexpr int SMEM_TOTAL = OFF_BAR + NUM_BARRIERS * 8 + 16;
   static constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;          // slack to align the dynamic base to 1024 B
   static_assert(SMEM_ALLOC <= 232448, "over the 227 KB shared memory limit");
@@ -315,9 +322,9 @@ __device__ __forceinline__ void split_parts16(const float (&partv)[16], int n_pa
   }
 }
 
-template <int EPI, int P, int NIN, int BN>
+template <int EPI, int P, int NIN, int BN, int RES = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<P, NIN, BN>;
+  using C = Cfg<P, NIN, BN, RES>;
   constexpr int IN_STAGE_BYTES = C::IN_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // swizzled TMA / UMMA tiles need a 1024-byte aligned base; the offset is identical in both CTAs of the pair
@@ -332,6 +339,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
   auto in_free_bar = [&](int e) { return bar0 + 8 * (2 * C::OP_STAGES + 4 + C::IN_STAGES + e); };
   auto out_full_bar = [&](int o) { return bar0 + 8 * (2 * C::OP_STAGES + 4 + 2 * C::IN_STAGES + o); };
   auto out_free_bar = [&](int o) { return bar0 + 8 * (2 * C::OP_STAGES + 4 + 2 * C::IN_STAGES + C::OUT_STAGES + o); };
+  const uint32_t bres_full_bar = bar0 + 8 * (C::NUM_BARRIERS - 1);
+  const uint32_t sBres = sbase + C::OFF_BRES;
   const uint32_t tmem_slot = bar0 + C::NUM_BARRIERS * 8;
 
   const int warp = threadIdx.x >> 5;
@@ -362,6 +371,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
       mbar_init(full_bar(s), 2);   // one arrive per CTA's producer (used in the leader only)
       mbar_init(empty_bar(s), 1);  // multicast tcgen05.commit
     }
+    mbar_init(bres_full_bar, 2);   // resident B: one arrive per CTA's producer (used in the leader only)
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);                     // multicast tcgen05.commit
       mbar_init(tmem_empty_bar(a), 2 * NUM_MATH_WARPS);   // every math warp of both CTAs (used in the leader only)
@@ -394,6 +404,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
   if (warp == 0) {
     // ================================ operand producer (both CTAs) ================================
     const bool a_blocked = (p.blocked_mask & BLK_A) != 0;
+    if (RES > 0 && w_begin < w_end) {
+      // resident B: every K block of this CTA's half of the (single) B tile, once per launch
+      if (elect_one_sync()) {
+        if (leader) mbar_arrive_expect_tx(bres_full_bar, 2 * p.k_blocks * C::BRES_KB_BYTES);
+        else mbar_arrive_remote(bres_full_bar, 0);
+        for (int kb = 0; kb < p.k_blocks; ++kb)
+#pragma unroll
+          for (int q = 0; q < P; ++q)
+            tma_load_2d_pair(sBres + kb * C::BRES_KB_BYTES + q * C::B_TILE_BYTES, &p.tmB, bres_full_bar,
+                             q * p.b_part_stride + kb * C::BK, cta_rank * C::HALF_N, kEvictLast);
+      }
+      __syncwarp();
+    }
     uint32_t it = 0;
     for (int w = w_begin; w < w_end; w += w_step) {
       const TileCoord c = decode_tile<BN>(p, w, cta_rank);
@@ -417,10 +440,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
               tma_load_2d_pair(dst + q * C::TILE_BYTES, &p.tmA, full_bar(s), q * p.a_part_stride + kba * C::BK, arow,
                                kEvictNormal);
           }
+          if (RES == 0) {
 #pragma unroll
-          for (int q = 0; q < P; ++q)
-            tma_load_2d_pair(dst + P * C::TILE_BYTES + q * C::B_TILE_BYTES, &p.tmB, full_bar(s),
-                             q * p.b_part_stride + kb * C::BK, c.n0 + cta_rank * C::HALF_N, kEvictLast);
+            for (int q = 0; q < P; ++q)
+              tma_load_2d_pair(dst + P * C::TILE_BYTES + q * C::B_TILE_BYTES, &p.tmB, full_bar(s),
+                               q * p.b_part_stride + kb * C::BK, c.n0 + cta_rank * C::HALF_N, kEvictLast);
+          }
         }
         __syncwarp();
       }
@@ -430,6 +455,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(PAIR_M, BN);
       uint32_t it = 0, tile_iter = 0;
+      if (RES > 0 && w_begin < w_end) {
+        mbar_wait(bres_full_bar, 0);
+        tc_fence_after();
+      }
       for (int w = w_begin; w < w_end; w += w_step, ++tile_iter) {
         const TileCoord c = decode_tile<BN>(p, w, cta_rank);
         const int acc = tile_iter & 1;
@@ -448,7 +477,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
 #pragma unroll
             for (int pr = 0; pr < C::NPAIRS; ++pr) {
               const uint64_t adesc = make_kmajor_desc(stage + pair_a(P, pr) * C::TILE_BYTES, C::SPAN);
-              const uint64_t bdesc = make_kmajor_desc(stage + P * C::TILE_BYTES + pair_b(P, pr) * C::B_TILE_BYTES, C::SPAN);
+              const uint32_t bbase = RES > 0 ? sBres + kb * C::BRES_KB_BYTES : stage + P * C::TILE_BYTES;
+              const uint64_t bdesc = make_kmajor_desc(bbase + pair_b(P, pr) * C::B_TILE_BYTES, C::SPAN);
 #pragma unroll
               for (int k = 0; k < C::BK / UMMA_K; ++k) {
                 // +32 bytes (16 bf16) per K step inside the swizzle span -> +2 in the (address >> 4) field

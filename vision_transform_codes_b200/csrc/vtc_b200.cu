@@ -241,9 +241,9 @@ struct GemmCall {
   int blk_sy = 1, blk_sx = 1, pix_y0 = 0, pix_y1 = 0, pix_x0 = 0, pix_x1 = 0;
 };
 
-template <int EPI, int P, int NIN, int BN>
+template <int EPI, int P, int NIN, int BN, int RES = 0>
 int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream) {
-  using Cf = Cfg<P, NIN, BN>;
+  using Cf = Cfg<P, NIN, BN, RES>;
   GemmParams p;
   memset(&p, 0, sizeof(p));
   TRY(map_operand(&p.tmA, c.A, Cf::BK, "A operand"));
@@ -295,6 +295,8 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
     p.blocked_mask |= BLK_A;
     p.a_blocks_per_part = static_cast<int>(c.A.Kp / c.A.block);
   }
+  if (RES > 0 && (p.num_n_blocks != 1 || p.k_blocks > RES || p.ksplits != 1))
+    return fail(VTC_ERR_ARG, "resident-B tile variant used outside its range");
   const long long tiles = 1ll * p.num_m_blocks * p.num_n_blocks * p.ksplits;
   if (tiles > 0x7fffffffll) return fail(VTC_ERR_ARG, "too many tiles");
   static bool attr_set_dev[64] = {};  // the attribute is per device
@@ -302,7 +304,7 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   CUDA_TRY(cudaGetDevice(&dev));
   bool& attr_set = attr_set_dev[dev & 63];
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(vtc_gemm_kernel<EPI, P, NIN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
+    CUDA_TRY(cudaFuncSetAttribute(vtc_gemm_kernel<EPI, P, NIN, BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
     attr_set = true;
   }
   long long max_pairs = info.sm_count / 2;
@@ -323,9 +325,21 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (tune_flags() & TUNE_NO_PDL) ? 1 : 2;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_gemm_kernel<EPI, P, NIN, BN>, p));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_gemm_kernel<EPI, P, NIN, BN, RES>, p));
   COUNT_LAUNCH();
   return VTC_OK;
+}
+
+// Convolutional launches whose whole B operand (N <= 64 outputs, <= 8 K blocks) stays resident in shared memory:
+// 64-wide tiles, the ring carries A only. VTC_B200_CONV_RESIDENT=0 keeps the 128-wide streaming tiles.
+bool conv_resident_b(const GemmCall& c, int P) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("VTC_B200_CONV_RESIDENT");
+    enabled = e ? (atoi(e) != 0) : 1;
+  }
+  const int64_t bk = (P == 1) ? 64 : 32;
+  return enabled && c.nseg > 0 && P <= 2 && c.N <= 64 && c.ksplits == 1 && c.B.Kp / bk <= 8;
 }
 
 template <int EPI>
@@ -346,6 +360,10 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     //  but measured 10-15 % slower: the A panel is staged twice and the N = 128 MMA is shared-memory bound)
     // narrow outputs (the convolutional path: N = code channels or pixels per block) take the 128-wide tile so that
     // fewer MMA columns are spent on zero padding
+    if (conv_resident_b(c, P)) {
+      return P == 1 ? launch_gemm_p<EPI_STORE, 1, 1, 64, 8>(c, info, stream)
+                    : launch_gemm_p<EPI_STORE, 2, 1, 64, 8>(c, info, stream);
+    }
     if (c.N <= 128 && c.nseg > 0) {
       switch (P) {
         case 1: return launch_gemm_p<EPI_STORE, 1, 1, 128>(c, info, stream);
@@ -360,6 +378,10 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     }
   }
   if (nin <= 2) {
+    if (conv_resident_b(c, P)) {
+      return P == 1 ? launch_gemm_p<EPI_FISTA, 1, 2, 64, 8>(c, info, stream)
+                    : launch_gemm_p<EPI_FISTA, 2, 2, 64, 8>(c, info, stream);
+    }
     if (c.N <= 128 && c.nseg > 0) {
       switch (P) {
         case 1: return launch_gemm_p<EPI_FISTA, 1, 2, 128>(c, info, stream);
