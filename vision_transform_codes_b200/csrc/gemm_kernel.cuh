@@ -55,8 +55,16 @@ constexpr int EPI_PART_BYTES = BLOCK_M * EPI_COLS * 2;   // 4 KB: one bf16 [128 
 // RES > 0: "resident B" -- the launch has a single column of tiles (N <= BN) and at most RES K blocks, so this CTA's half
 // of B is the same for every tile: it is loaded once into its own region and the ring carries A only (the
 // convolutional launches: B is the 16-64 KB dictionary operand, re-fetching it per tile was a third of the L2->SM bytes).
-template <int P, int NIN, int BN, int RES = 0>
+// NBANDS > 0 (with RES > 0): "halo" staging of a segmented A. The taps of one kernel row (qy fixed, qx = 0..tx-1) read
+// the same operand rows shifted by qx: instead of one 128-row tile per tap, each stage holds NBANDS bands of HALO_ROWS =
+// 128 + halo rows (one per kernel row qy) and every tap's UMMA descriptor starts a few rows into its band -- the
+// swizzle is a function of the shared-memory address, so a row offset is just a byte offset. 16x16 kernels at stride 8:
+// 2 bands of 144 rows instead of 4 tiles of 128 rows per K column block (0.56x the A bytes through L2).
+constexpr int HALO_ROWS = 144;
+constexpr int HALO_LEAD = 8;        // rows in front of the tile in a band that serves negative tap shifts
+template <int P, int NIN, int BN, int RES = 0, int NBANDS = 0>
 struct Cfg {
+  static_assert(NBANDS == 0 || RES > 0, "halo staging needs the resident B");
   static_assert(BN == 256 || BN == 128 || BN == 64, "tile width");
   static constexpr int HALF_N = BN / 2;                         // B rows staged by each CTA of the pair
   static constexpr int TMEM_COLS = 2 * BN;                      // two accumulators
@@ -64,20 +72,24 @@ struct Cfg {
   static constexpr int SPAN = BK * 2;                           // bytes per operand row = swizzle span (128 / 64)
   static constexpr int TILE_BYTES = BLOCK_M * SPAN;             // one part tile of A
   static constexpr int B_TILE_BYTES = HALF_N * SPAN;            // one part tile of this CTA's half of B
-  static constexpr int STAGE_BYTES = RES > 0 ? P * TILE_BYTES : P * (TILE_BYTES + B_TILE_BYTES);
+  static constexpr int BAND_BYTES = HALO_ROWS * SPAN;           // one part of one band
+  static constexpr int STAGE_BYTES = NBANDS > 0 ? NBANDS * P * BAND_BYTES
+                                   : RES > 0 ? P * TILE_BYTES : P * (TILE_BYTES + B_TILE_BYTES);
   static constexpr int BRES_KB_BYTES = P * B_TILE_BYTES;        // one K block of the resident B
   static constexpr int BRES_BYTES = RES * BRES_KB_BYTES;
   static constexpr int IN_STAGE_BYTES = NIN * EPI_ARRAY_BYTES;
-  static constexpr int OP_STAGES = RES > 0 ? (NIN == 1 ? 6 : (P == 3 ? 2 : 3))
+  static constexpr int OP_STAGES = NBANDS > 0 ? (NIN == 1 ? 3 : 2)
+                                 : RES > 0 ? (NIN == 1 ? 6 : (P == 3 ? 2 : 3))
                                  : NIN == 3 ? ((P == 3) ? 2 : 3)
                                  : NIN == 2 ? 2
                                             : ((P == 3) ? 3 : 4);
   // IN_STAGES is a multiple of NUM_MATH_GROUPS: every input stage is always consumed by the same math group, so a
   // group sees the phases of "its" stages strictly in order (parity waits must never run a whole phase ahead).
-  static constexpr int IN_STAGES = NIN == 3 ? ((P == 3) ? 2 : 4)
+  static constexpr int IN_STAGES = NBANDS > 0 ? (NIN == 1 ? 6 : 4)
+                                 : NIN == 3 ? ((P == 3) ? 2 : 4)
                                  : NIN == 2 ? ((P == 3) ? 4 : 6)
                                             : ((P == 3) ? 2 : 6);
-  static constexpr int OUT_STAGES = (NIN == 3 && P != 3) ? 2 : 3;
+  static constexpr int OUT_STAGES = (NBANDS > 0 && NIN == 1) ? 2 : (NIN == 3 && P != 3) ? 2 : 3;
   static_assert(IN_STAGES % NUM_MATH_GROUPS == 0, "input stages must have a fixed owner group");
   static constexpr int OUT_STAGE_BYTES = EPI_ARRAY_BYTES + P * EPI_PART_BYTES;
   static constexpr int NPAIRS = (P == 1) ? 1 : (P == 2) ? 3 : 6;
@@ -145,6 +157,11 @@ struct GemmParams {
   // against B columns kb * BK as usual. Rows shifted outside the matrix read as zero (TMA fill). seg_kb = 0: off.
   int seg_kb;
   int seg_shift[MAX_SEGMENTS];
+  // halo staging (Cfg NBANDS > 0): band b of a stage holds rows [m0 + halo_band_row[b], + HALO_ROWS) of A (tmAh, box
+  // HALO_ROWS rows); tap q reads band halo_tap_band[q] from row halo_tap_row[q] on
+  CUtensorMap tmAh;
+  int halo_band_row[4];
+  int halo_tap_band[MAX_SEGMENTS], halo_tap_row[MAX_SEGMENTS];
   // Rows are (image, i, j) on a grid_h x grid_w grid of stride-sized image blocks (grid_w = 0: no grid).
   //   EPI_FISTA: code positions exist for i < code_h, j < code_w; the other rows are padding and stay exactly zero.
   //   EPI_STORE: columns are (channel, dy, dx) of a blk_sy x blk_sx block; outputs whose pixel (i*sy+dy, j*sx+dx) lies
@@ -322,9 +339,9 @@ __device__ __forceinline__ void split_parts16(const float (&partv)[16], int n_pa
   }
 }
 
-template <int EPI, int P, int NIN, int BN, int RES = 0>
+template <int EPI, int P, int NIN, int BN, int RES = 0, int NBANDS = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<P, NIN, BN, RES>;
+  using C = Cfg<P, NIN, BN, RES, NBANDS>;
   constexpr int IN_STAGE_BYTES = C::IN_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // swizzled TMA / UMMA tiles need a 1024-byte aligned base; the offset is identical in both CTAs of the pair
@@ -420,7 +437,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     uint32_t it = 0;
     for (int w = w_begin; w < w_end; w += w_step) {
       const TileCoord c = decode_tile<BN>(p, w, cta_rank);
-      for (int kb = c.kb0; kb < c.kb1; ++kb, ++it) {
+      if (NBANDS > 0) {
+        // halo staging: one stage per K column block, NBANDS bands of HALO_ROWS rows, all parts
+        for (int kba = 0; kba < p.seg_kb; ++kba, ++it) {
+          const int s = it % C::OP_STAGES;
+          const uint32_t ph = (it / C::OP_STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          if (elect_one_sync()) {
+            if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
+            else mbar_arrive_remote(full_bar(s), 0);
+            const uint32_t dst = sOp + s * C::STAGE_BYTES;
+#pragma unroll
+            for (int b = 0; b < NBANDS; ++b)
+#pragma unroll
+              for (int q = 0; q < P; ++q)
+                tma_load_3d_pair(dst + (b * P + q) * C::BAND_BYTES, &p.tmAh, full_bar(s), 0, c.m0 + p.halo_band_row[b],
+                                 q * p.a_blocks_per_part + kba, kEvictNormal);
+          }
+          __syncwarp();
+        }
+      }
+      for (int kb = c.kb0; NBANDS == 0 && kb < c.kb1; ++kb, ++it) {
         const int s = it % C::OP_STAGES;
         const uint32_t ph = (it / C::OP_STAGES) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
@@ -467,7 +504,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         uint32_t accumulate = 0;
-        for (int kb = c.kb0; kb < c.kb1; ++kb, ++it) {
+        if (NBANDS > 0) {
+          const int nseg = p.k_blocks / p.seg_kb;
+          for (int kba = 0; kba < p.seg_kb; ++kba, ++it) {
+            const int s = it % C::OP_STAGES;
+            mbar_wait(full_bar(s), (it / C::OP_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t stage = sOp + s * C::STAGE_BYTES;
+            if (elect_one_sync()) {
+              for (int q = 0; q < nseg; ++q) {
+                // tap q: rows halo_tap_row[q].. of its band; B K block (q, kba) from the resident operand
+                const uint32_t abase = stage + p.halo_tap_band[q] * (P * C::BAND_BYTES) + p.halo_tap_row[q] * C::SPAN;
+                const uint32_t bbase = sBres + (q * p.seg_kb + kba) * C::BRES_KB_BYTES;
+#pragma unroll
+                for (int pr = 0; pr < C::NPAIRS; ++pr) {
+                  const uint64_t adesc = make_kmajor_desc(abase + pair_a(P, pr) * C::BAND_BYTES, C::SPAN);
+                  const uint64_t bdesc = make_kmajor_desc(bbase + pair_b(P, pr) * C::B_TILE_BYTES, C::SPAN);
+#pragma unroll
+                  for (int k = 0; k < C::BK / UMMA_K; ++k) {
+                    umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                    accumulate = 1;
+                  }
+                }
+              }
+              umma_commit_pair(empty_bar(s), 3);
+            }
+            accumulate = 1;
+            __syncwarp();
+          }
+        }
+        for (int kb = c.kb0; NBANDS == 0 && kb < c.kb1; ++kb, ++it) {
           const int s = it % C::OP_STAGES;
           const uint32_t ph = (it / C::OP_STAGES) & 1;
           mbar_wait(full_bar(s), ph);

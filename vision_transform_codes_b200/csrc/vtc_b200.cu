@@ -138,13 +138,14 @@ struct F32Mat {
   bool blocked = false;  // tile-contiguous [ceil(cols/16)][rows][16] instead of row-major with pitch ld
 };
 
-int map_operand(CUtensorMap* m, const PartsMat& a, int block_k, const char* what, int box_rows = BLOCK_M) {
+int map_operand(CUtensorMap* m, const PartsMat& a, int block_k, const char* what, int box_rows = BLOCK_M,
+                int blocked_box_rows = BLOCK_M) {
   if (a.block) {
     if (a.block != block_k) return fail(VTC_ERR_ARG, "%s: blocked operand of width %d read with K block %d", what, a.block, block_k);
     const uint64_t dims[3] = {static_cast<uint64_t>(a.block), static_cast<uint64_t>(a.rows),
                               static_cast<uint64_t>(a.parts * (a.Kp / a.block))};
     const uint64_t str[2] = {static_cast<uint64_t>(a.block) * 2, static_cast<uint64_t>(a.rows) * a.block * 2};
-    const uint32_t box[3] = {static_cast<uint32_t>(block_k), BLOCK_M, 1};
+    const uint32_t box[3] = {static_cast<uint32_t>(block_k), static_cast<uint32_t>(blocked_box_rows), 1};
     return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a.ptr, dims, str, box,
                   block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, what);
   }
@@ -237,16 +238,26 @@ struct GemmCall {
   // segmented K and grid masks of the convolutional path (GemmParams has the semantics)
   int seg_kb = 0, nseg = 0;
   int seg_shift[MAX_SEGMENTS] = {};
+  // halo staging of the taps (GemmParams): bands per stage (0 = off), row of each band, band and row of each tap
+  int halo_bands = 0;
+  int halo_band_row[4] = {};
+  int halo_tap_band[MAX_SEGMENTS] = {}, halo_tap_row[MAX_SEGMENTS] = {};
   int grid_h = 0, grid_w = 0, code_h = 0, code_w = 0;
   int blk_sy = 1, blk_sx = 1, pix_y0 = 0, pix_y1 = 0, pix_x0 = 0, pix_x1 = 0;
 };
 
-template <int EPI, int P, int NIN, int BN, int RES = 0>
+template <int EPI, int P, int NIN, int BN, int RES = 0, int NBANDS = 0>
 int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream) {
-  using Cf = Cfg<P, NIN, BN, RES>;
+  using Cf = Cfg<P, NIN, BN, RES, NBANDS>;
   GemmParams p;
   memset(&p, 0, sizeof(p));
   TRY(map_operand(&p.tmA, c.A, Cf::BK, "A operand"));
+  if (NBANDS > 0) {
+    if (c.halo_bands != NBANDS || !c.A.block) return fail(VTC_ERR_ARG, "halo tile variant used outside its range");
+    TRY(map_operand(&p.tmAh, c.A, Cf::BK, "A operand (halo bands)", BLOCK_M, HALO_ROWS));
+    for (int b = 0; b < NBANDS; ++b) p.halo_band_row[b] = c.halo_band_row[b];
+    for (int q = 0; q < c.nseg; ++q) p.halo_tap_band[q] = c.halo_tap_band[q], p.halo_tap_row[q] = c.halo_tap_row[q];
+  }
   TRY(map_operand(&p.tmB, c.B, Cf::BK, "B operand", Cf::HALF_N));
   for (int i = 0; i < 3; ++i)
     if (c.in_mask & (1 << i)) TRY(map_f32(&p.tmIn[i], c.in[i], "epilogue input"));
@@ -304,7 +315,7 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   CUDA_TRY(cudaGetDevice(&dev));
   bool& attr_set = attr_set_dev[dev & 63];
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(vtc_gemm_kernel<EPI, P, NIN, BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
+    CUDA_TRY(cudaFuncSetAttribute(vtc_gemm_kernel<EPI, P, NIN, BN, RES, NBANDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
     attr_set = true;
   }
   long long max_pairs = info.sm_count / 2;
@@ -325,7 +336,7 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (tune_flags() & TUNE_NO_PDL) ? 1 : 2;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_gemm_kernel<EPI, P, NIN, BN, RES>, p));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_gemm_kernel<EPI, P, NIN, BN, RES, NBANDS>, p));
   COUNT_LAUNCH();
   return VTC_OK;
 }
@@ -361,6 +372,9 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     // narrow outputs (the convolutional path: N = code channels or pixels per block) take the 128-wide tile so that
     // fewer MMA columns are spent on zero padding
     if (conv_resident_b(c, P)) {
+      if (c.halo_bands == 2)
+        return P == 1 ? launch_gemm_p<EPI_STORE, 1, 1, 64, 8, 2>(c, info, stream)
+                      : launch_gemm_p<EPI_STORE, 2, 1, 64, 8, 2>(c, info, stream);
       return P == 1 ? launch_gemm_p<EPI_STORE, 1, 1, 64, 8>(c, info, stream)
                     : launch_gemm_p<EPI_STORE, 2, 1, 64, 8>(c, info, stream);
     }
@@ -379,6 +393,9 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
   }
   if (nin <= 2) {
     if (conv_resident_b(c, P)) {
+      if (c.halo_bands == 2)
+        return P == 1 ? launch_gemm_p<EPI_FISTA, 1, 2, 64, 8, 2>(c, info, stream)
+                      : launch_gemm_p<EPI_FISTA, 2, 2, 64, 8, 2>(c, info, stream);
       return P == 1 ? launch_gemm_p<EPI_FISTA, 1, 2, 64, 8>(c, info, stream)
                     : launch_gemm_p<EPI_FISTA, 2, 2, 64, 8>(c, info, stream);
     }
@@ -1466,6 +1483,26 @@ int conv_dictionary_operands(const float* dictionary, const ConvShape& cs, const
   return VTC_OK;
 }
 
+// Halo staging of the taps: one band of rows per kernel row qy, the taps qx of that row start qx rows into it (analysis,
+// positive shifts) or HALO_LEAD - qx rows into a band loaded HALO_LEAD rows early (synthesis, negative shifts).
+// VTC_B200_CONV_HALO=0 keeps one tile per tap.
+void conv_halo(GemmCall& c, const ConvGeom& g, bool negative) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("VTC_B200_CONV_HALO");
+    enabled = e ? (atoi(e) != 0) : 1;
+  }
+  if (!enabled || g.ty != 2 || g.tx - 1 > HALO_ROWS - BLOCK_M - HALO_LEAD) return;
+  c.halo_bands = g.ty;
+  for (int qy = 0; qy < g.ty; ++qy) {
+    c.halo_band_row[qy] = negative ? -(qy * g.gw) - HALO_LEAD : qy * g.gw;
+    for (int qx = 0; qx < g.tx; ++qx) {
+      c.halo_tap_band[qy * g.tx + qx] = qy;
+      c.halo_tap_row[qy * g.tx + qx] = negative ? HALO_LEAD - qx : qx;
+    }
+  }
+}
+
 // r = mask * (conv_transpose(y) - x) on the block grid: synthesis contraction over (tap, channel), taps = row shifts
 void conv_synthesis_call(GemmCall& r, const ConvShape& cs, const ConvWs& w, const PartsMat& y, int precision) {
   const ConvGeom& g = cs.g;
@@ -1475,6 +1512,7 @@ void conv_synthesis_call(GemmCall& r, const ConvShape& cs, const ConvWs& w, cons
   r.nseg = cs.nq;
   for (int qy = 0; qy < g.ty; ++qy)
     for (int qx = 0; qx < g.tx; ++qx) r.seg_shift[qy * g.tx + qx] = -(qy * g.gw + qx);
+  conv_halo(r, g, true);
   r.in[0] = F32Mat{w.xblk, cs.rows, g.db, w.ldD}, r.in_mask = 1;
   r.grid_h = g.gh, r.grid_w = g.gw;
   r.blk_sy = g.sy, r.blk_sx = g.sx;
@@ -1575,6 +1613,7 @@ int vtc_fista_conv(const float* images_padded, const float* dictionary, const fl
     c.nseg = cs.nq;
     for (int qy = 0; qy < g.ty; ++qy)
       for (int qx = 0; qx < g.tx; ++qx) c.seg_shift[qy * g.tx + qx] = qy * g.gw + qx;
+    conv_halo(c, g, false);
     c.grid_h = g.gh, c.grid_w = g.gw, c.code_h = g.ch, c.code_w = g.cw;
     c.in[0] = a_prev, c.in_mask = 1;
     if (variant == VTC_VARIANT_FISTA && beta_prev != 0.f) c.in[2] = a_prev2, c.in_mask |= 4;
