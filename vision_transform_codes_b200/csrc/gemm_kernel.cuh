@@ -64,6 +64,11 @@ constexpr int HALO_ROWS = 144;
 constexpr int HALO_LEAD = 8;        // rows in front of the tile in a band that serves negative tap shifts
 template <int P, int NIN, int BN, int RES = 0, int NBANDS = 0>
 struct Cfg {
+  // epilogue math groups (four warps each). (A third group for the 64-wide halo tiles, which have only four sub-tiles
+  // each, measured neutral: 0.238 against 0.232 ms per convolutional iteration, it costs an operand stage.)
+  static constexpr int GROUPS = NUM_MATH_GROUPS;
+  static constexpr int MATH_WARPS = 4 * GROUPS;
+  static constexpr int THREADS = 128 + 32 * MATH_WARPS;
   static_assert(NBANDS == 0 || RES > 0, "halo staging needs the resident B");
   static_assert(BN == 256 || BN == 128 || BN == 64, "tile width");
   static constexpr int HALF_N = BN / 2;                         // B rows staged by each CTA of the pair
@@ -90,7 +95,11 @@ struct Cfg {
                                  : NIN == 2 ? ((P == 3) ? 4 : 6)
                                             : ((P == 3) ? 2 : 6);
   static constexpr int OUT_STAGES = (NBANDS > 0 && NIN == 1) ? 2 : (NIN == 3 && P != 3) ? 2 : 3;
-  static_assert(IN_STAGES % NUM_MATH_GROUPS == 0, "input stages must have a fixed owner group");
+  static_assert(IN_STAGES % GROUPS == 0, "input stages must have a fixed owner group");
+  // output stages: with two groups the in-order storer keeps a stage's barrier at most one phase behind any waiter
+  // (three stages are fine); with three groups a slow group can leave it two phases behind, so every stage then needs a
+  // fixed writer group as well
+  static_assert(GROUPS == 2 || OUT_STAGES % GROUPS == 0, "output stages must have a fixed writer group");
   static constexpr int OUT_STAGE_BYTES = EPI_ARRAY_BYTES + P * EPI_PART_BYTES;
   static constexpr int NPAIRS = (P == 1) ? 1 : (P == 2) ? 3 : 6;
   static constexpr int OFF_OP = 0;
@@ -340,7 +349,8 @@ __device__ __forceinline__ void split_parts16(const float (&partv)[16], int n_pa
 }
 
 template <int EPI, int P, int NIN, int BN, int RES = 0, int NBANDS = 0>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__((Cfg<P, NIN, BN, RES, NBANDS>::THREADS), 1)
+vtc_gemm_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<P, NIN, BN, RES, NBANDS>;
   constexpr int IN_STAGE_BYTES = C::IN_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
     mbar_init(bres_full_bar, 2);   // resident B: one arrive per CTA's producer (used in the leader only)
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);                     // multicast tcgen05.commit
-      mbar_init(tmem_empty_bar(a), 2 * NUM_MATH_WARPS);   // every math warp of both CTAs (used in the leader only)
+      mbar_init(tmem_empty_bar(a), 2 * C::MATH_WARPS);   // every math warp of both CTAs (used in the leader only)
     }
     for (int e = 0; e < C::IN_STAGES; ++e) {
       mbar_init(in_full_bar(e), 1);
@@ -648,8 +658,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       // last sub-tile of this tile that belongs to this warp's group (-1: none)
       int j_last = -1;
-      for (int j = c.nsub - 1; j >= 0 && j >= c.nsub - NUM_MATH_GROUPS; --j)
-        if ((q + j) % NUM_MATH_GROUPS == group) {
+      for (int j = c.nsub - 1; j >= 0 && j >= c.nsub - C::GROUPS; --j)
+        if ((q + j) % C::GROUPS == group) {
           j_last = j;
           break;
         }
@@ -661,7 +671,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vtc_gemm_kernel(const __grid_
         }
       }
       for (int j = 0; j < c.nsub; ++j, ++q) {
-        if (q % NUM_MATH_GROUPS != group) continue;
+        if (q % C::GROUPS != group) continue;
         const int e = q % C::IN_STAGES;
         const uint32_t in_ph = (q / C::IN_STAGES) & 1;
         const int o = q % C::OUT_STAGES;

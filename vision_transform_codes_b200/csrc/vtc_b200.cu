@@ -324,7 +324,7 @@ int launch_gemm_p(const GemmCall& c, const DeviceInfo& info, cudaStream_t stream
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(Cf::THREADS);
   cfg.dynamicSmemBytes = Cf::SMEM_ALLOC;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
