@@ -148,6 +148,35 @@ def conv_benchmark(world, rank, dev, timed, pk, precision, images_per_gpu=CONV_I
   }
 
 
+def subspace_benchmark(world, rank, dev, timed, pk, precision, batch=131072):
+  """BASELINE.json configs[3]: subspace FISTA with group soft-thresholding (groups of 2), 32x32 patches (D = 1024),
+  4096 atoms, batch 131,072 per GPU, 300 iterations. D > 256: the two-launch synthesis schedule, tensor-bound."""
+  import numpy as np
+  import vision_transform_codes_b200 as pkg
+  from oracle import vtc_oracle as oracle  # seeded input generators only
+  from vision_transform_codes_b200.analysis_transforms.fully_connected import subspace_ista_fista
+  s4, d4 = 4096, 1024
+  phi = oracle.synthetic_dictionary(s4, d4).to(dev)
+  gx = torch.Generator(device=dev).manual_seed(200 + rank)
+  x = 0.3 * torch.randn(batch, d4, generator=gx, device=dev)
+  groups = [list(map(int, g)) for g in np.array_split(np.arange(s4), s4 // 2)]
+  saved = pkg.config.precision
+  pkg.config.precision = precision
+  ms, launches = timed(lambda: subspace_ista_fista.run(x, phi, groups, LAM, T), 1, 1)
+  pkg.config.precision = saved
+  nprod = pkg.PRECISIONS[precision]
+  executed = nprod * 4.0 * batch * s4 * d4 * T
+  return {
+      'workload': 'configs[3]: subspace FISTA, groups of 2, 32x32 patches (D=1024), 4096 atoms, batch %d per GPU, '
+                  '%d iters' % (batch, T),
+      'value': world * batch / (ms * 1e-3), 'unit': 'patches/s', 'ms_per_step': ms, 'precision': precision,
+      'gpu_launches': int(launches),
+      'executed_mma_tflops': executed / (ms * 1e-3) / 1e12,
+      'executed_frac_of_tensor_peak': executed / (ms * 1e-3) / 1e12 / pk['bf16_sustained'],
+      'tflops_gram_equivalent': 2.0 * batch * s4 * s4 * T / (ms * 1e-3) / 1e12,
+  }
+
+
 def run_reference(args, rank):
   if rank != 0:
     return
@@ -372,6 +401,7 @@ def main():
     except ImportError:
       pass
     line['conv_path'] = conv_benchmark(world, rank, dev, timed, pk, args.precision)
+    line['subspace_path'] = subspace_benchmark(world, rank, dev, timed, pk, args.precision)
     if rank == 0 and world == 1:
       v, cores, secs = cpu_reference_patches_per_sec(CPU_SAMPLE)
       line['cpu_baseline'] = {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': 'port',

@@ -233,3 +233,29 @@ def test_conv_lean_trainer_matches_reference_trainer(tmp_path):
                            dict(params, code_inference_algorithm='fista',
                                 dictionary_update_algorithm='sc_steepest_descent', checkpoint_schedule=None))
   assert oracle.relative_l2(phi2.cpu(), g['fista_steepest']) < 5e-5
+
+
+@pytest.mark.parametrize('env', [{'VTC_B200_CONV_HALO': '0'}, {'VTC_B200_CONV_RESIDENT': '0'}])
+def test_conv_tile_variants_agree(env):
+  """The convolutional launches have three tile variants (one tile per tap on 128-wide tiles; resident dictionary
+  operand on 64-wide tiles; + halo staging of the taps, the default). The switches are read once per process, so the
+  other two run in a subprocess; all three must agree with the oracle."""
+  import os
+  import subprocess
+  import sys
+  from conftest import ROOT
+  code = (
+      "import sys; sys.path.insert(0, %r)\n"
+      "import torch\n"
+      "from oracle import vtc_oracle as oracle\n"
+      "from vision_transform_codes_b200.analysis_transforms.convolutional import ista_fista\n"
+      "x, pad = oracle.synthetic_padded_images(3, 1, 96, 80, (16, 16), (8, 8))\n"
+      "phi = oracle.synthetic_conv_dictionary(64, 1, 16, 16)\n"
+      "want = oracle.conv_ista_fista(x, phi, (8, 8), pad, 0.05, 30)\n"
+      "got = ista_fista.run(x.cuda(), phi.cuda(), (8, 8), pad, 0.05, 30).cpu()\n"
+      "err = oracle.relative_l2(got, want)\n"
+      "assert err <= 1e-4, err\n"
+      "print('VARIANT_OK', err)\n" % ROOT)
+  out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, **env))
+  assert out.returncode == 0 and 'VARIANT_OK' in out.stdout, out.stdout + out.stderr
