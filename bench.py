@@ -337,13 +337,13 @@ def main():
   if os.path.exists(tpath) and form == 'synthesis' and Bn == B_PER_GPU:
     traffic = json.load(open(tpath)).get(args.precision, {}).get('iter_bytes' if fused_iter else 'fused_bytes')
   roofline.update({
-      'kernel': ('vtc_fista_iter_kernel<%d> (one launch per iteration, y_k on chip)' % nparts) if fused_iter else
+      'kernel': ('vtc_fista_iter_kernel<%d> (panel-resident, y_k on chip; launch_ms is per iteration)' % nparts) if fused_iter else
                 'vtc_gemm_kernel<EPI_FISTA,%d> (%s form)' % (nparts, form), 'traffic': traffic,
       'launch_ms': fused_ms, 'first_launch_ms': first_ms if (form == 'synthesis' and not fused_iter) else None,
       'algorithmic_bytes_per_launch': bytes_fused, 'executed_mma_flops_per_launch': nprod * flops_fused,
       'hbm_floor_ms': bytes_fused / (pk['hbm_gbs'] * 1e9) * 1e3,
       'tensor_floor_ms': nprod * flops_fused / (pk['bf16_sustained'] * 1e12) * 1e3,
-      'formulation': form, 'launches_per_iteration': n_launch // max(1, n_iter), 'ms_per_iteration': iter_ms_each,
+      'formulation': form, 'launches_per_iteration': n_launch / max(1, n_iter), 'ms_per_iteration': iter_ms_each,
       'setup_ms_per_step': setup_ms,
       # whole iteration loop against the tensor roofline, both flop conventions
       'iteration_tflops_executed_form': flops_iter / (iter_ms_each * 1e-3) / 1e12,
@@ -376,7 +376,9 @@ def main():
       'vs_baseline': None, 'dtype': args.precision + ' (bf16 products, fp32 accumulate)', 'data': 'synthetic',
       'config': {'workload': WORKLOAD, 'batch_per_gpu': Bn, 'atoms': S, 'pixels': D, 'iters': T,
                  'precision': args.precision, 'formulation': form,
-                 'schedule': 'one launch per iteration' if fused_iter else '%d launch(es) per iteration' % (n_launch // max(1, n_iter)),
+                 'schedule': ('one persistent launch for all %d iterations' % n_iter if n_launch == 1 else
+                              'one launch per iteration') if fused_iter else
+                             '%d launch(es) per iteration' % (n_launch // max(1, n_iter)),
                  'parallelism': 'batch sharded over %d GPU(s), dictionary replicated, '
                  'no data-path collective' % world,
                  'l2': 'inputs larger than L2 (per-iteration state %.0f MB vs 126 MB L2)' % (Bn * S * 4 * 3 / 1e6)},

@@ -118,9 +118,9 @@ struct IterParams {
   CUtensorMap tmR;      // r_op (bf16 parts, tile-contiguous [part][Dp/BK][rows][BK]): box BK x 128, A operand of G
   CUtensorMap tmPhi;    // phi_op (S x parts*Dp, row-major): box BK x 64, B operand of G
   CUtensorMap tmPhiT;   // phiT_op (D x parts*Sp, row-major): box 32 x 128, SWIZZLE_64B, B operand of R
-  CUtensorMap tmIn[3];  // fp32 state: [0] = a_{k-1}, [2] = a_{k-2} (slot 1 unused), box 16 x 128
+  CUtensorMap tmState[4];  // fp32 code arrays, box 16 x 128: [0] the starting point a_0, [1] a_k for odd k, [2] a_k for
+                           // even k (a_k overwrites a_{k-2} in place), [3] where the final iterate goes
   CUtensorMap tmX;      // images (B x D fp32, row-major), box 16 x 128
-  CUtensorMap tmOut;    // a_k
   CUtensorMap tmROut;   // r_op as a store target: box 16 x 128, SWIZZLE_32B
   int num_panels;       // ceil(B / 256)
   int S;
@@ -130,18 +130,19 @@ struct IterParams {
   int phiT_part_stride; // Sp
   int nsub_r;           // Dp / 16: sub-tiles of r written at the panel end
   int r_block_w;        // BK of r_op's layout
-  int in_mask;          // bit 0: a_{k-1}; bit 2: a_{k-2}
-  int blocked_mask;     // BLK_IN0 << i, BLK_OUT
-  int do_r;             // produce r_k (0 on the last iteration: nothing consumes it)
+  int state_blocked[4]; // tmState[i] is tile-contiguous (3-D map) instead of row-major
+  // One launch runs iterations k_first .. k_first + k_count - 1 of every panel. The jobs (iteration, panel) are dealt
+  // round-robin to the CTA pairs in iteration-major order, so every pair gets the same number of jobs whatever the panel
+  // count (no quantisation of panels onto pairs), and a panel's state simply moves from pair to pair through HBM / L2;
+  // job (k, panel) waits until both CTAs of job (k - 1, panel) have published `done[panel]`.
+  int k_first, k_count;
+  int k_final;          // the iteration whose output is the result: written to tmState[3], no r_k produced (nothing
+                        // consumes it); INT_MAX when the caller stops on its own criterion
+  const float* betas;   // device: betas[k] = FISTA momentum coefficient of iteration k, betas[0] = 0
+  int* done;            // device, per panel: CTAs that have completed a job of this launch on it (nullptr: k_count == 1)
   int prox, group, use_momentum;
-  float beta_prev, beta_next;
   const float* scalars;  // device: [0] = eta, [1] = theta
   double* stat;          // optional: += sum |a_k - a_{k-1}|
-  // L2 prefetch of the state stream (tile-contiguous inputs only): a sub-tile is one contiguous span of rows * 64 bytes
-  const char* pf_base[2];          // a_{k-1}, a_{k-2} (nullptr: not prefetched)
-  unsigned long long pf_block_bytes;  // bytes between column blocks = rows * 64
-  int rows;                        // B
-  int pf_distance;                 // sub-tiles ahead of the shared-memory loads (0 = off)
   unsigned long long* trace;  // optional (tools/iter_trace.py): 4 regions of 2048 words, [0] = event count, then
                               // (event id << 48 | SM clock) words, written by four threads of CTA 0
 };
@@ -165,10 +166,16 @@ struct Tracer {
   }
 };
 
-// bring `bytes` (a multiple of 16) at a 16-byte aligned global address into L2; no shared memory, no barrier
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+// completion flags between jobs of one launch (a panel's iteration k may run on another CTA pair than k - 1)
+__device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
 }
+__device__ __forceinline__ void red_release_gpu_add(int* ptr, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // non-blocking tests (the MMA issuer polls several barriers)
 __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
@@ -202,8 +209,50 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
   const int NT = p.num_n_tiles;
-  const int my_panels = (p.num_panels - cluster_id + num_clusters - 1) / num_clusters;  // panels cluster_id, +num_clusters, ...
-  const int my_tiles = my_panels * NT;
+  // jobs of this pair: tickets cluster_id, cluster_id + num_clusters, ... of the k_count x num_panels grid, k slowest
+  const long long total_jobs = static_cast<long long>(p.k_count) * p.num_panels;
+  const int my_jobs = total_jobs > cluster_id
+                          ? static_cast<int>((total_jobs - cluster_id + num_clusters - 1) / num_clusters) : 0;
+  const int my_tiles = my_jobs * NT;
+  struct Job {
+    int k, m0, panel, wait_target;
+    bool do_r, has_prev2;
+    int prev, prev2, out;   // indices into tmState
+    float beta_prev, beta_next;
+  };
+  auto job_at = [&](int ji) {
+    Job j;
+    const long long ticket = cluster_id + static_cast<long long>(ji) * num_clusters;
+    const int ko = static_cast<int>(ticket / p.num_panels);
+    j.k = p.k_first + ko;
+    j.panel = static_cast<int>(ticket - static_cast<long long>(ko) * p.num_panels);
+    j.m0 = j.panel * PAIR_M + cta_rank * BLOCK_M;
+    j.wait_target = 2 * ko;   // both CTAs of every earlier job of this launch on this panel
+    j.do_r = j.k < p.k_final;
+    j.beta_prev = __ldg(p.betas + j.k - 1);
+    j.beta_next = __ldg(p.betas + j.k);
+    j.has_prev2 = p.use_momentum != 0 && j.beta_prev != 0.f;
+    j.prev = (j.k == 1) ? 0 : (((j.k - 1) & 1) ? 1 : 2);
+    j.prev2 = (j.k <= 2) ? 0 : ((j.k & 1) ? 1 : 2);
+    j.out = (j.k == p.k_final) ? 3 : ((j.k & 1) ? 1 : 2);
+    return j;
+  };
+  // the data of job (k - 1, panel) must be complete before anything of job (k, panel) is read
+  auto wait_for_previous = [&](const Job& j) {
+    if (p.done != nullptr && j.wait_target > 0) {
+      if (lane == 0) {
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(p.done + j.panel) < j.wait_target) {
+          if (++spins > (1u << 28)) {
+            printf("vtc_b200: job (k %d, panel %d) never saw its predecessor (block %d)\n", j.k, j.panel, (int)blockIdx.x);
+            __trap();
+          }
+        }
+      }
+      __syncwarp();
+      fence_proxy_async_all();   // the acquired data is read through TMA (async proxy)
+    }
+  };
   const int nsub_r_pad = (p.nsub_r + C::PANEL_END_PAD - 1) / C::PANEL_END_PAD * C::PANEL_END_PAD;
   // sub-tiles of tile nt: an even number (whole chunks); columns at or beyond S are zero everywhere (TMA fill)
   auto tile_chunks = [&](int nt) { return (min(IT_BN, p.S - nt * IT_BN) + C::CHUNK - 1) / C::CHUNK; };
@@ -212,10 +261,8 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
     tma_prefetch_desc(&p.tmR);
     tma_prefetch_desc(&p.tmPhi);
     tma_prefetch_desc(&p.tmPhiT);
-    tma_prefetch_desc(&p.tmIn[0]);
-    if (p.in_mask & 4) tma_prefetch_desc(&p.tmIn[2]);
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmState[i]);
     tma_prefetch_desc(&p.tmX);
-    tma_prefetch_desc(&p.tmOut);
     tma_prefetch_desc(&p.tmROut);
   }
   if (warp == 1 && lane == 0) {
@@ -263,8 +310,10 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
     // ================================ G operand producer (both CTAs) ================================
     Tracer trace(p, 0, lane == 0);
     uint32_t it = 0;
-    for (int pi = 0; pi < my_panels; ++pi) {
-      const int m0 = (cluster_id + pi * num_clusters) * PAIR_M + cta_rank * BLOCK_M;
+    for (int ji = 0; ji < my_jobs; ++ji) {
+      const Job job = job_at(ji);
+      const int m0 = job.m0;
+      wait_for_previous(job);   // r_op[panel] is the previous iteration's output
       for (int nt = 0; nt < NT; ++nt) {
         const int n0 = nt * IT_BN;
         for (int kb = 0; kb < p.kb_g; ++kb, ++it) {
@@ -291,9 +340,10 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
     }
   } else if (warp == C::PT_WARP) {
     // ================================ Phi^T chunk producer (both CTAs) ================================
-    if (p.do_r) {
+    {
       uint32_t it = 0;
-      for (int pi = 0; pi < my_panels; ++pi) {
+      for (int ji = 0; ji < my_jobs; ++ji) {
+        if (!job_at(ji).do_r) continue;
         for (int nt = 0; nt < NT; ++nt) {
           const int nch = tile_chunks(nt);
           for (int c = 0; c < nch; ++c, ++it) {
@@ -330,9 +380,19 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
       int r_tile = 0, r_chunk = 0;
       uint32_t r_it = 0;
       uint32_t idle = 0;
-      while (g_tile < my_tiles || (p.do_r && r_tile < my_tiles)) {
+      int r_job = -1;
+      bool r_job_do_r = false;
+      while (g_tile < my_tiles || r_tile < my_tiles) {
         bool progressed = false;
-        if (p.do_r && r_tile < my_tiles) {
+        if (r_tile < my_tiles && r_tile / NT != r_job) {   // entering a job: does it produce r_k at all?
+          r_job = r_tile / NT;
+          r_job_do_r = job_at(r_job).do_r;
+        }
+        if (r_tile < my_tiles && !r_job_do_r) {
+          r_tile += NT;   // the final iteration has no R
+          continue;
+        }
+        if (r_tile < my_tiles) {
           const int pi = r_tile / NT, nt = r_tile % NT;
           const bool first = (nt == 0 && r_chunk == 0);
           const int ys = r_it % C::Y_STAGES, ps = r_it % C::PT_STAGES;
@@ -418,48 +478,20 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
     }
   } else if (warp == 3) {
     // ================================ epilogue input loader ================================
-    const uint32_t state_bytes = __popc(p.in_mask) * EPI_ARRAY_BYTES;
-    // L2 prefetch cursor: runs pf_distance state sub-tiles ahead of the shared-memory loads, so that those find their
-    // data in L2 (a fraction of the HBM latency) and the few stages of the in/out ring are enough bytes in flight
-    int ppi = 0, pnt = 0, pj = 0;
-    const int s_blocks = (p.S + EPI_COLS - 1) / EPI_COLS;
-    auto prefetch_next = [&](bool issue) {
-      if (ppi >= my_panels) return;
-      if (issue) {
-        const int pm0 = (cluster_id + ppi * num_clusters) * PAIR_M + cta_rank * BLOCK_M;
-        const int blk = pnt * (IT_BN / EPI_COLS) + pj;
-        const int nrows = min(BLOCK_M, p.rows - pm0);
-        if (nrows > 0 && blk < s_blocks) {
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-            if (p.pf_base[i] != nullptr)
-              bulk_prefetch_l2(p.pf_base[i] + blk * p.pf_block_bytes + static_cast<unsigned long long>(pm0) * 64,
-                               static_cast<uint32_t>(nrows) * 64);
-        }
-      }
-      if (++pj == C::SUBS * tile_chunks(pnt)) {
-        pj = 0;
-        if (++pnt == NT) pnt = 0, ++ppi;
-      }
-    };
-    const bool pf_on = p.pf_distance > 0 && (p.pf_base[0] != nullptr || p.pf_base[1] != nullptr);
-    if (pf_on && elect_one_sync()) {
-      for (int i = 0; i < C::IN_STAGES; ++i) prefetch_next(false);   // these are loaded straight away
-      for (int i = C::IN_STAGES; i < p.pf_distance; ++i) prefetch_next(true);
-    }
-    __syncwarp();
     uint32_t q = 0;
-    for (int pi = 0; pi < my_panels; ++pi) {
-      const int m0 = (cluster_id + pi * num_clusters) * PAIR_M + cta_rank * BLOCK_M;
+    for (int ji = 0; ji < my_jobs; ++ji) {
+      const Job job = job_at(ji);
+      const int m0 = job.m0;
+      const uint32_t state_bytes = (job.has_prev2 ? 2 : 1) * EPI_ARRAY_BYTES;
+      wait_for_previous(job);   // a_{k-1} (and the slot a_k overwrites) belong to the previous iterations
       for (int nt = 0; nt <= NT; ++nt) {
         const bool panel_end = (nt == NT);
-        if (panel_end && !p.do_r) break;
+        if (panel_end && !job.do_r) break;
         const int nsub = panel_end ? nsub_r_pad : C::SUBS * tile_chunks(nt);
         for (int j = 0; j < nsub; ++j, ++q) {
           const int e = q % C::IN_STAGES;
           mbar_wait(bar(C::B_IN_FREE + e), ((q / C::IN_STAGES) & 1) ^ 1);
           if (elect_one_sync()) {
-            if (pf_on && !panel_end) prefetch_next(true);
             const uint32_t full = bar(C::B_IN_FULL + e);
             const uint32_t dst = sIn + e * C::IN_STAGE;
             if (panel_end && j >= p.nsub_r) {
@@ -470,13 +502,11 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
             } else {
               mbar_arrive_expect_tx(full, state_bytes);
               const int col = nt * IT_BN + j * EPI_COLS;
-              int slot = 0;
-              for (int i = 0; i < 3; i += 2) {
-                if (!(p.in_mask & (1 << i))) continue;
-                const uint32_t d = dst + slot * EPI_ARRAY_BYTES;
-                ++slot;
-                if (p.blocked_mask & (BLK_IN0 << i)) tma_load_3d(d, &p.tmIn[i], full, 0, m0, col / EPI_COLS, kEvictNormal);
-                else tma_load_2d(d, &p.tmIn[i], full, col, m0, kEvictNormal);
+              for (int i = 0; i < (job.has_prev2 ? 2 : 1); ++i) {
+                const int src = i == 0 ? job.prev : job.prev2;
+                const uint32_t d = dst + i * EPI_ARRAY_BYTES;
+                if (p.state_blocked[src]) tma_load_3d(d, &p.tmState[src], full, 0, m0, col / EPI_COLS, kEvictNormal);
+                else tma_load_2d(d, &p.tmState[src], full, col, m0, kEvictNormal);
               }
             }
           }
@@ -487,11 +517,12 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
   } else if (warp == 2) {
     // ================================ epilogue storer ================================
     uint32_t q = 0;
-    for (int pi = 0; pi < my_panels; ++pi) {
-      const int m0 = (cluster_id + pi * num_clusters) * PAIR_M + cta_rank * BLOCK_M;
+    for (int ji = 0; ji < my_jobs; ++ji) {
+      const Job job = job_at(ji);
+      const int m0 = job.m0;
       for (int nt = 0; nt <= NT; ++nt) {
         const bool panel_end = (nt == NT);
-        if (panel_end && !p.do_r) break;
+        if (panel_end && !job.do_r) break;
         const int nsub = panel_end ? nsub_r_pad : C::SUBS * tile_chunks(nt);
         for (int j = 0; j < nsub; ++j, ++q) {
           const int e = q % C::IN_STAGES;
@@ -508,8 +539,8 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
                              part * p.kb_g + col / p.r_block_w);
             } else {
               const int col = nt * IT_BN + j * EPI_COLS;
-              if (p.blocked_mask & BLK_OUT) tma_store_3d(&p.tmOut, src, 0, m0, col / EPI_COLS);
-              else tma_store_2d(&p.tmOut, src, col, m0);
+              if (p.state_blocked[job.out]) tma_store_3d(&p.tmState[job.out], src, 0, m0, col / EPI_COLS);
+              else tma_store_2d(&p.tmState[job.out], src, col, m0);
             }
             bulk_commit();
             if (q >= C::STORES_IN_FLIGHT) {
@@ -520,6 +551,15 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
           }
           __syncwarp();
         }
+      }
+      if (p.done != nullptr) {
+        // every store of this job has been performed: publish it to the pair that runs the panel's next iteration
+        if (elect_one_sync()) {
+          bulk_wait<0>();
+          fence_proxy_async_all();
+          red_release_gpu_add(p.done + job.panel, 1);
+        }
+        __syncwarp();
       }
     }
     if (elect_one_sync()) bulk_wait<0>();
@@ -532,20 +572,22 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
     const uint32_t sw64 = (row >> 1) & 3;
     const uint32_t sw32 = (row >> 2) & 1;
     UpdateArgs ua;
-    ua.in_mask = p.in_mask, ua.prox = p.prox, ua.group = p.group, ua.use_momentum = p.use_momentum;
-    ua.beta_prev = p.beta_prev, ua.beta_next = p.beta_next;
+    ua.prox = p.prox, ua.group = p.group, ua.use_momentum = p.use_momentum;
     ua.eta = __ldg(p.scalars + 0), ua.theta = __ldg(p.scalars + 1);
     ua.want_stat = p.stat != nullptr;
-    const bool has_prev = (p.in_mask & 4) != 0;
     Tracer trace(p, 2, warp == 4 && lane == 0);
     float stat_local = 0.f;
     uint32_t q = 0, yc = 0;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     int t = 0;
-    for (int pi = 0; pi < my_panels; ++pi) {
+    for (int pi = 0; pi < my_jobs; ++pi) {
+      const Job job = job_at(pi);
+      const bool has_prev = job.has_prev2;
+      ua.in_mask = has_prev ? 5 : 1;
+      ua.beta_prev = job.beta_prev, ua.beta_next = job.beta_next;
       for (int nt = 0; nt <= NT; ++nt) {
         const bool panel_end = (nt == NT);
-        if (panel_end && !p.do_r) break;
+        if (panel_end && !job.do_r) break;
         const int nsub = panel_end ? p.nsub_r : C::SUBS * tile_chunks(nt);   // real sub-tiles
         const int nsub_all = panel_end ? nsub_r_pad : nsub;                  // + padding at the panel end
         uint32_t t_row, drained_bar;
@@ -637,7 +679,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
               sts128(out_stage + row * 64 + ((ch ^ sw64) << 4), outv[4 * ch], outv[4 * ch + 1], outv[4 * ch + 2],
                      outv[4 * ch + 3]);
             uint32_t yfull = 0;
-            if (p.do_r) {
+            if (job.do_r) {
               // y_k parts straight into the A operand of R, K-major with rows of CHUNK * 2 bytes in the matching TMA /
               // UMMA swizzle: 64-byte rows (this sub-tile is the 32-byte half j % 2 of the row) or 32-byte rows
               const int ys = chunk % C::Y_STAGES;
@@ -657,7 +699,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
             __syncwarp();
             if (lane == 0) {
               mbar_arrive(bar(C::B_OUT_FULL + e));
-              if (p.do_r) mbar_arrive_remote(yfull, 0);
+              if (job.do_r) mbar_arrive_remote(yfull, 0);
             }
             trace(TR_E_ARR, j);
           }

@@ -48,6 +48,7 @@ struct Profile {
   cudaEvent_t begin = nullptr, iter_begin = nullptr, iter_end = nullptr;
   cudaEvent_t k1_begin[kProfSamples], k1_end[kProfSamples], k2_end[kProfSamples];  // sampled iterations
   int iter_launches = 0, iters = 0, samples = 0;
+  int launch_iters = 1;   // iterations per sampled launch (the persistent schedule runs all of them in one)
   bool two_launches = false;
 };
 Profile g_prof;
@@ -425,10 +426,13 @@ struct IterCall {
   PartsMat r_op, phi_op, phiT_op;
   int precision = VTC_PRECISION_BF16X3;
   int64_t B = 0, S = 0, D = 0;
-  F32Mat a_prev, a_prev2, x, out;
-  bool has_prev2 = false, do_r = true;
+  F32Mat state[4];       // a_0 (starting point), a_k for odd k, a_k for even k, where the final iterate goes
+  F32Mat x;
+  int k_first = 1, k_count = 1;   // iterations run by this launch
+  int k_final = 0x7fffffff;       // iteration whose output is the result (none: the caller stops on its own criterion)
+  const float* betas = nullptr;   // device table, betas[k] = momentum coefficient of iteration k, betas[0] = 0
+  int* done = nullptr;            // device per-panel completion counters, zeroed (required when k_count > 1)
   int prox = 0, group = 1, use_momentum = 0;
-  float beta_prev = 0.f, beta_next = 0.f;
   const float* scalars = nullptr;
   double* stat = nullptr;
   int max_pairs = 0;
@@ -444,6 +448,15 @@ bool fused_iter_enabled() {
     g_fused_iter = e ? (atoi(e) != 0) : 1;
   }
   return g_fused_iter != 0;
+}
+// VTC_B200_PERSISTENT=0: one launch per iteration instead of one launch for all of them
+bool persistent_iterations_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("VTC_B200_PERSISTENT");
+    cached = e ? (atoi(e) != 0) : 1;
+  }
+  return cached != 0;
 }
 bool fused_iter_ok(int64_t S, int64_t D, int precision) {
   return fused_iter_enabled() && formulation_for(S, D) == FORM_SYNTHESIS && D <= IT_RN && parts_for(precision) <= 2;
@@ -469,10 +482,15 @@ int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream
   TRY(map_operand(&p.tmR, c.r_op, Cf::BK, "r operand"));
   TRY(map_operand(&p.tmPhi, c.phi_op, Cf::BK, "dictionary operand", IT_BN / 2));
   TRY(map_operand(&p.tmPhiT, c.phiT_op, Cf::CHUNK, "transposed dictionary operand", IT_RN / 2));
-  TRY(map_f32(&p.tmIn[0], c.a_prev, "a_{k-1}"));
-  if (c.has_prev2) TRY(map_f32(&p.tmIn[2], c.a_prev2, "a_{k-2}"));
+  for (int i = 0; i < 4; ++i) {
+    TRY(map_f32(&p.tmState[i], c.state[i], "code array"));
+    p.state_blocked[i] = c.state[i].blocked ? 1 : 0;
+  }
+  if (c.k_count > 1 && c.done == nullptr) return fail(VTC_ERR_ARG, "fused iteration: several iterations per launch need the completion counters");
+  p.k_first = c.k_first, p.k_count = c.k_count, p.k_final = c.k_final;
+  p.betas = c.betas;
+  p.done = c.k_count > 1 ? c.done : nullptr;
   TRY(map_f32(&p.tmX, c.x, "images"));
-  TRY(map_f32(&p.tmOut, c.out, "a_k"));
   TRY(map_parts_out(&p.tmROut, c.r_op, "r parts output"));
   p.num_panels = static_cast<int>(ceil_div(c.B, PAIR_M));
   p.S = static_cast<int>(c.S);
@@ -482,27 +500,9 @@ int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream
   p.phiT_part_stride = static_cast<int>(c.phiT_op.Kp);
   p.nsub_r = static_cast<int>(c.r_op.Kp / EPI_COLS);
   p.r_block_w = Cf::BK;
-  p.in_mask = 1 | (c.has_prev2 ? 4 : 0);
-  if (c.a_prev.blocked) p.blocked_mask |= BLK_IN0;
-  if (c.has_prev2 && c.a_prev2.blocked) p.blocked_mask |= (BLK_IN0 << 2);
-  if (c.out.blocked) p.blocked_mask |= BLK_OUT;
-  p.do_r = c.do_r ? 1 : 0;
   p.prox = c.prox, p.group = c.group, p.use_momentum = c.use_momentum;
-  p.beta_prev = c.beta_prev, p.beta_next = c.beta_next;
   p.scalars = c.scalars;
   p.stat = c.stat;
-  // L2 prefetch of the tile-contiguous state inputs, VTC_B200_ITER_PREFETCH sub-tiles ahead (0 = off)
-  static int pf_distance = -1;
-  if (pf_distance < 0) {
-    const char* e = getenv("VTC_B200_ITER_PREFETCH");
-    pf_distance = e ? atoi(e) : 0;  // measured slower at every distance (profiles/README.md): off
-    if (pf_distance > 0 && pf_distance < Cf::IN_STAGES) pf_distance = Cf::IN_STAGES;
-  }
-  p.pf_distance = pf_distance;
-  p.rows = static_cast<int>(c.B);
-  p.pf_block_bytes = static_cast<unsigned long long>(c.B) * EPI_COLS * 4;
-  p.pf_base[0] = c.a_prev.blocked ? static_cast<const char*>(c.a_prev.ptr) : nullptr;
-  p.pf_base[1] = (c.has_prev2 && c.a_prev2.blocked) ? static_cast<const char*>(c.a_prev2.ptr) : nullptr;
   p.trace = g_iter_trace;
   g_iter_trace = nullptr;  // one shot: only the next launch is traced
   static bool attr_set_dev[64] = {};
@@ -646,9 +646,12 @@ int run_lipschitz(const float* dict, int64_t S, int64_t D, const LipschitzWs& w,
 }
 
 // ---------------------------------------------------------------------------------------------- FISTA
+constexpr int kMaxFusedIters = 16384;   // iterations one persistent launch can run (size of the momentum table)
 struct FistaWs {
   float* scalars;
   double* stats;
+  float* betas;   // device: momentum coefficient of every iteration (fused schedule)
+  int* done;      // device: per-panel completion counters of the persistent launch
   LipschitzWs lip;
   PartsMat phi_op, x_op, G_op, yop[2], phiT_op, r_op;
   // bvec, X1, X2: tile-contiguous fp32 state [ceil(S/16)][B][16]; init_pad / out_pad / x_pad: row-major staging for
@@ -662,6 +665,8 @@ FistaWs carve_fista(Carver& cv, int64_t B, int64_t S, int64_t D, int precision) 
   const int bk = (P == 1) ? 64 : 32;  // K block of the iteration GEMMs = block width of the streamed A operands
   w.scalars = static_cast<float*>(cv.take(64));
   w.stats = static_cast<double*>(cv.take(8 * 4096));
+  w.betas = static_cast<float*>(cv.take(sizeof(float) * (kMaxFusedIters + 1)));
+  w.done = static_cast<int*>(cv.take(sizeof(int) * ceil_div(B, PAIR_M)));
   w.lip = carve_lipschitz(cv, D);
   w.phi_op = carve_parts(cv, S, D, 3);
   const bool gram = formulation_for(S, D) == FORM_GRAM;
@@ -741,6 +746,7 @@ int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches, int* i
     else fused += t1;
   }
   if (g_prof.samples > 0) fused /= g_prof.samples, first /= g_prof.samples;
+  fused /= g_prof.launch_iters;   // per iteration
   if (fused_launch_ms) *fused_launch_ms = fused;
   if (first_launch_ms) *first_launch_ms = first;
   return VTC_OK;
@@ -896,6 +902,31 @@ int chain_setup(const FistaCommon& cm, FistaChain& ch) {
   return VTC_OK;
 }
 
+// Iterations k_first .. k_first + k_count - 1 of one chain in ONE launch of the panel-resident kernel. k_count > 1: the
+// persistent schedule (jobs = (iteration, panel) dealt round-robin to the SM pairs, no launch boundary and no panel
+// quantisation); the momentum table w.betas must have been uploaded, w.done is zeroed here.
+int chain_iterate_fused(const FistaCommon& cm, FistaChain& ch, int k_first, int k_count) {
+  FistaWs& w = ch.w;
+  IterCall c;
+  c.r_op = w.r_op, c.phi_op = w.phi_op, c.phiT_op = w.phiT_op;
+  c.precision = cm.precision;
+  c.B = ch.B, c.S = cm.S, c.D = cm.D;
+  c.state[0] = ch.init, c.state[1] = ch.X1, c.state[2] = ch.X2, c.state[3] = ch.final_out;
+  c.x = F32Mat{ch.x_in, ch.B, cm.D, ch.ld_x};
+  c.k_first = k_first, c.k_count = k_count;
+  c.k_final = cm.early ? 0x7fffffff : cm.num_iters;
+  c.betas = w.betas;
+  if (k_count > 1) {
+    CUDA_TRY(cudaMemsetAsync(w.done, 0, sizeof(int) * ceil_div(ch.B, PAIR_M), ch.st));
+    c.done = w.done;
+  }
+  c.prox = cm.prox, c.group = cm.group_size, c.use_momentum = (cm.variant == VTC_VARIANT_FISTA);
+  c.scalars = w.scalars;
+  c.stat = cm.early ? w.stats + (k_first - 1) : nullptr;
+  c.max_pairs = ch.max_pairs;
+  return launch_iter(c, ch.st);
+}
+
 // iteration k (1-based) of one chain; `sample` >= 0 records profile events around its launches
 int chain_iterate(const FistaCommon& cm, FistaChain& ch, int k, float beta_prev, float beta_k, int sample) {
   FistaWs& w = ch.w;
@@ -908,22 +939,8 @@ int chain_iterate(const FistaCommon& cm, FistaChain& ch, int k, float beta_prev,
   const F32Mat& a_out = (k == cm.num_iters && !cm.early) ? ch.final_out : (k & 1) ? ch.X1 : ch.X2;
   if (sample >= 0) CUDA_TRY(cudaEventRecord(g_prof.k1_begin[sample], st));
   if (cm.fused_iter) {
-    IterCall c;
-    c.r_op = w.r_op, c.phi_op = w.phi_op, c.phiT_op = w.phiT_op;
-    c.precision = cm.precision;
-    c.B = B, c.S = S, c.D = D;
-    c.a_prev = a_prev;
-    c.has_prev2 = (cm.variant == VTC_VARIANT_FISTA && beta_prev != 0.f);
-    c.a_prev2 = a_prev2;
-    c.x = F32Mat{ch.x_in, B, D, ch.ld_x};
-    c.out = a_out;
-    c.do_r = k < cm.num_iters;
-    c.prox = cm.prox, c.group = cm.group_size, c.use_momentum = (cm.variant == VTC_VARIANT_FISTA);
-    c.beta_prev = beta_prev, c.beta_next = beta_k;
-    c.scalars = w.scalars;
-    c.stat = cm.early ? w.stats + (k - 1) : nullptr;
-    c.max_pairs = ch.max_pairs;
-    TRY(launch_iter(c, st));
+    (void)a_prev, (void)a_prev2, (void)a_out, (void)beta_prev, (void)beta_k;
+    TRY(chain_iterate_fused(cm, ch, k, 1));
     if (sample >= 0) {
       CUDA_TRY(cudaEventRecord(g_prof.k1_end[sample], st));
       CUDA_TRY(cudaEventRecord(g_prof.k2_end[sample], st));
@@ -1119,8 +1136,35 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   double t_k = 1.0;
   float beta_prev = 0.f;
   int k_done = 0;
+  if (cm.fused_iter) {
+    // the panel-resident kernel takes the momentum coefficients from a device table: betas[k], betas[0] = 0
+    if (num_iters > kMaxFusedIters) return fail(VTC_ERR_UNSUPPORTED, "at most %d iterations per call", kMaxFusedIters);
+    std::vector<float> betas(num_iters + 1, 0.f);
+    double t = 1.0;
+    for (int k = 1; k <= num_iters; ++k) {
+      const double t_next = (1.0 + sqrt(1.0 + 4.0 * t * t)) / 2.0;
+      betas[k] = (variant == VTC_VARIANT_FISTA) ? static_cast<float>((t - 1.0) / t_next) : 0.f;
+      t = t_next;
+    }
+    for (int c = 0; c < chains; ++c)
+      CUDA_TRY(cudaMemcpyAsync(ch[c].w.betas, betas.data(), sizeof(float) * (num_iters + 1), cudaMemcpyHostToDevice,
+                               ch[c].st));
+  }
   if (g_prof.on) CUDA_TRY(cudaEventRecord(g_prof.iter_begin, st));
-  for (int k = 1; k <= num_iters; ++k) {
+  const bool persistent = cm.fused_iter && !cm.early && chains == 1 && persistent_iterations_enabled();
+  if (persistent) {
+    // every iteration of every panel in ONE launch
+    if (g_prof.on) CUDA_TRY(cudaEventRecord(g_prof.k1_begin[0], st));
+    TRY(chain_iterate_fused(cm, ch[0], 1, num_iters));
+    if (g_prof.on) {
+      CUDA_TRY(cudaEventRecord(g_prof.k1_end[0], st));
+      CUDA_TRY(cudaEventRecord(g_prof.k2_end[0], st));
+      g_prof.samples = 1;
+      g_prof.two_launches = false;
+    }
+    k_done = num_iters;
+  }
+  for (int k = 1; k <= num_iters && !persistent; ++k) {
     const double t_next = (1.0 + sqrt(1.0 + 4.0 * t_k * t_k)) / 2.0;
     const float beta_k = (variant == VTC_VARIANT_FISTA) ? static_cast<float>((t_k - 1.0) / t_next) : 0.f;
     t_k = t_next;
@@ -1147,7 +1191,8 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   }
   if (g_prof.on) {
     CUDA_TRY(cudaEventRecord(g_prof.iter_end, st));
-    g_prof.iter_launches = k_done * ((cm.gram || cm.fused_iter) ? 1 : 2) * chains;
+    g_prof.iter_launches = persistent ? 1 : k_done * ((cm.gram || cm.fused_iter) ? 1 : 2) * chains;
+    g_prof.launch_iters = persistent ? k_done : 1;
     g_prof.iters = k_done;
     g_prof.valid = true;
   }
