@@ -62,9 +62,10 @@ int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches, int* i
 int vtc_set_formulation(int formulation);
 int vtc_get_formulation(int64_t S, int64_t D);
 
-/* Schedule of a synthesis-form iteration: 1 (default) = ONE launch per iteration that keeps the operand y_k on chip
+/* Schedule of a synthesis-form iteration: 1 (default) = the panel-resident kernel that keeps the operand y_k on chip
  * (panel-resident kernel: r_{k-1} Phi^T -> fused update -> y_k Phi - x accumulated in TMEM), used when D <= 256 and the
- * precision is bf16 or bf16x3; 0 = the two-launch schedule (r = y Phi - x, then r Phi^T with the fused update), which
+ * precision is bf16 or bf16x3 -- all iterations of a call in one persistent launch (VTC_B200_PERSISTENT=0: one launch
+ * per iteration; early stopping always launches per iteration); 0 = the two-launch schedule (r = y Phi - x, then r Phi^T with the fused update), which
  * is also what larger D and bf16x6 use. Both give identical iterates for identical arithmetic order per element up to
  * the fp32 accumulation order of the synthesis contraction. Also VTC_B200_FUSED_ITER. vtc_get_fused_iteration reports
  * whether a problem of this shape would run the one-launch schedule. */

@@ -1,11 +1,14 @@
-// Panel-resident ISTA/FISTA iteration (sm_100a): ONE launch per iteration of the synthesis form
+// Panel-resident ISTA/FISTA iterations (sm_100a): the synthesis form with the operand y_k kept on chip; one launch runs
+// one iteration or (persistent schedule, the default) all of them
 //
 //   grad = r_{k-1} Phi^T                       (analysis contraction,  K = D, N = S)        ista_fista.py:105-106
 //   a_k  = prox(y_{k-1} - eta * grad) ,  y_k = a_k + beta_k (a_k - a_{k-1})                 ista_fista.py:107-133
 //   r_k  = y_k Phi - x                         (synthesis contraction, K = S, N = D)
 //
-// with the next operand y_k never leaving the chip. A CTA pair (cluster of 2, cta_group::2) owns a 256-row panel of
-// patches for the whole launch and walks its atoms in tiles of 128:
+// with the next operand y_k never leaving the chip. A job = one iteration of one 256-row panel of patches, run by a CTA
+// pair (cluster of 2, cta_group::2) that walks the panel's atoms in tiles of 128; the jobs (iteration, panel) of a launch
+// are dealt round-robin to the pairs, and a panel's iteration k waits for the completion counter of its iteration k - 1
+// (IterParams::done), which may have run on another pair:
 //
 //   tensor pipe   G(t): acc_g[t&1] (256 x 128, TMEM) = r_op[panel] * Phi[tile]^T           operands by TMA
 //                 R(t): acc_r (256 x 256, TMEM)     += y_k[panel, tile] * Phi[tile]         A operand written to shared

@@ -531,6 +531,18 @@ int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (tune_flags() & TUNE_NO_PDL) ? 1 : 2;
+  if (c.k_count > 1) {
+    // jobs of a persistent launch wait on jobs of other pairs: every pair of the grid must be resident at once
+    static int max_clusters_dev[64] = {};
+    int& max_clusters = max_clusters_dev[dev & 63];
+    if (max_clusters == 0) {
+      cudaLaunchConfig_t query = cfg;
+      query.numAttrs = 1;  // cluster dimension only
+      CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, vtc_fista_iter_kernel<P, V>, &query));
+      if (max_clusters < 1) return fail(VTC_ERR_CUDA, "the iteration kernel does not fit on this device");
+    }
+    if (pairs > max_clusters) cfg.gridDim = dim3(2 * max_clusters);
+  }
   CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_fista_iter_kernel<P, V>, p));
   COUNT_LAUNCH();
   return VTC_OK;
