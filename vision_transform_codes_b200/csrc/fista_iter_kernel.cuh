@@ -50,10 +50,10 @@ template <int P, int V>
 struct IterCfg {
   static_assert(P == 1 || P == 2, "parts");
   static_assert(V >= 0 && V < IT_VARIANTS, "variant");
-  // tuning variants (VTC_B200_ITER_VARIANT); see profiles/README.md for what each measured
+  // tuning variants (VTC_B200_ITER_VARIANT; default 0 for bf16x3, 1 for bf16); see profiles/README.md for what each measured
   //                     math groups   chunk   G (P=2 / P=1)   y   Phi^T   in/out stages
   //   0                     3          32       2 / 3          3   2       6
-  //   1                     2          32       4 / 4          2   2       4
+  //   1                     2          32       4 / 2          2   2       4 / 8
   //   2                     3          16       3 / 4          3   3       6
   // epilogue math: GROUPS groups of four warps (one warp per TMEM lane quarter) on sub-tiles round-robin
   static constexpr int GROUPS = (V == 1) ? 2 : 3;
@@ -78,12 +78,12 @@ struct IterCfg {
                                                           // over the second 8 KB of its input stage and stored from there
   static constexpr int STORES_IN_FLIGHT = 1;              // TMA stores whose shared-memory reads may still be pending
   // shared memory split between the rings (P = 2: G 24 KB, y 16 KB, Phi^T 16 KB, in/out 16 KB per stage)
-  static constexpr int G_STAGES = (V == 0) ? (P == 2 ? 2 : 3) : (V == 2 && P == 2) ? 3 : 4;
+  static constexpr int G_STAGES = (V == 0) ? (P == 2 ? 2 : 3) : (V == 1) ? (P == 2 ? 4 : 2) : (V == 2 && P == 2) ? 3 : 4;
   // every y stage must always be written by the same math groups (a group then sees the phases of the stage's
   // barrier strictly in order, like the in/out stages): Y_STAGES * SUBS is a multiple of GROUPS
   static constexpr int Y_STAGES = (V == 1) ? 2 : 3;
   static constexpr int PT_STAGES = (V == 2) ? 3 : 2;
-  static constexpr int IN_STAGES = (V == 1) ? 4 : 6;      // a multiple of GROUPS: fixed owner group per stage
+  static constexpr int IN_STAGES = (V == 1) ? (P == 2 ? 4 : 8) : 6;      // a multiple of GROUPS: fixed owner group per stage
   static constexpr int OFF_G = 0;
   static constexpr int OFF_Y = OFF_G + G_STAGES * G_STAGE;
   static constexpr int OFF_PT = OFF_Y + Y_STAGES * Y_STAGE;

@@ -462,15 +462,17 @@ bool fused_iter_ok(int64_t S, int64_t D, int precision) {
   return fused_iter_enabled() && formulation_for(S, D) == FORM_SYNTHESIS && D <= IT_RN && parts_for(precision) <= 2;
 }
 
-// tuning variant of the fused iteration kernel (stage counts / math warps); VTC_B200_ITER_VARIANT overrides
-int iter_variant() {
-  static int cached = -1;
-  if (cached < 0) {
+// tuning variant of the fused iteration kernel (stage counts / math warps); VTC_B200_ITER_VARIANT overrides the
+// default: bf16x3 is bound by shared-memory bandwidth and does best with three math groups (variant 0), plain bf16 is
+// bound by the state bytes in flight and does best with the deepest input ring (variant 1: 8 stages, two math groups)
+int iter_variant(int parts) {
+  static int cached = -2;
+  if (cached == -2) {
     const char* e = getenv("VTC_B200_ITER_VARIANT");
-    cached = e ? atoi(e) : 0;
-    if (cached < 0 || cached >= IT_VARIANTS) cached = 0;
+    cached = e ? atoi(e) : -1;
+    if (cached >= IT_VARIANTS) cached = -1;
   }
-  return cached;
+  return cached >= 0 ? cached : (parts == 1 ? 1 : 0);
 }
 
 template <int P, int V>
@@ -552,7 +554,7 @@ int launch_iter(const IterCall& c, cudaStream_t stream) {
   TRY(require_sm100(&info));
   if (c.D > IT_RN) return fail(VTC_ERR_ARG, "fused iteration needs D <= %d", IT_RN);
   const bool one = parts_for(c.precision) == 1;
-  switch (iter_variant()) {
+  switch (iter_variant(parts_for(c.precision))) {
     case 1: return one ? launch_iter_p<1, 1>(c, info, stream) : launch_iter_p<2, 1>(c, info, stream);
     case 2: return one ? launch_iter_p<1, 2>(c, info, stream) : launch_iter_p<2, 2>(c, info, stream);
     default: return one ? launch_iter_p<1, 0>(c, info, stream) : launch_iter_p<2, 0>(c, info, stream);
