@@ -342,3 +342,22 @@ def test_one_launch_schedule_matches_two_launch_schedule(formulation):
         assert one[1] == two[1], (one[1], two[1])
         one, two = one[0], two[0]
       assert torch.equal(one, two), (precision, oracle.relative_l2(one.cpu(), two.cpu()))
+
+
+@pytest.mark.parametrize('num_iters', [1, 2, 3, 4, 7])
+@pytest.mark.parametrize('shape', [(1, 160, 8), (130, 328, 72), (513, 1024, 256)])
+def test_persistent_launch_short_runs_and_tiny_batches(num_iters, shape):
+  """The persistent schedule rotates the iterate through (start, odd, even, final) buffers and hands panels from pair
+  to pair: the first iterations (no a_{k-2} yet, output straight to the caller's buffer when the run is that short), a
+  single patch and a ragged last panel are its corner cases."""
+  ista_fista = modules()[0]
+  B, S, D = shape
+  phi = oracle.synthetic_dictionary(S, D)
+  x = oracle.synthetic_patches(B, D)
+  for kw in ({}, {'variant': 'ista'}):
+    want = oracle.ista_fista(x, phi, 0.1, num_iters, **kw)
+    got = ista_fista.run(x.cuda(), phi.cuda(), 0.1, num_iters, **kw)
+    check_codes(got, want, phi)
+  warm = oracle.ista_fista(x, phi, 0.1, 3)
+  want = oracle.ista_fista(x, phi, 0.1, num_iters, initial_codes=warm)
+  check_codes(ista_fista.run(x.cuda(), phi.cuda(), 0.1, num_iters, initial_codes=warm.cuda()), want, phi)
