@@ -1088,7 +1088,7 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   cm.group_size = group_size;
   cm.precision = precision, cm.P = parts_for(precision);
   cm.gram = formulation_for(S, D) == FORM_GRAM;
-  cm.fused_iter = fused_iter_ok(S, D, precision);
+  cm.fused_iter = fused_iter_ok(S, D, precision) && num_iters <= kMaxFusedIters;  // else: the two-launch schedule
   cm.early = early_stopping_epsilon >= 0.f;
   if (cm.early && num_iters > 4096) return fail(VTC_ERR_UNSUPPORTED, "early stopping supports at most 4096 iterations");
 
@@ -1152,7 +1152,6 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   int k_done = 0;
   if (cm.fused_iter) {
     // the panel-resident kernel takes the momentum coefficients from a device table: betas[k], betas[0] = 0
-    if (num_iters > kMaxFusedIters) return fail(VTC_ERR_UNSUPPORTED, "at most %d iterations per call", kMaxFusedIters);
     std::vector<float> betas(num_iters + 1, 0.f);
     double t = 1.0;
     for (int k = 1; k <= num_iters; ++k) {
