@@ -653,6 +653,24 @@ vtc_gemm_kernel(const __grid_constant__ GemmParams p) {
       const TileCoord c = decode_tile<BN>(p, w, cta_rank);
       const int acc = tile_iter & 1;
       const uint32_t acc_ph = (tile_iter >> 1) & 1;
+      // grid position of this thread's row (convolutional launches), once per tile: the integer divisions are not cheap.
+      // mask_mode: 0 = the row's whole pixel block is inside the un-masked region (or padding row handling is off),
+      // 1 = wholly outside (every output zero), 2 = straddles the border (per-pixel test)
+      int gi = 0, gj = 0, mask_mode = 0;
+      bool padding_row = false;
+      if (p.grid_w > 0) {
+        const int cell = (c.m0 + row) % (p.grid_h * p.grid_w);
+        gi = cell / p.grid_w;
+        gj = cell - gi * p.grid_w;
+        if (EPI == EPI_FISTA) {
+          padding_row = gi >= p.code_h || gj >= p.code_w;
+        } else {
+          const int py0 = gi * p.blk_sy, px0 = gj * p.blk_sx;
+          const bool inside = py0 >= p.pix_y0 && py0 + p.blk_sy <= p.pix_y1 && px0 >= p.pix_x0 && px0 + p.blk_sx <= p.pix_x1;
+          const bool outside = py0 + p.blk_sy <= p.pix_y0 || py0 >= p.pix_y1 || px0 + p.blk_sx <= p.pix_x0 || px0 >= p.pix_x1;
+          mask_mode = inside ? 0 : outside ? 1 : 2;
+        }
+      }
       mbar_wait(tmem_full_bar(acc), acc_ph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
@@ -705,16 +723,10 @@ vtc_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
         float outv[16];   // fp32 result
         float partv[16];  // value whose bf16 split is emitted as parts
-        int gi = 0, gj = 0;  // grid position of this thread's row
-        if (p.grid_w > 0) {
-          const int cell = (c.m0 + row) % (p.grid_h * p.grid_w);
-          gi = cell / p.grid_w;
-          gj = cell - gi * p.grid_w;
-          if (EPI == EPI_FISTA && (gi >= p.code_h || gj >= p.code_w)) {
-            // padding row of the code grid: its inputs are zero and stay zero (prox(0) = 0 for every variant)
+        if (EPI == EPI_FISTA && padding_row) {
+          // padding row of the code grid: its inputs are zero and stay zero (prox(0) = 0 for every variant)
 #pragma unroll
-            for (int x = 0; x < 16; ++x) v[x] = 0u;
-          }
+          for (int x = 0; x < 16; ++x) v[x] = 0u;
         }
         if (EPI == EPI_STORE) {
 #pragma unroll
@@ -722,7 +734,10 @@ vtc_gemm_kernel(const __grid_constant__ GemmParams p) {
             outv[x] = __uint_as_float(v[x]) - in[0][x];
             partv[x] = outv[x];
           }
-          if (p.grid_w > 0) {
+          if (mask_mode == 1) {
+#pragma unroll
+            for (int x = 0; x < 16; ++x) outv[x] = 0.f, partv[x] = 0.f;
+          } else if (mask_mode == 2) {
             // reconstruction mask: zero outside the un-padded image; column -> (dy, dx) walks incrementally
             const int col0 = c.n0 + j * EPI_COLS;
             int dx = col0 % p.blk_sx;
