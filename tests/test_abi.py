@@ -17,7 +17,8 @@ def declared_symbols():
 
 def test_header_declares_the_expected_entry_points():
   names = declared_symbols()
-  for must in ('vtc_fista_fc', 'vtc_sc_dict_grad', 'vtc_sc_dict_apply', 'vtc_hessian_diag_update', 'vtc_lipschitz'):
+  for must in ('vtc_fista_fc', 'vtc_sc_dict_grad', 'vtc_sc_dict_apply', 'vtc_hessian_diag_update', 'vtc_lipschitz',
+               'vtc_fista_conv', 'vtc_sc_conv_dict_grad', 'vtc_sc_conv_dict_apply', 'vtc_conv_hessian_diag_update'):
     assert must in names
 
 
@@ -76,7 +77,10 @@ def test_dropin_names_resolve_through_install():
                  'analysis_transforms.fully_connected.subspace_ista_fista',
                  'dict_update_rules.fully_connected.sc_cheap_quadratic_descent',
                  'dict_update_rules.fully_connected.sc_steepest_descent',
-                 'dict_update_rules.fully_connected.subspace_sc_cheap_quadratic_descent'):
+                 'dict_update_rules.fully_connected.subspace_sc_cheap_quadratic_descent',
+                 'analysis_transforms.convolutional.ista_fista',
+                 'dict_update_rules.convolutional.sc_cheap_quadratic_descent',
+                 'dict_update_rules.convolutional.sc_steepest_descent'):
       mod = importlib.import_module(name)
       assert callable(mod.run)
       assert mod.__file__.startswith(pkg.PACKAGE_ROOT)
