@@ -177,6 +177,33 @@ def subspace_benchmark(world, rank, dev, timed, pk, precision, batch=131072):
   }
 
 
+def config0_benchmark(rank, world, dev, timed, precision):
+  """BASELINE.json configs[0], the reference's own CPU-runnable case, timed IN FULL on both sides: batch 250, 256 atoms,
+  16x16 patches, 300 FISTA iterations, lambda 0.1. One call = one step (latency-bound on the GPU: 300 launches of the
+  Gram form, S <= 2 D); the CPU side is the float32 torch port of the reference on all host cores (rank 0, N = 1 only)."""
+  import vision_transform_codes_b200 as pkg
+  from oracle import vtc_oracle as oracle
+  from vision_transform_codes_b200.analysis_transforms.fully_connected import ista_fista
+  phi = oracle.synthetic_dictionary(256, 256)
+  x = oracle.synthetic_patches(250, 256, kind='whitened')
+  phid, xd = phi.to(dev), x.to(dev)
+  saved = pkg.config.precision
+  pkg.config.precision = precision
+  ms, launches = timed(lambda: ista_fista.run(xd, phid, LAM, T), 10, 3)
+  pkg.config.precision = saved
+  out = {'workload': 'configs[0]: batch 250, 256 atoms, D=256, 300 FISTA iterations', 'ms_per_call': ms / 10,
+         'patches_per_sec': 250 / (ms / 10 * 1e-3), 'gpu_launches_per_call': int(launches // 10)}
+  if rank == 0 and world == 1:
+    torch.set_num_threads(os.cpu_count() or 1)
+    oracle.ista_fista(x, phi, LAM, 10)
+    t0 = time.perf_counter()
+    oracle.ista_fista(x, phi, LAM, T)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    out.update({'cpu_reference_ms_per_call': cpu_ms, 'cpu_cores': os.cpu_count() or 1,
+                'speedup_over_cpu_reference': cpu_ms / (ms / 10)})
+  return out
+
+
 def run_reference(args, rank):
   if rank != 0:
     return
@@ -404,6 +431,7 @@ def main():
       pass
     line['conv_path'] = conv_benchmark(world, rank, dev, timed, pk, args.precision)
     line['subspace_path'] = subspace_benchmark(world, rank, dev, timed, pk, args.precision)
+    line['config0'] = config0_benchmark(rank, world, dev, timed, args.precision)
     if rank == 0 and world == 1:
       v, cores, secs = cpu_reference_patches_per_sec(CPU_SAMPLE)
       line['cpu_baseline'] = {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': 'port',
