@@ -1,0 +1,76 @@
+"""Randomised agreement check of the schedules of an iteration (panel-resident persistent launch vs two launches, both
+vs the Gram form within tolerance) over shapes, variants, thresholds, warm starts and group widths.
+usage: python tools/fuzz_schedules.py [cases] [seed]"""
+import os
+import random
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import vision_transform_codes_b200 as pkg
+from vision_transform_codes_b200 import _lib
+from vision_transform_codes_b200.analysis_transforms.fully_connected import ista_fista, subspace_ista_fista
+from oracle import vtc_oracle as oracle
+
+cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+lib = _lib.load()
+pkg.config.check_finite = False
+bad = 0
+for i in range(cases):
+  D = rng.choice([8, 20, 64, 100, 250, 256])
+  S = rng.choice([s for s in (16, 96, 200, 328, 520, 1000, 1024) if s > 2 * D] or [4 * D + 16])
+  B = rng.choice([1, 7, 128, 250, 257, 600, 1500, 5000])
+  T = rng.choice([1, 2, 3, 5, 17, 40])
+  variant = rng.choice(['ista', 'fista'])
+  prec = rng.choice(['bf16x3', 'bf16x3', 'bf16'])
+  mode = rng.choice(['soft', 'nonneg', 'hard', 'group2', 'group4', 'warm', 'early'])
+  pkg.config.precision = prec
+  phi = oracle.synthetic_dictionary(S, D, seed=i).cuda()
+  x = oracle.synthetic_patches(B, D, seed=100 + i).cuda()
+
+  def call():
+    if mode == 'nonneg':
+      return ista_fista.run(x, phi, 0.1, T, variant=variant, nonnegative_only=True)
+    if mode == 'hard':
+      return ista_fista.run(x, phi, 0.1, T, variant=variant, hard_threshold=True)
+    if mode in ('group2', 'group4'):
+      w = int(mode[-1])
+      groups = [list(map(int, g)) for g in np.array_split(np.arange(S), S // w)]
+      return subspace_ista_fista.run(x, phi, groups, 0.1, T, variant=variant)
+    if mode == 'warm':
+      warm = torch.full((B, S), 0.01, device='cuda')
+      return ista_fista.run(x, phi, 0.1, T, variant=variant, initial_codes=warm)
+    if mode == 'early':
+      return ista_fista.run(x, phi, 0.1, 60, variant=variant, early_stopping_epsilon=1e-2)
+    return ista_fista.run(x, phi, 0.1, T, variant=variant)
+
+  lib.vtc_set_formulation(2)
+  lib.vtc_set_fused_iteration(1)
+  one = call()
+  lib.vtc_set_fused_iteration(0)
+  two = call()
+  lib.vtc_set_formulation(1)
+  gram = call()
+  lib.vtc_set_formulation(0)
+  lib.vtc_set_fused_iteration(1)
+  same = torch.equal(one, two)
+  scale = float(two.abs().max()) + 1e-30
+  gerr = float((gram - two).abs().max()) / scale
+  finite = bool(torch.isfinite(one).all())
+  # max-norm: a hard-threshold tie flips a whole coefficient (Gram and synthesis forms differ in rounding), so that mode
+  # only has to agree on most of the support
+  gtol = 1.0 if mode == 'hard' else 2e-1 if (prec == 'bf16' or mode == 'early') else 2e-3
+  if mode == 'hard':
+    flips = int(((gram != 0) != (two != 0)).sum())
+    ok_support = flips <= 0.01 * two.numel()
+  else:
+    ok_support = True
+  ok = same and finite and gerr <= gtol and ok_support
+  bad += not ok
+  print('%s case %3d: B=%5d S=%5d D=%4d T=%3d %-5s %-7s %-6s  one==two %s  |gram-two|max/|two|max %.2e' %
+        ('ok  ' if ok else 'FAIL', i, B, S, D, T, variant, prec, mode, same, gerr), flush=True)
+print('%d of %d cases failed' % (bad, cases))
+sys.exit(1 if bad else 0)
