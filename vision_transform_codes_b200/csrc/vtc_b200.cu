@@ -413,6 +413,11 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
       default: return launch_gemm_p<EPI_FISTA, 3, 2, 256>(c, info, stream);
     }
   }
+  // Gram-form iteration. Small batches (BASELINE configs[0]: 250 patches = one row of tiles) are latency-bound: 64-wide
+  // tiles put four times as many SM pairs to work on the same launch and quarter every pair's epilogue
+  if (P <= 2 && ceil_div(c.M, PAIR_M) * ceil_div(c.N, 256) * 4 <= info.sm_count / 2) {
+    return P == 1 ? launch_gemm_p<EPI_FISTA, 1, 3, 64>(c, info, stream) : launch_gemm_p<EPI_FISTA, 2, 3, 64>(c, info, stream);
+  }
   switch (P) {
     case 1: return launch_gemm_p<EPI_FISTA, 1, 3, 256>(c, info, stream);
     case 2: return launch_gemm_p<EPI_FISTA, 2, 3, 256>(c, info, stream);
