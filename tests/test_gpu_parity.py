@@ -361,3 +361,17 @@ def test_persistent_launch_short_runs_and_tiny_batches(num_iters, shape):
   warm = oracle.ista_fista(x, phi, 0.1, 3)
   want = oracle.ista_fista(x, phi, 0.1, num_iters, initial_codes=warm)
   check_codes(ista_fista.run(x.cuda(), phi.cuda(), 0.1, num_iters, initial_codes=warm.cuda()), want, phi)
+
+
+def test_empty_batch_returns_empty_codes():
+  """The reference's loop runs on an empty batch without complaint and returns codes of shape (0, s)."""
+  from vision_transform_codes_b200.analysis_transforms.convolutional import ista_fista as conv_inf
+  ista_fista, subspace = modules()[:2]
+  phi = oracle.synthetic_dictionary(64, 16).cuda()
+  x = torch.empty(0, 16, device='cuda')
+  assert tuple(ista_fista.run(x, phi, 0.1, 5).shape) == (0, 64)
+  assert tuple(oracle.ista_fista(x.cpu(), phi.cpu(), 0.1, 5).shape) == (0, 64)
+  assert tuple(subspace.run(x, phi, [[i, i + 1] for i in range(0, 64, 2)], 0.1, 5).shape) == (0, 64)
+  kern = oracle.synthetic_conv_dictionary(8, 1, 8, 8).cuda()
+  xi = torch.empty(0, 1, 24, 24, device='cuda')
+  assert tuple(conv_inf.run(xi, kern, (4, 4), ((4, 4), (4, 4)), 0.1, 3).shape) == (0, 8, 5, 5)

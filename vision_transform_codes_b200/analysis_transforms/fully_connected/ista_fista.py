@@ -39,6 +39,9 @@ def infer(images, dictionary, sparsity_weight, num_iters, variant, initial_codes
   lib = _lib.load()
   B, D = images.shape
   S = dictionary.size(0)
+  if B == 0:
+    # an empty batch goes through the reference's loop untouched: codes of shape (0, s)
+    return torch.empty((0, S), dtype=torch.float32, device=device), int(num_iters)
   images_rm, ld_images = _lib.row_major(images)
   dictionary_c = dictionary.contiguous()
   codes = torch.empty((B, S), dtype=torch.float32, device=device)
