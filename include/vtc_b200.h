@@ -231,6 +231,15 @@ int vtc_sc_conv_dict_apply(float* dictionary, const float* grad_sum, const float
 int vtc_conv_hessian_diag_update(const float* codes, int64_t B, int64_t S, int64_t positions, int64_t batch_global,
                                  float* code_sq_sum, float* hessian_diagonal, int apply_ema, vtc_stream_t stream);
 
+/*
+ * Data feed: B crops of (ph x pw) pixels out of device-resident images (n, h, w, c), each flattened in (y, x, c) order --
+ * the patch extraction of utils/dataset_generation.py:207-218 (all_patches[p] = img[v:v+ph, u:u+pw], then reshape(N, -1))
+ * without the host loop. corners (B, 3) int32 on the device: image index, top row, left column (the caller draws them;
+ * out-of-range corners are the caller's error). patches (B, ph*pw*c) with row pitch ld_patches.
+ */
+int vtc_extract_patches(const float* images, int64_t n, int64_t h, int64_t w, int64_t c, const int32_t* corners,
+                        int64_t B, int64_t ph, int64_t pw, float* patches, int64_t ld_patches, vtc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -347,6 +347,17 @@ def synthetic_padded_images(batch, channels, height, width, kernel, stride, seed
   return padded.contiguous(), (pv, ph)
 
 
+def extract_patches(images, corners, patch_dimensions):
+  """utils/dataset_generation.py:207-218 followed by the final reshape(N, -1): patch p is
+  images[img, top:top+ph, left:left+pw] (channel last), flattened in (y, x, c) order. images (n, h, w, c)."""
+  ph, pw = patch_dimensions
+  out = images.new_zeros((corners.shape[0], ph * pw * images.shape[3]))
+  for p_idx in range(corners.shape[0]):
+    img, top, left = (int(v) for v in corners[p_idx])
+    out[p_idx] = images[img, top:top + ph, left:left + pw].reshape(-1)
+  return out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Seeded synthetic inputs (SURVEY.md section 8d); shared by tests, smoke() and bench.py so that the CUDA path and the
 # oracle always see identical tensors.

@@ -96,3 +96,25 @@ def test_hessian_diagonal_running_mean():
                                          _lib.stream_ptr(codes.device)))
   torch.cuda.synchronize()
   assert oracle.relative_l2(h.cpu(), want) < 1e-6
+
+
+def test_patch_extraction_is_the_reference_crop_loop():
+  """Device-side data feed: bit-exact copy of the crops the reference's host loop takes."""
+  from vision_transform_codes_b200.utils import dataset_generation as dg
+  g = torch.Generator().manual_seed(5)
+  for shape, patch in (((3, 64, 80), (16, 16)), ((2, 40, 33, 3), (8, 12)), ((1, 16, 16), (16, 16))):
+    images = torch.randn(*shape, generator=g)
+    full = images if images.dim() == 4 else images.unsqueeze(-1)
+    n, h, w = shape[:3]
+    edge = 0 if patch == (16, 16) and (h, w) == (16, 16) else 3
+    if (h, w) == patch:
+      corners = torch.zeros(5, 3, dtype=torch.int32)
+    else:
+      corners = dg.draw_patch_corners(500, n, (h, w), patch, edge, generator=g)
+      assert int(corners[:, 1].min()) >= edge and int(corners[:, 1].max()) < h - patch[0] - edge
+      assert int(corners[:, 2].min()) >= edge and int(corners[:, 2].max()) < w - patch[1] - edge
+    want = oracle.extract_patches(full, corners, patch)
+    got = dg.extract_patches(images.cuda(), corners.cuda(), patch)
+    assert torch.equal(got.cpu(), want)
+  batch = dg.sample_patches(torch.randn(4, 128, 128).cuda(), 4096, (16, 16), 5)
+  assert tuple(batch.shape) == (4096, 256) and torch.isfinite(batch).all()

@@ -192,3 +192,13 @@ def test_conv_padding_helpers():
   x, pad = oracle.synthetic_padded_images(2, 1, 40, 48, (16, 16), (8, 8))
   assert tuple(x.shape) == (2, 1, 56, 64) and pad == ((8, 8), (8, 8))
   assert float(x[:, :, :8].abs().max()) == 0.0 and float(x[:, :, :, -8:].abs().max()) == 0.0
+
+
+def test_patch_extraction_oracle_is_the_literal_crop():
+  g = torch.Generator().manual_seed(2)
+  images = torch.randn(2, 20, 24, 3, generator=g)
+  corners = torch.tensor([[0, 0, 0], [1, 4, 8], [1, 12, 16], [0, 7, 3]], dtype=torch.int32)
+  got = oracle.extract_patches(images, corners, (8, 8))
+  assert tuple(got.shape) == (4, 8 * 8 * 3)
+  assert torch.equal(got[1].view(8, 8, 3), images[1, 4:12, 8:16])
+  assert torch.equal(got[3].view(8, 8, 3)[2, 5], images[0, 9, 8])

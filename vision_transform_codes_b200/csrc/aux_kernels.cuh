@@ -518,4 +518,25 @@ __global__ void conv_dict_apply_kernel(float* __restrict__ dict, const float* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Data feed: crops of (ph x pw) pixels out of device-resident images (n, h, w, c), flattened in (y, x, c)
+// order like utils/dataset_generation.py:212-218 (all_patches[p] = img[v:v+ph, u:u+pw]) followed by its reshape(N, -1).
+// corners (B, 3) int32: image index, top row, left column. One warp-sized group of threads per patch row segment;
+// consecutive threads read consecutive (x, c) elements of an image row: coalesced on both sides.
+__global__ void extract_patches_kernel(const float* __restrict__ images, int64_t h, int64_t w, int64_t c,
+                                       const int32_t* __restrict__ corners, int64_t B, int64_t ph, int64_t pw,
+                                       float* __restrict__ patches, int64_t ld) {
+  const int64_t row_elems = pw * c;
+  const int64_t per_patch = ph * row_elems;
+  const int64_t total = B * per_patch;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = i / per_patch;
+    const int64_t e = i - b * per_patch;
+    const int64_t y = e / row_elems, xc = e - y * row_elems;
+    const int64_t img = corners[3 * b], top = corners[3 * b + 1], left = corners[3 * b + 2];
+    patches[b * ld + e] = images[((img * h + top + y) * w + left) * c + xc];
+  }
+}
+
 }  // namespace vtc

@@ -1844,4 +1844,19 @@ int vtc_conv_hessian_diag_update(const float* codes, int64_t B, int64_t S, int64
   return VTC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- data feed
+int vtc_extract_patches(const float* images, int64_t n, int64_t h, int64_t w, int64_t c, const int32_t* corners,
+                        int64_t B, int64_t ph, int64_t pw, float* patches, int64_t ld_patches, vtc_stream_t stream) {
+  if (!images || !corners || !patches || n <= 0 || h <= 0 || w <= 0 || c <= 0 || B <= 0 || ph <= 0 || pw <= 0 ||
+      ph > h || pw > w || ld_patches < ph * pw * c)
+    return fail(VTC_ERR_ARG, "vtc_extract_patches: bad argument");
+  DeviceInfo info;
+  TRY(device_info(&info));
+  extract_patches_kernel<<<grid_for(B * ph * pw * c, 256, info.sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      images, h, w, c, corners, B, ph, pw, patches, ld_patches);
+  COUNT_LAUNCH();
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
 }  // extern "C"
