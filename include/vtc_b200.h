@@ -232,6 +232,36 @@ int vtc_conv_hessian_diag_update(const float* codes, int64_t B, int64_t S, int64
                                  float* code_sq_sum, float* hessian_diagonal, int apply_ema, vtc_stream_t stream);
 
 /*
+ * Validation metrics of the trainer (training/sparse_coding.py:177-229, compute_metrics) from device-resident tensors,
+ * without copying images, codes or reconstructions to the host. totals (8 doubles, device):
+ *   [0] sum over items of 0.5 * ||codes*dictionary - image||^2          -> 'Average LASSO L2 component' * items
+ *   [1] sum over items of ||codes||_1, or of sum_g ||codes_g||_2 when group_slots is given (:199-210)
+ *   [2] sum over items of (number of non-zero codes / codes per item)   -> 'Average Normalized L0' * items
+ *   [3] sum over items with a non-zero mean squared error of log10(mse), [4] the number of such items
+ *       (pSNR_b = 10 log10(sig^2 / mse_b), utils/plotting.py:17-39, items with mse == 0 are skipped, :223)
+ *   [5], [6] min and max pixel of the batch (sig = max - min, :217)     [7] number of items
+ * group_slots (num_groups x group_width int32 on the device, -1 = padding) or NULL. Sums have a fixed order.
+ */
+size_t vtc_sc_metrics_workspace_bytes(int64_t B, int64_t S, int64_t D, int precision);
+int vtc_sc_metrics(const float* images, int64_t ld_images, const float* dictionary, const float* codes,
+                   int64_t ld_codes, int64_t B, int64_t S, int64_t D, const int32_t* group_slots, int64_t num_groups,
+                   int64_t group_width, int precision, double* totals, void* workspace, size_t workspace_bytes,
+                   vtc_stream_t stream);
+/*
+ * The same for the convolutional mode (:185-195): reconstruction = conv_transpose2d(codes, dictionary, stride); both it
+ * and the images are cropped to the un-padded region before any metric is taken. Arguments as vtc_fista_conv.
+ */
+size_t vtc_sc_conv_metrics_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t S, int64_t KH,
+                                           int64_t KW, int64_t SY, int64_t SX, int precision);
+int vtc_sc_conv_metrics(const float* images_padded, const float* dictionary, const float* codes, int64_t B, int64_t C,
+                        int64_t H, int64_t W, int64_t S, int64_t KH, int64_t KW, int64_t SY, int64_t SX, int pad_top,
+                        int pad_bottom, int pad_left, int pad_right, int precision, double* totals, void* workspace,
+                        size_t workspace_bytes, vtc_stream_t stream);
+/* mean_abs_change[s] = mean over the element's pixels of |dictionary - previous_dictionary| (:226-228) */
+int vtc_dict_change(const float* dictionary, const float* previous_dictionary, int64_t S, int64_t per_kernel,
+                    float* mean_abs_change, vtc_stream_t stream);
+
+/*
  * Data feed: B crops of (ph x pw) pixels out of device-resident images (n, h, w, c), each flattened in (y, x, c) order --
  * the patch extraction of utils/dataset_generation.py:207-218 (all_patches[p] = img[v:v+ph, u:u+pw], then reshape(N, -1))
  * without the host loop. corners (B, 3) int32 on the device: image index, top row, left column (the caller draws them;

@@ -24,6 +24,7 @@ Reference lines followed (paths relative to vision_transform_codes/):
   convolutional ISTA/FISTA   analysis_transforms/convolutional/ista_fista.py:104-197, utils/convolutions.py:7-24
   convolutional dict update  dict_update_rules/convolutional/sc_cheap_quadratic_descent.py:59-79,
                              sc_steepest_descent.py:55-72; Hessian running mean training/sparse_coding.py:158-161
+  validation metrics   training/sparse_coding.py:177-229, utils/plotting.py:17-39 (compute_pSNR)
 """
 import torch
 
@@ -356,6 +357,53 @@ def extract_patches(images, corners, patch_dimensions):
     img, top, left = (int(v) for v in corners[p_idx])
     out[p_idx] = images[img, top:top + ph, left:left + pw].reshape(-1)
   return out
+
+
+def compute_psnr(target, reconstruction, manual_sig_mag=None):
+  """utils/plotting.py:17-39 (numpy arrays in, numpy scalar out)."""
+  import numpy as np
+  sig = (np.max(target) - np.min(target)) if manual_sig_mag is None else manual_sig_mag
+  mse = np.mean(np.square(target - reconstruction))
+  return 10. * np.log10((sig**2) / mse) if mse != 0 else np.inf
+
+
+def compute_metrics(batch_images, batch_codes, dictionary, previous_dictionary, sparsity_weight, code_inf_alg='fista',
+                    group_assignments=None, kernel_strides=None, image_padding=None):
+  """training/sparse_coding.py:177-229: the validation metrics of one batch, on the host with numpy like the
+  reference (convolutional when kernel_strides is given: both images and reconstructions cropped to the un-padded
+  region, :185-195)."""
+  import numpy as np
+  metrics = {}
+  images_np = batch_images.numpy()
+  if kernel_strides is None:
+    recons = torch.mm(batch_codes, dictionary).numpy()
+    axes = 1
+  else:
+    recons = torch.nn.functional.conv_transpose2d(batch_codes, dictionary, stride=kernel_strides).numpy()
+    if image_padding is not None:
+      (pt, pb), (pl, pr) = image_padding
+      recons = recons[:, :, pt:-pb, pl:-pr]
+      images_np = images_np[:, :, pt:-pb, pl:-pr]
+    axes = (1, 2, 3)
+  metrics['Average LASSO L2 component'] = np.mean(0.5 * np.sum(np.square(recons - images_np), axis=axes))
+  if code_inf_alg in ('subspace_ista', 'subspace_fista'):
+    group_norms = np.zeros((len(batch_codes),))
+    for g in group_assignments:
+      group_norms += torch.norm(batch_codes[:, g], p=2, dim=1).numpy()
+    metrics['Average LASSO lagrange component'] = np.mean(sparsity_weight * group_norms)
+  else:
+    metrics['Average LASSO lagrange component'] = np.mean(
+        sparsity_weight * torch.norm(batch_codes, p=1, dim=axes).numpy())
+  metrics['Average LASSO Loss'] = (metrics['Average LASSO L2 component'] +
+                                   metrics['Average LASSO lagrange component'])
+  metrics['Average Normalized L0'] = float(torch.mean(
+      torch.norm(batch_codes, p=0, dim=axes) / np.prod(batch_codes.shape[1:])).numpy())
+  sig = np.max(images_np) - np.min(images_np)
+  psnrs = [compute_psnr(images_np[b], recons[b], manual_sig_mag=sig) for b in range(recons.shape[0])]
+  metrics['Average pSNR of reconstructions'] = np.mean([v for v in psnrs if v != np.inf])
+  metrics['Average change in dictionary kernels'] = torch.mean(
+      torch.abs(dictionary - previous_dictionary), dim=axes).numpy()
+  return metrics
 
 
 # ---------------------------------------------------------------------------------------------------------------

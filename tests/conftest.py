@@ -20,7 +20,7 @@ def load_golden(name):
   out = {}
   for k in data.files:
     v = data[k]
-    out[k] = torch.from_numpy(v) if v.ndim > 0 else v.item()
+    out[k] = v.item() if v.ndim == 0 else (torch.from_numpy(v) if v.dtype.kind in 'fiub' else v)
   return out
 
 

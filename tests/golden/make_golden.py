@@ -238,7 +238,90 @@ def make_conv():
   save('conv_training_small', batches=xb, dictionary=phi0, padding=np.array(padb), ista_cheap=d, fista_steepest=d_b)
 
 
+def _reference_function(path, name):
+  """Executes ONE function definition of a reference source file (here utils/plotting.py, whose module-level imports
+  need skimage / matplotlib) and returns it: the reference's own code, unmodified, without importing the module."""
+  import ast
+  src = open(os.path.join(REF, path)).read()
+  node = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name][0]
+  scope = {'np': np}
+  exec(compile(ast.Module(body=[node], type_ignores=[]), path, 'exec'), scope)
+  return scope[name]
+
+
+def make_metrics():
+  """Validation metrics (training/sparse_coding.py:177-229): the unmodified trainer with a
+  'training_visualization_schedule', tensorboard's SummaryWriter replaced by a recorder, the dictionary figures
+  (matplotlib, absent here) by an empty list, compute_pSNR executed from the reference's own source."""
+  import pathlib
+  import pickle
+  import tempfile
+  recorded = []
+
+  class Recorder:
+    def __init__(self, *a, **k):
+      pass
+
+    def add_scalar(self, tag, value, step):
+      recorded.append((tag, float(value), int(step)))
+
+    def add_image(self, *a, **k):
+      pass
+
+  tb = types.ModuleType('torch.utils.tensorboard')
+  tb.SummaryWriter = Recorder
+  sys.modules['torch.utils.tensorboard'] = tb
+  mpl = types.ModuleType('matplotlib')
+  mpl.pyplot = types.ModuleType('matplotlib.pyplot')
+  sys.modules.setdefault('matplotlib', mpl)
+  sys.modules.setdefault('matplotlib.pyplot', mpl.pyplot)
+  plotting = sys.modules['utils.plotting']
+  plotting.compute_pSNR = _reference_function('utils/plotting.py', 'compute_pSNR')
+  plotting.display_dictionary = lambda *a, **k: []
+
+  def run(name, train, val, phi0, params):
+    del recorded[:]
+    with tempfile.TemporaryDirectory() as tmp:
+      log = pathlib.Path(tmp) / 'log'
+      phi = phi0.clone()
+      sparse_coding.train_dictionary(train, val, phi, dict(
+          params, training_visualization_schedule={0, 2}, checkpoint_schedule={1, 2}, logging_folder_fullpath=log))
+      d1 = pickle.load(open(log / 'checkpoint_dictionary_iter_1', 'rb'))
+      d2 = pickle.load(open(log / 'checkpoint_dictionary_iter_2', 'rb'))
+    tags = sorted({t for t, _, _ in recorded})
+    table = np.array([[dict((t, v) for t, v, k in recorded if k == step)[tag] for tag in tags] for step in (0, 2)])
+    extra = {}
+    if 'padding' in params:
+      extra = {'padding': np.array(params['padding']), 'stride': np.array(params['strides'])}
+    save(name, training=train, validation=val, dictionary=phi0, dictionary_iter_1=d1, dictionary_iter_2=d2, metric_names=np.array(tags),
+         metrics=table, sparsity_weight=params['inference_param_schedule'][0]['sparsity_weight'],
+         num_iters=params['inference_param_schedule'][0]['num_iters'], **extra)
+
+  nb, b, n, s = 3, 48, 64, 128
+  x = patches((nb + 2) * b, n).view(nb + 2, b, n)
+  phi0 = dictionary(s, n)
+  params = {
+      'mode': 'fully-connected', 'num_epochs': 1,
+      'code_inference_algorithm': 'fista',
+      'inference_param_schedule': {0: {'sparsity_weight': 0.1, 'num_iters': 40}},
+      'dictionary_update_algorithm': 'sc_cheap_quadratic_descent',
+      'dict_update_param_schedule': {0: {'stepsize': 0.1, 'num_iters': 1}}}
+  run('metrics_fc', x[:nb], x[nb:], phi0, params)
+  pairs = [list(map(int, g)) for g in np.array_split(np.arange(s), s // 2)]
+  run('metrics_subspace', x[:nb], x[nb:], phi0, dict(
+      params, code_inference_algorithm='subspace_fista', group_assignments=pairs,
+      dictionary_update_algorithm='subspace_sc_cheap_quadratic_descent', subspace_alignment_penalty=0.0))
+  xb, phic, padb = conv_inputs((nb + 2) * 2, 1, (32, 32), (16, 16), (8, 8), 16, seed=9)
+  xb = xb.view(nb + 2, 2, *xb.shape[1:])
+  run('metrics_conv', xb[:nb], xb[nb:], phic, {
+      'mode': 'convolutional', 'num_epochs': 1, 'strides': (8, 8), 'padding': padb,
+      'code_inference_algorithm': 'ista',
+      'inference_param_schedule': {0: {'sparsity_weight': 0.05, 'num_iters': 15}},
+      'dictionary_update_algorithm': 'sc_cheap_quadratic_descent',
+      'dict_update_param_schedule': {0: {'stepsize': 0.05, 'num_iters': 1}}})
+
+
 if __name__ == '__main__':
-  which = sys.argv[1:] or ['inference', 'config1', 'overcomplete', 'subspace', 'dict_update', 'training', 'conv']
+  which = sys.argv[1:] or ['inference', 'config1', 'overcomplete', 'subspace', 'dict_update', 'training', 'conv', 'metrics']
   for name in which:
     globals()['make_' + name]()

@@ -4,6 +4,8 @@ the convolutional path, refusal of CPU tensors, workspace queries."""
 import inspect
 import os
 
+import numpy as np
+
 import pytest
 import torch
 
@@ -126,7 +128,32 @@ def test_trainer_parameter_checks():
     trainer.train_dictionary([], None, phi, dict(base, dictionary_update_algorithm='subspace_sc_cheap_quadratic_descent',
                                                  group_assignments=[[0, 1], [2, 3]], subspace_alignment_penalty=0.0))
   with pytest.raises(NotImplementedError):
+    trainer.train_dictionary([], None, phi, dict(base, dict_element_rp_schedule={0: {}}))
+  with pytest.raises(AssertionError):   # a visualisation schedule needs a pathlib.Path to log into (:330-343)
     trainer.train_dictionary([], None, phi, dict(base, training_visualization_schedule={0}))
   with pytest.raises(AssertionError):
     trainer.train_dictionary([], None, 2 * phi, base)   # dictionary not normalised
   assert trainer.train_dictionary([], None, phi, base) is not None   # an empty dataset: nothing to do, returns h
+
+
+def test_metrics_from_totals_follow_the_reference_definitions():
+  """Host side of training/metrics.py: the five scalars from the eight device totals (training/sparse_coding.py:196-225,
+  utils/plotting.py:35-39), against the oracle's compute_metrics on a small batch whose totals are formed here."""
+  from vision_transform_codes_b200.training import metrics
+  phi = oracle.synthetic_dictionary(24, 16)
+  x = oracle.synthetic_patches(10, 16)
+  codes = oracle.ista_fista(x, phi, 0.1, 20)
+  x[3] = torch.mm(codes, phi)[3]   # an exactly reconstructed patch: pSNR is inf and the reference leaves it out (:223)
+  want = oracle.compute_metrics(x, codes, phi, phi, 0.1)
+  r2 = ((torch.mm(codes, phi) - x)**2).sum(1).double()
+  mse = (r2 / 16).float()
+  keep = mse != 0
+  assert int(keep.sum()) == 9
+  totals = [float(0.5 * r2.sum()), float(codes.abs().sum()), float((codes != 0).sum(1).double().div(24).sum()),
+            float(torch.log10(mse[keep].double()).sum()), float(keep.sum()), float(x.min()), float(x.max()), 10.0]
+  got = metrics.metrics_from_totals(totals, 0.1)
+  for name in got:
+    assert abs(got[name] - float(want[name])) <= 1e-5 * max(1.0, abs(float(want[name]))), name
+  assert np.isnan(metrics.metrics_from_totals([0, 0, 0, 0, 0, 0.0, 1.0, 4], 0.1)[metrics.PSNR])
+  avg = metrics.average_metrics([{'a': 1.0, 'b': np.array([1.0, 3.0])}, {'a': 3.0, 'b': np.array([5.0, 7.0])}])
+  assert avg == {'a': 2.0, 'b': 4.0}

@@ -202,3 +202,41 @@ def test_patch_extraction_oracle_is_the_literal_crop():
   assert tuple(got.shape) == (4, 8 * 8 * 3)
   assert torch.equal(got[1].view(8, 8, 3), images[1, 4:12, 8:16])
   assert torch.equal(got[3].view(8, 8, 3)[2, 5], images[0, 9, 8])
+
+
+def metrics_cases():
+  """(golden name, oracle inference, compute_metrics keyword arguments) of the three validation-metric goldens."""
+  pairs = [list(map(int, g)) for g in np.array_split(np.arange(128), 64)]
+  yield 'metrics_fc', 'fista', {}
+  yield 'metrics_subspace', 'subspace_fista', {'group_assignments': pairs}
+  yield 'metrics_conv', 'ista', {'kernel_strides': (8, 8)}
+
+
+def oracle_validation_codes(g, alg, phi, kw, x):
+  lam, T = g['sparsity_weight'], g['num_iters']
+  if 'kernel_strides' in kw:
+    return oracle.conv_ista_fista(x, phi, kw['kernel_strides'], kw['image_padding'], lam, T, variant=alg)
+  if alg.startswith('subspace'):
+    return oracle.subspace_ista_fista(x, phi, kw['group_assignments'], lam, T, variant=alg[9:])
+  return oracle.ista_fista(x, phi, lam, T, variant=alg)
+
+
+def test_validation_metrics_match_reference_trainer():
+  """compute_metrics (training/sparse_coding.py:177-229) against the scalars the unmodified trainer sent to its
+  tensorboard writer at iterations 0 and 2, averaged over two validation batches (:505-506)."""
+  for name, alg, kw in metrics_cases():
+    g = load_golden(name)
+    kw = dict(kw)
+    if 'padding' in g:
+      kw['image_padding'] = tuple(tuple(int(v) for v in row) for row in g['padding'])
+    names = [str(n) for n in g['metric_names']]
+    for row, (phi, prev) in enumerate(((g['dictionary'], g['dictionary']),
+                                       (g['dictionary_iter_2'], g['dictionary_iter_1']))):
+      per_batch = []
+      for x in g['validation']:
+        codes = oracle_validation_codes(g, alg, phi, kw, x)
+        per_batch.append(oracle.compute_metrics(x, codes, phi, prev, g['sparsity_weight'], alg, **kw))
+      for col, metric in enumerate(names):
+        got = np.mean([m[metric] for m in per_batch])
+        want = float(g['metrics'][row, col])
+        assert abs(got - want) <= 2e-5 * max(1.0, abs(want)), (name, row, metric, got, want)

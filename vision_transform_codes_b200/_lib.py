@@ -50,6 +50,12 @@ SIGNATURES = {
     'vtc_sc_conv_dict_grad': (_int, [_ptr, _ptr, _ptr, _ptr] + [_i64] * 9 + [_int] * 4 + [_int, _ptr, _size, _ptr]),
     'vtc_sc_conv_dict_apply': (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _f32, _f32, _int, _ptr]),
     'vtc_conv_hessian_diag_update': (_int, [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _int, _ptr]),
+    'vtc_sc_metrics_workspace_bytes': (_size, [_i64, _i64, _i64, _int]),
+    'vtc_sc_metrics': (_int, [_ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _int, _ptr, _ptr, _size,
+                              _ptr]),
+    'vtc_sc_conv_metrics_workspace_bytes': (_size, [_i64] * 9 + [_int]),
+    'vtc_sc_conv_metrics': (_int, [_ptr, _ptr, _ptr] + [_i64] * 9 + [_int] * 4 + [_int, _ptr, _ptr, _size, _ptr]),
+    'vtc_dict_change': (_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr]),
     'vtc_extract_patches': (_int, [_ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr]),
 }
 

@@ -539,4 +539,197 @@ __global__ void extract_patches_kernel(const float* __restrict__ images, int64_t
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Validation metrics (training/sparse_coding.py:177-229) from device-resident residuals and codes:
+// one record of METRIC_FIELDS floats per item (patch or image):
+//   [0] sum of squared residuals   [1] l1 norm of the codes, or the sum of the group l2 norms (subspace)
+//   [2] number of non-zero codes   [3] min and [4] max of the item's (cropped) pixels
+// Every sum has a fixed order (lane-strided partials, then a shuffle/shared-memory tree), so results are
+// reproducible run to run.
+constexpr int METRIC_FIELDS = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// fully connected: one warp per patch. resid (B x D, pitch ld_r) = codes * dictionary - images.
+// slots != nullptr: (num_groups x group_width) atom indices, -1 = padding; field [1] becomes sum_g ||a_g||_2.
+__global__ void fc_metrics_rows_kernel(const float* __restrict__ resid, int64_t ld_r, const float* __restrict__ images,
+                                       int64_t ld_x, const float* __restrict__ codes, int64_t ld_a, int64_t B,
+                                       int64_t S, int64_t D, const int32_t* __restrict__ slots, int64_t num_groups,
+                                       int group_width, float* __restrict__ items) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t b = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+    float r2 = 0.f, lo = INFINITY, hi = -INFINITY;
+    for (int64_t d = lane; d < D; d += 32) {
+      const float r = resid[b * ld_r + d], x = images[b * ld_x + d];
+      r2 = fmaf(r, r, r2);
+      lo = fminf(lo, x), hi = fmaxf(hi, x);
+    }
+    float l1 = 0.f, l0 = 0.f;
+    for (int64_t s = lane; s < S; s += 32) {
+      const float a = codes[b * ld_a + s];
+      l1 += fabsf(a);
+      l0 += (a != 0.f) ? 1.f : 0.f;
+    }
+    if (slots) {
+      l1 = 0.f;
+      for (int64_t g = lane; g < num_groups; g += 32) {
+        float n2 = 0.f;
+        for (int j = 0; j < group_width; ++j) {
+          const int32_t s = slots[g * group_width + j];
+          if (s >= 0) {
+            const float a = codes[b * ld_a + s];
+            n2 = fmaf(a, a, n2);
+          }
+        }
+        l1 += sqrtf(n2);
+      }
+    }
+    r2 = warp_sum(r2), l1 = warp_sum(l1), l0 = warp_sum(l0), lo = warp_min(lo), hi = warp_max(hi);
+    if (lane == 0) {
+      float* o = items + b * METRIC_FIELDS;
+      o[0] = r2, o[1] = l1, o[2] = l0, o[3] = lo, o[4] = hi;
+    }
+  }
+}
+
+// convolutional, stage 1: grid (chunks, images); block j of image b takes the elements i = j*threads + t (+ k*chunks*
+// threads) of the image's masked residual blocks (rows x db, pitch ld_r), of its codes (contiguous n_codes) and of the
+// un-padded crop of its pixels, and writes one partial record.
+__global__ void conv_metrics_partial_kernel(const float* __restrict__ resid, int64_t ld_r, const float* __restrict__ img,
+                                            const float* __restrict__ codes, ConvGeom g, int pad_t, int pad_b,
+                                            int pad_l, int pad_r, float* __restrict__ partials) {
+  __shared__ float red[5][32];
+  const int64_t b = blockIdx.y;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t rows = static_cast<int64_t>(g.gh) * g.gw;
+  float r2 = 0.f, l1 = 0.f, l0 = 0.f, lo = INFINITY, hi = -INFINITY;
+  for (int64_t i = first; i < rows * g.db; i += stride) {
+    const int64_t r = i / g.db, c = i - r * g.db;
+    const float v = resid[(b * rows + r) * ld_r + c];
+    r2 = fmaf(v, v, r2);
+  }
+  const int64_t n_codes = static_cast<int64_t>(g.s) * g.ch * g.cw;
+  for (int64_t i = first; i < n_codes; i += stride) {
+    const float a = codes[b * n_codes + i];
+    l1 += fabsf(a);
+    l0 += (a != 0.f) ? 1.f : 0.f;
+  }
+  const int64_t hc = g.h - pad_t - pad_b, wc = g.w - pad_l - pad_r;
+  for (int64_t i = first; i < static_cast<int64_t>(g.c) * hc * wc; i += stride) {
+    const int64_t ch = i / (hc * wc), e = i - ch * hc * wc;
+    const int64_t y = e / wc, x = e - y * wc;
+    const float v = img[((b * g.c + ch) * g.h + pad_t + y) * g.w + pad_l + x];
+    lo = fminf(lo, v), hi = fmaxf(hi, v);
+  }
+  r2 = warp_sum(r2), l1 = warp_sum(l1), l0 = warp_sum(l0), lo = warp_min(lo), hi = warp_max(hi);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[0][warp] = r2, red[1][warp] = l1, red[2][warp] = l0, red[3][warp] = lo, red[4][warp] = hi;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    r2 = warp_sum(lane < nw ? red[0][lane] : 0.f);
+    l1 = warp_sum(lane < nw ? red[1][lane] : 0.f);
+    l0 = warp_sum(lane < nw ? red[2][lane] : 0.f);
+    lo = warp_min(lane < nw ? red[3][lane] : INFINITY);
+    hi = warp_max(lane < nw ? red[4][lane] : -INFINITY);
+    if (lane == 0) {
+      float* o = partials + (b * gridDim.x + blockIdx.x) * METRIC_FIELDS;
+      o[0] = r2, o[1] = l1, o[2] = l0, o[3] = lo, o[4] = hi;
+    }
+  }
+}
+// stage 2: one warp per image folds its chunk partials into the image's record
+__global__ void conv_metrics_fold_kernel(const float* __restrict__ partials, int chunks, int64_t B,
+                                         float* __restrict__ items) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  float r2 = 0.f, l1 = 0.f, l0 = 0.f, lo = INFINITY, hi = -INFINITY;
+  for (int j = lane; j < chunks; j += 32) {
+    const float* p = partials + (b * chunks + j) * METRIC_FIELDS;
+    r2 += p[0], l1 += p[1], l0 += p[2], lo = fminf(lo, p[3]), hi = fmaxf(hi, p[4]);
+  }
+  r2 = warp_sum(r2), l1 = warp_sum(l1), l0 = warp_sum(l0), lo = warp_min(lo), hi = warp_max(hi);
+  if (lane == 0) {
+    float* o = items + b * METRIC_FIELDS;
+    o[0] = r2, o[1] = l1, o[2] = l0, o[3] = lo, o[4] = hi;
+  }
+}
+
+// batch totals over the item records, one block, fp64:
+//   out[0] = sum_b 0.5 * r2_b            (LASSO l2 component, summed)
+//   out[1] = sum_b l1_b                  (lagrange component / sparsity_weight, summed)
+//   out[2] = sum_b l0_b / codes_per_item (normalised l0, summed)
+//   out[3] = sum over items with mse != 0 of log10(mse_b), mse_b = r2_b / pixels_per_item;  out[4] = their number
+//   out[5], out[6] = min, max pixel of the batch;  out[7] = number of items
+__global__ void metrics_totals_kernel(const float* __restrict__ items, int64_t B, double pixels_per_item,
+                                      double codes_per_item, double* __restrict__ out) {
+  __shared__ double red[7][32];
+  double l2 = 0.0, l1 = 0.0, l0 = 0.0, lg = 0.0, nf = 0.0, lo = INFINITY, hi = -INFINITY;
+  for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
+    const float* p = items + b * METRIC_FIELDS;
+    l2 += 0.5 * static_cast<double>(p[0]);
+    l1 += static_cast<double>(p[1]);
+    l0 += static_cast<double>(p[2]) / codes_per_item;
+    // the reference forms the mean squared error in fp32 (numpy mean of an fp32 array)
+    const float mse = static_cast<float>(static_cast<double>(p[0]) / pixels_per_item);
+    if (mse != 0.f) lg += log10(static_cast<double>(mse)), nf += 1.0;
+    lo = fmin(lo, static_cast<double>(p[3])), hi = fmax(hi, static_cast<double>(p[4]));
+  }
+  double v[7] = {l2, l1, l0, lg, nf, lo, hi};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int f = 0; f < 7; ++f) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double other = __shfl_xor_sync(0xffffffffu, v[f], o);
+      v[f] = (f == 5) ? fmin(v[f], other) : (f == 6) ? fmax(v[f], other) : v[f] + other;
+    }
+    if (lane == 0) red[f][warp] = v[f];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+#pragma unroll
+    for (int f = 0; f < 7; ++f) {
+      double x = (lane < nw) ? red[f][lane] : (f == 5 ? INFINITY : f == 6 ? -INFINITY : 0.0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, x, o);
+        x = (f == 5) ? fmin(x, other) : (f == 6) ? fmax(x, other) : x + other;
+      }
+      if (lane == 0) out[f] = x;
+    }
+    if (lane == 0) out[7] = static_cast<double>(B);
+  }
+}
+
+// mean over the pixels of |dictionary - previous| per dictionary element (training/sparse_coding.py:226-228)
+__global__ void dict_change_kernel(const float* __restrict__ dict, const float* __restrict__ prev, int64_t S,
+                                   int64_t per_kernel, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (s >= S) return;
+  float acc = 0.f;
+  for (int64_t i = lane; i < per_kernel; i += 32) acc += fabsf(dict[s * per_kernel + i] - prev[s * per_kernel + i]);
+  acc = warp_sum(acc);
+  if (lane == 0) out[s] = acc / static_cast<float>(per_kernel);
+}
+
 }  // namespace vtc

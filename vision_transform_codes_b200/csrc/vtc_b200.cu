@@ -1844,6 +1844,145 @@ int vtc_conv_hessian_diag_update(const float* codes, int64_t B, int64_t S, int64
   return VTC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- validation metrics
+}  // extern "C"
+namespace {
+struct MetricsWs {
+  PartsMat a_op, phiT_op;
+  float *resid, *items;
+  int64_t ldD;
+};
+MetricsWs carve_metrics(Carver& cv, int64_t B, int64_t S, int64_t D, int precision) {
+  MetricsWs w;
+  const int P = parts_for(precision);
+  w.a_op = carve_parts(cv, B, S, P);
+  w.phiT_op = carve_parts(cv, D, S, P);
+  w.ldD = round_up(D, 4);
+  w.resid = static_cast<float*>(cv.take(static_cast<size_t>(B) * w.ldD * 4));
+  w.items = static_cast<float*>(cv.take(static_cast<size_t>(B) * METRIC_FIELDS * 4));
+  return w;
+}
+constexpr int CONV_METRIC_CHUNKS = 64;
+}  // namespace
+extern "C" {
+
+size_t vtc_sc_metrics_workspace_bytes(int64_t B, int64_t S, int64_t D, int precision) {
+  if (!valid_precision(precision) || B <= 0 || S <= 0 || D <= 0) return 0;
+  Carver cv(nullptr, 0);
+  carve_metrics(cv, B, S, D, precision);
+  return cv.off + 1024;
+}
+
+int vtc_sc_metrics(const float* images, int64_t ld_images, const float* dictionary, const float* codes,
+                   int64_t ld_codes, int64_t B, int64_t S, int64_t D, const int32_t* group_slots, int64_t num_groups,
+                   int64_t group_width, int precision, double* totals, void* workspace, size_t workspace_bytes,
+                   vtc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!images || !dictionary || !codes || !totals) return fail(VTC_ERR_ARG, "vtc_sc_metrics: null pointer");
+  if (B <= 0 || S <= 0 || D <= 0 || ld_images < D || ld_codes < S) return fail(VTC_ERR_ARG, "vtc_sc_metrics: bad shape");
+  if (group_slots && (num_groups <= 0 || group_width <= 0)) return fail(VTC_ERR_ARG, "vtc_sc_metrics: bad group table");
+  if (!valid_precision(precision)) return fail(VTC_ERR_ARG, "precision must be 1, 3 or 6");
+  DeviceInfo info;
+  TRY(require_sm100(&info));
+  Carver cv(workspace, workspace_bytes);
+  MetricsWs w = carve_metrics(cv, B, S, D, precision);
+  if (!workspace || !cv.fits()) return fail(VTC_ERR_WORKSPACE, "vtc_sc_metrics: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
+  TRY(split_rows(codes, ld_codes, B, S, w.a_op, st));
+  TRY(transpose_split(dictionary, D, S, D, w.phiT_op, st));
+  // resid (B x D) = codes * dictionary - images   (training/sparse_coding.py:182, :196-197)
+  {
+    GemmCall g;
+    g.A = w.a_op, g.B = w.phiT_op;
+    g.precision = precision;
+    g.M = B, g.N = D, g.K = S;
+    if (tma_ok(images, ld_images)) {
+      g.in[0] = F32Mat{images, B, D, ld_images};
+    } else {
+      CUDA_TRY(cudaMemcpy2DAsync(w.resid, w.ldD * 4, images, ld_images * 4, D * 4, B, cudaMemcpyDeviceToDevice, st));
+      g.in[0] = F32Mat{w.resid, B, D, w.ldD};
+    }
+    g.in_mask = 1;
+    g.out = F32Mat{w.resid, B, D, w.ldD}, g.store_out = true;
+    TRY(launch_gemm<EPI_STORE>(g, st));
+  }
+  fc_metrics_rows_kernel<<<grid_for(B * 32, 256, info.sm_count), 256, 0, st>>>(
+      w.resid, w.ldD, images, ld_images, codes, ld_codes, B, S, D, group_slots, num_groups,
+      static_cast<int>(group_width), w.items);
+  COUNT_LAUNCH();
+  metrics_totals_kernel<<<1, 1024, 0, st>>>(w.items, B, static_cast<double>(D), static_cast<double>(S), totals);
+  COUNT_LAUNCH();
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+size_t vtc_sc_conv_metrics_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t S, int64_t KH,
+                                           int64_t KW, int64_t SY, int64_t SX, int precision) {
+  ConvShape cs;
+  if (!valid_precision(precision) || conv_shape(B, C, H, W, S, KH, KW, SY, SX, 0, 0, 0, 0, &cs) != VTC_OK) return 0;
+  Carver cv(nullptr, 0);
+  carve_conv(cv, cs, precision);
+  cv.take(static_cast<size_t>(cs.rows) * round_up(cs.g.db, 4) * 4);
+  cv.take(static_cast<size_t>(B) * (CONV_METRIC_CHUNKS + 1) * METRIC_FIELDS * 4);
+  return cv.off + 2048;
+}
+
+int vtc_sc_conv_metrics(const float* images_padded, const float* dictionary, const float* codes, int64_t B, int64_t C,
+                        int64_t H, int64_t W, int64_t S, int64_t KH, int64_t KW, int64_t SY, int64_t SX, int pad_top,
+                        int pad_bottom, int pad_left, int pad_right, int precision, double* totals, void* workspace,
+                        size_t workspace_bytes, vtc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!images_padded || !dictionary || !codes || !totals) return fail(VTC_ERR_ARG, "vtc_sc_conv_metrics: null pointer");
+  if (!valid_precision(precision)) return fail(VTC_ERR_ARG, "precision must be 1, 3 or 6");
+  ConvShape cs;
+  TRY(conv_shape(B, C, H, W, S, KH, KW, SY, SX, pad_top, pad_bottom, pad_left, pad_right, &cs));
+  const ConvGeom& g = cs.g;
+  if (pad_top + pad_bottom >= H || pad_left + pad_right >= W) return fail(VTC_ERR_ARG, "vtc_sc_conv_metrics: the padding leaves no pixels");
+  if (B > 65535) return fail(VTC_ERR_ARG, "vtc_sc_conv_metrics: at most 65535 images per call");
+  DeviceInfo info;
+  TRY(require_sm100(&info));
+  Carver cv(workspace, workspace_bytes);
+  ConvWs w = carve_conv(cv, cs, precision);
+  float* rblk = static_cast<float*>(cv.take(static_cast<size_t>(cs.rows) * w.ldD * 4));
+  float* partials = static_cast<float*>(cv.take(static_cast<size_t>(B) * CONV_METRIC_CHUNKS * METRIC_FIELDS * 4));
+  float* items = static_cast<float*>(cv.take(static_cast<size_t>(B) * METRIC_FIELDS * 4));
+  if (!workspace || !cv.fits()) return fail(VTC_ERR_WORKSPACE, "vtc_sc_conv_metrics: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
+  const int64_t R = cs.rows;
+  conv_codes_to_grid_kernel<<<grid_for(R * S, 256, info.sm_count), 256, 0, st>>>(codes, g, w.init_pad, w.ldS);
+  COUNT_LAUNCH();
+  TRY(split_rows(w.init_pad, w.ldS, R, S, w.yop[0], st));
+  TRY(conv_dictionary_operands(dictionary, cs, w, st));
+  conv_image_to_blocks_kernel<<<grid_for(R * g.db, 256, info.sm_count), 256, 0, st>>>(images_padded, g, w.xblk, w.ldD);
+  COUNT_LAUNCH();
+  // reconstruction minus image inside the un-padded region, zero outside it (training/sparse_coding.py:185-197)
+  {
+    GemmCall r;
+    conv_synthesis_call(r, cs, w, w.yop[0], precision);
+    r.out = F32Mat{rblk, R, g.db, w.ldD}, r.store_out = true;
+    TRY(launch_gemm<EPI_STORE>(r, st));
+  }
+  conv_metrics_partial_kernel<<<dim3(CONV_METRIC_CHUNKS, static_cast<unsigned>(B)), 256, 0, st>>>(
+      rblk, w.ldD, images_padded, codes, g, pad_top, pad_bottom, pad_left, pad_right, partials);
+  COUNT_LAUNCH();
+  conv_metrics_fold_kernel<<<static_cast<unsigned>(ceil_div(B * 32, 256)), 256, 0, st>>>(partials, CONV_METRIC_CHUNKS, B, items);
+  COUNT_LAUNCH();
+  const double pixels = static_cast<double>(C) * (H - pad_top - pad_bottom) * (W - pad_left - pad_right);
+  metrics_totals_kernel<<<1, 1024, 0, st>>>(items, B, pixels, static_cast<double>(S) * g.ch * g.cw, totals);
+  COUNT_LAUNCH();
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+int vtc_dict_change(const float* dictionary, const float* previous_dictionary, int64_t S, int64_t per_kernel,
+                    float* mean_abs_change, vtc_stream_t stream) {
+  if (!dictionary || !previous_dictionary || !mean_abs_change || S <= 0 || per_kernel <= 0)
+    return fail(VTC_ERR_ARG, "vtc_dict_change: bad argument");
+  dict_change_kernel<<<static_cast<unsigned>(ceil_div(S * 32, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dictionary, previous_dictionary, S, per_kernel, mean_abs_change);
+  COUNT_LAUNCH();
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- data feed
 int vtc_extract_patches(const float* images, int64_t n, int64_t h, int64_t w, int64_t c, const int32_t* corners,
                         int64_t B, int64_t ph, int64_t pw, float* patches, int64_t ld_patches, vtc_stream_t stream) {

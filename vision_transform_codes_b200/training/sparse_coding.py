@@ -5,8 +5,10 @@ The reference's ``training/sparse_coding.py`` (train_dictionary, :9-519) is the 
 working unmodified on top of the drop-in modules (``vision_transform_codes_b200.install()``). This module is the
 lean equivalent for when the reference tree is not on the machine, and the only trainer that is correct under data
 parallelism: it mirrors the reference's parameter dictionary and per-batch body (:460-465 schedules, :513-515
-infer -> update, :154 Hessian running mean, :170-175 pickle checkpoints) and leaves out what is not on the hot path
-(tensorboard visualisation :177-271, dictionary-element reset/prune :522-764), which raise NotImplementedError.
+infer -> update, :154 Hessian running mean, :170-175 pickle checkpoints, :498-506 validation metrics on the
+'training_visualization_schedule', computed on the device by training/metrics.py) and leaves out what is not on the
+hot path: the matplotlib dictionary figures (:237-271) are skipped, dictionary-element reset/prune (:522-764) raises
+NotImplementedError.
 
 Data parallel (``vision_transform_codes_b200.enable_data_parallel()``): every rank holds a replica of the
 dictionary and its contiguous shard of each batch. Inference needs no communication. Per dictionary-update
@@ -23,6 +25,7 @@ from vision_transform_codes_b200.analysis_transforms.fully_connected import ista
 from vision_transform_codes_b200.analysis_transforms.convolutional import ista_fista as conv_ista_fista
 from vision_transform_codes_b200.dict_update_rules.convolutional import _common as _conv_common
 from vision_transform_codes_b200.dict_update_rules.fully_connected import _common
+from vision_transform_codes_b200.training import metrics as _metrics
 
 CHEAP_QUADRATIC = ('sc_cheap_quadratic_descent', 'subspace_sc_cheap_quadratic_descent')
 UPDATE_RULES = ('sc_steepest_descent', 'sc_cheap_quadratic_descent', 'subspace_sc_steepest_descent',
@@ -152,10 +155,9 @@ def train_dictionary(training_image_dataset, validation_image_dataset, init_dict
       raise KeyError('Havent implemented subspace ISTA for convolutional yet')
     if dict_update_alg not in ('sc_steepest_descent', 'sc_cheap_quadratic_descent'):
       raise KeyError('Not implemented for convolutional')
-  for key in ('training_visualization_schedule', 'dict_element_rp_schedule'):
-    if key in all_params:
-      raise NotImplementedError('%s is host-side orchestration outside the B200 hot path; run the reference '
-                                'trainer on top of vision_transform_codes_b200.install() for it' % key)
+  if 'dict_element_rp_schedule' in all_params:
+    raise NotImplementedError('dict_element_rp_schedule is host-side orchestration outside the B200 hot path; run the '
+                              'reference trainer on top of vision_transform_codes_b200.install() for it')
   if dict_update_alg == 'subspace_sc_steepest_descent':
     raise ImportError('dict_update_rules.fully_connected.subspace_sc_steepest_descent does not exist in the '
                       'reference either')
@@ -180,6 +182,14 @@ def train_dictionary(training_image_dataset, validation_image_dataset, init_dict
     assert logging_path is not None and not isinstance(logging_path, str), 'should be pathlib.Path'
     logging_path.mkdir(parents=True, exist_ok=True)
   print_interval = all_params.get('stdout_print_interval', 1000)
+  # :355-366, :498-506: validation metrics at the scheduled iterations -> tensorboard scalars (when tensorboard is
+  # importable) and, as (iteration, metrics) pairs, appended to all_params['validation_metrics_log'] if that is a list
+  vis_sched = all_params.get('training_visualization_schedule')
+  tb_writer, previous_dictionary = None, None
+  metrics_log = all_params.get('validation_metrics_log')
+  if vis_sched is not None:
+    assert logging_path is not None and not isinstance(logging_path, str), 'should be pathlib.Path'
+    previous_dictionary = init_dictionary.clone()
 
   dictionary = init_dictionary  # no copying, just a new reference
   hessian_diag = None
@@ -187,6 +197,13 @@ def train_dictionary(training_image_dataset, validation_image_dataset, init_dict
     hessian_diag = init_dictionary.new_zeros(init_dictionary.shape[0])
   state = None if convolutional else _UpdateState(dictionary)
   rank0 = (not config.data_parallel) or torch.distributed.get_rank(config.process_group) == 0
+  if vis_sched is not None and rank0:
+    logging_path.mkdir(parents=True, exist_ok=True)
+    try:
+      from torch.utils.tensorboard import SummaryWriter
+      tb_writer = SummaryWriter(logging_path)
+    except ImportError:
+      tb_writer = None
 
   starttime = time.time()
   total_iter_idx = 0
@@ -205,10 +222,28 @@ def train_dictionary(training_image_dataset, validation_image_dataset, init_dict
       if ckpt_sched is not None and total_iter_idx in ckpt_sched and rank0:
         pickle.dump(dictionary.cpu().numpy(),
                     open(logging_path / ('checkpoint_dictionary_iter_' + str(total_iter_idx)), 'wb'))
+      if vis_sched is not None and total_iter_idx in vis_sched:
+        val_metrics = []
+        for v_batch_images in validation_image_dataset:
+          if dictionary.device != v_batch_images.device:
+            v_batch_images = v_batch_images.to(dictionary.device)
+          v_codes = infer_codes(v_batch_images, dictionary, code_inf_alg, sparsity_weight, inf_num_iters, nonneg_only,
+                                hard_threshold, group_assignments, kernel_strides, image_padding)
+          val_metrics.append(_metrics.compute_metrics(
+              v_batch_images, v_codes, dictionary, previous_dictionary, sparsity_weight, code_inf_alg,
+              group_assignments, kernel_strides, image_padding))
+        averaged = _metrics.average_metrics(val_metrics)
+        if metrics_log is not None:
+          metrics_log.append((total_iter_idx, averaged))
+        if tb_writer is not None:
+          for name in averaged:
+            tb_writer.add_scalar(name, averaged[name], total_iter_idx)
       if dictionary.device != t_batch_images.device:
         t_batch_images = t_batch_images.to(dictionary.device)
       t_codes = infer_codes(t_batch_images, dictionary, code_inf_alg, sparsity_weight, inf_num_iters, nonneg_only,
                             hard_threshold, group_assignments, kernel_strides, image_padding)
+      if previous_dictionary is not None:
+        previous_dictionary.copy_(dictionary)
       if convolutional:
         update_dictionary_convolutional(t_batch_images, dictionary, t_codes, hessian_diag, kernel_strides,
                                         image_padding, d_upd_stp, d_upd_niters)
