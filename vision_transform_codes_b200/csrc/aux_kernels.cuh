@@ -127,11 +127,22 @@ __global__ void gram_fp64_kernel(const float* __restrict__ phi, int64_t S, int64
 }
 
 // C = (A / *trace_in)^2 for symmetric A (n x n, n % 32 == 0); accumulates tr C into *trace_out.
+// Squaring number `step` >= 1 reads *trace_in = tr (A_{step-1} / tr A_{step-1})^2 = sum_i w_i^2 of the normalised
+// eigenvalue weights w_i: once that is within kLipschitzConverged of 1 a single eigen-direction carries all the weight
+// (the Rayleigh quotient is then exact to ~(1 - sum w_i^2) / 2 relative), the step index is recorded in *stop and this
+// and every later squaring returns at once. A (nearly) degenerate top eigenvalue never triggers it and runs them all.
+constexpr double kLipschitzConverged = 1e-11;
 __global__ void square_fp64_kernel(const double* __restrict__ A, int n, const double* __restrict__ trace_in,
-                                   double* __restrict__ C, double* __restrict__ trace_out) {
+                                   double* __restrict__ C, double* __restrict__ trace_out, int step,
+                                   double* __restrict__ stop) {
   __shared__ double As[32][33], Bs[32][33];
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  if (*stop != 0.0) return;
+  if (step >= 1 && 1.0 - *trace_in < kLipschitzConverged) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tx == 0 && ty == 0) *stop = static_cast<double>(step);
+    return;
+  }
   const double scale = 1.0 / *trace_in;
   double acc[4] = {0, 0, 0, 0};
   for (int k0 = 0; k0 < n; k0 += 32) {
@@ -160,21 +171,33 @@ __global__ void square_fp64_kernel(const double* __restrict__ A, int n, const do
 }
 
 // scalars[0] = eta = 1/L, [1] = theta = lambda * eta, [2] = L, [3] = status bits (1 = non-finite / non-positive L)
-__global__ void lipschitz_finalize_kernel(const double* __restrict__ Ap, const double* __restrict__ M, int n,
-                                          const double* __restrict__ trace_p, float sparsity_weight,
-                                          float* __restrict__ scalars, float* __restrict__ lipschitz_out) {
-  __shared__ double red[256];
-  double s = 0.0;
+// traces[j] = trace of iterate j (A_0 = M; iterate j >= 1 lives in A0 for odd j, A1 for even j); traces[squarings + 1] =
+// the iterate the squarings stopped at (0: all of them ran).
+__global__ void lipschitz_finalize_kernel(const double* __restrict__ A0, const double* __restrict__ A1,
+                                          const double* __restrict__ M, int n, const double* __restrict__ traces,
+                                          int squarings, float sparsity_weight, float* __restrict__ scalars,
+                                          float* __restrict__ lipschitz_out) {
+  __shared__ double red[1024];
+  const double stop = traces[squarings + 1];
+  const int last = (stop != 0.0) ? static_cast<int>(stop) : squarings;
+  const double* __restrict__ Ap = (last & 1) ? A0 : A1;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   const int64_t total = static_cast<int64_t>(n) * n;
-  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) s += Ap[i] * M[i];
-  red[threadIdx.x] = s;
+  const int64_t bd = blockDim.x;
+  for (int64_t i = threadIdx.x; i < total; i += 4 * bd) {   // four independent chains of loads per thread
+    s0 += Ap[i] * M[i];
+    if (i + bd < total) s1 += Ap[i + bd] * M[i + bd];
+    if (i + 2 * bd < total) s2 += Ap[i + 2 * bd] * M[i + 2 * bd];
+    if (i + 3 * bd < total) s3 += Ap[i + 3 * bd] * M[i + 3 * bd];
+  }
+  red[threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const float L = static_cast<float>(red[0] / *trace_p);
+    const float L = static_cast<float>(red[0] / traces[last]);
     if (lipschitz_out) *lipschitz_out = L;
     if (scalars) {
       const float eta = 1.f / L;  // stepsize = 1. / lipschitz_constant  (ista_fista.py:80), float32 arithmetic

@@ -652,13 +652,14 @@ int run_lipschitz(const float* dict, int64_t S, int64_t D, const LipschitzWs& w,
   const double* src = w.M;
   double* dst = w.A0;
   for (int j = 0; j < kSquarings; ++j) {
-    square_fp64_kernel<<<grid, block, 0, st>>>(src, w.n, w.traces + j, dst, w.traces + j + 1);
+    square_fp64_kernel<<<grid, block, 0, st>>>(src, w.n, w.traces + j, dst, w.traces + j + 1, j,
+                                               w.traces + kSquarings + 1);
     COUNT_LAUNCH();
     src = dst;
     dst = (dst == w.A0) ? w.A1 : w.A0;
   }
-  lipschitz_finalize_kernel<<<1, 256, 0, st>>>(src, w.M, w.n, w.traces + kSquarings, sparsity_weight, scalars,
-                                               lipschitz_dev);
+  lipschitz_finalize_kernel<<<1, 1024, 0, st>>>(w.A0, w.A1, w.M, w.n, w.traces, kSquarings, sparsity_weight,
+                                                       scalars, lipschitz_dev);
   COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
