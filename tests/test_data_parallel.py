@@ -72,6 +72,19 @@ def _worker(rank, world, port, result_path):
                                          extra_gradient=g_sum - g_local)
   want = oracle.conv_sc_dictionary_update(xi, kern, ci, (4, 4), pad, hc, stepsize=0.05)
   ok = ok and oracle.relative_l2(got, want) < 1e-6
+  # validation metrics (training/metrics.py): every rank holds the totals of its shard (restated here on the CPU the way
+  # metrics_totals_kernel defines them); after the all-reduce both report the metrics of the whole batch
+  from vision_transform_codes_b200.training import metrics
+  r2 = ((torch.mm(cs, phi) - xs)**2).sum(1).double()
+  mse = (r2 / D).float()
+  totals = torch.tensor([float(0.5 * r2.sum()), float(cs.abs().sum()), float((cs != 0).sum(1).double().div(S).sum()),
+                         float(torch.log10(mse.double()).sum()), float(len(mse)), float(xs.min()), float(xs.max()),
+                         float(len(mse))], dtype=torch.float64)
+  metrics._allreduce_totals(totals)
+  got_m = metrics.metrics_from_totals(totals.tolist(), 0.1)
+  want_m = oracle.compute_metrics(x, codes, phi, phi, 0.1)
+  for name in got_m:
+    ok = ok and abs(got_m[name] - float(want_m[name])) <= 1e-5 * max(1.0, abs(float(want_m[name])))
   with open(result_path + str(rank), 'w') as f:
     f.write('ok' if ok else 'fail')
   dist.destroy_process_group()

@@ -209,6 +209,22 @@ def test_conv_determinism_and_image_shard_independence():
   assert torch.equal(a[3:], ista_fista.run(xd[3:], phi, (8, 8), pad, 0.05, 40))
 
 
+def test_conv_size_independent_properties_at_benchmark_shape():
+  """BASELINE configs[4] at its full per-GPU size (128 images of 512x512 padded to 528x528, 64 kernels of 16x16 at
+  stride 8, codes 64x65x65, 300 iterations), which the oracle cannot cover: determinism, image-shard independence, codes
+  confined to what the mask lets through, and oracle parity on one image."""
+  ista_fista = modules()[0]
+  x, pad = oracle.synthetic_padded_images(128, 1, 512, 512, (16, 16), (8, 8))
+  phi = oracle.synthetic_conv_dictionary(64, 1, 16, 16)
+  xd, pd = x.cuda(), phi.cuda()
+  a = ista_fista.run(xd, pd, (8, 8), pad, 0.05, 300)
+  assert tuple(a.shape) == (128, 64, 65, 65) and torch.isfinite(a).all()
+  assert torch.equal(a, ista_fista.run(xd, pd, (8, 8), pad, 0.05, 300))
+  assert torch.equal(a[96:], ista_fista.run(xd[96:], pd, (8, 8), pad, 0.05, 300))
+  assert torch.equal(a[5:6], ista_fista.run(xd[5:6], pd, (8, 8), pad, 0.05, 300))
+  check(a[5:6], oracle.conv_ista_fista(x[5:6], phi, (8, 8), pad, 0.05, 300))
+
+
 def test_conv_lean_trainer_matches_reference_trainer(tmp_path):
   """The package's own train_dictionary in convolutional mode, with the reference's parameter dictionary
   (tests/sparse_coding_4.py), against the unmodified reference trainer's result; checkpoints in its pickle format."""

@@ -294,10 +294,11 @@ def test_dictionary_update_larger_batch_against_oracle():
 
 
 def test_size_independent_properties_at_benchmark_shape():
-  """BASELINE configs[1] shape at a batch the oracle cannot cover: determinism, batch-shard independence (what
-  multi-GPU sharding relies on), fixed point of the converged code, and oracle parity on a sub-batch."""
+  """BASELINE configs[1] at its full size (65 536 patches, 1024 atoms, 300 iterations), which the oracle cannot cover:
+  determinism, batch-shard independence (what multi-GPU sharding relies on), fixed point of the converged code, and
+  oracle parity on a sub-batch."""
   ista_fista = modules()[0]
-  B, S, D, T = 16384, 1024, 256, 300
+  B, S, D, T = 65536, 1024, 256, 300
   phi = oracle.synthetic_dictionary(S, D)
   x = oracle.synthetic_patches(B, D, kind='whitened')
   xd, pd = x.cuda(), phi.cuda()
@@ -309,6 +310,30 @@ def test_size_independent_properties_at_benchmark_shape():
   assert oracle.relative_l2(more.cpu(), a.cpu()) < 1e-4
   want = oracle.ista_fista(x[:384], phi, 0.1, T)
   check_codes(a[:384], want, phi)
+
+
+def test_size_independent_properties_at_subspace_benchmark_shape():
+  """BASELINE configs[3] at its full size (131 072 patches of 32x32, 4096 atoms in groups of 2, 300 iterations):
+  determinism, batch independence, every group either entirely zero or entirely non-zero (the group shrinkage scales a
+  group as a whole, subspace_ista_fista.py:144-156), and oracle parity on a sub-batch."""
+  import numpy as np
+  subspace = modules()[1]
+  B, S, D, T = 131072, 4096, 1024, 300
+  phi = oracle.synthetic_dictionary(S, D)
+  x = oracle.synthetic_patches(B, D)
+  groups = [list(map(int, g)) for g in np.array_split(np.arange(S), S // 2)]
+  xd, pd = x.cuda(), phi.cuda()
+  a = subspace.run(xd, pd, groups, 0.1, T)
+  assert torch.isfinite(a).all()
+  again = subspace.run(xd, pd, groups, 0.1, T)
+  assert torch.equal(a, again)
+  del again
+  sub = subspace.run(xd[70000:70300], pd, groups, 0.1, T)
+  assert torch.equal(a[70000:70300], sub)
+  nz = (a != 0).view(B, S // 2, 2)
+  assert bool((nz[:, :, 0] == nz[:, :, 1]).all())
+  want = oracle.subspace_ista_fista(x[70000:70128], phi, groups, 0.1, T)
+  check_codes(sub[:128], want, phi)
 
 
 def test_one_launch_schedule_matches_two_launch_schedule(formulation):
