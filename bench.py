@@ -204,6 +204,34 @@ def config0_benchmark(rank, world, dev, timed, precision):
   return out
 
 
+def metrics_benchmark(rank, world, dev, timed, codes, x, phi):
+  """the trainer's validation metrics (training/sparse_coding.py:177-229) of one configs[1] batch, computed
+  on the device from resident codes (one residual contraction + one pass over residuals, codes and pixels; 8 doubles
+  and 1024 floats cross to the host), next to the reference's host-side definition (the oracle's compute_metrics: numpy
+  on copies of images, reconstructions and norms, a Python loop over the batch for the pSNR) on a sample of the batch."""
+  from oracle import vtc_oracle as oracle
+  from vision_transform_codes_b200.training import metrics
+  prev = phi.clone()
+  ms, launches = timed(lambda: metrics.compute_metrics(x, codes, phi, prev, LAM), 5, 2)
+  out = {'workload': 'validation metrics of one configs[1] batch (%d patches, %d atoms)' % tuple(codes.shape),
+         'ms_per_call': ms / 5, 'gpu_launches_per_call': int(launches // 5),
+         'd2h_bytes_per_call': 8 * 8 + 4 * codes.shape[1]}
+  if rank == 0 and world == 1:
+    n = 8192
+    xs, cs, ps = x[:n].cpu(), codes[:n].cpu(), phi.cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    want = oracle.compute_metrics(xs, cs, ps, ps, LAM)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    got = metrics.compute_metrics(x[:n], codes[:n], phi, prev, LAM)
+    err = max(abs(float(got[k]) - float(want[k])) / max(1.0, abs(float(want[k])))
+              for k in want if k != metrics.CHANGE)
+    out.update({'cpu_reference_ms_per_call_extrapolated': cpu_ms * codes.shape[0] / n,
+                'cpu_sample': '%d of %d patches, scaled linearly' % (n, codes.shape[0]),
+                'max_rel_difference_on_sample': err})
+  return out
+
+
 def run_reference(args, rank):
   if rank != 0:
     return
@@ -432,6 +460,7 @@ def main():
     line['conv_path'] = conv_benchmark(world, rank, dev, timed, pk, args.precision)
     line['subspace_path'] = subspace_benchmark(world, rank, dev, timed, pk, args.precision)
     line['config0'] = config0_benchmark(rank, world, dev, timed, args.precision)
+    line['metrics_path'] = metrics_benchmark(rank, world, dev, timed, ista_fista.run(x, phi, LAM, T), x, phi)
     if rank == 0 and world == 1:
       v, cores, secs = cpu_reference_patches_per_sec(CPU_SAMPLE)
       line['cpu_baseline'] = {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': 'port',
