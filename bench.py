@@ -451,6 +451,14 @@ def main():
                            'frac_of_tensor_peak_gram_equivalent':
                                (T * gram_flops_iter) / (ms * 1e-3) / 1e12 / pk['bf16_sustained'],
                            'tolerance': 'codes rel-L2 <= 5e-2, reconstructions <= 1e-2 (tests/test_gpu_parity.py)'}
+      if fused_iter:
+        # the plain-bf16 iteration kernel is HBM-bound: fp32 state 12 B per code element + x, r parts per pixel; the
+        # whole call (setup included) against the measured copy bandwidth
+        bytes_bf16 = Bn * S * 12 + Bn * D * (4 + 4 * 1)
+        gbs = T * bytes_bf16 / (ms * 1e-3) / 1e9
+        line['bf16_path']['roofline'] = {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                                         'frac': gbs / pk['hbm_gbs'], 'algorithmic_bytes_per_iteration': bytes_bf16,
+                                         'basis': 'whole call / %d iterations' % T}
       pkg.config.precision = args.precision
     try:
       from vision_transform_codes_b200.training import sparse_coding as trainer
