@@ -270,6 +270,19 @@ int vtc_dict_change(const float* dictionary, const float* previous_dictionary, i
 int vtc_extract_patches(const float* images, int64_t n, int64_t h, int64_t w, int64_t c, const int32_t* corners,
                         int64_t B, int64_t ph, int64_t pw, float* patches, int64_t ld_patches, vtc_stream_t stream);
 
+/*
+ * Data feed: centre-surround whitening of whole images (utils/image_processing.py:267-308, whiten_center_surround; the
+ * low-pass factor is get_low_pass_filter :173-231 with shape 'exponential', the ramp get_whitening_ramp_filter :234-264).
+ * vtc_whitening_filter writes the real transfer function of an (h, w) DFT, fp64 arithmetic, float32 result:
+ *   max(|f|, cutoff_low) * exp(-(|f| / (0.5 * cutoff_high))^order), |f| from fftfreq; with norm_and_threshold divided by its
+ *   maximum and floored at 1e-3 (:300-302). scratch8: 8 bytes of device scratch.
+ * vtc_spectrum_filter multiplies a complex64 spectrum (n, h*w, c), in place, by that function (filter_fd :63-92: every
+ * colour channel is filtered independently). The DFTs on either side are the caller's (cuFFT through torch.fft).
+ */
+int vtc_whitening_filter(int64_t h, int64_t w, double cutoff_low, double cutoff_high, double order,
+                         int norm_and_threshold, float* filter_out, void* scratch8, vtc_stream_t stream);
+int vtc_spectrum_filter(void* spectrum, int64_t n, int64_t hw, int64_t c, const float* filter, vtc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

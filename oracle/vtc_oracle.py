@@ -25,6 +25,7 @@ Reference lines followed (paths relative to vision_transform_codes/):
   convolutional dict update  dict_update_rules/convolutional/sc_cheap_quadratic_descent.py:59-79,
                              sc_steepest_descent.py:55-72; Hessian running mean training/sparse_coding.py:158-161
   validation metrics   training/sparse_coding.py:177-229, utils/plotting.py:17-39 (compute_pSNR)
+  image whitening      utils/image_processing.py:63-92 (filter_fd), :173-231, :234-264, :267-308 (whiten_center_surround)
 """
 import torch
 
@@ -356,6 +357,32 @@ def extract_patches(images, corners, patch_dimensions):
   for p_idx in range(corners.shape[0]):
     img, top, left = (int(v) for v in corners[p_idx])
     out[p_idx] = images[img, top:top + ph, left:left + pw].reshape(-1)
+  return out
+
+
+def whitening_filter(dft_num_samples, cutoffs, norm_and_threshold=True):
+  """utils/image_processing.py:292-302: exponential low-pass (order 8, :216-221, un-normalised) times the ramp |f|
+  (:251-264, un-normalised) rolled off at cutoffs['low']; numpy float64 (h, w)."""
+  import numpy as np
+  fv, fh = np.meshgrid(np.fft.fftfreq(dft_num_samples[0]), np.fft.fftfreq(dft_num_samples[1]), indexing='ij')
+  mag = np.sqrt(np.square(fv) + np.square(fh))
+  lpf = np.exp(-1. * np.power(mag / (0.5 * cutoffs['high']), 8.0))
+  combined = np.maximum(mag, cutoffs['low'] * np.ones(mag.shape)) * lpf
+  if norm_and_threshold:
+    combined /= np.max(np.abs(combined))
+    combined[np.abs(combined) < 1e-3] = 1e-3
+  return combined
+
+
+def whiten_center_surround(image, cutoffs, norm_and_threshold=True):
+  """utils/image_processing.py:267-308 with filter_fd (:63-92): image ndarray (h, w, c) float32 -> float32, each colour
+  channel filtered in the DFT domain."""
+  import numpy as np
+  filt = whitening_filter(image.shape, cutoffs, norm_and_threshold)
+  out = np.zeros(image.shape, dtype='float32')
+  for ch in range(image.shape[2]):
+    out[:, :, ch] = np.real(np.fft.ifft2(filt * np.fft.fft2(image[:, :, ch], filt.shape),
+                                         filt.shape)).astype('float32')[0:image.shape[0], 0:image.shape[1]]
   return out
 
 

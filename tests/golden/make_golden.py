@@ -321,7 +321,27 @@ def make_metrics():
       'dict_update_param_schedule': {0: {'stepsize': 0.05, 'num_iters': 1}}})
 
 
+def make_whitening():
+  """utils/image_processing.py whiten_center_surround (the module imports matplotlib at the top: stubbed) on two small
+  seeded images, with the dataset defaults (cutoffs low 1e-3, high 0.9) and an un-normalised variant."""
+  mpl = types.ModuleType('matplotlib')
+  mpl.pyplot = types.ModuleType('matplotlib.pyplot')
+  sys.modules.setdefault('matplotlib', mpl)
+  sys.modules.setdefault('matplotlib.pyplot', mpl.pyplot)
+  from utils import image_processing
+  rng = np.random.RandomState(4)
+  gray = rng.rand(40, 52, 1).astype('float32')
+  colour = rng.rand(33, 24, 3).astype('float32')   # odd height: both fftfreq conventions
+  cut = {'low': 1e-3, 'high': 0.9}
+  g_out, g_filt = image_processing.whiten_center_surround(gray, cut, return_filter=True)
+  c_out, c_filt = image_processing.whiten_center_surround(colour, cut, return_filter=True)
+  raw_out, raw_filt = image_processing.whiten_center_surround(gray, {'low': 0.05, 'high': 0.6}, return_filter=True,
+                                                              norm_and_threshold=False)
+  save('whitening_small', gray=gray, gray_whitened=g_out, gray_filter=np.real(g_filt), colour=colour,
+       colour_whitened=c_out, colour_filter=np.real(c_filt), raw_whitened=raw_out, raw_filter=np.real(raw_filt))
+
+
 if __name__ == '__main__':
-  which = sys.argv[1:] or ['inference', 'config1', 'overcomplete', 'subspace', 'dict_update', 'training', 'conv', 'metrics']
+  which = sys.argv[1:] or ['inference', 'config1', 'overcomplete', 'subspace', 'dict_update', 'training', 'conv', 'metrics', 'whitening']
   for name in which:
     globals()['make_' + name]()

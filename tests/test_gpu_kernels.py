@@ -118,3 +118,38 @@ def test_patch_extraction_is_the_reference_crop_loop():
     assert torch.equal(got.cpu(), want)
   batch = dg.sample_patches(torch.randn(4, 128, 128).cuda(), 4096, (16, 16), 5)
   assert tuple(batch.shape) == (4096, 256) and torch.isfinite(batch).all()
+
+
+def test_whitening_against_reference_outputs_and_oracle():
+  """Device-side whiten_center_surround (utils/image_processing.py; vtc_whitening_filter + cuFFT + vtc_spectrum_filter)
+  against outputs of the reference (tests/golden/whitening_small.npz) and the oracle on a batch of larger images.
+  Tolerance: the transfer function is fp64 rounded to float32 (1e-6 relative); the reference transforms in complex128,
+  cuFFT in complex64: 1e-5 of the image range."""
+  import numpy as np
+  from conftest import load_golden
+  from vision_transform_codes_b200.utils import image_processing
+  g = load_golden('whitening_small')
+  cut = {'low': 1e-3, 'high': 0.9}
+  for key in ('gray', 'colour'):
+    img = g[key].cuda()
+    out, filt = image_processing.whiten_center_surround(img, cut, return_filter=True)
+    assert tuple(out.shape) == tuple(img.shape) and out.dtype == torch.float32
+    assert np.allclose(filt.cpu().numpy(), g[key + '_filter'].numpy(), rtol=1e-6, atol=0)
+    assert float((out.cpu() - g[key + '_whitened']).abs().max()) < 1e-5
+  raw = {'low': 0.05, 'high': 0.6}
+  out, filt = image_processing.whiten_center_surround(g['gray'].cuda(), raw, return_filter=True,
+                                                      norm_and_threshold=False)
+  # un-normalised: the tail of the low-pass factor falls below the float32 range (absolute tolerance there)
+  assert np.allclose(filt.cpu().numpy(), g['raw_filter'].numpy(), rtol=1e-6, atol=1e-30)
+  assert float((out.cpu() - g['raw_whitened']).abs().max()) < 1e-5
+  # a batch of 512x512 images (the size of BASELINE configs[4]'s inputs), every image filtered independently
+  gen = torch.Generator().manual_seed(11)
+  batch = torch.rand(3, 512, 512, 1, generator=gen)
+  got = image_processing.whiten_center_surround(batch.cuda(), cut).cpu()
+  for i in range(3):
+    want = torch.from_numpy(oracle.whiten_center_surround(batch[i].numpy(), cut))
+    assert float((got[i] - want).abs().max()) < 2e-5
+  std = image_processing.standardize_data_range(3.0 * batch.cuda() - 1.0)
+  assert float(std.min()) == 0.0 and float(std.max()) == 1.0
+  with pytest.raises(RuntimeError):
+    image_processing.whiten_center_surround(batch, cut)   # CPU tensor: no fallback

@@ -240,3 +240,19 @@ def test_validation_metrics_match_reference_trainer():
         got = np.mean([m[metric] for m in per_batch])
         want = float(g['metrics'][row, col])
         assert abs(got - want) <= 2e-5 * max(1.0, abs(want)), (name, row, metric, got, want)
+
+
+def test_whitening_matches_reference_outputs():
+  """utils/image_processing.py:267-308 on the committed reference outputs: transfer function and filtered images, the
+  dataset defaults and an un-normalised filter, even and odd DFT sizes, one and three colour channels."""
+  g = load_golden('whitening_small')
+  cut = {'low': 1e-3, 'high': 0.9}
+  for key in ('gray', 'colour'):
+    img = g[key].numpy()
+    assert np.allclose(oracle.whitening_filter(img.shape, cut), g[key + '_filter'].numpy(), rtol=1e-12, atol=0)
+    got = oracle.whiten_center_surround(img, cut)
+    assert got.dtype == np.float32 and np.allclose(got, g[key + '_whitened'].numpy(), rtol=0, atol=1e-6)
+  raw = {'low': 0.05, 'high': 0.6}
+  assert np.allclose(oracle.whitening_filter((40, 52), raw, False), g['raw_filter'].numpy(), rtol=1e-12, atol=0)
+  assert np.allclose(oracle.whiten_center_surround(g['gray'].numpy(), raw, False), g['raw_whitened'].numpy(),
+                     rtol=0, atol=1e-6)

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libvtc_b200.so')
 VTC_OK, VTC_ERR_ARG, VTC_ERR_CUDA, VTC_ERR_WORKSPACE, VTC_ERR_UNSUPPORTED, VTC_ERR_NONFINITE = range(6)
 
 _c = ctypes
-_i64, _int, _f32, _ptr, _size = _c.c_int64, _c.c_int, _c.c_float, _c.c_void_p, _c.c_size_t
+_i64, _int, _f32, _f64, _ptr, _size = _c.c_int64, _c.c_int, _c.c_float, _c.c_double, _c.c_void_p, _c.c_size_t
 
 # name -> (restype, argtypes); must list every symbol declared in include/vtc_b200.h
 SIGNATURES = {
@@ -56,6 +56,8 @@ SIGNATURES = {
     'vtc_sc_conv_metrics_workspace_bytes': (_size, [_i64] * 9 + [_int]),
     'vtc_sc_conv_metrics': (_int, [_ptr, _ptr, _ptr] + [_i64] * 9 + [_int] * 4 + [_int, _ptr, _ptr, _size, _ptr]),
     'vtc_dict_change': (_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr]),
+    'vtc_whitening_filter': (_int, [_i64, _i64, _f64, _f64, _f64, _int, _ptr, _ptr, _ptr]),
+    'vtc_spectrum_filter': (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr]),
     'vtc_extract_patches': (_int, [_ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr]),
 }
 

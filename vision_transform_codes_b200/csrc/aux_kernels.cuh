@@ -755,4 +755,56 @@ __global__ void dict_change_kernel(const float* __restrict__ dict, const float* 
   if (lane == 0) out[s] = acc / static_cast<float>(per_kernel);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Data feed: centre-surround whitening of whole images in the DFT domain
+// (utils/image_processing.py:267-308). The transfer function is real and depends on the DFT size only:
+//   raw(i, j) = max(|f|, low) * exp(-(|f| / (0.5 * high))^order),  |f| = hypot(fftfreq(h)[i], fftfreq(w)[j])
+// normalised to a maximum of 1 and floored at 1e-3 when norm_and_threshold (:300-302). fp64 like numpy; the FFTs
+// themselves are cuFFT (torch.fft), only the filter and its application are kernels here.
+__device__ __forceinline__ double whitening_raw(int64_t i, int64_t j, int64_t h, int64_t w, double low, double high,
+                                                double order) {
+  // np.fft.fftfreq(n)[i] = i / n for i < (n - 1) / 2 + 1, (i - n) / n after that
+  const double fv = static_cast<double>(i < (h - 1) / 2 + 1 ? i : i - h) / static_cast<double>(h);
+  const double fh = static_cast<double>(j < (w - 1) / 2 + 1 ? j : j - w) / static_cast<double>(w);
+  const double mag = sqrt(fv * fv + fh * fh);
+  return fmax(mag, low) * exp(-pow(mag / (0.5 * high), order));
+}
+// *max_bits = max over the grid of raw (a non-negative double compares like its bit pattern)
+__global__ void whitening_filter_max_kernel(int64_t h, int64_t w, double low, double high, double order,
+                                            unsigned long long* __restrict__ max_bits) {
+  double m = 0.0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < h * w;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    m = fmax(m, whitening_raw(i / w, i % w, h, w, low, high, order));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(max_bits, static_cast<unsigned long long>(__double_as_longlong(m)));
+}
+__global__ void whitening_filter_kernel(int64_t h, int64_t w, double low, double high, double order,
+                                        const unsigned long long* __restrict__ max_bits, int norm_and_threshold,
+                                        float* __restrict__ out) {
+  const double mx = norm_and_threshold ? __longlong_as_double(static_cast<long long>(*max_bits)) : 1.0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < h * w;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    double v = whitening_raw(i / w, i % w, h, w, low, high, order);
+    if (norm_and_threshold) {
+      v /= mx;
+      if (v < 1e-3) v = 1e-3;
+    }
+    out[i] = static_cast<float>(v);
+  }
+}
+// spectrum (n, h*w, c) complex64, in place: every channel of every image times the real transfer function (h*w)
+__global__ void spectrum_filter_kernel(float2* __restrict__ spectrum, int64_t n, int64_t hw, int64_t c,
+                                       const float* __restrict__ filter) {
+  const int64_t total = n * hw * c;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float f = filter[(i / c) % hw];
+    float2 v = spectrum[i];
+    v.x *= f, v.y *= f;
+    spectrum[i] = v;
+  }
+}
+
 }  // namespace vtc

@@ -1985,6 +1985,38 @@ int vtc_dict_change(const float* dictionary, const float* previous_dictionary, i
 }
 
 // ---------------------------------------------------------------------------------------------- data feed
+int vtc_whitening_filter(int64_t h, int64_t w, double cutoff_low, double cutoff_high, double order,
+                         int norm_and_threshold, float* filter_out, void* scratch8, vtc_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!filter_out || !scratch8 || h <= 0 || w <= 0 || !(cutoff_high > 0.0) || !(order >= 1.0) || cutoff_low < 0.0)
+    return fail(VTC_ERR_ARG, "vtc_whitening_filter: bad argument");
+  DeviceInfo info;
+  TRY(device_info(&info));
+  unsigned long long* max_bits = static_cast<unsigned long long*>(scratch8);
+  CUDA_TRY(cudaMemsetAsync(max_bits, 0, 8, st));
+  const unsigned grid = grid_for(h * w, 256, info.sm_count);
+  if (norm_and_threshold) {
+    whitening_filter_max_kernel<<<grid, 256, 0, st>>>(h, w, cutoff_low, cutoff_high, order, max_bits);
+    COUNT_LAUNCH();
+  }
+  whitening_filter_kernel<<<grid, 256, 0, st>>>(h, w, cutoff_low, cutoff_high, order, max_bits, norm_and_threshold,
+                                                filter_out);
+  COUNT_LAUNCH();
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
+int vtc_spectrum_filter(void* spectrum, int64_t n, int64_t hw, int64_t c, const float* filter, vtc_stream_t stream) {
+  if (!spectrum || !filter || n <= 0 || hw <= 0 || c <= 0) return fail(VTC_ERR_ARG, "vtc_spectrum_filter: bad argument");
+  DeviceInfo info;
+  TRY(device_info(&info));
+  spectrum_filter_kernel<<<grid_for(n * hw * c, 256, info.sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<float2*>(spectrum), n, hw, c, filter);
+  COUNT_LAUNCH();
+  CUDA_TRY(cudaGetLastError());
+  return VTC_OK;
+}
+
 int vtc_extract_patches(const float* images, int64_t n, int64_t h, int64_t w, int64_t c, const int32_t* corners,
                         int64_t B, int64_t ph, int64_t pw, float* patches, int64_t ld_patches, vtc_stream_t stream) {
   if (!images || !corners || !patches || n <= 0 || h <= 0 || w <= 0 || c <= 0 || B <= 0 || ph <= 0 || pw <= 0 ||
