@@ -400,3 +400,24 @@ def test_empty_batch_returns_empty_codes():
   kern = oracle.synthetic_conv_dictionary(8, 1, 8, 8).cuda()
   xi = torch.empty(0, 1, 24, 24, device='cuda')
   assert tuple(conv_inf.run(xi, kern, (4, 4), ((4, 4), (4, 4)), 0.1, 3).shape) == (0, 8, 5, 5)
+
+
+def test_calls_on_two_streams_are_independent():
+  """Stream-ordered and re-entrant per stream: two calls enqueued on two streams at once (each a persistent
+  launch that wants every SM pair, with its own scratch memory) give the results of the same calls made one after the
+  other."""
+  ista_fista = modules()[0]
+  S, D, T = 1024, 256, 40
+  phi = oracle.synthetic_dictionary(S, D).cuda()
+  x1 = oracle.synthetic_patches(24000, D, seed=3).cuda()
+  x2 = oracle.synthetic_patches(20000, D, seed=4).cuda()
+  want1, want2 = ista_fista.run(x1, phi, 0.1, T), ista_fista.run(x2, phi, 0.1, T)
+  s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+  torch.cuda.synchronize()
+  for _ in range(3):
+    with torch.cuda.stream(s1):
+      a1 = ista_fista.run(x1, phi, 0.1, T)
+    with torch.cuda.stream(s2):
+      a2 = ista_fista.run(x2, phi, 0.1, T)
+    torch.cuda.synchronize()
+    assert torch.equal(a1, want1) and torch.equal(a2, want2)

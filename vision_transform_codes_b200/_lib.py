@@ -123,8 +123,10 @@ _workspaces = {}
 
 
 def workspace(nbytes, device, tag):
-  """Grow-only scratch buffer per (device, tag); the library never allocates device memory itself."""
-  key = (device.index, tag)
+  """Grow-only scratch buffer per (device, current stream, tag); the library never allocates device memory itself.
+  Keyed by stream so that calls enqueued on different streams never share scratch memory (calls on one stream are
+  ordered, so one buffer per stream is enough)."""
+  key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
   buf = _workspaces.get(key)
   if buf is None or buf.numel() < nbytes:
     _workspaces.pop(key, None)

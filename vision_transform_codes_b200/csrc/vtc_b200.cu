@@ -539,7 +539,13 @@ int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream
   cfg.attrs = attr;
   cfg.numAttrs = (tune_flags() & TUNE_NO_PDL) ? 1 : 2;
   if (c.k_count > 1) {
-    // jobs of a persistent launch wait on jobs of other pairs: every pair of the grid must be resident at once
+    // jobs of a persistent launch wait on jobs of other pairs: every pair of the grid must be resident at once. The grid
+    // is capped by the occupancy query below, and the launch is cooperative, so that the driver only starts it once all
+    // of it fits next to whatever else runs on the device (e.g. a second persistent launch on another stream) -- two
+    // half-resident grids spinning on their missing halves cannot happen.
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.numAttrs = 2;
     static int max_clusters_dev[64] = {};
     int& max_clusters = max_clusters_dev[dev & 63];
     if (max_clusters == 0) {
