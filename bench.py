@@ -256,7 +256,26 @@ def run_reference(args, rank):
       'e2e': {'value': value, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
   }
-  print(json.dumps(line), flush=True)
+  emit(line)
+
+
+RESULT_STREAM = None
+
+
+def claim_stdout():
+  """stdout carries the ONE JSON line and nothing else: keep a private handle on it and point file descriptor 1 at
+  stderr, so that whatever a library writes to stdout (NCCL prints its version banner there when NCCL_DEBUG=VERSION,
+  and ignores NCCL_DEBUG_FILE at that level) ends up on stderr."""
+  global RESULT_STREAM
+  if RESULT_STREAM is None:
+    sys.stdout.flush()
+    RESULT_STREAM = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def emit(line):
+  RESULT_STREAM.write(json.dumps(line) + '\n')
+  RESULT_STREAM.flush()
 
 
 def main():
@@ -269,6 +288,7 @@ def main():
   ap.add_argument('--batch', type=int, default=B_PER_GPU, help='patches per GPU (default: the BASELINE config)')
   ap.add_argument('--no-extras', action='store_true', help='skip the bf16-path, train-step and CPU side measurements')
   args = ap.parse_args()
+  claim_stdout()
 
   rank = int(os.environ.get('RANK', '0'))
   world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -475,7 +495,7 @@ def main():
                               'sample': '%d of %d patches x %d iterations (%.1f s), float32 torch on the host'
                               % (CPU_SAMPLE, Bn, T, secs)}
   if rank == 0:
-    print(json.dumps(line), flush=True)
+    emit(line)
   if world > 1:
     dist.destroy_process_group()
 
