@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "aux_kernels.cuh"
@@ -539,13 +540,7 @@ int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream
   cfg.attrs = attr;
   cfg.numAttrs = (tune_flags() & TUNE_NO_PDL) ? 1 : 2;
   if (c.k_count > 1) {
-    // jobs of a persistent launch wait on jobs of other pairs: every pair of the grid must be resident at once. The grid
-    // is capped by the occupancy query below, and the launch is cooperative, so that the driver only starts it once all
-    // of it fits next to whatever else runs on the device (e.g. a second persistent launch on another stream) -- two
-    // half-resident grids spinning on their missing halves cannot happen.
-    attr[1].id = cudaLaunchAttributeCooperative;
-    attr[1].val.cooperative = 1;
-    cfg.numAttrs = 2;
+    // jobs of a persistent launch wait on jobs of other pairs: every pair of the grid must be resident at once
     static int max_clusters_dev[64] = {};
     int& max_clusters = max_clusters_dev[dev & 63];
     if (max_clusters == 0) {
@@ -555,6 +550,21 @@ int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream
       if (max_clusters < 1) return fail(VTC_ERR_CUDA, "the iteration kernel does not fit on this device");
     }
     if (pairs > max_clusters) cfg.gridDim = dim3(2 * max_clusters);
+    if (c.max_pairs == 0) {
+      // A launch that may take every SM pair: two of them on different streams could each become half resident and spin
+      // on their missing halves for ever. They are ordered through an event instead (each would use the whole device
+      // anyway); launches restricted to a share of the pairs (the two-chain mode) are sized to fit side by side.
+      static std::mutex mu;
+      static cudaEvent_t last_dev[64] = {};
+      std::lock_guard<std::mutex> lock(mu);
+      cudaEvent_t& last = last_dev[dev & 63];
+      if (!last) CUDA_TRY(cudaEventCreateWithFlags(&last, cudaEventDisableTiming));
+      CUDA_TRY(cudaStreamWaitEvent(stream, last, 0));   // no-op until the event has been recorded once
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_fista_iter_kernel<P, V>, p));
+      COUNT_LAUNCH();
+      CUDA_TRY(cudaEventRecord(last, stream));
+      return VTC_OK;
+    }
   }
   CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_fista_iter_kernel<P, V>, p));
   COUNT_LAUNCH();
