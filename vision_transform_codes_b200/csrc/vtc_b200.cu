@@ -550,7 +550,11 @@ int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream
       if (max_clusters < 1) return fail(VTC_ERR_CUDA, "the iteration kernel does not fit on this device");
     }
     if (pairs > max_clusters) cfg.gridDim = dim3(2 * max_clusters);
-    if (c.max_pairs == 0) {
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    CUDA_TRY(cudaStreamIsCapturing(stream, &capturing));
+    // (a stream being captured into a graph cannot wait on an event recorded outside the capture; graph launches are
+    // ordered by the graph's own stream)
+    if (c.max_pairs == 0 && capturing == cudaStreamCaptureStatusNone) {
       // A launch that may take every SM pair: two of them on different streams could each become half resident and spin
       // on their missing halves for ever. They are ordered through an event instead (each would use the whole device
       // anyway); launches restricted to a share of the pairs (the two-chain mode) are sized to fit side by side.
