@@ -421,3 +421,48 @@ def test_calls_on_two_streams_are_independent():
       a2 = ista_fista.run(x2, phi, 0.1, T)
     torch.cuda.synchronize()
     assert torch.equal(a1, want1) and torch.equal(a2, want2)
+
+
+def test_inference_call_is_capturable_into_a_cuda_graph():
+  """A call enqueues work on the current stream and never synchronises (config.check_finite off), so it can be
+  captured into a CUDA graph: the replay, also on new input data in the same buffers, equals the eager call bit for bit.
+  (The momentum table is built by a kernel, not copied from host memory that is gone at replay time.)"""
+  import vision_transform_codes_b200 as pkg
+  from vision_transform_codes_b200.analysis_transforms.convolutional import ista_fista as conv_inf
+  ista_fista = modules()[0]
+  saved = pkg.config.check_finite
+  pkg.config.check_finite = False
+  try:
+    phi = oracle.synthetic_dictionary(1024, 256).cuda()
+    x = oracle.synthetic_patches(4096, 256).cuda()
+    eager = ista_fista.run(x, phi, 0.1, 50)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+      ista_fista.run(x, phi, 0.1, 50)   # scratch buffers of the capture stream exist before the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+      captured = ista_fista.run(x, phi, 0.1, 50)
+    captured.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, eager)
+    x.mul_(0.5)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, ista_fista.run(x, phi, 0.1, 50))
+    xi, pad = oracle.synthetic_padded_images(4, 1, 64, 64, (16, 16), (8, 8))
+    kern = oracle.synthetic_conv_dictionary(32, 1, 16, 16).cuda()
+    xi = xi.cuda()
+    conv_eager = conv_inf.run(xi, kern, (8, 8), pad, 0.05, 20)
+    with torch.cuda.stream(side):
+      conv_inf.run(xi, kern, (8, 8), pad, 0.05, 20)
+    torch.cuda.synchronize()
+    conv_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(conv_graph, stream=side):
+      conv_captured = conv_inf.run(xi, kern, (8, 8), pad, 0.05, 20)
+    conv_graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(conv_captured, conv_eager)
+  finally:
+    pkg.config.check_finite = saved

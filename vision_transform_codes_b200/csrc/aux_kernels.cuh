@@ -807,4 +807,20 @@ __global__ void spectrum_filter_kernel(float2* __restrict__ spectrum, int64_t n,
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// FISTA momentum table (ista_fista.py:123-125): t_1 = 1, t_{k+1} = (1 + sqrt(1 + 4 t_k^2)) / 2,
+// betas[k] = float((t_k - 1) / t_{k+1}), betas[0] = 0; all zero for ISTA. The recurrence is sequential: one thread, IEEE
+// double operations without contraction, so the table is bit-identical to the host-side double arithmetic of the
+// reference. (A device table instead of a host-to-device copy keeps a call capturable into a CUDA graph.)
+__global__ void fista_betas_kernel(float* __restrict__ betas, int num_iters, int fista) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  betas[0] = 0.f;
+  double t = 1.0;
+  for (int k = 1; k <= num_iters; ++k) {
+    const double t_next = __ddiv_rn(__dadd_rn(1.0, __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(__dmul_rn(4.0, t), t)))), 2.0);
+    betas[k] = fista ? static_cast<float>(__ddiv_rn(__dadd_rn(t, -1.0), t_next)) : 0.f;
+    t = t_next;
+  }
+}
+
 }  // namespace vtc

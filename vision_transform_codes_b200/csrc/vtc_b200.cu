@@ -1178,16 +1178,11 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   int k_done = 0;
   if (cm.fused_iter) {
     // the panel-resident kernel takes the momentum coefficients from a device table: betas[k], betas[0] = 0
-    std::vector<float> betas(num_iters + 1, 0.f);
-    double t = 1.0;
-    for (int k = 1; k <= num_iters; ++k) {
-      const double t_next = (1.0 + sqrt(1.0 + 4.0 * t * t)) / 2.0;
-      betas[k] = (variant == VTC_VARIANT_FISTA) ? static_cast<float>((t - 1.0) / t_next) : 0.f;
-      t = t_next;
+    for (int c = 0; c < chains; ++c) {
+      fista_betas_kernel<<<1, 32, 0, ch[c].st>>>(ch[c].w.betas, num_iters, variant == VTC_VARIANT_FISTA ? 1 : 0);
+      COUNT_LAUNCH();
     }
-    for (int c = 0; c < chains; ++c)
-      CUDA_TRY(cudaMemcpyAsync(ch[c].w.betas, betas.data(), sizeof(float) * (num_iters + 1), cudaMemcpyHostToDevice,
-                               ch[c].st));
+    CUDA_TRY(cudaGetLastError());
   }
   if (g_prof.on) CUDA_TRY(cudaEventRecord(g_prof.iter_begin, st));
   const bool persistent = cm.fused_iter && !cm.early && chains == 1 && persistent_iterations_enabled();
