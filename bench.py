@@ -31,7 +31,7 @@ B_PER_GPU, S, D, T, LAM = 65536, 1024, 256, 300, 0.1
 TRAIN_GLOBAL_BATCH = 524288
 WORKLOAD = ('configs[1]: fully-connected FISTA, 16x16 whitened patches (D=256), 1024 atoms, '
             'batch 65536 per GPU, 300 iters, lambda 0.1')
-CPU_SAMPLE = 32768
+CPU_SAMPLE = int(os.environ.get('VTC_BENCH_CPU_SAMPLE', '32768'))  # patches per CPU step (the contract test shrinks it)
 CONV_IMAGES_PER_GPU, CONV_LAM = 128, 0.05
 
 
