@@ -44,7 +44,7 @@ namespace vtc {
 
 constexpr int IT_BN = 128;     // atoms per gradient tile (UMMA N of G)
 constexpr int IT_RN = 256;     // UMMA N of R = padded pixel count
-constexpr int IT_VARIANTS = 3;  // tuning variants (stage counts / math warps), VTC_B200_ITER_VARIANT
+constexpr int IT_VARIANTS = 4;  // tuning variants (stage counts / math warps), VTC_B200_ITER_VARIANT
 
 template <int P, int V>
 struct IterCfg {
@@ -55,6 +55,7 @@ struct IterCfg {
   //   0                     3          32       2 / 3          3   2       6
   //   1                     2          32       4 / 2          2   2       4 / 8
   //   2                     3          16       3 / 4          3   3       6
+  //   3                     3          16       2 / 2          -   3       9     y parts in the in/out stage (YIN)
   // epilogue math: GROUPS groups of four warps (one warp per TMEM lane quarter) on sub-tiles round-robin
   static constexpr int GROUPS = (V == 1) ? 2 : 3;
   static constexpr int MATH_WARPS = 4 * GROUPS;
@@ -67,7 +68,7 @@ struct IterCfg {
   static constexpr int G_STAGE = P * (A_TILE + B_TILE);
   // atoms per y / Phi^T chunk (K extent of one group of R MMAs): 32 = two sub-tiles (64-byte rows, SWIZZLE_64B) or
   // 16 = one sub-tile (32-byte rows, SWIZZLE_32B: half the ring bytes, twice the handshakes)
-  static constexpr int CHUNK = (V == 2) ? 16 : 32;
+  static constexpr int CHUNK = (V == 2 || V == 3) ? 16 : 32;
   static constexpr int SUBS = CHUNK / EPI_COLS;           // sub-tiles per chunk
   static constexpr int Y_TILE = BLOCK_M * CHUNK * 2;      // one part of y: 128 rows x CHUNK atoms
   static constexpr int Y_STAGE = P * Y_TILE;
@@ -78,12 +79,16 @@ struct IterCfg {
                                                           // over the second 8 KB of its input stage and stored from there
   static constexpr int STORES_IN_FLIGHT = 1;              // TMA stores whose shared-memory reads may still be pending
   // shared memory split between the rings (P = 2: G 24 KB, y 16 KB, Phi^T 16 KB, in/out 16 KB per stage)
-  static constexpr int G_STAGES = (V == 0) ? (P == 2 ? 2 : 3) : (V == 1) ? (P == 2 ? 4 : 2) : (V == 2 && P == 2) ? 3 : 4;
+  static constexpr int G_STAGES = (V == 0) ? (P == 2 ? 2 : 3) : (V == 1) ? (P == 2 ? 4 : 2) : (V == 3) ? 2 : (V == 2 && P == 2) ? 3 : 4;
+  // YIN: no y ring. The y parts of a sub-tile (P x 128 rows x 32 B, SWIZZLE_32B) are written over the a_{k-1} slot of
+  // the sub-tile's own in/out stage once the group has read it, and R takes its A operand from there; the stage goes
+  // back to the loader when both the TMA store of a_k and the R MMAs have read it.
+  static constexpr bool YIN = (V == 3);
   // every y stage must always be written by the same math groups (a group then sees the phases of the stage's
   // barrier strictly in order, like the in/out stages): Y_STAGES * SUBS is a multiple of GROUPS
-  static constexpr int Y_STAGES = (V == 1) ? 2 : 3;
-  static constexpr int PT_STAGES = (V == 2) ? 3 : 2;
-  static constexpr int IN_STAGES = (V == 1) ? (P == 2 ? 4 : 8) : 6;      // a multiple of GROUPS: fixed owner group per stage
+  static constexpr int Y_STAGES = YIN ? 0 : (V == 1) ? 2 : 3;
+  static constexpr int PT_STAGES = (V == 2 || V == 3) ? 3 : 2;
+  static constexpr int IN_STAGES = (V == 1) ? (P == 2 ? 4 : 8) : (V == 3) ? 9 : 6;      // a multiple of GROUPS: fixed owner group per stage
   static constexpr int OFF_G = 0;
   static constexpr int OFF_Y = OFF_G + G_STAGES * G_STAGE;
   static constexpr int OFF_PT = OFF_Y + Y_STAGES * Y_STAGE;
@@ -103,7 +108,8 @@ struct IterCfg {
   static constexpr int B_IN_FULL = B_ACCR_EMPTY + 1;
   static constexpr int B_IN_FREE = B_IN_FULL + IN_STAGES;
   static constexpr int B_OUT_FULL = B_IN_FREE + IN_STAGES;   // one per in/out stage
-  static constexpr int NUM_BARRIERS = B_OUT_FULL + IN_STAGES;
+  static constexpr int B_YS_FULL = B_OUT_FULL + IN_STAGES;   // YIN: the y parts of the stage are written (leader's barrier)
+  static constexpr int NUM_BARRIERS = B_YS_FULL + IN_STAGES;
   static constexpr int SMEM_TOTAL = OFF_BAR + NUM_BARRIERS * 8 + 16;
   static constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
   static constexpr int NPAIRS = (P == 1) ? 1 : 3;
@@ -114,6 +120,7 @@ struct IterCfg {
   static constexpr int PANEL_END_PAD = 6;
   static_assert(PANEL_END_PAD % GROUPS == 0, "padding must keep the group assignment aligned");
   static_assert(P * EPI_PART_BYTES <= OUT_SLOT, "r parts must fit the output slot");
+  static_assert(!YIN || (SUBS == 1 && P * BLOCK_M * 32 <= EPI_ARRAY_BYTES), "y parts must fit the a_{k-1} slot");
   static_assert(SMEM_ALLOC <= 232448, "over the 227 KB shared memory limit");
 };
 
@@ -259,6 +266,8 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
   const int nsub_r_pad = (p.nsub_r + C::PANEL_END_PAD - 1) / C::PANEL_END_PAD * C::PANEL_END_PAD;
   // sub-tiles of tile nt: an even number (whole chunks); columns at or beyond S are zero everywhere (TMA fill)
   auto tile_chunks = [&](int nt) { return (min(IT_BN, p.S - nt * IT_BN) + C::CHUNK - 1) / C::CHUNK; };
+  int job_tile_subs = 0;   // sub-tiles of the atom tiles of one job (without its panel end)
+  for (int nt = 0; nt < NT; ++nt) job_tile_subs += C::SUBS * tile_chunks(nt);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmR);
@@ -289,7 +298,9 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
     mbar_init(bar(C::B_ACCR_EMPTY), 2 * C::MATH_WARPS);
     for (int e = 0; e < C::IN_STAGES; ++e) {
       mbar_init(bar(C::B_IN_FULL + e), 1);
-      mbar_init(bar(C::B_IN_FREE + e), 1);    // the storer, once the TMA store of the stage's result has read it
+      // the storer, once the TMA store of the stage's result has read it (+ YIN: the commit of the R MMAs that read y)
+      mbar_init(bar(C::B_IN_FREE + e), C::YIN ? 2 : 1);
+      mbar_init(bar(C::B_YS_FULL + e), 2 * 4);   // YIN: 2 CTAs x the 4 warps of the stage's group, every use of the stage
       mbar_init(bar(C::B_OUT_FULL + e), 4);   // the four math warps that wrote the result
     }
     fence_barrier_init();
@@ -382,6 +393,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
       uint32_t g_it = 0, g_accumulate = 0;
       int r_tile = 0, r_chunk = 0;
       uint32_t r_it = 0;
+      uint32_t r_q = 0;   // running sub-tile index of the next R chunk (YIN: its in/out stage is r_q % IN_STAGES)
       uint32_t idle = 0;
       int r_job = -1;
       bool r_job_do_r = false;
@@ -393,26 +405,38 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
         }
         if (r_tile < my_tiles && !r_job_do_r) {
           r_tile += NT;   // the final iteration has no R
+          r_q += job_tile_subs;
           continue;
         }
         if (r_tile < my_tiles) {
           const int pi = r_tile / NT, nt = r_tile % NT;
           const bool first = (nt == 0 && r_chunk == 0);
-          const int ys = r_it % C::Y_STAGES, ps = r_it % C::PT_STAGES;
-          bool ready = mbar_test_wait(bar(C::B_Y_FULL + ys), (r_it / C::Y_STAGES) & 1) &&
-                       mbar_test_wait(bar(C::B_PT_FULL + ps), (r_it / C::PT_STAGES) & 1);
+          const int ps = r_it % C::PT_STAGES;
+          // A operand of this chunk: a stage of the y ring, or (YIN) the a_{k-1} slot of the sub-tile's in/out stage
+          uint32_t ystage, a_part_bytes, y_release;
+          bool ready;
+          if constexpr (C::YIN) {
+            const int e = r_q % C::IN_STAGES;
+            ready = mbar_test_wait(bar(C::B_YS_FULL + e), (r_q / C::IN_STAGES) & 1);
+            ystage = sIn + e * C::IN_STAGE, a_part_bytes = BLOCK_M * 32, y_release = bar(C::B_IN_FREE + e);
+          } else {
+            const int ys = r_it % C::Y_STAGES;
+            ready = mbar_test_wait(bar(C::B_Y_FULL + ys), (r_it / C::Y_STAGES) & 1);
+            ystage = sY + ys * C::Y_STAGE, a_part_bytes = C::Y_TILE, y_release = bar(C::B_Y_EMPTY + ys);
+          }
+          ready = ready && mbar_test_wait(bar(C::B_PT_FULL + ps), (r_it / C::PT_STAGES) & 1);
           // the panel-end epilogue of the previous panel must have drained acc_r before it is overwritten
           if (ready && first) ready = mbar_test_wait(bar(C::B_ACCR_EMPTY), (pi & 1) ^ 1);
           if (ready) {
             tc_fence_after();
-            const uint32_t ystage = sY + ys * C::Y_STAGE, pstage = sPT + ps * C::PT_STAGE;
+            const uint32_t pstage = sPT + ps * C::PT_STAGE;
             const bool last = (nt == NT - 1) && (r_chunk == tile_chunks(nt) - 1);
             if (elect_one_sync()) {
               trace(TR_R_ISSUE, r_tile * 4 + r_chunk);
               uint32_t accumulate = first ? 0u : 1u;
 #pragma unroll
               for (int pr = 0; pr < C::NPAIRS; ++pr) {
-                const uint64_t adesc = make_kmajor_desc(ystage + pair_a(P, pr) * C::Y_TILE, C::CHUNK * 2);
+                const uint64_t adesc = make_kmajor_desc(ystage + pair_a(P, pr) * a_part_bytes, C::CHUNK * 2);
                 const uint64_t bdesc = make_kmajor_desc(pstage + pair_b(P, pr) * C::PT_TILE, C::CHUNK * 2);
 #pragma unroll
                 for (int k = 0; k < C::CHUNK / UMMA_K; ++k) {
@@ -420,13 +444,17 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
                   accumulate = 1;
                 }
               }
-              umma_commit_pair(bar(C::B_Y_EMPTY + ys), 3);
+              umma_commit_pair(y_release, 3);
               umma_commit_pair(bar(C::B_PT_EMPTY + ps), 3);
               if (last) umma_commit_pair(bar(C::B_ACCR_FULL), 3);
             }
             __syncwarp();
             ++r_it;
-            if (++r_chunk == tile_chunks(nt)) r_chunk = 0, ++r_tile;
+            ++r_q;
+            if (++r_chunk == tile_chunks(nt)) {
+              r_chunk = 0, ++r_tile;
+              if (r_tile % NT == 0) r_q += nsub_r_pad;   // the sub-tiles of this job's panel end carry no y
+            }
             progressed = true;
           }
         }
@@ -520,6 +548,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
   } else if (warp == 2) {
     // ================================ epilogue storer ================================
     uint32_t q = 0;
+    uint32_t prev_has_y = 0;   // bit i: did the sub-tile i + 1 stores ago put y parts for R into its stage (YIN)
     for (int ji = 0; ji < my_jobs; ++ji) {
       const Job job = job_at(ji);
       const int m0 = job.m0;
@@ -549,10 +578,14 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
             if (q >= C::STORES_IN_FLIGHT) {
               // all but the STORES_IN_FLIGHT most recent stores have read their stage: hand the oldest back to the loader
               bulk_wait_read<C::STORES_IN_FLIGHT>();
-              mbar_arrive(bar(C::B_IN_FREE + (q - C::STORES_IN_FLIGHT) % C::IN_STAGES));
+              const uint32_t free_bar = bar(C::B_IN_FREE + (q - C::STORES_IN_FLIGHT) % C::IN_STAGES);
+              mbar_arrive(free_bar);
+              // YIN: a stage whose a_{k-1} slot holds no y for R (panel end, final iteration) gets the MMA's arrival here
+              if (C::YIN && !((prev_has_y >> (C::STORES_IN_FLIGHT - 1)) & 1u)) mbar_arrive(free_bar);
             }
           }
           __syncwarp();
+          prev_has_y = (prev_has_y << 1) | ((!panel_end && job.do_r) ? 1u : 0u);
         }
       }
       if (p.done != nullptr) {
@@ -628,7 +661,10 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
           if (j >= nsub) {  // padding sub-tile of the panel end: pass the stage on
             mbar_wait(bar(C::B_IN_FULL + e), (q / C::IN_STAGES) & 1);
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(C::B_OUT_FULL + e));
+            if (lane == 0) {
+              mbar_arrive(bar(C::B_OUT_FULL + e));
+              if (C::YIN) mbar_arrive_remote(bar(C::B_YS_FULL + e), 0);   // every use of a stage completes a phase
+            }
             continue;
           }
           uint32_t v[16];
@@ -675,12 +711,36 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
             });
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(C::B_OUT_FULL + e));
+            if (lane == 0) {
+              mbar_arrive(bar(C::B_OUT_FULL + e));
+              if (C::YIN) mbar_arrive_remote(bar(C::B_YS_FULL + e), 0);
+            }
           } else {
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch)
               sts128(out_stage + row * 64 + ((ch ^ sw64) << 4), outv[4 * ch], outv[4 * ch + 1], outv[4 * ch + 2],
                      outv[4 * ch + 3]);
+            if constexpr (C::YIN) {
+              if (job.do_r) {
+                // y_k parts over the a_{k-1} slot of this stage, as the A operand of R (K-major, 32-byte rows,
+                // SWIZZLE_32B). A y row lands on another thread's a_{k-1} row: all four warps of the group must have
+                // read their inputs first.
+                named_bar_sync(1 + group, 128);
+                trace(TR_E_YW, j);
+                const uint32_t yrow = in_stage + row * 32;
+                split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
+                  const uint32_t prow = yrow + part * (BLOCK_M * 32);
+                  sts128u(prow + ((0 ^ sw32) << 4), w32[0], w32[1], w32[2], w32[3]);
+                  sts128u(prow + ((1 ^ sw32) << 4), w32[4], w32[5], w32[6], w32[7]);
+                });
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive(bar(C::B_OUT_FULL + e));
+                mbar_arrive_remote(bar(C::B_YS_FULL + e), 0);
+              }
+            } else {
             uint32_t yfull = 0;
             if (job.do_r) {
               // y_k parts straight into the A operand of R, K-major with rows of CHUNK * 2 bytes in the matching TMA /
@@ -703,6 +763,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
             if (lane == 0) {
               mbar_arrive(bar(C::B_OUT_FULL + e));
               if (job.do_r) mbar_arrive_remote(yfull, 0);
+            }
             }
             trace(TR_E_ARR, j);
           }

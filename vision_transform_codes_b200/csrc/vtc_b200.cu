@@ -582,6 +582,7 @@ int launch_iter(const IterCall& c, cudaStream_t stream) {
   switch (iter_variant(parts_for(c.precision))) {
     case 1: return one ? launch_iter_p<1, 1>(c, info, stream) : launch_iter_p<2, 1>(c, info, stream);
     case 2: return one ? launch_iter_p<1, 2>(c, info, stream) : launch_iter_p<2, 2>(c, info, stream);
+    case 3: return one ? launch_iter_p<1, 3>(c, info, stream) : launch_iter_p<2, 3>(c, info, stream);
     default: return one ? launch_iter_p<1, 0>(c, info, stream) : launch_iter_p<2, 0>(c, info, stream);
   }
 }
