@@ -55,7 +55,7 @@ struct IterCfg {
   //   0                     3          32       2 / 3          3   2       6
   //   1                     2          32       4 / 2          2   2       4 / 8
   //   2                     3          16       3 / 4          3   3       6
-  //   3                     3          16       2 / 2          -   3       9     y parts in the in/out stage (YIN)
+  //   3                     3          16       2 / 2          -   2 (x32) 9     y parts in the in/out stage (YIN)
   // epilogue math: GROUPS groups of four warps (one warp per TMEM lane quarter) on sub-tiles round-robin
   static constexpr int GROUPS = (V == 1) ? 2 : 3;
   static constexpr int MATH_WARPS = 4 * GROUPS;
@@ -72,7 +72,10 @@ struct IterCfg {
   static constexpr int SUBS = CHUNK / EPI_COLS;           // sub-tiles per chunk
   static constexpr int Y_TILE = BLOCK_M * CHUNK * 2;      // one part of y: 128 rows x CHUNK atoms
   static constexpr int Y_STAGE = P * Y_TILE;
-  static constexpr int PT_TILE = (IT_RN / 2) * CHUNK * 2;  // one part of this CTA's 128 pixel rows of Phi^T
+  // atoms per Phi^T chunk: CHUNK, except YIN, which keeps 32-atom chunks (two 16-atom R chunks read one each: half the
+  // TMA loads and ring handshakes) -- the A and B operands of an MMA may use different swizzle spans
+  static constexpr int PT_CHUNK = (V == 3) ? 32 : CHUNK;
+  static constexpr int PT_TILE = (IT_RN / 2) * PT_CHUNK * 2;  // one part of this CTA's 128 pixel rows of Phi^T
   static constexpr int PT_STAGE = P * PT_TILE;
   static constexpr int IN_STAGE = 2 * EPI_ARRAY_BYTES;
   static constexpr int OUT_SLOT = EPI_ARRAY_BYTES;        // the result (a_k fp32, or P bf16 part sub-tiles of r) is written
@@ -87,7 +90,7 @@ struct IterCfg {
   // every y stage must always be written by the same math groups (a group then sees the phases of the stage's
   // barrier strictly in order, like the in/out stages): Y_STAGES * SUBS is a multiple of GROUPS
   static constexpr int Y_STAGES = YIN ? 0 : (V == 1) ? 2 : 3;
-  static constexpr int PT_STAGES = (V == 2 || V == 3) ? 3 : 2;
+  static constexpr int PT_STAGES = (V == 2) ? 3 : 2;
   static constexpr int IN_STAGES = (V == 1) ? (P == 2 ? 4 : 8) : (V == 3) ? 9 : 6;      // a multiple of GROUPS: fixed owner group per stage
   static constexpr int OFF_G = 0;
   static constexpr int OFF_Y = OFF_G + G_STAGES * G_STAGE;
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
       for (int ji = 0; ji < my_jobs; ++ji) {
         if (!job_at(ji).do_r) continue;
         for (int nt = 0; nt < NT; ++nt) {
-          const int nch = tile_chunks(nt);
+          const int nch = (tile_chunks(nt) * C::CHUNK + C::PT_CHUNK - 1) / C::PT_CHUNK;
           for (int c = 0; c < nch; ++c, ++it) {
             const int s = it % C::PT_STAGES;
             const uint32_t ph = (it / C::PT_STAGES) & 1;
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
 #pragma unroll
               for (int q = 0; q < P; ++q)
                 tma_load_2d_pair(sPT + s * C::PT_STAGE + q * C::PT_TILE, &p.tmPhiT, full,
-                                 q * p.phiT_part_stride + nt * IT_BN + c * C::CHUNK, cta_rank * (IT_RN / 2), kEvictLast);
+                                 q * p.phiT_part_stride + nt * IT_BN + c * C::PT_CHUNK, cta_rank * (IT_RN / 2), kEvictLast);
             }
             __syncwarp();
           }
@@ -393,6 +396,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
       uint32_t g_it = 0, g_accumulate = 0;
       int r_tile = 0, r_chunk = 0;
       uint32_t r_it = 0;
+      uint32_t r_pt = 0;  // running Phi^T chunk index
       uint32_t r_q = 0;   // running sub-tile index of the next R chunk (YIN: its in/out stage is r_q % IN_STAGES)
       uint32_t idle = 0;
       int r_job = -1;
@@ -411,7 +415,8 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
         if (r_tile < my_tiles) {
           const int pi = r_tile / NT, nt = r_tile % NT;
           const bool first = (nt == 0 && r_chunk == 0);
-          const int ps = r_it % C::PT_STAGES;
+          constexpr int R_PER_PT = C::PT_CHUNK / C::CHUNK;   // R chunks served by one Phi^T chunk
+          const int ps = r_pt % C::PT_STAGES;
           // A operand of this chunk: a stage of the y ring, or (YIN) the a_{k-1} slot of the sub-tile's in/out stage
           uint32_t ystage, a_part_bytes, y_release;
           bool ready;
@@ -424,20 +429,23 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
             ready = mbar_test_wait(bar(C::B_Y_FULL + ys), (r_it / C::Y_STAGES) & 1);
             ystage = sY + ys * C::Y_STAGE, a_part_bytes = C::Y_TILE, y_release = bar(C::B_Y_EMPTY + ys);
           }
-          ready = ready && mbar_test_wait(bar(C::B_PT_FULL + ps), (r_it / C::PT_STAGES) & 1);
+          ready = ready && mbar_test_wait(bar(C::B_PT_FULL + ps), (r_pt / C::PT_STAGES) & 1);
           // the panel-end epilogue of the previous panel must have drained acc_r before it is overwritten
           if (ready && first) ready = mbar_test_wait(bar(C::B_ACCR_EMPTY), (pi & 1) ^ 1);
           if (ready) {
             tc_fence_after();
             const uint32_t pstage = sPT + ps * C::PT_STAGE;
             const bool last = (nt == NT - 1) && (r_chunk == tile_chunks(nt) - 1);
+            // the Phi^T chunk is done with after its last R chunk (the last chunk of a tile may use only its first half)
+            const bool pt_done = (r_chunk % R_PER_PT == R_PER_PT - 1) || (r_chunk == tile_chunks(nt) - 1);
+            const uint32_t pt_koff = 2 * (C::CHUNK / UMMA_K) * (r_chunk % R_PER_PT);   // in 16-byte units
             if (elect_one_sync()) {
               trace(TR_R_ISSUE, r_tile * 4 + r_chunk);
               uint32_t accumulate = first ? 0u : 1u;
 #pragma unroll
               for (int pr = 0; pr < C::NPAIRS; ++pr) {
                 const uint64_t adesc = make_kmajor_desc(ystage + pair_a(P, pr) * a_part_bytes, C::CHUNK * 2);
-                const uint64_t bdesc = make_kmajor_desc(pstage + pair_b(P, pr) * C::PT_TILE, C::CHUNK * 2);
+                const uint64_t bdesc = make_kmajor_desc(pstage + pair_b(P, pr) * C::PT_TILE, C::PT_CHUNK * 2) + pt_koff;
 #pragma unroll
                 for (int k = 0; k < C::CHUNK / UMMA_K; ++k) {
                   umma_bf16_pair(acc_r, adesc + 2 * k, bdesc + 2 * k, idesc_r, accumulate);
@@ -445,12 +453,13 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
                 }
               }
               umma_commit_pair(y_release, 3);
-              umma_commit_pair(bar(C::B_PT_EMPTY + ps), 3);
+              if (pt_done) umma_commit_pair(bar(C::B_PT_EMPTY + ps), 3);
               if (last) umma_commit_pair(bar(C::B_ACCR_FULL), 3);
             }
             __syncwarp();
             ++r_it;
             ++r_q;
+            if (pt_done) ++r_pt;
             if (++r_chunk == tile_chunks(nt)) {
               r_chunk = 0, ++r_tile;
               if (r_tile % NT == 0) r_q += nsub_r_pad;   // the sub-tiles of this job's panel end carry no y

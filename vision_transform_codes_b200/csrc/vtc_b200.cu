@@ -489,7 +489,7 @@ int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream
   if (c.r_op.block != Cf::BK) return fail(VTC_ERR_ARG, "fused iteration: r_op must be tile-contiguous with block %d", Cf::BK);
   TRY(map_operand(&p.tmR, c.r_op, Cf::BK, "r operand"));
   TRY(map_operand(&p.tmPhi, c.phi_op, Cf::BK, "dictionary operand", IT_BN / 2));
-  TRY(map_operand(&p.tmPhiT, c.phiT_op, Cf::CHUNK, "transposed dictionary operand", IT_RN / 2));
+  TRY(map_operand(&p.tmPhiT, c.phiT_op, Cf::PT_CHUNK, "transposed dictionary operand", IT_RN / 2));
   for (int i = 0; i < 4; ++i) {
     TRY(map_f32(&p.tmState[i], c.state[i], "code array"));
     p.state_blocked[i] = c.state[i].blocked ? 1 : 0;
