@@ -157,3 +157,15 @@ def test_metrics_from_totals_follow_the_reference_definitions():
   assert np.isnan(metrics.metrics_from_totals([0, 0, 0, 0, 0, 0.0, 1.0, 4], 0.1)[metrics.PSNR])
   avg = metrics.average_metrics([{'a': 1.0, 'b': np.array([1.0, 3.0])}, {'a': 3.0, 'b': np.array([5.0, 7.0])}])
   assert avg == {'a': 2.0, 'b': 4.0}
+
+
+def test_tools_and_entry_points_compile():
+  """The measurement / debugging scripts under tools/ and the root entry points at least parse (they only run on a GPU)."""
+  import glob
+  import py_compile
+  from conftest import ROOT
+  files = sorted(glob.glob(os.path.join(ROOT, 'tools', '*.py'))) + [os.path.join(ROOT, f) for f in
+                                                                   ('bench.py', '__graft_entry__.py')]
+  assert len(files) > 10
+  for f in files:
+    py_compile.compile(f, doraise=True)
