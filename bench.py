@@ -210,7 +210,7 @@ def metrics_benchmark(rank, world, dev, timed, codes, x, phi):
   and 1024 floats cross to the host), next to the reference's host-side definition (the oracle's compute_metrics: numpy
   on copies of images, reconstructions and norms, a Python loop over the batch for the pSNR) on a sample of the batch."""
   from oracle import vtc_oracle as oracle
-  from vision_transform_codes_b200.training import metrics
+  from vision_transform_codes_b200.lean import metrics
   prev = phi.clone()
   ms, launches = timed(lambda: metrics.compute_metrics(x, codes, phi, prev, LAM), 5, 2)
   out = {'workload': 'validation metrics of one configs[1] batch (%d patches, %d atoms)' % tuple(codes.shape),
@@ -484,7 +484,7 @@ def main():
                                          'basis': 'whole call / %d iterations' % T}
       pkg.config.precision = args.precision
     try:
-      from vision_transform_codes_b200.training import sparse_coding as trainer
+      from vision_transform_codes_b200.lean import sparse_coding as trainer
       line['train_step'] = trainer.benchmark_train_step(TRAIN_GLOBAL_BATCH, S, D, T, LAM, world, rank, dev, timed)
     except ImportError:
       pass

@@ -209,7 +209,10 @@ def train_steps(batches, dictionary, sparsity_weight, num_iters, stepsize, varia
       phi = sc_dictionary_update(x, phi, codes, h, stepsize=stepsize, group_assignments=group_assignments,
                                  alignment_penalty=alignment_penalty)
     else:
-      phi = sc_dictionary_update(x, phi, codes, None, stepsize=stepsize)
+      # sc_steepest_descent.py:37-41; 'subspace_sc_steepest_descent' (named at training/sparse_coding.py:421-427 but
+      # absent from the reference tree) = the same step with the alignment term of the subspace cheap rule
+      phi = sc_dictionary_update(x, phi, codes, None, stepsize=stepsize, group_assignments=group_assignments,
+                                 alignment_penalty=alignment_penalty if update_rule.startswith('subspace') else 0.0)
   return phi, h, codes
 
 

@@ -29,7 +29,7 @@ def _worker(rank, world, port, result_path):
   os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
   dist.init_process_group('gloo', rank=rank, world_size=world)
   import vision_transform_codes_b200 as pkg
-  from vision_transform_codes_b200.training import sparse_coding as trainer
+  from vision_transform_codes_b200.lean import sparse_coding as trainer
   pkg.enable_data_parallel()
   torch.manual_seed(0)
   B, S, D = 96, 48, 24
@@ -74,7 +74,7 @@ def _worker(rank, world, port, result_path):
   ok = ok and oracle.relative_l2(got, want) < 1e-6
   # validation metrics (training/metrics.py): every rank holds the totals of its shard (restated here on the CPU the way
   # metrics_totals_kernel defines them); after the all-reduce both report the metrics of the whole batch
-  from vision_transform_codes_b200.training import metrics
+  from vision_transform_codes_b200.lean import metrics
   r2 = ((torch.mm(cs, phi) - xs)**2).sum(1).double()
   mse = (r2 / D).float()
   totals = torch.tensor([float(0.5 * r2.sum()), float(cs.abs().sum()), float((cs != 0).sum(1).double().div(S).sum()),

@@ -229,7 +229,7 @@ def test_conv_lean_trainer_matches_reference_trainer(tmp_path):
   """The package's own train_dictionary in convolutional mode, with the reference's parameter dictionary
   (tests/sparse_coding_4.py), against the unmodified reference trainer's result; checkpoints in its pickle format."""
   import numpy as np
-  from vision_transform_codes_b200.training import sparse_coding as trainer
+  from vision_transform_codes_b200.lean import sparse_coding as trainer
   g = load_golden('conv_training_small')
   pad = tuple(tuple(int(v) for v in row) for row in g['padding'])
   params = {

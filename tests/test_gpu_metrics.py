@@ -26,7 +26,7 @@ def default_precision():
 
 
 def trainer_modules():
-  from vision_transform_codes_b200.training import metrics, sparse_coding
+  from vision_transform_codes_b200.lean import metrics, sparse_coding
   return metrics, sparse_coding
 
 

@@ -23,7 +23,7 @@ def params(inference, update, **extra):
 
 
 def test_trainer_matches_reference_trainer_outputs(capsys):
-  from vision_transform_codes_b200.training import sparse_coding as trainer
+  from vision_transform_codes_b200.lean import sparse_coding as trainer
   g = load_golden('training_small')
   batches, phi0 = g['batches'].cuda(), g['dictionary']
   s = phi0.size(0)
@@ -48,7 +48,7 @@ def test_trainer_matches_reference_trainer_outputs(capsys):
 
 def test_checkpoint_format_matches_reference(tmp_path):
   import pickle
-  from vision_transform_codes_b200.training import sparse_coding as trainer
+  from vision_transform_codes_b200.lean import sparse_coding as trainer
   g = load_golden('training_small')
   phi = g['dictionary'].cuda()
   trainer.train_dictionary(g['batches'].cuda(), None, phi,

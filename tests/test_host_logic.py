@@ -116,7 +116,7 @@ def test_conv_workspace_queries_need_no_gpu():
 def test_trainer_parameter_checks():
   """The lean trainer keeps the reference's parameter dictionary and its refusals (training/sparse_coding.py:289-330,
   :394-436) -- checked before anything touches a device."""
-  from vision_transform_codes_b200.training import sparse_coding as trainer
+  from vision_transform_codes_b200.lean import sparse_coding as trainer
   phi = oracle.synthetic_conv_dictionary(4, 1, 8, 8)
   base = {'mode': 'convolutional', 'num_epochs': 1, 'strides': (4, 4), 'padding': ((4, 4), (4, 4)),
           'code_inference_algorithm': 'ista', 'inference_param_schedule': {0: {'sparsity_weight': 0.1, 'num_iters': 2}},
@@ -139,7 +139,7 @@ def test_trainer_parameter_checks():
 def test_metrics_from_totals_follow_the_reference_definitions():
   """Host side of training/metrics.py: the five scalars from the eight device totals (training/sparse_coding.py:196-225,
   utils/plotting.py:35-39), against the oracle's compute_metrics on a small batch whose totals are formed here."""
-  from vision_transform_codes_b200.training import metrics
+  from vision_transform_codes_b200.lean import metrics
   phi = oracle.synthetic_dictionary(24, 16)
   x = oracle.synthetic_patches(10, 16)
   codes = oracle.ista_fista(x, phi, 0.1, 20)

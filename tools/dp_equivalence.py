@@ -8,7 +8,7 @@ import torch.distributed as dist  # noqa: E402
 
 import vision_transform_codes_b200 as pkg  # noqa: E402
 from oracle import vtc_oracle as oracle  # noqa: E402  (seeded inputs + comparison metric)
-from vision_transform_codes_b200.training import sparse_coding as trainer  # noqa: E402
+from vision_transform_codes_b200.lean import sparse_coding as trainer  # noqa: E402
 
 rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
 dev = torch.device('cuda', int(os.environ['LOCAL_RANK']))

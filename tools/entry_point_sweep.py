@@ -20,7 +20,7 @@ from vision_transform_codes_b200.analysis_transforms.fully_connected import ista
 from vision_transform_codes_b200.dict_update_rules.convolutional import sc_cheap_quadratic_descent as conv_cheap  # noqa: E402
 from vision_transform_codes_b200.dict_update_rules.fully_connected import (  # noqa: E402
     sc_cheap_quadratic_descent, subspace_sc_cheap_quadratic_descent)
-from vision_transform_codes_b200.training import metrics  # noqa: E402
+from vision_transform_codes_b200.lean import metrics  # noqa: E402
 from vision_transform_codes_b200.utils import dataset_generation  # noqa: E402
 
 

@@ -158,6 +158,21 @@ struct IterParams {
   double* stat;          // optional: += sum |a_k - a_{k-1}|
   unsigned long long* trace;  // optional (tools/iter_trace.py): 4 regions of 2048 words, [0] = event count, then
                               // (event id << 48 | SM clock) words, written by four threads of CTA 0
+  int ablate;            // timing experiments only (VTC_B200_ABLATE, results are WRONG when non-zero): see AblateBits
+};
+// What a timing experiment leaves out of the kernel (tools/ablate.sh): the time that disappears with a piece is what
+// that piece costs in situ.
+enum AblateBits {
+  ABL_STATE_LOAD = 1,    // no TMA loads of a_{k-1}, a_{k-2}
+  ABL_STATE_STORE = 2,   // no TMA stores of a_k
+  ABL_R_STREAM = 4,      // r_op K blocks loaded for the first atom tile of a job only (as if r_k were resident)
+  ABL_STATE_LSU = 8,     // math warps neither read the state from shared memory nor write a_k to it
+  ABL_R_MMA = 16,        // no R MMAs (commits only)
+  ABL_G_MMA = 32,        // no G MMAs (commits only)
+  ABL_Y_STS = 64,        // math warps do not write the y parts
+  ABL_TMEM_LD = 128,     // math warps do not read the accumulator
+  ABL_G_LOAD = 256,      // no TMA loads into the G operand ring at all (producer arrives only)
+  ABL_PT_LOAD = 512,     // no TMA loads of the Phi^T chunks
 };
 
 // timeline events of CTA 0 for tools/iter_trace.py: id = kind << 8 | index
@@ -339,16 +354,20 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
           mbar_wait(bar(C::B_G_EMPTY + s), ph ^ 1);
           if (elect_one_sync()) {
             const uint32_t full = bar(C::B_G_FULL + s);
-            if (leader) mbar_arrive_expect_tx(full, 2 * C::G_STAGE);
-            else mbar_arrive_remote(full, 0);
+            const bool load_a = !((p.ablate & ABL_R_STREAM) && nt > 0) && !(p.ablate & ABL_G_LOAD);
+            const bool load_b = !(p.ablate & ABL_G_LOAD);
+            if (leader) {
+              if (load_b) mbar_arrive_expect_tx(full, load_a ? 2 * C::G_STAGE : 2 * P * C::B_TILE);
+              else mbar_arrive(full);
+            } else mbar_arrive_remote(full, 0);
             const uint32_t dst = sG + s * C::G_STAGE;
             trace(TR_G_LOAD, nt * p.kb_g + kb);
 #pragma unroll
             for (int q = 0; q < P; ++q)
-              tma_load_3d_pair(dst + q * C::A_TILE, &p.tmR, full, 0, m0, q * p.kb_g + kb, kEvictNormal);
+              if (load_a) tma_load_3d_pair(dst + q * C::A_TILE, &p.tmR, full, 0, m0, q * p.kb_g + kb, kEvictNormal);
 #pragma unroll
             for (int q = 0; q < P; ++q)
-              tma_load_2d_pair(dst + P * C::A_TILE + q * C::B_TILE, &p.tmPhi, full, q * p.phi_part_stride + kb * C::BK,
+              if (load_b) tma_load_2d_pair(dst + P * C::A_TILE + q * C::B_TILE, &p.tmPhi, full, q * p.phi_part_stride + kb * C::BK,
                                n0 + cta_rank * (IT_BN / 2), kEvictLast);
           }
           __syncwarp();
@@ -369,11 +388,14 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
             mbar_wait(bar(C::B_PT_EMPTY + s), ph ^ 1);
             if (elect_one_sync()) {
               const uint32_t full = bar(C::B_PT_FULL + s);
-              if (leader) mbar_arrive_expect_tx(full, 2 * C::PT_STAGE);
-              else mbar_arrive_remote(full, 0);
+              const bool load_pt = !(p.ablate & ABL_PT_LOAD);
+              if (leader) {
+                if (load_pt) mbar_arrive_expect_tx(full, 2 * C::PT_STAGE);
+                else mbar_arrive(full);
+              } else mbar_arrive_remote(full, 0);
 #pragma unroll
               for (int q = 0; q < P; ++q)
-                tma_load_2d_pair(sPT + s * C::PT_STAGE + q * C::PT_TILE, &p.tmPhiT, full,
+                if (load_pt) tma_load_2d_pair(sPT + s * C::PT_STAGE + q * C::PT_TILE, &p.tmPhiT, full,
                                  q * p.phiT_part_stride + nt * IT_BN + c * C::PT_CHUNK, cta_rank * (IT_RN / 2), kEvictLast);
             }
             __syncwarp();
@@ -448,7 +470,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
                 const uint64_t bdesc = make_kmajor_desc(pstage + pair_b(P, pr) * C::PT_TILE, C::PT_CHUNK * 2) + pt_koff;
 #pragma unroll
                 for (int k = 0; k < C::CHUNK / UMMA_K; ++k) {
-                  umma_bf16_pair(acc_r, adesc + 2 * k, bdesc + 2 * k, idesc_r, accumulate);
+                  if (!(p.ablate & ABL_R_MMA)) umma_bf16_pair(acc_r, adesc + 2 * k, bdesc + 2 * k, idesc_r, accumulate);
                   accumulate = 1;
                 }
               }
@@ -488,7 +510,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
                 const uint64_t bdesc = make_kmajor_desc(stage + P * C::A_TILE + pair_b(P, pr) * C::B_TILE, C::SPAN);
 #pragma unroll
                 for (int k = 0; k < C::BK / UMMA_K; ++k) {
-                  umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_g, accumulate);
+                  if (!(p.ablate & ABL_G_MMA)) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_g, accumulate);
                   accumulate = 1;
                 }
               }
@@ -539,6 +561,8 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
             } else if (panel_end) {
               mbar_arrive_expect_tx(full, EPI_ARRAY_BYTES);
               tma_load_2d(dst, &p.tmX, full, j * EPI_COLS, m0, kEvictNormal);
+            } else if (p.ablate & ABL_STATE_LOAD) {
+              mbar_arrive(full);
             } else {
               mbar_arrive_expect_tx(full, state_bytes);
               const int col = nt * IT_BN + j * EPI_COLS;
@@ -578,7 +602,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
               for (int part = 0; part < P; ++part)
                 tma_store_3d(&p.tmROut, src + part * EPI_PART_BYTES, col % p.r_block_w, m0,
                              part * p.kb_g + col / p.r_block_w);
-            } else {
+            } else if (!(p.ablate & ABL_STATE_STORE)) {
               const int col = nt * IT_BN + j * EPI_COLS;
               if (p.state_blocked[job.out]) tma_store_3d(&p.tmState[job.out], src, 0, m0, col / EPI_COLS);
               else tma_store_2d(&p.tmState[job.out], src, col, m0);
@@ -678,7 +702,11 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
           }
           uint32_t v[16];
           trace(TR_E_SUB, j);
-          tmem_ld16(t_row + j * EPI_COLS, v);
+          if (!(p.ablate & ABL_TMEM_LD)) tmem_ld16(t_row + j * EPI_COLS, v);
+          else {
+#pragma unroll
+            for (int x = 0; x < 16; ++x) v[x] = 0u;
+          }
           mbar_wait(bar(C::B_IN_FULL + e), (q / C::IN_STAGES) & 1);
           trace(TR_E_IN, j);
           tmem_ld_wait();
@@ -694,11 +722,12 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
           float in[3][16];
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
-            const float4 a = lds128(in_stage + row * 64 + ((ch ^ sw64) << 4));
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!(p.ablate & ABL_STATE_LSU) || panel_end) a = lds128(in_stage + row * 64 + ((ch ^ sw64) << 4));
             in[0][4 * ch + 0] = a.x, in[0][4 * ch + 1] = a.y, in[0][4 * ch + 2] = a.z, in[0][4 * ch + 3] = a.w;
             in[1][4 * ch + 0] = 0.f, in[1][4 * ch + 1] = 0.f, in[1][4 * ch + 2] = 0.f, in[1][4 * ch + 3] = 0.f;
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_prev && !panel_end) b = lds128(in_stage + EPI_ARRAY_BYTES + row * 64 + ((ch ^ sw64) << 4));
+            if (has_prev && !panel_end && !(p.ablate & ABL_STATE_LSU)) b = lds128(in_stage + EPI_ARRAY_BYTES + row * 64 + ((ch ^ sw64) << 4));
             in[2][4 * ch + 0] = b.x, in[2][4 * ch + 1] = b.y, in[2][4 * ch + 2] = b.z, in[2][4 * ch + 3] = b.w;
           }
           float outv[16], partv[16];
@@ -725,10 +754,12 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
               if (C::YIN) mbar_arrive_remote(bar(C::B_YS_FULL + e), 0);
             }
           } else {
+            if (!(p.ablate & ABL_STATE_LSU)) {
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
-              sts128(out_stage + row * 64 + ((ch ^ sw64) << 4), outv[4 * ch], outv[4 * ch + 1], outv[4 * ch + 2],
-                     outv[4 * ch + 3]);
+              for (int ch = 0; ch < 4; ++ch)
+                sts128(out_stage + row * 64 + ((ch ^ sw64) << 4), outv[4 * ch], outv[4 * ch + 1], outv[4 * ch + 2],
+                       outv[4 * ch + 3]);
+            }
             if constexpr (C::YIN) {
               if (job.do_r) {
                 // y_k parts over the a_{k-1} slot of this stage, as the A operand of R (K-major, 32-byte rows,
@@ -760,7 +791,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
               const uint32_t ystage = sY + ys * C::Y_STAGE + row * (C::CHUNK * 2);
               const uint32_t c0 = 2 * (j % C::SUBS);
               const uint32_t sw = (C::CHUNK == 32) ? sw64 : sw32;
-              split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
+              if (!(p.ablate & ABL_Y_STS)) split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
                 const uint32_t prow = ystage + part * C::Y_TILE;
                 sts128u(prow + (((c0 + 0) ^ sw) << 4), w32[0], w32[1], w32[2], w32[3]);
                 sts128u(prow + (((c0 + 1) ^ sw) << 4), w32[4], w32[5], w32[6], w32[7]);

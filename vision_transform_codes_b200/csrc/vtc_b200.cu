@@ -513,6 +513,14 @@ int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream
   p.stat = c.stat;
   p.trace = g_iter_trace;
   g_iter_trace = nullptr;  // one shot: only the next launch is traced
+  {
+    static int ablate = -1;   // timing experiments (tools/ablate.sh): pieces of the kernel left out, results wrong
+    if (ablate < 0) {
+      const char* e = getenv("VTC_B200_ABLATE");
+      ablate = e ? atoi(e) : 0;
+    }
+    p.ablate = ablate;
+  }
   static bool attr_set_dev[64] = {};
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));

@@ -25,7 +25,7 @@ from vision_transform_codes_b200.analysis_transforms.fully_connected import ista
 from vision_transform_codes_b200.analysis_transforms.convolutional import ista_fista as conv_ista_fista
 from vision_transform_codes_b200.dict_update_rules.convolutional import _common as _conv_common
 from vision_transform_codes_b200.dict_update_rules.fully_connected import _common
-from vision_transform_codes_b200.training import metrics as _metrics
+from vision_transform_codes_b200.lean import metrics as _metrics
 
 CHEAP_QUADRATIC = ('sc_cheap_quadratic_descent', 'subspace_sc_cheap_quadratic_descent')
 UPDATE_RULES = ('sc_steepest_descent', 'sc_cheap_quadratic_descent', 'subspace_sc_steepest_descent',
@@ -54,7 +54,6 @@ class _UpdateState:
     self.packed = torch.empty(S * D + S, dtype=torch.float32, device=dictionary.device)
     self.grad = self.packed[:S * D].view(S, D)
     self.sq_sum = self.packed[S * D:]
-    self.batch_global = None
     self.slots, self.width, self.reg = None, 0, None  # subspace alignment penalty
 
 
@@ -72,13 +71,19 @@ def update_dictionary(images, dictionary, codes, hessian_diag, stepsize, num_ite
   hessian_diag is given) followed by num_iters descent steps, with ONE all-reduce per step when data parallel.
   """
   lib = _lib.load()
+  _lib.require_cuda_f32(dictionary, 'dictionary')
   device = dictionary.device
   S, D = dictionary.shape
   B = codes.size(0)
+  # the kernels read and write a dense row-major (S, D) array: a strided view (e.g. a transposed init_dictionary) is
+  # updated through a contiguous working copy and written back, like dict_update_rules/fully_connected/_common.descend
+  target = dictionary
+  if not dictionary.is_contiguous():
+    dictionary = dictionary.contiguous()
   if batch_global is None:
-    if state.batch_global is None or state.batch_global[0] != B:
-      state.batch_global = (B, _common.global_batch_size(B, device))
-    batch_global = state.batch_global[1]
+    # summed over the ranks EVERY step: a rank cannot tell from its own shard size that another rank's shard changed
+    # (ragged last batch), and a stale divisor or a one-sided extra collective would desynchronise the replicas
+    batch_global = _common.global_batch_size(B, device)
   codes_rm, ld_codes = _lib.row_major(codes)
   with torch.cuda.device(device):
     st = _lib.stream_ptr(device)
@@ -104,6 +109,8 @@ def update_dictionary(images, dictionary, codes, hessian_diag, stepsize, num_ite
       _lib.check(lib.vtc_sc_dict_apply(_lib.ptr(dictionary), _lib.ptr(state.grad), _lib.ptr(hessian_diag),
                                        _lib.ptr(reg), float(alignment_penalty), S, D, int(batch_global),
                                        float(stepsize), float(lowest_code_val), int(bool(normalize_dictionary)), st))
+  if dictionary is not target:
+    target.copy_(dictionary)
 
 
 def update_dictionary_convolutional(images_padded, dictionary, codes, hessian_diag, kernel_strides, image_padding,
@@ -158,9 +165,6 @@ def train_dictionary(training_image_dataset, validation_image_dataset, init_dict
   if 'dict_element_rp_schedule' in all_params:
     raise NotImplementedError('dict_element_rp_schedule is host-side orchestration outside the B200 hot path; run the '
                               'reference trainer on top of vision_transform_codes_b200.install() for it')
-  if dict_update_alg == 'subspace_sc_steepest_descent':
-    raise ImportError('dict_update_rules.fully_connected.subspace_sc_steepest_descent does not exist in the '
-                      'reference either')
   nonneg_only = all_params.get('nonnegative_only', False)
   hard_threshold = all_params.get('hard_threshold', False)
   group_assignments = all_params.get('group_assignments')
