@@ -55,6 +55,11 @@ long long vtc_launch_count(void);
 int vtc_profile_enable(int on);
 int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches, int* iters, float* fused_launch_ms,
                      float* first_launch_ms);
+/* Every profiled vtc_fista_fc call since vtc_profile_enable(1) (a ring of the last 64), oldest first: device time of the
+ * setup (step size, operand splits), of the iteration launches, of the finishing copy, and the idle time of the stream
+ * until the next profiled call began (0 for the last). Measurement plumbing of bench.py; no reference counterpart. */
+int vtc_profile_history_count(void);
+int vtc_profile_history(int index, float* setup_ms, float* iter_ms, float* finish_ms, float* gap_to_next_ms);
 
 /* Contraction used by one ISTA/FISTA iteration: 1 = Gram form (y G - b, G = Phi Phi^T; 2*S*S flops per patch, one
  * launch), 2 = synthesis/analysis form ((y Phi - x) Phi^T as in ista_fista.py:105-106; 4*S*D flops, two launches),

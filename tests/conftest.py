@@ -37,3 +37,27 @@ def ragged_groups(g):
     groups.append([int(v) for v in flat[pos:pos + n]])
     pos += n
   return groups
+
+
+# ---- parity records: every comparison of the CUDA path with reference outputs appends one record; the session writes
+# them to gpurun_out/parity_r02.json (the directory gpurun brings back; copied to profiles/ by hand) -- SURVEY 7.3-1:
+# the guard band AND the count of flips inside it belong in the report
+PARITY_RECORDS = []
+
+
+def record_parity(test, case, **numbers):
+  PARITY_RECORDS.append(dict(test=test, case=case, **numbers))
+
+
+def pytest_sessionfinish(session, exitstatus):
+  if not PARITY_RECORDS:
+    return
+  import json
+  out_dir = os.path.join(ROOT, 'gpurun_out')
+  try:
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, 'parity_r02.json'), 'w') as f:
+      json.dump({'records': PARITY_RECORDS, 'device': torch.cuda.get_device_name(0) if torch.cuda.is_available() else None},
+                f, indent=1)
+  except OSError:
+    pass

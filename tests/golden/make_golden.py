@@ -63,6 +63,50 @@ def make_inference():
        fista_early=ista_fista.run(x, phi, lam, 1000, variant='fista', early_stopping_epsilon=1e-3))
 
 
+PROX_VARIANTS = (('soft', {}), ('nonneg', {'nonnegative_only': True}), ('hard', {'hard_threshold': True}),
+                 ('hard_nonneg', {'hard_threshold': True, 'nonnegative_only': True}))
+
+
+def make_threshold_steps():
+  """What pins the prox kernels themselves: ONE and THREE iterations of the reference, warm-started
+  from the reference's own iterate a_{T-1}, for every threshold variant -- a discontinuous prox cannot be judged on a
+  whole trajectory. Plus float64 runs of the same reference code for the two hard-threshold trajectories of
+  inference_small.npz, so that the float32 reference's own sensitivity is on record."""
+  b, n, s, T, lam = 48, 64, 128, 60, 0.1
+  x, phi = patches(b, n), dictionary(s, n)
+  out = {}
+  for variant in ('ista', 'fista'):
+    for name, kw in PROX_VARIANTS:
+      warm = ista_fista.run(x, phi, lam, T - 1, variant=variant, **kw)
+      out['%s_%s_warm' % (variant, name)] = warm
+      out['%s_%s_one' % (variant, name)] = ista_fista.run(x, phi, lam, 1, variant=variant, initial_codes=warm, **kw)
+      out['%s_%s_three' % (variant, name)] = ista_fista.run(x, phi, lam, 3, variant=variant, initial_codes=warm, **kw)
+  xd, pd = x.double(), phi.double()
+  out['fista_hard_f64'] = ista_fista.run(xd, pd, lam, T, variant='fista', hard_threshold=True)
+  out['ista_hard_nonneg_f64'] = ista_fista.run(xd, pd, lam, T, variant='ista', hard_threshold=True,
+                                               nonnegative_only=True)
+  out['fista_f64'] = ista_fista.run(xd, pd, lam, T, variant='fista')
+  save('threshold_steps', images=x, dictionary=phi, sparsity_weight=lam, num_iters=T, **out)
+
+
+def make_conv_threshold_steps():
+  from analysis_transforms.convolutional import ista_fista as conv_ista_fista
+  lam, T = 0.05, 40
+  x, phi, pad = conv_inputs(3, 1, (48, 40), (16, 16), (8, 8), 24)
+  st = (8, 8)
+  out = {}
+  for variant in ('ista', 'fista'):
+    for name, kw in PROX_VARIANTS:
+      warm = conv_ista_fista.run(x, phi, st, pad, lam, T - 1, variant=variant, **kw)
+      out['%s_%s_warm' % (variant, name)] = warm
+      out['%s_%s_one' % (variant, name)] = conv_ista_fista.run(x, phi, st, pad, lam, 1, variant=variant,
+                                                               initial_codes=warm, **kw)
+  out['ista_hard_nonneg_f64'] = conv_ista_fista.run(x.double(), phi.double(), st, pad, lam, T, variant='ista',
+                                                    nonnegative_only=True, hard_threshold=True)
+  save('conv_threshold_steps', images_padded=x, dictionary=phi, stride=np.array(st), padding=np.array(pad),
+       sparsity_weight=lam, num_iters=T, **out)
+
+
 def make_config1():
   # BASELINE.json configs[0]: 16x16 patches, 256 atoms, batch 250, 300 iterations, lambda 0.1
   b, n, s, T, lam = 250, 256, 256, 300, 0.1
@@ -342,6 +386,6 @@ def make_whitening():
 
 
 if __name__ == '__main__':
-  which = sys.argv[1:] or ['inference', 'config1', 'overcomplete', 'subspace', 'dict_update', 'training', 'conv', 'metrics', 'whitening']
+  which = sys.argv[1:] or ['inference', 'threshold_steps', 'conv_threshold_steps', 'config1', 'overcomplete', 'subspace', 'dict_update', 'training', 'conv', 'metrics', 'whitening']
   for name in which:
     globals()['make_' + name]()

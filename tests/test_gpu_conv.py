@@ -3,10 +3,12 @@ Parity of the convolutional CUDA path (drop-in modules -> ctypes -> C ABI) with 
 (tests/golden/conv_*.npz, made by make_golden.py from /root/reference) and with the CPU oracle on seeded inputs.
 Same tolerances as the fully-connected path: relative L2 <= 1e-4 on codes (bf16x3 arithmetic), 1e-5 on dictionaries.
 """
+import os
+
 import pytest
 import torch
 
-from conftest import load_golden
+from conftest import load_golden, record_parity
 from oracle import vtc_oracle as oracle
 
 pytestmark = pytest.mark.gpu
@@ -36,14 +38,17 @@ def conv_args(g):
   return g['images_padded'], g['dictionary'], stride, padding, g['sparsity_weight'], g['num_iters']
 
 
-def check(got, want, tol=CODE_TOL, band=1e-4):
+def check(got, want, tol=CODE_TOL, band=1e-4, case=''):
   got = got.cpu()
   assert got.shape == want.shape and got.dtype == torch.float32
   assert torch.isfinite(got).all()
   err = oracle.relative_l2(got, want)
+  flips, outside = oracle.support_mismatches(got, want, band=0.0 if band is None else band)
+  test = os.environ.get('PYTEST_CURRENT_TEST', '').split(' ')[0].split('::')[-1]
+  record_parity(test, case, rel_l2=err, flips_total=flips, flips_in_band=flips - outside, flips_outside_band=outside,
+                band=band, elements=got.numel(), tol=tol)
   assert err <= tol, err
   if band is not None:
-    flips, outside = oracle.support_mismatches(got, want, band=band)
     assert outside == 0, (flips, outside)
   return err
 
@@ -59,10 +64,9 @@ def test_conv_inference_call_matrix_against_reference_outputs():
   check(ista_fista.run(xd, pd, st, pad, lam, T, variant='ista'), g['ista'])
   check(ista_fista.run(xd, g['plain_dictionary'].cuda(), st, pad, lam, T, variant='ista'), g['ista_plain'])
   check(ista_fista.run(xd, pd, st, pad, lam, T, nonnegative_only=True), g['fista_nonneg'])
+  # hard thresholding at the ordinary tolerance: such calls run in config.hard_threshold_precision (bf16x6)
   got = ista_fista.run(xd, pd, st, pad, lam, T, variant='ista', nonnegative_only=True, hard_threshold=True)
-  err = check(got, g['ista_hard_nonneg'], tol=8e-2, band=None)  # discontinuous prox: ties move whole coefficients
-  flips, _ = oracle.support_mismatches(got.cpu(), g['ista_hard_nonneg'])
-  assert flips <= 0.005 * got.numel(), (flips, err)
+  check(got, g['ista_hard_nonneg'], case='ista_hard_nonneg')
   check(ista_fista.run(xd, pd, st, pad, lam, 500, variant='ista', early_stopping_epsilon=1e-3), g['ista_early'],
         tol=2e-3, band=None)
   warm = g['warm_start'].cuda()
@@ -72,6 +76,43 @@ def test_conv_inference_call_matrix_against_reference_outputs():
   # the reference's own assertions (tests/ista_fista_2.py:56-68): nothing passed in is mutated
   assert torch.equal(xd, keep_x) and torch.equal(pd, keep_p) and torch.equal(warm, keep_w)
   assert not torch.allclose(out, warm)
+
+
+PROX_VARIANTS = (('soft', {}), ('nonneg', {'nonnegative_only': True}), ('hard', {'hard_threshold': True}),
+                 ('hard_nonneg', {'hard_threshold': True, 'nonnegative_only': True}))
+
+
+@pytest.mark.parametrize('precision', ['bf16x3', 'bf16x6'])
+def test_conv_single_step_of_every_threshold_variant_against_the_reference(precision):
+  """ONE convolutional iteration from the reference's own iterate a_{T-1} for all four thresholds (analysis_transforms/
+  convolutional/ista_fista.py:141-165): pins the prox kernels. Elements whose float64 pre-threshold value ties with the
+  cutoff (relative band 1e-5) are excluded and counted."""
+  import vision_transform_codes_b200 as pkg
+  ista_fista = modules()[0]
+  g = load_golden('conv_threshold_steps')
+  x, phi, st, pad, lam, _ = conv_args(g)
+  xd, pd = x.cuda(), phi.cuda()
+  eta64 = 1.0 / float(torch.linalg.eigvalsh(phi.double().flatten(1).t() @ phi.double().flatten(1))[-1])
+  mask = oracle.create_mask(x, pad).double()
+  for variant in ('ista', 'fista'):
+    for name, kw in PROX_VARIANTS:
+      warm, want = g['%s_%s_warm' % (variant, name)], g['%s_%s_one' % (variant, name)]
+      got, _ = ista_fista.infer(xd, pd, st, pad, lam, 1, variant, warm.cuda(), None, kw.get('nonnegative_only', False),
+                                kw.get('hard_threshold', False), precision=pkg.PRECISIONS[precision])
+      got = got.cpu()
+      y = warm.double()
+      resid = mask * (torch.nn.functional.conv_transpose2d(y, phi.double(), stride=st) - x.double())
+      u = y - eta64 * torch.nn.functional.conv2d(resid, phi.double(), stride=st)
+      mag = u if kw.get('nonnegative_only', False) else u.abs()
+      ties = (mag - lam * eta64).abs() <= 1e-5 * torch.clamp(u.abs(), min=1.0)
+      keep = ~ties
+      err = float(torch.norm((got - want)[keep]) / torch.norm(want[keep]))
+      flips = int((((got != 0) != (want != 0)) & keep).sum())
+      record_parity('test_conv_single_step_of_every_threshold_variant_against_the_reference',
+                    '%s %s %s' % (precision, variant, name), rel_l2=err, flips_outside_ties=flips,
+                    ties_excluded=int(ties.sum()), tie_band=1e-5, elements=got.numel())
+      assert err <= CODE_TOL, (precision, variant, name, err)
+      assert flips == 0, (precision, variant, name, flips)
 
 
 def test_conv_two_channels_rectangular_kernels():

@@ -4,19 +4,21 @@ committed outputs of the reference. Tolerances are the ones BASELINE.json's nort
 on codes and reconstructions for the float32-parity path (bf16x3 arithmetic), identical supports outside a guard
 band around the threshold; the plain-bf16 path has its own, looser tolerance.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, ragged_groups
+from conftest import load_golden, ragged_groups, record_parity
 from oracle import vtc_oracle as oracle
 
 pytestmark = pytest.mark.gpu
 
 CODE_TOL = 1e-4       # north_star: relative L2 on codes, float32-parity path
 RECON_TOL = 1e-4      # north_star: relative L2 on reconstructions
-BF16_CODE_TOL = 5e-2  # separately toleranced plain-bf16 path
-BF16_RECON_TOL = 1e-2
+BF16_CODE_TOL = 3e-2  # separately toleranced plain-bf16 path: <= 2x the largest value measured over this suite
+BF16_RECON_TOL = 6e-3  # (profiles/parity_r02.json: codes 1.5e-2, reconstructions 2.8e-3 on the overcomplete shape)
 GUARD_BAND = 1e-4     # a support flip whose non-zero side is below this is a tie at the threshold
 
 
@@ -37,13 +39,16 @@ def modules():
       subspace_sc_cheap_quadratic_descent
 
 
-def check_codes(got, want, phi, tol=CODE_TOL, recon_tol=RECON_TOL, band=GUARD_BAND):
+def check_codes(got, want, phi, tol=CODE_TOL, recon_tol=RECON_TOL, band=GUARD_BAND, case=''):
   got = got.cpu()
   assert got.shape == want.shape and got.dtype == torch.float32
   assert torch.isfinite(got).all()
   err = oracle.relative_l2(got, want)
   rerr = oracle.relative_l2(got @ phi, want @ phi)
   flips, outside = oracle.support_mismatches(got, want, band=0.0 if band is None else band)
+  test = os.environ.get('PYTEST_CURRENT_TEST', '').split(' ')[0].split('::')[-1]
+  record_parity(test, case, rel_l2=err, recon_rel_l2=rerr, flips_total=flips, flips_in_band=flips - outside,
+                flips_outside_band=outside, band=band, elements=got.numel(), tol=tol, recon_tol=recon_tol)
   assert err <= tol, ('codes', err)
   assert rerr <= recon_tol, ('recon', rerr)
   if band is not None:
@@ -58,20 +63,19 @@ def test_inference_call_matrix_against_reference_outputs():
   x, phi, lam, T = g['images'], g['dictionary'], g['sparsity_weight'], g['num_iters']
   xd, pd = x.cuda(), phi.cuda()
   keep_x, keep_p = xd.clone(), pd.clone()
-  check_codes(ista_fista.run(xd, pd, lam, T), g['fista'], phi)
-  check_codes(ista_fista.run(xd, pd, lam, T, 'ista'), g['ista'], phi)
-  check_codes(ista_fista.run(xd, pd, lam, T, nonnegative_only=True), g['fista_nonneg'], phi)
-  # hard thresholding is discontinuous: one tie at the cutoff moves a whole coefficient and the iteration amplifies
-  # it, so the comparison is loose on values and asks for agreement of (almost) the whole support instead
+  check_codes(ista_fista.run(xd, pd, lam, T), g['fista'], phi, case='fista')
+  check_codes(ista_fista.run(xd, pd, lam, T, 'ista'), g['ista'], phi, case='ista')
+  check_codes(ista_fista.run(xd, pd, lam, T, nonnegative_only=True), g['fista_nonneg'], phi, case='fista_nonneg')
+  # hard thresholding (ista_fista.py:107-111) at the SAME tolerance as everything else: a call with
+  # hard_threshold=True runs in config.hard_threshold_precision (bf16x6), because the discontinuous prox turns the
+  # 2^-17 product error of bf16x3 into whole-coefficient flips (test_hard_threshold_trajectories_by_precision)
   for kw, key in (({'hard_threshold': True}, 'fista_hard'),
                   ({'variant': 'ista', 'hard_threshold': True, 'nonnegative_only': True}, 'ista_hard_nonneg')):
-    got = ista_fista.run(xd, pd, lam, T, **kw)
-    _, _, flips = check_codes(got, g[key], phi, tol=8e-2, recon_tol=8e-2, band=None)
-    assert flips <= 0.002 * got.numel(), flips
+    check_codes(ista_fista.run(xd, pd, lam, T, **kw), g[key], phi, case=key)
   warm = g['warm_start'].cuda()
   keep_w = warm.clone()
   out = ista_fista.run(xd, pd, lam, T, initial_codes=warm)
-  check_codes(out, g['fista_warm'], phi)
+  check_codes(out, g['fista_warm'], phi, case='fista_warm')
   # the reference's own assertions (tests/ista_fista_1.py:45-54): nothing passed in is mutated
   assert torch.equal(xd, keep_x) and torch.equal(pd, keep_p) and torch.equal(warm, keep_w)
   assert not torch.allclose(out, warm)
@@ -87,7 +91,15 @@ def test_early_stopping_matches_reference_outputs():
                                       return_iters=True)
     got, iters = ista_fista.infer(xd, pd, lam, 1000, variant, None, 1e-3, False, False, 1)
     assert abs(iters - want_iters) <= 1, (iters, want_iters)
-    check_codes(got, g[key], phi, tol=2e-3, recon_tol=2e-3, band=None)
+    record_parity('test_early_stopping_matches_reference_outputs', key + '_iterations', got=iters, want=want_iters)
+    if iters == want_iters:
+      # same stopping iteration: the same iterate, so the ordinary tolerance applies
+      check_codes(got, g[key], phi, case=key + ' (same stopping iteration)')
+    else:
+      # the global statistic crossed epsilon one iteration apart: one more (or one fewer) step of the same sequence
+      check_codes(got, g[key], phi, tol=2e-3, recon_tol=2e-3, band=None, case=key + ' (stopped one iteration apart)')
+      same = oracle.ista_fista(x, phi, lam, iters, variant=variant)
+      check_codes(got, same, phi, case=key + ' (against the oracle stopped at our iteration)')
 
 
 @pytest.mark.parametrize('name', ['inference_config1', 'inference_overcomplete'])
@@ -96,7 +108,95 @@ def test_baseline_config_shapes_against_reference_outputs(name):
   g = load_golden(name)
   phi = g['dictionary']
   got = ista_fista.run(g['images'].cuda(), phi.cuda(), g['sparsity_weight'], g['num_iters'])
-  check_codes(got, g['fista'], phi)
+  check_codes(got, g['fista'], phi, case=name)
+
+
+PROX_VARIANTS = (('soft', {}), ('nonneg', {'nonnegative_only': True}), ('hard', {'hard_threshold': True}),
+                 ('hard_nonneg', {'hard_threshold': True, 'nonnegative_only': True}))
+TIE_BAND = 1e-5   # relative half-width of the band around the cutoff inside which a pre-threshold value is a tie
+
+
+def pre_threshold_ties(x, phi, warm, lam, nonneg):
+  """Elements whose pre-threshold value u = y - eta ((y Phi - x) Phi^T) (float64, y = the warm start: first iteration)
+  lies within TIE_BAND * max(1, |u|) of the cutoff theta = lambda * eta: there the prox decision is a coin toss between
+  two correctly rounded implementations."""
+  xd, pd, yd = x.double(), phi.double(), warm.double()
+  eta = 1.0 / float(torch.linalg.eigvalsh(pd.t() @ pd)[-1])
+  u = yd - eta * ((yd @ pd - xd) @ pd.t())
+  mag = u if nonneg else u.abs()
+  return (mag - lam * eta).abs() <= TIE_BAND * torch.clamp(u.abs(), min=1.0)
+
+
+@pytest.mark.parametrize('precision', ['bf16x3', 'bf16x6'])
+def test_single_step_of_every_threshold_variant_against_the_reference(precision):
+  """Pins the prox kernels themselves (ista_fista.py:105-121): ONE iteration from the reference's own iterate a_{T-1},
+  all four thresholds, ISTA and FISTA, in both parity precisions. Elements whose pre-threshold value ties with the
+  cutoff are excluded and counted; every other element must match at 1e-4 with an identical support."""
+  import vision_transform_codes_b200 as pkg
+  ista_fista = modules()[0]
+  g = load_golden('threshold_steps')
+  x, phi, lam = g['images'], g['dictionary'], g['sparsity_weight']
+  xd, pd = x.cuda(), phi.cuda()
+  prec = pkg.PRECISIONS[precision]
+  for variant in ('ista', 'fista'):
+    for name, kw in PROX_VARIANTS:
+      warm = g['%s_%s_warm' % (variant, name)]
+      want = g['%s_%s_one' % (variant, name)]
+      got, _ = ista_fista.infer(xd, pd, lam, 1, variant, warm.cuda(), None, kw.get('nonnegative_only', False),
+                                kw.get('hard_threshold', False), 1, precision=prec)
+      got = got.cpu()
+      ties = pre_threshold_ties(x, phi, warm, lam, kw.get('nonnegative_only', False))
+      keep = ~ties
+      err = float(torch.norm((got - want)[keep]) / torch.norm(want[keep]))
+      flips = int((((got != 0) != (want != 0)) & keep).sum())
+      record_parity('test_single_step_of_every_threshold_variant_against_the_reference',
+                    '%s %s %s' % (precision, variant, name), rel_l2=err, flips_outside_ties=flips,
+                    ties_excluded=int(ties.sum()), tie_band=TIE_BAND, elements=got.numel(),
+                    flips_inside_ties=int((((got != 0) != (want != 0)) & ties).sum()))
+      assert err <= CODE_TOL, (precision, variant, name, err)
+      assert flips == 0, (precision, variant, name, flips)
+
+
+@pytest.mark.parametrize('steps', ['three'])
+def test_three_steps_of_every_threshold_variant_against_the_reference(steps):
+  """Three iterations from a_{T-1} (the FISTA momentum term is live from the third on), default precisions."""
+  ista_fista = modules()[0]
+  g = load_golden('threshold_steps')
+  x, phi, lam = g['images'], g['dictionary'], g['sparsity_weight']
+  for variant in ('ista', 'fista'):
+    for name, kw in PROX_VARIANTS:
+      got = ista_fista.run(x.cuda(), phi.cuda(), lam, 3, variant=variant,
+                           initial_codes=g['%s_%s_warm' % (variant, name)].cuda(), **kw)
+      check_codes(got, g['%s_%s_%s' % (variant, name, steps)], phi, case='%s %s' % (variant, name))
+
+
+def test_hard_threshold_trajectories_by_precision():
+  """Whole 60-iteration hard-threshold trajectories of inference_small.npz in every arithmetic mode, against the
+  reference in float32 AND the same reference code run in float64 (tests/golden/make_golden.py): the reference's own
+  float32 sensitivity is 1e-6 with no support flip, so what bf16x3 shows on these runs is ours -- hence hard-threshold
+  calls default to bf16x6 (config.hard_threshold_precision), which must meet the ordinary tolerance."""
+  import vision_transform_codes_b200 as pkg
+  ista_fista = modules()[0]
+  g, g64 = load_golden('inference_small'), load_golden('threshold_steps')
+  x, phi, lam, T = g['images'], g['dictionary'], g['sparsity_weight'], g['num_iters']
+  for key, variant, nonneg in (('fista_hard', 'fista', False), ('ista_hard_nonneg', 'ista', True)):
+    ref32, ref64 = g[key], g64[key + '_f64']
+    base = oracle.relative_l2(ref32.double(), ref64)
+    for precision in ('bf16x6', 'bf16x3', 'bf16'):
+      got, _ = ista_fista.infer(x.cuda(), phi.cuda(), lam, T, variant, None, None, nonneg, True, 1,
+                                precision=pkg.PRECISIONS[precision])
+      got = got.cpu()
+      err32 = oracle.relative_l2(got, ref32)
+      err64 = oracle.relative_l2(got.double(), ref64)
+      flips, _ = oracle.support_mismatches(got, ref32)
+      record_parity('test_hard_threshold_trajectories_by_precision', '%s %s' % (key, precision), rel_l2=err32,
+                    rel_l2_vs_float64_reference=err64, reference_float32_vs_float64=base, flips_total=flips,
+                    elements=got.numel())
+      if precision == 'bf16x6':
+        assert err32 <= CODE_TOL and flips == 0, (key, err32, flips)
+  # the default path of a hard-threshold call IS the strict one
+  assert pkg.config.inference_precision_code(True) == pkg.PRECISIONS['bf16x6']
+  assert pkg.config.inference_precision_code(False) == pkg.PRECISIONS['bf16x3']
 
 
 @pytest.mark.parametrize('precision,tol,rtol', [('bf16x6', 2e-5, 1e-5), ('bf16x3', CODE_TOL, RECON_TOL),
@@ -108,7 +208,8 @@ def test_precision_modes_on_overcomplete_shape(precision, tol, rtol):
   g = load_golden('inference_overcomplete')
   phi = g['dictionary']
   got = ista_fista.run(g['images'].cuda(), phi.cuda(), g['sparsity_weight'], g['num_iters'])
-  check_codes(got, g['fista'], phi, tol=tol, recon_tol=rtol, band=GUARD_BAND if precision != 'bf16' else None)
+  check_codes(got, g['fista'], phi, tol=tol, recon_tol=rtol, band=GUARD_BAND if precision != 'bf16' else None,
+              case=precision)
 
 
 @pytest.fixture
@@ -137,7 +238,7 @@ def test_both_formulations_against_reference_outputs(formulation, which, name):
   g = load_golden(name)
   phi = g['dictionary']
   got = ista_fista.run(g['images'].cuda(), phi.cuda(), g['sparsity_weight'], g['num_iters'])
-  check_codes(got, g['fista'], phi)
+  check_codes(got, g['fista'], phi, case='%s %s' % (which, name))
 
 
 @pytest.mark.parametrize('shape', [(130, 200, 100), (700, 328, 72)])

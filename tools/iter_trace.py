@@ -35,8 +35,9 @@ KIND = {1: 'G_BEGIN', 2: 'G_END', 3: 'R_ISSUE', 4: 'E_BEGIN', 5: 'E_SUB', 6: 'E_
 rows = sorted(((e & 0xFFFFFFFFFFFF), (e >> 56) & 255, (e >> 48) & 255) for e in ev)
 # keep the first launch (between the first START and the first STOP)
 t0 = None
+has_start = any(kind == 8 for _, kind, _ in rows)
 for clk, kind, idx in rows:
-  if kind == 8 and t0 is None:
+  if t0 is None and (kind == 8 or not has_start):
     t0 = clk
   if t0 is None:
     continue

@@ -5,7 +5,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libvtc_b200.so')
+# (VTC_B200_LIB: A/B timing of another build of the same library, tools/ab_build.sh)
+LIB_PATH = os.environ.get('VTC_B200_LIB') or os.path.join(_HERE, 'lib', 'libvtc_b200.so')
 
 VTC_OK, VTC_ERR_ARG, VTC_ERR_CUDA, VTC_ERR_WORKSPACE, VTC_ERR_UNSUPPORTED, VTC_ERR_NONFINITE = range(6)
 
@@ -20,6 +21,8 @@ SIGNATURES = {
     'vtc_profile_enable': (_int, [_int]),
     'vtc_profile_last': (_int, [_c.POINTER(_f32), _c.POINTER(_f32), _c.POINTER(_int), _c.POINTER(_int),
                                 _c.POINTER(_f32), _c.POINTER(_f32)]),
+    'vtc_profile_history_count': (_int, []),
+    'vtc_profile_history': (_int, [_int] + [_c.POINTER(_f32)] * 4),
     'vtc_set_formulation': (_int, [_int]),
     'vtc_get_formulation': (_int, [_i64, _i64]),
     'vtc_set_fused_iteration': (_int, [_int]),

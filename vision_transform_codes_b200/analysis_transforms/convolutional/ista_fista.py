@@ -74,7 +74,7 @@ def infer(images_padded, dictionary, kernel_stride, padding_dims, sparsity_weigh
   codes = torch.empty((B, S, SH, SW), dtype=torch.float32, device=device)
   if B == 0:
     return codes, int(num_iters)   # an empty batch: codes of shape (0, s, sh, sw), as the reference's loop leaves it
-  prec = config.precision_code() if precision is None else precision
+  prec = config.inference_precision_code(hard_threshold) if precision is None else precision
   with torch.cuda.device(device):
     nbytes = lib.vtc_fista_conv_workspace_bytes(B, C, H, W, S, KH, KW, SY, SX, prec)
     if nbytes == 0:

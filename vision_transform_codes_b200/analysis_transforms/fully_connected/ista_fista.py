@@ -3,9 +3,12 @@ Iterative Shrinkage/Thresholding (ISTA / FISTA) for fully-connected sparse infer
 
 Drop-in for the reference module of the same dotted name
 (vision_transform_codes/analysis_transforms/fully_connected/ista_fista.py:14-148): same signature, same return
-value, same exceptions. The arithmetic runs in ``vtc_fista_fc`` (include/vtc_b200.h): Gram form
-``a <- prox(y - eta (y G - b))`` with ``G = Phi Phi^T`` and ``b = x Phi^T`` precomputed by tcgen05 GEMMs, every
-iteration one tcgen05 GEMM whose epilogue applies the gradient step, the threshold and the FISTA momentum.
+value, same exceptions. The arithmetic runs in ``vtc_fista_fc`` (include/vtc_b200.h), which picks the contraction
+with fewer flops: for s > 2 n the reference's own synthesis form ``a <- prox(y - eta ((y Phi - x) Phi^T))`` -- all
+iterations in ONE persistent launch of the panel-resident tcgen05 kernel when n <= 256 (csrc/fista_iter_kernel.cuh),
+two launches per iteration otherwise -- and for s <= 2 n the Gram form ``a <- prox(y - eta (y G - b))`` with
+``G = Phi Phi^T`` and ``b = x Phi^T`` precomputed by tcgen05 GEMMs. In every schedule the gradient step, the threshold
+and the FISTA momentum are the epilogue of the contraction (DESIGN.md sections 2 and 4).
 """
 import ctypes
 import os
@@ -51,7 +54,7 @@ def infer(images, dictionary, sparsity_weight, num_iters, variant, initial_codes
     if tuple(initial_codes.shape) != (B, S):
       raise ValueError('initial_codes must have shape (b, s)')
     init = initial_codes.contiguous()
-  prec = config.precision_code() if precision is None else precision
+  prec = config.inference_precision_code(hard_threshold) if precision is None else precision
   with torch.cuda.device(device):
     nbytes = lib.vtc_fista_workspace_bytes(B, S, D, prec)
     ws = _lib.workspace(nbytes, device, 'fista')

@@ -13,7 +13,7 @@ namespace vtc {
 // block == 0: row-major, part p in columns [p*Cp, (p+1)*Cp). block > 0 (even, divides Cp): tile-contiguous layout
 // [part][Cp/block][R][block], so that a (128 rows x block columns) operand tile is one contiguous span.
 __global__ void split_rows_kernel(const float* __restrict__ in, int64_t ld, int64_t R, int64_t C, int64_t Cp,
-                                  int nparts, int block, __nv_bfloat16* __restrict__ out) {
+                                  int nparts, int block, __nv_bfloat16* __restrict__ out, float scale = 1.f) {
   const int64_t half = Cp / 2;
   const int64_t total = R * half;
   const int64_t pitch = static_cast<int64_t>(nparts) * Cp;
@@ -21,8 +21,8 @@ __global__ void split_rows_kernel(const float* __restrict__ in, int64_t ld, int6
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t r = i / half;
     const int64_t c = (i - r * half) * 2;
-    float v0 = (c < C) ? in[r * ld + c] : 0.f;
-    float v1 = (c + 1 < C) ? in[r * ld + c + 1] : 0.f;
+    float v0 = (c < C) ? scale * in[r * ld + c] : 0.f;       // scale = +-1: exact
+    float v1 = (c + 1 < C) ? scale * in[r * ld + c + 1] : 0.f;
     for (int p = 0; p < nparts; ++p) {
       const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
       v0 = __fsub_rn(v0, __bfloat162float(h0));
@@ -44,6 +44,40 @@ __global__ void unblock_f32_kernel(const float* __restrict__ in, int64_t R, int6
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t r = i / C, c = i - r * C;
     out[r * ld + c] = in[((c / 16) * R + r) * 16 + (c % 16)];
+  }
+}
+
+// "Quad-blocked" fp32 state of the second-generation iteration kernel (fista_iter2_kernel.cuh): sub-tile (col block cb
+// of 16 atoms, row block rb of 128 rows) is one contiguous 8 KB block [4 quads][128 rows][4 floats] at
+// ((cb * RB + rb) * 2048) floats. Rows at or beyond R and columns at or beyond C are zero.
+__global__ void block_quad_kernel(const float* __restrict__ in, int64_t ld, int64_t R, int64_t C, int64_t RB, int64_t CB,
+                                  float* __restrict__ out) {
+  const int64_t total = CB * RB * 512;   // float4 slots
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t blk = i / 512;
+    const int w = static_cast<int>(i - blk * 512);
+    const int quad = w / 128, row = w % 128;
+    const int64_t cb = blk / RB, rb = blk - cb * RB;
+    const int64_t r = rb * 128 + row, c = cb * 16 + quad * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < R) {
+      if (c + 0 < C) v.x = in[r * ld + c + 0];
+      if (c + 1 < C) v.y = in[r * ld + c + 1];
+      if (c + 2 < C) v.z = in[r * ld + c + 2];
+      if (c + 3 < C) v.w = in[r * ld + c + 3];
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+__global__ void unblock_quad_kernel(const float* __restrict__ in, int64_t R, int64_t C, int64_t RB,
+                                    float* __restrict__ out, int64_t ld) {
+  const int64_t total = R * C;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / C, c = i - r * C;
+    const int64_t cb = c / 16, rb = r / 128;
+    out[r * ld + c] = in[(cb * RB + rb) * 2048 + ((c % 16) / 4) * 512 + (r % 128) * 4 + (c % 4)];
   }
 }
 
@@ -812,13 +846,14 @@ __global__ void spectrum_filter_kernel(float2* __restrict__ spectrum, int64_t n,
 // betas[k] = float((t_k - 1) / t_{k+1}), betas[0] = 0; all zero for ISTA. The recurrence is sequential: one thread, IEEE
 // double operations without contraction, so the table is bit-identical to the host-side double arithmetic of the
 // reference. (A device table instead of a host-to-device copy keeps a call capturable into a CUDA graph.)
-__global__ void fista_betas_kernel(float* __restrict__ betas, int num_iters, int fista) {
+// Window form: entries k_lo .. num_iters are written to betas[k - k_lo] (runs longer than the table take it in windows).
+__global__ void fista_betas_kernel(float* __restrict__ betas, int num_iters, int fista, int k_lo = 0) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  betas[0] = 0.f;
+  if (k_lo == 0) betas[0] = 0.f;
   double t = 1.0;
   for (int k = 1; k <= num_iters; ++k) {
     const double t_next = __ddiv_rn(__dadd_rn(1.0, __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(__dmul_rn(4.0, t), t)))), 2.0);
-    betas[k] = fista ? static_cast<float>(__ddiv_rn(__dadd_rn(t, -1.0), t_next)) : 0.f;
+    if (k >= k_lo) betas[k - k_lo] = fista ? static_cast<float>(__ddiv_rn(__dadd_rn(t, -1.0), t_next)) : 0.f;
     t = t_next;
   }
 }

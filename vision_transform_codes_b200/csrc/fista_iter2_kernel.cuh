@@ -1,0 +1,740 @@
+// Panel-resident ISTA/FISTA iterations, second generation (sm_100a). Same algorithm, job structure, persistent schedule
+// and bit-exact arithmetic as fista_iter_kernel.cuh (read that header first); what changed is how the epilogue is fed,
+// after the round-2 ablations (profiles/README.md) showed that the first kernel was bound by its own handshakes and by
+// the bytes its rings could keep in flight, not by HBM, the tensor pipe or shared-memory bandwidth:
+//
+//   * work unit of the epilogue = one 32-atom CHUNK (two 16-column sub-tiles), owned by ONE group of four warps: the
+//     y stage of a chunk has a single writer group, and the y-ring handshake (wait for the stage, publish it to the R
+//     issuer across the CTA pair) happens once per chunk instead of once per sub-tile and group;
+//   * a_{k-2} does not go through shared memory: the math warps read it with coalesced ld.global (prefetched one
+//     sub-tile ahead into registers) from a state layout made for it -- every sub-tile is one contiguous 8 KB block
+//     [4 column quads][128 rows][4 floats], so a warp's 128-bit load covers 512 contiguous bytes. Only a_{k-1} is
+//     staged (1-D bulk copy, no tensor map) and a_k is written over it in place (each thread touches its own row
+//     only): in/out stages are 8 KB instead of 16, twelve of them (four per group) fit where six did;
+//   * G and R MMAs are issued by two warps that block on their own barriers; the operand "full" barriers take one
+//     arrival (the leader's expect_tx for both CTAs' bytes) instead of a cross-CTA arrive per stage.
+//
+// State buffers (IterParams2::state) are "quad-blocked": [col block cb = atom / 16][row block rb = row / 128][quad][row % 128][4].
+// The caller converts a warm start into that layout and the result back to row-major (block_quad / unblock_quad
+// kernels in aux_kernels.cuh); rows beyond the batch and atoms beyond S are zero and stay zero.
+//
+// Warp roles (20 warps):
+//   0        TMA producer of the G operand ring (r_op K blocks + Phi tile halves), both CTAs
+//   1        tcgen05.mma issuer of G (leader CTA)
+//   2        TMEM allocator, then bulk / TMA stores (a_k sub-tiles, r_op parts)
+//   3        bulk loader of a_{k-1}
+//   4 .. 15  epilogue math, three groups of four warps (one warp per TMEM lane quarter) on chunks round-robin
+//   16       TMA producer of the Phi^T chunk ring (B operand of R), both CTAs
+//   17       tcgen05.mma issuer of R (leader CTA)
+//   18, 19   none (they complete the fifth warpgroup)
+#pragma once
+#include "fista_iter_kernel.cuh"
+
+namespace vtc {
+
+template <int P>
+struct Iter2Cfg {
+  static_assert(P == 1 || P == 2, "parts");
+  static constexpr int GROUPS = 3;
+  static constexpr int MATH_WARPS = 4 * GROUPS;
+  static constexpr int PT_WARP = 4 + MATH_WARPS;
+  static constexpr int R_WARP = PT_WARP + 1;
+  // 20 warps = five whole warpgroups (setmaxnreg is a warpgroup-wide instruction); warps 18 and 19 have no role
+  static constexpr int THREADS = 32 * 20;
+  // The launch gives every warp the compiled 96 registers (5 warps per scheduler): the CTA's pool is 20 x 32 x 96 =
+  // 61440 registers. The eight non-math warps hand most of theirs back and the twelve math warps take 128:
+  // (8 x 40 + 12 x 128) x 32 = 59392 <= 61440 (setmaxnreg.inc blocks for ever when the pool cannot cover it).
+  static constexpr int REGS_MATH = 128, REGS_OTHER = 40;
+  static_assert((8 * REGS_OTHER + MATH_WARPS * REGS_MATH) * 32 <= THREADS * 96, "register pool of the CTA");
+  static constexpr int BK = (P == 1) ? 64 : 32;          // K extent of a G stage
+  static constexpr int SPAN = BK * 2;
+  static constexpr int A_TILE = BLOCK_M * SPAN;           // one part of this CTA's 128 rows of r_op
+  static constexpr int B_TILE = (IT_BN / 2) * SPAN;       // one part of this CTA's 64 atoms of the Phi tile
+  static constexpr int G_STAGE = P * (A_TILE + B_TILE);
+  static constexpr int CHUNK = 32;                        // atoms per epilogue unit = K extent of one group of R MMAs
+  static constexpr int Y_TILE = BLOCK_M * CHUNK * 2;      // one part of y: 128 rows x 32 atoms, SWIZZLE_64B
+  static constexpr int Y_STAGE = P * Y_TILE;
+  static constexpr int PT_TILE = (IT_RN / 2) * CHUNK * 2; // one part of this CTA's 128 pixel rows of Phi^T
+  static constexpr int PT_STAGE = P * PT_TILE;
+  static constexpr int IN_STAGE = EPI_ARRAY_BYTES;        // a_{k-1} in, a_k (or the r parts of a panel-end sub-tile) out
+  static constexpr int IN_STAGES = 12;                    // four per group: two chunks
+  static constexpr int G_STAGES = (P == 2) ? 2 : 3;
+  static constexpr int Y_STAGES = 3;
+  static constexpr int PT_STAGES = (P == 2) ? 2 : 4;
+  static constexpr int OFF_G = 0;
+  static constexpr int OFF_Y = OFF_G + G_STAGES * G_STAGE;
+  static constexpr int OFF_PT = OFF_Y + Y_STAGES * Y_STAGE;
+  static constexpr int OFF_IN = OFF_PT + PT_STAGES * PT_STAGE;
+  static constexpr int OFF_BAR = OFF_IN + IN_STAGES * IN_STAGE;
+  static constexpr int B_G_FULL = 0;
+  static constexpr int B_G_EMPTY = B_G_FULL + G_STAGES;
+  static constexpr int B_PT_FULL = B_G_EMPTY + G_STAGES;
+  static constexpr int B_PT_EMPTY = B_PT_FULL + PT_STAGES;
+  static constexpr int B_Y_FULL = B_PT_EMPTY + PT_STAGES;
+  static constexpr int B_Y_EMPTY = B_Y_FULL + Y_STAGES;
+  static constexpr int B_ACCG_FULL = B_Y_EMPTY + Y_STAGES;
+  static constexpr int B_ACCG_EMPTY = B_ACCG_FULL + 2;
+  static constexpr int B_ACCR_FULL = B_ACCG_EMPTY + 2;
+  static constexpr int B_ACCR_EMPTY = B_ACCR_FULL + 1;
+  static constexpr int B_IN_FULL = B_ACCR_EMPTY + 1;
+  static constexpr int B_IN_FREE = B_IN_FULL + IN_STAGES;
+  static constexpr int B_OUT_FULL = B_IN_FREE + IN_STAGES;
+  static constexpr int NUM_BARRIERS = B_OUT_FULL + IN_STAGES;
+  static constexpr int SMEM_TOTAL = OFF_BAR + NUM_BARRIERS * 8 + 16;
+  static constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
+  static constexpr int NPAIRS = (P == 1) ? 1 : 3;
+  static constexpr int STORES_IN_FLIGHT = 1;
+  // a stage is always consumed by the same group (stage e belongs to group (e % 6) / 2): a group sees the phases of
+  // its stages' barriers strictly in order
+  static_assert(IN_STAGES % (2 * GROUPS) == 0, "input stages must have a fixed owner group");
+  static_assert(P * EPI_PART_BYTES <= IN_STAGE, "r parts must fit a stage");
+  static_assert(SMEM_ALLOC <= 232448, "over the 227 KB shared memory limit");
+};
+
+struct IterParams2 {
+  CUtensorMap tmR;      // r_op (bf16 parts, tile-contiguous [part][Dp/BK][rows][BK]): box BK x 128, A operand of G
+  CUtensorMap tmPhi;    // phi_op (S x parts*Dp, row-major): box BK x 64, B operand of G
+  CUtensorMap tmPhiT;   // phiT_op (D x parts*Sp, row-major): box 32 x 128, SWIZZLE_64B, B operand of R
+  CUtensorMap tmROut;   // r_op as a store target: box 16 x 128, SWIZZLE_32B
+  float* state[3];      // quad-blocked fp32 code arrays: [0] the starting point a_0 (unused when init_zero), [1] a_k
+                        // for odd k, [2] a_k for even k (a_k overwrites a_{k-2} in place; the final iterate too)
+  const float* x;       // images, row-major (B x D), pitch ld_x floats (16-byte aligned rows)
+  long long ld_x;
+  int B, D;
+  int init_zero;        // a_0 = 0: iteration 1 loads no state at all
+  int num_panels;       // ceil(B / 256)
+  int S;
+  int num_n_tiles;      // ceil(S / 128)
+  int kb_g;             // Dp / BK: K blocks of G (= column blocks per part of r_op)
+  int phi_part_stride;  // Dp
+  int phiT_part_stride; // Sp
+  int nsub_r;           // Dp / 16: sub-tiles of r written at the panel end
+  int r_block_w;        // BK of r_op's layout
+  int k_first, k_count; // this launch runs iterations k_first .. k_first + k_count - 1 of every panel
+  int k_final;          // the iteration whose output is the result: no r_k produced (INT_MAX: the caller decides)
+  const float* betas;   // device: betas[k] = FISTA momentum coefficient of iteration k, betas[0] = 0
+  int* done;            // device, per panel: CTAs that have completed a job of this launch on it (nullptr: k_count == 1)
+  int prox, group, use_momentum;
+  const float* scalars;  // device: [0] = eta, [1] = theta
+  double* stat;          // optional: += sum |a_k - a_{k-1}|
+  unsigned long long* trace;
+  int ablate;            // timing experiments only (AblateBits; results are wrong when non-zero)
+  int l2_prefetch;       // sub-tiles of a_{k-2} prefetched into L2 by the loader alongside the a_{k-1} loads
+};
+
+// ---- 1-D bulk copies (no tensor map): contiguous global <-> shared, sizes and addresses multiples of 16 bytes
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+// state written by another SM earlier in this launch: L2 is the point of coherence, never a (possibly stale) L1 line
+__device__ __forceinline__ float4 ldg_cg_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_nc_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+template <int P>
+__global__ void __launch_bounds__(Iter2Cfg<P>::THREADS, 1) vtc_fista_iter2_kernel(const __grid_constant__ IterParams2 p) {
+  using C = Iter2Cfg<P>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sG = sbase + C::OFF_G, sY = sbase + C::OFF_Y, sPT = sbase + C::OFF_PT;
+  const uint32_t sIn = sbase + C::OFF_IN;
+  const uint32_t bar0 = sbase + C::OFF_BAR;
+  auto bar = [&](int idx) { return bar0 + 8 * idx; };
+  const uint32_t tmem_slot = bar0 + C::NUM_BARRIERS * 8;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = static_cast<int>(cluster_ctarank());
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int NT = p.num_n_tiles;
+  const long long total_jobs = static_cast<long long>(p.k_count) * p.num_panels;
+  const int my_jobs = total_jobs > cluster_id
+                          ? static_cast<int>((total_jobs - cluster_id + num_clusters - 1) / num_clusters) : 0;
+  const int my_tiles = my_jobs * NT;
+  struct Job {
+    int k, m0, panel, wait_target;
+    bool do_r, has_prev, has_prev2;
+    int prev, prev2, out;   // indices into state
+    float beta_prev, beta_next;
+  };
+  auto job_at = [&](int ji) {
+    Job j;
+    const long long ticket = cluster_id + static_cast<long long>(ji) * num_clusters;
+    const int ko = static_cast<int>(ticket / p.num_panels);
+    j.k = p.k_first + ko;
+    j.panel = static_cast<int>(ticket - static_cast<long long>(ko) * p.num_panels);
+    j.m0 = j.panel * PAIR_M + cta_rank * BLOCK_M;
+    j.wait_target = 2 * ko;   // both CTAs of every earlier job of this launch on this panel
+    j.do_r = j.k < p.k_final;
+    j.beta_prev = __ldg(p.betas + j.k - 1);
+    j.beta_next = __ldg(p.betas + j.k);
+    j.has_prev = !(j.k == 1 && p.init_zero);
+    j.has_prev2 = p.use_momentum != 0 && j.beta_prev != 0.f;
+    j.prev = (j.k == 1) ? 0 : (((j.k - 1) & 1) ? 1 : 2);
+    j.prev2 = (j.k & 1) ? 1 : 2;     // only read when has_prev2 (k >= 3)
+    j.out = (j.k & 1) ? 1 : 2;
+    return j;
+  };
+  // the data of job (k - 1, panel) must be complete before anything of job (k, panel) is read
+  auto wait_for_previous = [&](const Job& j, bool for_tma) {
+    if (p.done != nullptr && j.wait_target > 0) {
+      if (lane == 0) {
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(p.done + j.panel) < j.wait_target) {
+          if (++spins > (1u << 28)) {
+            printf("vtc_b200: job (k %d, panel %d) never saw its predecessor (block %d)\n", j.k, j.panel, (int)blockIdx.x);
+            __trap();
+          }
+        }
+      }
+      __syncwarp();
+      if (for_tma) fence_proxy_async_all();   // the acquired data is read through TMA / bulk copies (async proxy)
+    }
+  };
+  // chunks of tile nt (whole chunks; atoms at or beyond S are zero everywhere)
+  auto tile_chunks = [&](int nt) { return (min(IT_BN, p.S - nt * IT_BN) + C::CHUNK - 1) / C::CHUNK; };
+  int state_units = 0;   // chunks of one job
+  for (int nt = 0; nt < NT; ++nt) state_units += tile_chunks(nt);
+  const int pe_units = (p.nsub_r + 1) / 2;          // panel-end units: two 16-pixel sub-tiles of r each
+  const long long row_blocks = static_cast<long long>(p.num_panels) * 2;
+  // float offset of sub-tile (col block cb, this CTA's row block of panel) in a quad-blocked state array
+  auto state_offset = [&](int panel, int cb) {
+    return (static_cast<long long>(cb) * row_blocks + panel * 2 + cta_rank) * (EPI_ARRAY_BYTES / 4);
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmR);
+    tma_prefetch_desc(&p.tmPhi);
+    tma_prefetch_desc(&p.tmPhiT);
+    tma_prefetch_desc(&p.tmROut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::G_STAGES; ++s) {
+      // one arrival: the leader's expect_tx for BOTH CTAs' bytes (the peer's loads complete their bytes on the same
+      // barrier; bytes that land before the expect_tx leave the transaction count negative until it is posted)
+      mbar_init(bar(C::B_G_FULL + s), 1);
+      mbar_init(bar(C::B_G_EMPTY + s), 1);   // multicast tcgen05.commit
+    }
+    for (int s = 0; s < C::PT_STAGES; ++s) {
+      mbar_init(bar(C::B_PT_FULL + s), 1);
+      mbar_init(bar(C::B_PT_EMPTY + s), 1);
+    }
+    for (int s = 0; s < C::Y_STAGES; ++s) {
+      mbar_init(bar(C::B_Y_FULL + s), 2 * 4);     // 2 CTAs x the 4 warps of the chunk's group (leader's barrier)
+      mbar_init(bar(C::B_Y_EMPTY + s), 1);        // multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar(C::B_ACCG_FULL + a), 1);
+      mbar_init(bar(C::B_ACCG_EMPTY + a), 2 * C::MATH_WARPS);
+    }
+    mbar_init(bar(C::B_ACCR_FULL), 1);
+    mbar_init(bar(C::B_ACCR_EMPTY), 2 * C::MATH_WARPS);
+    for (int e = 0; e < C::IN_STAGES; ++e) {
+      mbar_init(bar(C::B_IN_FULL + e), 1);
+      mbar_init(bar(C::B_IN_FREE + e), 1);    // the storer, once the store of the stage's result has read it
+      mbar_init(bar(C::B_OUT_FULL + e), 4);   // the four math warps that wrote the result
+    }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const bool is_math = warp >= 4 && warp < 4 + C::MATH_WARPS;
+
+  if (!is_math) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_OTHER));
+  if (warp == 0) {
+    // ================================ G operand producer (both CTAs) ================================
+    Tracer trace(p, 0, lane == 0);
+    uint32_t it = 0;
+    for (int ji = 0; ji < my_jobs; ++ji) {
+      const Job job = job_at(ji);
+      const int m0 = job.m0;
+      wait_for_previous(job, true);   // r_op[panel] is the previous iteration's output
+      for (int nt = 0; nt < NT; ++nt) {
+        const int n0 = nt * IT_BN;
+        for (int kb = 0; kb < p.kb_g; ++kb, ++it) {
+          const int s = it % C::G_STAGES;
+          const uint32_t ph = (it / C::G_STAGES) & 1;
+          mbar_wait(bar(C::B_G_EMPTY + s), ph ^ 1);
+          if (elect_one_sync()) {
+            const uint32_t full = bar(C::B_G_FULL + s);
+            const bool load_b = !(ablate_of(p) & ABL_G_LOAD);
+            const bool load_a = load_b && !((ablate_of(p) & ABL_R_STREAM) && nt > 0);
+            if (leader) {
+              if (load_b) mbar_arrive_expect_tx(full, load_a ? 2 * C::G_STAGE : 2 * P * C::B_TILE);
+              else mbar_arrive(full);
+            }
+            const uint32_t dst = sG + s * C::G_STAGE;
+            trace(TR_G_LOAD, nt * p.kb_g + kb);
+#pragma unroll
+            for (int q = 0; q < P; ++q)
+              if (load_a) tma_load_3d_pair(dst + q * C::A_TILE, &p.tmR, full, 0, m0, q * p.kb_g + kb, kEvictNormal);
+#pragma unroll
+            for (int q = 0; q < P; ++q)
+              if (load_b) tma_load_2d_pair(dst + P * C::A_TILE + q * C::B_TILE, &p.tmPhi, full,
+                                           q * p.phi_part_stride + kb * C::BK, n0 + cta_rank * (IT_BN / 2), kEvictLast);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == C::PT_WARP) {
+    // ================================ Phi^T chunk producer (both CTAs) ================================
+    uint32_t it = 0;
+    for (int ji = 0; ji < my_jobs; ++ji) {
+      if (!job_at(ji).do_r) continue;
+      for (int nt = 0; nt < NT; ++nt) {
+        const int nch = tile_chunks(nt);
+        for (int c = 0; c < nch; ++c, ++it) {
+          const int s = it % C::PT_STAGES;
+          const uint32_t ph = (it / C::PT_STAGES) & 1;
+          mbar_wait(bar(C::B_PT_EMPTY + s), ph ^ 1);
+          if (elect_one_sync()) {
+            const uint32_t full = bar(C::B_PT_FULL + s);
+            const bool load_pt = !(ablate_of(p) & ABL_PT_LOAD);
+            if (leader) {
+              if (load_pt) mbar_arrive_expect_tx(full, 2 * C::PT_STAGE);
+              else mbar_arrive(full);
+            }
+#pragma unroll
+            for (int q = 0; q < P; ++q)
+              if (load_pt) tma_load_2d_pair(sPT + s * C::PT_STAGE + q * C::PT_TILE, &p.tmPhiT, full,
+                                            q * p.phiT_part_stride + nt * IT_BN + c * C::CHUNK, cta_rank * (IT_RN / 2),
+                                            kEvictLast);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ G MMA issuer (leader CTA) ================================
+    if (leader) {
+      constexpr uint32_t idesc_g = make_idesc_bf16(PAIR_M, IT_BN);
+      Tracer trace(p, 1, lane == 0);
+      uint32_t g_it = 0;
+      for (int g_tile = 0; g_tile < my_tiles; ++g_tile) {
+        const int acc = g_tile & 1;
+        mbar_wait(bar(C::B_ACCG_EMPTY + acc), ((g_tile >> 1) & 1) ^ 1);
+        const uint32_t d_tmem = tmem_base + acc * IT_BN;
+        uint32_t accumulate = 0;
+        for (int g_kb = 0; g_kb < p.kb_g; ++g_kb, ++g_it) {
+          const int s = g_it % C::G_STAGES;
+          mbar_wait(bar(C::B_G_FULL + s), (g_it / C::G_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t stage = sG + s * C::G_STAGE;
+          const bool last = (g_kb == p.kb_g - 1);
+          if (elect_one_sync()) {
+            if (g_kb == 0) trace(TR_G_BEGIN, g_tile);
+            if (last) trace(TR_G_END, g_tile);
+#pragma unroll
+            for (int pr = 0; pr < C::NPAIRS; ++pr) {
+              const uint64_t adesc = make_kmajor_desc(stage + pair_a(P, pr) * C::A_TILE, C::SPAN);
+              const uint64_t bdesc = make_kmajor_desc(stage + P * C::A_TILE + pair_b(P, pr) * C::B_TILE, C::SPAN);
+#pragma unroll
+              for (int k = 0; k < C::BK / UMMA_K; ++k) {
+                if (!(ablate_of(p) & ABL_G_MMA)) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_g, accumulate);
+                accumulate = 1;
+              }
+            }
+            umma_commit_pair(bar(C::B_G_EMPTY + s), 3);
+            if (last) umma_commit_pair(bar(C::B_ACCG_FULL + acc), 3);
+          }
+          accumulate = 1;
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == C::R_WARP) {
+    // ================================ R MMA issuer (leader CTA) ================================
+    if (leader) {
+      constexpr uint32_t idesc_r = make_idesc_bf16(PAIR_M, IT_RN);
+      const uint32_t acc_r = tmem_base + 2 * IT_BN;
+      uint32_t r_it = 0;  // running chunk index: y stage r_it % Y_STAGES, Phi^T stage r_it % PT_STAGES
+      int r_jobs = 0;     // jobs with an R so far (parity of the acc_r barriers)
+      for (int pi = 0; pi < my_jobs; ++pi) {
+        if (!job_at(pi).do_r) continue;   // the final iteration has no R
+        for (int nt = 0; nt < NT; ++nt) {
+          const int nch = tile_chunks(nt);
+          for (int c = 0; c < nch; ++c, ++r_it) {
+            const bool first = (nt == 0 && c == 0);
+            const int ys = r_it % C::Y_STAGES, ps = r_it % C::PT_STAGES;
+            mbar_wait(bar(C::B_Y_FULL + ys), (r_it / C::Y_STAGES) & 1);
+            mbar_wait(bar(C::B_PT_FULL + ps), (r_it / C::PT_STAGES) & 1);
+            // the panel-end epilogue of the previous job with an R must have drained acc_r before it is overwritten
+            if (first) mbar_wait(bar(C::B_ACCR_EMPTY), (r_jobs & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t ystage = sY + ys * C::Y_STAGE, pstage = sPT + ps * C::PT_STAGE;
+            const bool last = (nt == NT - 1) && (c == nch - 1);
+            if (elect_one_sync()) {
+              uint32_t accumulate = first ? 0u : 1u;
+#pragma unroll
+              for (int pr = 0; pr < C::NPAIRS; ++pr) {
+                const uint64_t adesc = make_kmajor_desc(ystage + pair_a(P, pr) * C::Y_TILE, C::CHUNK * 2);
+                const uint64_t bdesc = make_kmajor_desc(pstage + pair_b(P, pr) * C::PT_TILE, C::CHUNK * 2);
+#pragma unroll
+                for (int k = 0; k < C::CHUNK / UMMA_K; ++k) {
+                  if (!(ablate_of(p) & ABL_R_MMA)) umma_bf16_pair(acc_r, adesc + 2 * k, bdesc + 2 * k, idesc_r, accumulate);
+                  accumulate = 1;
+                }
+              }
+              umma_commit_pair(bar(C::B_Y_EMPTY + ys), 3);
+              umma_commit_pair(bar(C::B_PT_EMPTY + ps), 3);
+              if (last) umma_commit_pair(bar(C::B_ACCR_FULL), 3);
+            }
+            __syncwarp();
+          }
+        }
+        ++r_jobs;
+      }
+    }
+  } else if (warp == 3) {
+    // ================================ loader of a_{k-1} ================================
+    uint32_t q = 0;   // running sub-tile index: stage q % IN_STAGES
+    for (int ji = 0; ji < my_jobs; ++ji) {
+      const Job job = job_at(ji);
+      wait_for_previous(job, true);   // a_{k-1} (and the block a_k overwrites) belong to the previous iterations
+      const float* src = p.state[job.prev];
+      const float* src2 = p.state[job.prev2];
+      const int units = state_units + (job.do_r ? pe_units : 0);
+      for (int u = 0; u < units; ++u) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h, ++q) {
+          const int e = q % C::IN_STAGES;
+          mbar_wait(bar(C::B_IN_FREE + e), ((q / C::IN_STAGES) & 1) ^ 1);
+          if (elect_one_sync()) {
+            const uint32_t full = bar(C::B_IN_FULL + e);
+            if (u < state_units && job.has_prev && !(ablate_of(p) & ABL_STATE_LOAD)) {
+              const long long off = state_offset(job.panel, 2 * u + h);
+              mbar_arrive_expect_tx(full, EPI_ARRAY_BYTES);
+              bulk_load_1d(sIn + e * C::IN_STAGE, src + off, EPI_ARRAY_BYTES, full);
+              if (p.l2_prefetch && job.has_prev2) bulk_prefetch_l2(src2 + off, EPI_ARRAY_BYTES);
+            } else {
+              mbar_arrive(full);   // nothing staged: iteration 1 from zero, or a panel-end sub-tile (x is read directly)
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================ storer ================================
+    uint32_t q = 0;
+    for (int ji = 0; ji < my_jobs; ++ji) {
+      const Job job = job_at(ji);
+      float* dst = p.state[job.out];
+      const int units = state_units + (job.do_r ? pe_units : 0);
+      for (int u = 0; u < units; ++u) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h, ++q) {
+          const int e = q % C::IN_STAGES;
+          mbar_wait(bar(C::B_OUT_FULL + e), (q / C::IN_STAGES) & 1);
+          const uint32_t src = sIn + e * C::IN_STAGE;
+          if (elect_one_sync()) {
+            if (u < state_units) {
+              if (!(ablate_of(p) & ABL_STATE_STORE)) bulk_store_1d(dst + state_offset(job.panel, 2 * u + h), src, EPI_ARRAY_BYTES);
+            } else {
+              const int j = 2 * (u - state_units) + h;   // 16-pixel sub-tile of r
+              if (j < p.nsub_r) {
+                const int col = j * EPI_COLS;
+#pragma unroll
+                for (int part = 0; part < P; ++part)
+                  tma_store_3d(&p.tmROut, src + part * EPI_PART_BYTES, col % p.r_block_w, job.m0,
+                               part * p.kb_g + col / p.r_block_w);
+              }
+            }
+            bulk_commit();
+            if (q >= C::STORES_IN_FLIGHT) {
+              bulk_wait_read<C::STORES_IN_FLIGHT>();
+              mbar_arrive(bar(C::B_IN_FREE + (q - C::STORES_IN_FLIGHT) % C::IN_STAGES));
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (p.done != nullptr) {
+        // every store of this job has been performed: publish it to the pair that runs the panel's next iteration
+        if (elect_one_sync()) {
+          bulk_wait<0>();
+          fence_proxy_async_all();
+          red_release_gpu_add(p.done + job.panel, 1);
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one_sync()) bulk_wait<0>();
+    __syncwarp();
+  }
+  } else {
+    // ================================ epilogue math ================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_MATH));
+    const int group = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t sw64 = (row >> 1) & 3;
+    const uint32_t sw32 = (row >> 2) & 1;
+    UpdateArgs ua;
+    ua.prox = p.prox, ua.group = p.group, ua.use_momentum = p.use_momentum;
+    ua.eta = __ldg(p.scalars + 0), ua.theta = __ldg(p.scalars + 1);
+    ua.want_stat = p.stat != nullptr;
+    float stat_local = 0.f;
+    Tracer trace(p, 2, warp == 4 && lane == 0);
+    uint32_t uq = 0;    // running unit index (all units of all jobs): group uq % 3, stages 2 uq, 2 uq + 1 (mod 12)
+    uint32_t yc = 0;    // running chunk index of the jobs with an R: y stage yc % 3
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t row_in = row * 16;            // this thread's 16 bytes inside a quad plane of a stage
+    int t = 0;          // running atom tile: accumulator t & 1
+    int r_jobs = 0;
+    for (int pi = 0; pi < my_jobs; ++pi) {
+      const Job job = job_at(pi);
+      const bool has_prev = job.has_prev, has_prev2 = job.has_prev2;
+      ua.in_mask = has_prev2 ? 5 : 1;
+      ua.beta_prev = job.beta_prev, ua.beta_next = job.beta_next;
+      if (has_prev2) wait_for_previous(job, false);   // a_{k-2} is read with plain loads by this warp
+      const float* prev2 = p.state[job.prev2] + row * 4;
+      // a_{k-2} of this group's NEXT sub-tile, loaded one sub-tile ahead (the group's units inside a job are
+      // u_first, u_first + 3, ...; column block of (unit u, half h) = 2 u + h)
+      float4 pf[4];
+      auto prefetch_prev2 = [&](int cb) {
+        const float* src = prev2 + state_offset(job.panel, cb);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) pf[ch] = ldg_cg_v4(src + ch * (BLOCK_M * 4));
+      };
+      {
+        const int u_first = (group + C::GROUPS - static_cast<int>(uq % C::GROUPS)) % C::GROUPS;
+        if (has_prev2 && u_first < state_units) prefetch_prev2(2 * u_first);
+      }
+      int u = 0;   // unit inside the job
+      for (int nt = 0; nt < NT; ++nt, ++t) {
+        const int nch = tile_chunks(nt);
+        const int acc = t & 1;
+        mbar_wait(bar(C::B_ACCG_FULL + acc), (t >> 1) & 1);
+        tc_fence_after();
+        trace(TR_E_BEGIN, pi * (NT + 1) + nt);
+        const uint32_t t_row = lane_base + acc * IT_BN;
+        const uint32_t drained_bar = bar(C::B_ACCG_EMPTY + acc);
+        // chunks of this tile that belong to this warp's group: c0, c0 + 3, ...
+        const int c0 = (group + C::GROUPS - static_cast<int>((uq + u) % C::GROUPS)) % C::GROUPS;
+        const int c_last = (c0 < nch) ? c0 + ((nch - 1 - c0) / C::GROUPS) * C::GROUPS : -1;
+        if (c_last < 0) {
+          __syncwarp();
+          if (lane == 0) {
+            tc_fence_before();
+            mbar_arrive_remote(drained_bar, 0);
+          }
+        }
+        for (int c = c0; c < nch; c += C::GROUPS) {
+          const uint32_t unit = uq + u + c;
+          const uint32_t chunk = yc + u + c;
+          const int ys = chunk % C::Y_STAGES;
+          bool y_ready = !job.do_r;
+          const uint32_t ystage = sY + ys * C::Y_STAGE + row * (C::CHUNK * 2);
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t q = 2 * unit + h;
+            const int e = q % C::IN_STAGES;
+            uint32_t v[16];
+            trace(TR_E_SUB, 2 * c + h);
+            if (!(ablate_of(p) & ABL_TMEM_LD)) tmem_ld16(t_row + (2 * c + h) * EPI_COLS, v);
+            else {
+#pragma unroll
+              for (int x = 0; x < 16; ++x) v[x] = 0u;
+            }
+            float in[3][16];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const float4 b = has_prev2 ? pf[ch] : make_float4(0.f, 0.f, 0.f, 0.f);
+              in[2][4 * ch + 0] = b.x, in[2][4 * ch + 1] = b.y, in[2][4 * ch + 2] = b.z, in[2][4 * ch + 3] = b.w;
+            }
+            if (has_prev2) {
+              const int un = (h == 0) ? u + c : u + c + C::GROUPS;   // unit of this group's next sub-tile
+              if (un < state_units) prefetch_prev2(2 * un + (h == 0 ? 1 : 0));
+            }
+            mbar_wait(bar(C::B_IN_FULL + e), (q / C::IN_STAGES) & 1);
+            trace(TR_E_IN, 2 * c + h);
+            const uint32_t in_stage = sIn + e * C::IN_STAGE + row_in;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (has_prev && !(ablate_of(p) & ABL_STATE_LSU)) a = lds128(in_stage + ch * (BLOCK_M * 16));
+              in[0][4 * ch + 0] = a.x, in[0][4 * ch + 1] = a.y, in[0][4 * ch + 2] = a.z, in[0][4 * ch + 3] = a.w;
+              in[1][4 * ch + 0] = 0.f, in[1][4 * ch + 1] = 0.f, in[1][4 * ch + 2] = 0.f, in[1][4 * ch + 3] = 0.f;
+            }
+            tmem_ld_wait();
+            trace(TR_E_LD, 2 * c + h);
+            if (c == c_last && h == 1) {   // this warp has drained its share of the accumulator
+              __syncwarp();
+              if (lane == 0) {
+                tc_fence_before();
+                mbar_arrive_remote(drained_bar, 0);
+              }
+            }
+            float outv[16], partv[16];
+            fista_update16(ua, v, in, outv, partv, stat_local);
+            trace(TR_E_CMP, 2 * c + h);
+            // a_k over a_{k-1}, in place: every thread reads and writes its own 4 x 16 bytes only
+            if (!(ablate_of(p) & ABL_STATE_LSU)) {
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch)
+                sts128(in_stage + ch * (BLOCK_M * 16), outv[4 * ch], outv[4 * ch + 1], outv[4 * ch + 2], outv[4 * ch + 3]);
+            }
+            if (job.do_r) {
+              // y_k parts straight into the A operand of R: K-major 64-byte rows (SWIZZLE_64B), this sub-tile is the
+              // 32-byte half h of the row
+              if (!y_ready) {
+                mbar_wait(bar(C::B_Y_EMPTY + ys), ((chunk / C::Y_STAGES) & 1) ^ 1);
+                y_ready = true;
+              }
+              trace(TR_E_YW, 2 * c + h);
+              const uint32_t c2 = 2 * h;
+              if (!(ablate_of(p) & ABL_Y_STS)) split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
+                const uint32_t prow = ystage + part * C::Y_TILE;
+                sts128u(prow + (((c2 + 0) ^ sw64) << 4), w32[0], w32[1], w32[2], w32[3]);
+                sts128u(prow + (((c2 + 1) ^ sw64) << 4), w32[4], w32[5], w32[6], w32[7]);
+              });
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(bar(C::B_OUT_FULL + e));
+              if (h == 1 && job.do_r) mbar_arrive_remote(bar(C::B_Y_FULL + ys), 0);
+            }
+            trace(TR_E_ARR, 2 * c + h);
+          }
+        }
+        trace(TR_E_END, pi * (NT + 1) + nt);
+        u += nch;
+      }
+      uq += state_units;
+      if (job.do_r) {
+        yc += state_units;
+        // ---- panel end: r_k = acc_r - x -> bf16 parts -> r_op[panel]. x is read straight from the caller's row-major
+        // images, one sub-tile ahead (the first one before the wait for the synthesis accumulator)
+        const long long grow = static_cast<long long>(job.m0) + row;
+        const float* xrow = p.x + grow * p.ld_x;
+        const bool row_ok = grow < p.B;
+        float4 px[4];
+        auto prefetch_x = [&](int j) {
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const int col = j * EPI_COLS + 4 * ch;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_ok) {
+              if (col + 4 <= p.D) {
+                a = ldg_nc_v4(xrow + col);
+              } else {
+                if (col + 0 < p.D) a.x = __ldg(xrow + col + 0);
+                if (col + 1 < p.D) a.y = __ldg(xrow + col + 1);
+                if (col + 2 < p.D) a.z = __ldg(xrow + col + 2);
+              }
+            }
+            px[ch] = a;
+          }
+        };
+        {
+          const int c_first = (group + C::GROUPS - static_cast<int>(uq % C::GROUPS)) % C::GROUPS;
+          if (2 * c_first < p.nsub_r) prefetch_x(2 * c_first);
+        }
+        mbar_wait(bar(C::B_ACCR_FULL), r_jobs & 1);
+        tc_fence_after();
+        trace(TR_E_BEGIN, pi * (NT + 1) + NT);
+        ++r_jobs;
+        const uint32_t t_row = lane_base + 2 * IT_BN;
+        const uint32_t drained_bar = bar(C::B_ACCR_EMPTY);
+        const int c0 = (group + C::GROUPS - static_cast<int>(uq % C::GROUPS)) % C::GROUPS;
+        const int c_last = (c0 < pe_units) ? c0 + ((pe_units - 1 - c0) / C::GROUPS) * C::GROUPS : -1;
+        if (c_last < 0) {
+          __syncwarp();
+          if (lane == 0) {
+            tc_fence_before();
+            mbar_arrive_remote(drained_bar, 0);
+          }
+        }
+        for (int c = c0; c < pe_units; c += C::GROUPS) {
+          const uint32_t unit = uq + c;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t q = 2 * unit + h;
+            const int e = q % C::IN_STAGES;
+            const int j = 2 * c + h;   // 16-pixel sub-tile of r
+            const bool real = j < p.nsub_r;
+            uint32_t v[16];
+            float xin[16];
+            if (real) {
+              tmem_ld16(t_row + j * EPI_COLS, v);
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch)
+                xin[4 * ch + 0] = px[ch].x, xin[4 * ch + 1] = px[ch].y, xin[4 * ch + 2] = px[ch].z, xin[4 * ch + 3] = px[ch].w;
+              // x of this group's next sub-tile of r
+              const int jn = (h == 0) ? j + 1 : 2 * (c + C::GROUPS);
+              if (jn < p.nsub_r) prefetch_x(jn);
+            }
+            mbar_wait(bar(C::B_IN_FULL + e), (q / C::IN_STAGES) & 1);
+            if (real) {
+              tmem_ld_wait();
+              if (c == c_last && (h == 1 || j + 1 >= p.nsub_r)) {
+                __syncwarp();
+                if (lane == 0) {
+                  tc_fence_before();
+                  mbar_arrive_remote(drained_bar, 0);
+                }
+              }
+              float partv[16];
+#pragma unroll
+              for (int x = 0; x < 16; ++x) partv[x] = __uint_as_float(v[x]) - xin[x];  // r_k = y_k Phi - x
+              const uint32_t out_stage = sIn + e * C::IN_STAGE;
+              split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
+                const uint32_t prow = out_stage + part * EPI_PART_BYTES + row * 32;
+                sts128u(prow + ((0 ^ sw32) << 4), w32[0], w32[1], w32[2], w32[3]);
+                sts128u(prow + ((1 ^ sw32) << 4), w32[4], w32[5], w32[6], w32[7]);
+              });
+              fence_proxy_async_smem();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(C::B_OUT_FULL + e));
+          }
+        }
+        trace(TR_E_END, pi * (NT + 1) + NT);
+        uq += pe_units;
+      }
+    }
+    if (p.stat) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) stat_local += __shfl_xor_sync(0xffffffffu, stat_local, o);
+      if (lane == 0) atomicAdd(p.stat, static_cast<double>(stat_local));
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+}
+
+}  // namespace vtc

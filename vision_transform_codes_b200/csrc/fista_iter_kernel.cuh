@@ -30,13 +30,14 @@
 //
 // Requirements (the host falls back to the two-launch schedule otherwise): D <= 256, P <= 2.
 //
-// Warp roles (4 + 4 * GROUPS + 1 warps):
+// Warp roles (4 + 4 * GROUPS + 2 warps):
 //   0        TMA producer of the G operand ring (r_op K blocks + Phi tile halves), both CTAs
-//   1        tcgen05.mma issuer (leader CTA)
+//   1        tcgen05.mma issuer of G (leader CTA)
 //   2        TMEM allocator, then TMA stores (a_k sub-tiles, r_op parts)
 //   3        TMA loader of the epilogue inputs (a_{k-1}, a_{k-2}; x at the panel end)
 //   4 ..     epilogue math, GROUPS groups of four warps on sub-tiles round-robin
-//   last     TMA producer of the Phi^T chunk ring (B operand of R), both CTAs
+//   last - 1 TMA producer of the Phi^T chunk ring (B operand of R), both CTAs
+//   last     tcgen05.mma issuer of R (leader CTA)
 #pragma once
 #include "gemm_kernel.cuh"
 
@@ -59,8 +60,12 @@ struct IterCfg {
   // epilogue math: GROUPS groups of four warps (one warp per TMEM lane quarter) on sub-tiles round-robin
   static constexpr int GROUPS = (V == 1) ? 2 : 3;
   static constexpr int MATH_WARPS = 4 * GROUPS;
-  static constexpr int PT_WARP = 4 + MATH_WARPS;           // Phi^T chunk producer: the last warp
-  static constexpr int THREADS = 32 * (PT_WARP + 1);
+  static constexpr int PT_WARP = 4 + MATH_WARPS;           // Phi^T chunk producer
+  // bf16x3: G and R MMAs are issued by two warps (this one more); plain bf16 keeps the single polling issuer (same-box
+  // A/B, profiles/README.md: two issuers -4 % for bf16x3, +17 % for plain bf16)
+  static constexpr bool SPLIT_ISSUE = (P == 2);
+  static constexpr int R_WARP = PT_WARP + 1;               // issuer of the R MMAs: the last warp (SPLIT_ISSUE)
+  static constexpr int THREADS = 32 * (PT_WARP + 1 + (SPLIT_ISSUE ? 1 : 0));
   static constexpr int BK = (P == 1) ? 64 : 32;          // K extent of a G stage
   static constexpr int SPAN = BK * 2;
   static constexpr int A_TILE = BLOCK_M * SPAN;           // one part of this CTA's 128 rows of r_op
@@ -162,6 +167,13 @@ struct IterParams {
 };
 // What a timing experiment leaves out of the kernel (tools/ablate.sh): the time that disappears with a piece is what
 // that piece costs in situ.
+// The switches exist only in a library built with -DVTC_ABLATE (tools/ab_build.sh): the shipped kernels carry none of
+// the tests (they cost the plain-bf16 kernel 7-17 % when they were run-time flags).
+#ifdef VTC_ABLATE
+template <typename Params> __device__ __forceinline__ int ablate_of(const Params& p) { return p.ablate; }
+#else
+template <typename Params> __device__ __forceinline__ constexpr int ablate_of(const Params&) { return 0; }
+#endif
 enum AblateBits {
   ABL_STATE_LOAD = 1,    // no TMA loads of a_{k-1}, a_{k-2}
   ABL_STATE_STORE = 2,   // no TMA stores of a_k
@@ -183,7 +195,8 @@ enum TraceKind { TR_G_BEGIN = 1, TR_G_END = 2, TR_R_ISSUE = 3, TR_E_BEGIN = 4, T
 struct Tracer {
   unsigned long long* base;
   uint32_t n;
-  __device__ __forceinline__ Tracer(const IterParams& p, int role, bool mine)
+  template <typename Params>
+  __device__ __forceinline__ Tracer(const Params& p, int role, bool mine)
       : base((p.trace != nullptr && blockIdx.x == 0 && mine) ? p.trace + role * 2048 : nullptr), n(0) {}
   __device__ __forceinline__ void operator()(int kind, int index) {
     if (base != nullptr && n < 2047) {
@@ -297,11 +310,15 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::G_STAGES; ++s) {
-      mbar_init(bar(C::B_G_FULL + s), 2);    // one arrive per CTA's producer (leader's barrier is the one waited on)
+      // the leader's producer arrives (with the expected bytes of BOTH CTAs' loads); the peer's loads complete their
+      // bytes on the same barrier and need no arrival of their own: a peer load of phase n + 1 can only be issued after
+      // the commit that ended phase n, and bytes that land before the leader's expect_tx just leave the transaction
+      // count negative until it is posted. (A remote arrive per K block put a cross-CTA round trip into every stage cycle.)
+      mbar_init(bar(C::B_G_FULL + s), 1);
       mbar_init(bar(C::B_G_EMPTY + s), 1);   // multicast tcgen05.commit
     }
     for (int s = 0; s < C::PT_STAGES; ++s) {
-      mbar_init(bar(C::B_PT_FULL + s), 2);
+      mbar_init(bar(C::B_PT_FULL + s), 1);
       mbar_init(bar(C::B_PT_EMPTY + s), 1);
     }
     for (int s = 0; s < C::Y_STAGES; ++s) {
@@ -354,12 +371,12 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
           mbar_wait(bar(C::B_G_EMPTY + s), ph ^ 1);
           if (elect_one_sync()) {
             const uint32_t full = bar(C::B_G_FULL + s);
-            const bool load_a = !((p.ablate & ABL_R_STREAM) && nt > 0) && !(p.ablate & ABL_G_LOAD);
-            const bool load_b = !(p.ablate & ABL_G_LOAD);
+            const bool load_a = !((ablate_of(p) & ABL_R_STREAM) && nt > 0) && !(ablate_of(p) & ABL_G_LOAD);
+            const bool load_b = !(ablate_of(p) & ABL_G_LOAD);
             if (leader) {
               if (load_b) mbar_arrive_expect_tx(full, load_a ? 2 * C::G_STAGE : 2 * P * C::B_TILE);
               else mbar_arrive(full);
-            } else mbar_arrive_remote(full, 0);
+            }
             const uint32_t dst = sG + s * C::G_STAGE;
             trace(TR_G_LOAD, nt * p.kb_g + kb);
 #pragma unroll
@@ -388,11 +405,11 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
             mbar_wait(bar(C::B_PT_EMPTY + s), ph ^ 1);
             if (elect_one_sync()) {
               const uint32_t full = bar(C::B_PT_FULL + s);
-              const bool load_pt = !(p.ablate & ABL_PT_LOAD);
+              const bool load_pt = !(ablate_of(p) & ABL_PT_LOAD);
               if (leader) {
                 if (load_pt) mbar_arrive_expect_tx(full, 2 * C::PT_STAGE);
                 else mbar_arrive(full);
-              } else mbar_arrive_remote(full, 0);
+              }
 #pragma unroll
               for (int q = 0; q < P; ++q)
                 if (load_pt) tma_load_2d_pair(sPT + s * C::PT_STAGE + q * C::PT_TILE, &p.tmPhiT, full,
@@ -403,8 +420,8 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer (leader CTA) ================================
+  } else if (warp == 1 && !C::SPLIT_ISSUE) {
+    // ================================ MMA issuer of G and R (leader CTA), plain bf16 ================================
     if (leader) {
       constexpr uint32_t idesc_g = make_idesc_bf16(PAIR_M, IT_BN);
       constexpr uint32_t idesc_r = make_idesc_bf16(PAIR_M, IT_RN);
@@ -470,7 +487,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
                 const uint64_t bdesc = make_kmajor_desc(pstage + pair_b(P, pr) * C::PT_TILE, C::PT_CHUNK * 2) + pt_koff;
 #pragma unroll
                 for (int k = 0; k < C::CHUNK / UMMA_K; ++k) {
-                  if (!(p.ablate & ABL_R_MMA)) umma_bf16_pair(acc_r, adesc + 2 * k, bdesc + 2 * k, idesc_r, accumulate);
+                  umma_bf16_pair(acc_r, adesc + 2 * k, bdesc + 2 * k, idesc_r, accumulate);
                   accumulate = 1;
                 }
               }
@@ -510,7 +527,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
                 const uint64_t bdesc = make_kmajor_desc(stage + P * C::A_TILE + pair_b(P, pr) * C::B_TILE, C::SPAN);
 #pragma unroll
                 for (int k = 0; k < C::BK / UMMA_K; ++k) {
-                  if (!(p.ablate & ABL_G_MMA)) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_g, accumulate);
+                  umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_g, accumulate);
                   accumulate = 1;
                 }
               }
@@ -538,6 +555,117 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
         }
       }
     }
+  } else if (warp == 1) {
+    // ================================ G MMA issuer (leader CTA) ================================
+    // G(t) = r_{k-1}[panel] * Phi[tile]^T into acc_g[t & 1], K block by K block as the operands land; at most two tiles
+    // ahead of the epilogue (acc_g is double buffered). G and R are issued by two different warps (this one and
+    // R_WARP): each blocks on its own barriers (a hardware-suspended try_wait wakes in ~60 cycles, a test_wait poll
+    // costs ~150), where a single thread polling both streams spent ~1400 cycles per (R chunk, G K block) pair on
+    // barrier tests and commits -- 5.6 us per atom tile with nothing else to do (profiles/README.md, round 2
+    // ablations). The two accumulate into different TMEM columns, so no order between the two streams is needed;
+    // tcgen05.commit tracks the MMAs of the issuing thread only.
+    if (leader) {
+      constexpr uint32_t idesc_g = make_idesc_bf16(PAIR_M, IT_BN);
+      Tracer trace(p, 1, lane == 0);
+      uint32_t g_it = 0;
+      for (int g_tile = 0; g_tile < my_tiles; ++g_tile) {
+        const int acc = g_tile & 1;
+        mbar_wait(bar(C::B_ACCG_EMPTY + acc), ((g_tile >> 1) & 1) ^ 1);
+        const uint32_t d_tmem = tmem_base + acc * IT_BN;
+        uint32_t accumulate = 0;
+        for (int g_kb = 0; g_kb < p.kb_g; ++g_kb, ++g_it) {
+          const int s = g_it % C::G_STAGES;
+          mbar_wait(bar(C::B_G_FULL + s), (g_it / C::G_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t stage = sG + s * C::G_STAGE;
+          const bool last = (g_kb == p.kb_g - 1);
+          if (elect_one_sync()) {
+            if (g_kb == 0) trace(TR_G_BEGIN, g_tile);
+            if (last) trace(TR_G_END, g_tile);
+#pragma unroll
+            for (int pr = 0; pr < C::NPAIRS; ++pr) {
+              const uint64_t adesc = make_kmajor_desc(stage + pair_a(P, pr) * C::A_TILE, C::SPAN);
+              const uint64_t bdesc = make_kmajor_desc(stage + P * C::A_TILE + pair_b(P, pr) * C::B_TILE, C::SPAN);
+#pragma unroll
+              for (int k = 0; k < C::BK / UMMA_K; ++k) {
+                if (!(ablate_of(p) & ABL_G_MMA)) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_g, accumulate);
+                accumulate = 1;
+              }
+            }
+            umma_commit_pair(bar(C::B_G_EMPTY + s), 3);
+            if (last) umma_commit_pair(bar(C::B_ACCG_FULL + acc), 3);
+          }
+          accumulate = 1;
+          __syncwarp();
+        }
+      }
+    }
+  } else if (C::SPLIT_ISSUE && warp == C::R_WARP) {
+    // ================================ R MMA issuer (leader CTA) ================================
+    // R(t): acc_r += y_k[panel, tile] * Phi[tile], chunk by chunk as the epilogue of tile t writes y_k
+    if (leader) {
+      constexpr uint32_t idesc_r = make_idesc_bf16(PAIR_M, IT_RN);
+      constexpr int R_PER_PT = C::PT_CHUNK / C::CHUNK;   // R chunks served by one Phi^T chunk
+      const uint32_t acc_r = tmem_base + 2 * IT_BN;
+      Tracer trace(p, 1, false);
+      uint32_t r_it = 0;  // running R chunk index (y ring)
+      uint32_t r_pt = 0;  // running Phi^T chunk index
+      uint32_t r_q = 0;   // running sub-tile index of the next R chunk (YIN: its in/out stage is r_q % IN_STAGES)
+      int r_jobs = 0;     // jobs with an R so far (parity of the acc_r barriers)
+      for (int pi = 0; pi < my_jobs; ++pi) {
+        if (!job_at(pi).do_r) {   // the final iteration has no R (and no panel end)
+          r_q += job_tile_subs;
+          continue;
+        }
+        for (int nt = 0; nt < NT; ++nt) {
+          const int nch = tile_chunks(nt);
+          for (int r_chunk = 0; r_chunk < nch; ++r_chunk, ++r_it, ++r_q) {
+            const bool first = (nt == 0 && r_chunk == 0);
+            const int ps = r_pt % C::PT_STAGES;
+            // A operand of this chunk: a stage of the y ring, or (YIN) the a_{k-1} slot of the sub-tile's in/out stage
+            uint32_t ystage, a_part_bytes, y_release;
+            if constexpr (C::YIN) {
+              const int e = r_q % C::IN_STAGES;
+              mbar_wait(bar(C::B_YS_FULL + e), (r_q / C::IN_STAGES) & 1);
+              ystage = sIn + e * C::IN_STAGE, a_part_bytes = BLOCK_M * 32, y_release = bar(C::B_IN_FREE + e);
+            } else {
+              const int ys = r_it % C::Y_STAGES;
+              mbar_wait(bar(C::B_Y_FULL + ys), (r_it / C::Y_STAGES) & 1);
+              ystage = sY + ys * C::Y_STAGE, a_part_bytes = C::Y_TILE, y_release = bar(C::B_Y_EMPTY + ys);
+            }
+            if (r_chunk % R_PER_PT == 0) mbar_wait(bar(C::B_PT_FULL + ps), (r_pt / C::PT_STAGES) & 1);
+            // the panel-end epilogue of the previous job with an R must have drained acc_r before it is overwritten
+            if (first) mbar_wait(bar(C::B_ACCR_EMPTY), (r_jobs & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t pstage = sPT + ps * C::PT_STAGE;
+            const bool last = (nt == NT - 1) && (r_chunk == nch - 1);
+            // the Phi^T chunk is done with after its last R chunk (the last chunk of a tile may use only its first half)
+            const bool pt_done = (r_chunk % R_PER_PT == R_PER_PT - 1) || (r_chunk == nch - 1);
+            const uint32_t pt_koff = 2 * (C::CHUNK / UMMA_K) * (r_chunk % R_PER_PT);   // in 16-byte units
+            if (elect_one_sync()) {
+              uint32_t accumulate = first ? 0u : 1u;
+#pragma unroll
+              for (int pr = 0; pr < C::NPAIRS; ++pr) {
+                const uint64_t adesc = make_kmajor_desc(ystage + pair_a(P, pr) * a_part_bytes, C::CHUNK * 2);
+                const uint64_t bdesc = make_kmajor_desc(pstage + pair_b(P, pr) * C::PT_TILE, C::PT_CHUNK * 2) + pt_koff;
+#pragma unroll
+                for (int k = 0; k < C::CHUNK / UMMA_K; ++k) {
+                  if (!(ablate_of(p) & ABL_R_MMA)) umma_bf16_pair(acc_r, adesc + 2 * k, bdesc + 2 * k, idesc_r, accumulate);
+                  accumulate = 1;
+                }
+              }
+              umma_commit_pair(y_release, 3);
+              if (pt_done) umma_commit_pair(bar(C::B_PT_EMPTY + ps), 3);
+              if (last) umma_commit_pair(bar(C::B_ACCR_FULL), 3);
+            }
+            __syncwarp();
+            if (pt_done) ++r_pt;
+          }
+        }
+        r_q += nsub_r_pad;   // the sub-tiles of this job's panel end carry no y
+        ++r_jobs;
+      }
+    }
   } else if (warp == 3) {
     // ================================ epilogue input loader ================================
     uint32_t q = 0;
@@ -561,7 +689,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
             } else if (panel_end) {
               mbar_arrive_expect_tx(full, EPI_ARRAY_BYTES);
               tma_load_2d(dst, &p.tmX, full, j * EPI_COLS, m0, kEvictNormal);
-            } else if (p.ablate & ABL_STATE_LOAD) {
+            } else if (ablate_of(p) & ABL_STATE_LOAD) {
               mbar_arrive(full);
             } else {
               mbar_arrive_expect_tx(full, state_bytes);
@@ -602,7 +730,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
               for (int part = 0; part < P; ++part)
                 tma_store_3d(&p.tmROut, src + part * EPI_PART_BYTES, col % p.r_block_w, m0,
                              part * p.kb_g + col / p.r_block_w);
-            } else if (!(p.ablate & ABL_STATE_STORE)) {
+            } else if (!(ablate_of(p) & ABL_STATE_STORE)) {
               const int col = nt * IT_BN + j * EPI_COLS;
               if (p.state_blocked[job.out]) tma_store_3d(&p.tmState[job.out], src, 0, m0, col / EPI_COLS);
               else tma_store_2d(&p.tmState[job.out], src, col, m0);
@@ -702,7 +830,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
           }
           uint32_t v[16];
           trace(TR_E_SUB, j);
-          if (!(p.ablate & ABL_TMEM_LD)) tmem_ld16(t_row + j * EPI_COLS, v);
+          if (!(ablate_of(p) & ABL_TMEM_LD)) tmem_ld16(t_row + j * EPI_COLS, v);
           else {
 #pragma unroll
             for (int x = 0; x < 16; ++x) v[x] = 0u;
@@ -723,11 +851,11 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!(p.ablate & ABL_STATE_LSU) || panel_end) a = lds128(in_stage + row * 64 + ((ch ^ sw64) << 4));
+            if (!(ablate_of(p) & ABL_STATE_LSU) || panel_end) a = lds128(in_stage + row * 64 + ((ch ^ sw64) << 4));
             in[0][4 * ch + 0] = a.x, in[0][4 * ch + 1] = a.y, in[0][4 * ch + 2] = a.z, in[0][4 * ch + 3] = a.w;
             in[1][4 * ch + 0] = 0.f, in[1][4 * ch + 1] = 0.f, in[1][4 * ch + 2] = 0.f, in[1][4 * ch + 3] = 0.f;
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_prev && !panel_end && !(p.ablate & ABL_STATE_LSU)) b = lds128(in_stage + EPI_ARRAY_BYTES + row * 64 + ((ch ^ sw64) << 4));
+            if (has_prev && !panel_end && !(ablate_of(p) & ABL_STATE_LSU)) b = lds128(in_stage + EPI_ARRAY_BYTES + row * 64 + ((ch ^ sw64) << 4));
             in[2][4 * ch + 0] = b.x, in[2][4 * ch + 1] = b.y, in[2][4 * ch + 2] = b.z, in[2][4 * ch + 3] = b.w;
           }
           float outv[16], partv[16];
@@ -754,7 +882,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
               if (C::YIN) mbar_arrive_remote(bar(C::B_YS_FULL + e), 0);
             }
           } else {
-            if (!(p.ablate & ABL_STATE_LSU)) {
+            if (!(ablate_of(p) & ABL_STATE_LSU)) {
 #pragma unroll
               for (int ch = 0; ch < 4; ++ch)
                 sts128(out_stage + row * 64 + ((ch ^ sw64) << 4), outv[4 * ch], outv[4 * ch + 1], outv[4 * ch + 2],
@@ -791,7 +919,7 @@ __global__ void __launch_bounds__(IterCfg<P, V>::THREADS, 1) vtc_fista_iter_kern
               const uint32_t ystage = sY + ys * C::Y_STAGE + row * (C::CHUNK * 2);
               const uint32_t c0 = 2 * (j % C::SUBS);
               const uint32_t sw = (C::CHUNK == 32) ? sw64 : sw32;
-              if (!(p.ablate & ABL_Y_STS)) split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
+              if (!(ablate_of(p) & ABL_Y_STS)) split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
                 const uint32_t prow = ystage + part * C::Y_TILE;
                 sts128u(prow + (((c0 + 0) ^ sw) << 4), w32[0], w32[1], w32[2], w32[3]);
                 sts128u(prow + (((c0 + 1) ^ sw) << 4), w32[4], w32[5], w32[6], w32[7]);

@@ -15,6 +15,7 @@
 #include "aux_kernels.cuh"
 #include "gemm_kernel.cuh"
 #include "fista_iter_kernel.cuh"
+#include "fista_iter2_kernel.cuh"
 
 namespace {
 
@@ -44,9 +45,14 @@ long long g_launches = 0;
 #define COUNT_LAUNCH() (++g_launches)
 
 constexpr int kProfSamples = 16;
+constexpr int kProfHistory = 64;   // profiled vtc_fista_fc calls kept (ring): begin / iter_begin / iter_end / end events
 struct Profile {
   bool on = false, valid = false;
-  cudaEvent_t begin = nullptr, iter_begin = nullptr, iter_end = nullptr;
+  cudaEvent_t begin = nullptr, iter_begin = nullptr, iter_end = nullptr;   // of the last profiled call (ring slots)
+  cudaEvent_t h_begin[kProfHistory] = {}, h_iter_begin[kProfHistory] = {}, h_iter_end[kProfHistory] = {},
+              h_end[kProfHistory] = {};
+  long long calls = 0;     // profiled calls since profiling was switched on
+  bool events_made = false;
   cudaEvent_t k1_begin[kProfSamples], k1_end[kProfSamples], k2_end[kProfSamples];  // sampled iterations
   int iter_launches = 0, iters = 0, samples = 0;
   int launch_iters = 1;   // iterations per sampled launch (the persistent schedule runs all of them in one)
@@ -442,6 +448,9 @@ struct IterCall {
   const float* scalars = nullptr;
   double* stat = nullptr;
   int max_pairs = 0;
+  // second-generation kernel (fista_iter2_kernel.cuh): quad-blocked state arrays and the images read directly
+  float* qstate[3] = {nullptr, nullptr, nullptr};
+  bool init_zero = false;
 };
 
 unsigned long long* g_iter_trace = nullptr;  // vtc_debug_iter_trace
@@ -466,6 +475,27 @@ bool persistent_iterations_enabled() {
 }
 bool fused_iter_ok(int64_t S, int64_t D, int precision) {
   return fused_iter_enabled() && formulation_for(S, D) == FORM_SYNTHESIS && D <= IT_RN && parts_for(precision) <= 2;
+}
+
+// VTC_B200_ITER_GEN=2 selects the experimental second-generation panel-resident kernel (fista_iter2_kernel.cuh:
+// chunk-granular epilogue, a_{k-2} read directly, 8 KB in/out stages; measured 9 % slower than the default on
+// configs[1], profiles/README.md); default 1 (fista_iter_kernel.cuh)
+int iter_generation() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("VTC_B200_ITER_GEN");
+    cached = e ? atoi(e) : 1;
+    if (cached != 2) cached = 1;
+  }
+  return cached;
+}
+int ablate_flags() {
+  static int ablate = -1;   // timing experiments (tools/ablate.sh): pieces of the kernel left out, results wrong
+  if (ablate < 0) {
+    const char* e = getenv("VTC_B200_ABLATE");
+    ablate = e ? atoi(e) : 0;
+  }
+  return ablate;
 }
 
 // tuning variant of the fused iteration kernel (stage counts / math warps); VTC_B200_ITER_VARIANT overrides the
@@ -513,14 +543,7 @@ int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream
   p.stat = c.stat;
   p.trace = g_iter_trace;
   g_iter_trace = nullptr;  // one shot: only the next launch is traced
-  {
-    static int ablate = -1;   // timing experiments (tools/ablate.sh): pieces of the kernel left out, results wrong
-    if (ablate < 0) {
-      const char* e = getenv("VTC_B200_ABLATE");
-      ablate = e ? atoi(e) : 0;
-    }
-    p.ablate = ablate;
-  }
+  p.ablate = ablate_flags();
   static bool attr_set_dev[64] = {};
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
@@ -582,10 +605,123 @@ int launch_iter_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream
   COUNT_LAUNCH();
   return VTC_OK;
 }
+// Persistent launches that fill the device and wait on one another must not share it with a second such launch on
+// another stream: they are ordered through an event (see launch_iter_p).
+template <typename Kernel, typename Params>
+int launch_persistent(cudaLaunchConfig_t& cfg, Kernel kernel, const Params& p, int pairs, bool whole_device, int dev,
+                      int& max_clusters, cudaStream_t stream) {
+  if (max_clusters == 0) {
+    cudaLaunchConfig_t query = cfg;
+    query.numAttrs = 1;  // cluster dimension only
+    CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &query));
+    if (max_clusters < 1) return fail(VTC_ERR_CUDA, "the iteration kernel does not fit on this device");
+  }
+  if (pairs > max_clusters) cfg.gridDim = dim3(2 * max_clusters);
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  CUDA_TRY(cudaStreamIsCapturing(stream, &capturing));
+  if (whole_device && capturing == cudaStreamCaptureStatusNone) {
+    static std::mutex mu;
+    static cudaEvent_t last_dev[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    cudaEvent_t& last = last_dev[dev & 63];
+    if (!last) CUDA_TRY(cudaEventCreateWithFlags(&last, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamWaitEvent(stream, last, 0));   // no-op until the event has been recorded once
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, p));
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaEventRecord(last, stream));
+    return VTC_OK;
+  }
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, p));
+  COUNT_LAUNCH();
+  return VTC_OK;
+}
+
+template <int P>
+int launch_iter2_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream) {
+  using Cf = Iter2Cfg<P>;
+  IterParams2 p;
+  memset(&p, 0, sizeof(p));
+  if (c.r_op.block != Cf::BK) return fail(VTC_ERR_ARG, "fused iteration: r_op must be tile-contiguous with block %d", Cf::BK);
+  TRY(map_operand(&p.tmR, c.r_op, Cf::BK, "r operand"));
+  TRY(map_operand(&p.tmPhi, c.phi_op, Cf::BK, "dictionary operand", IT_BN / 2));
+  TRY(map_operand(&p.tmPhiT, c.phiT_op, Cf::CHUNK, "transposed dictionary operand", IT_RN / 2));
+  TRY(map_parts_out(&p.tmROut, c.r_op, "r parts output"));
+  for (int i = 0; i < 3; ++i) p.state[i] = c.qstate[i];
+  p.init_zero = c.init_zero ? 1 : 0;
+  if (!p.state[1] || !p.state[2] || (!p.init_zero && !p.state[0])) return fail(VTC_ERR_ARG, "fused iteration: state arrays missing");
+  p.x = static_cast<const float*>(c.x.ptr);
+  p.ld_x = c.x.ld;
+  if ((reinterpret_cast<uintptr_t>(p.x) & 15) != 0 || (p.ld_x % 4) != 0)
+    return fail(VTC_ERR_ARG, "fused iteration: images must be 16-byte aligned with a pitch that is a multiple of 4");
+  p.B = static_cast<int>(c.B), p.D = static_cast<int>(c.D);
+  if (c.k_count > 1 && c.done == nullptr) return fail(VTC_ERR_ARG, "fused iteration: several iterations per launch need the completion counters");
+  p.k_first = c.k_first, p.k_count = c.k_count, p.k_final = c.k_final;
+  p.betas = c.betas;
+  p.done = c.k_count > 1 ? c.done : nullptr;
+  p.num_panels = static_cast<int>(ceil_div(c.B, PAIR_M));
+  p.S = static_cast<int>(c.S);
+  p.num_n_tiles = static_cast<int>(ceil_div(c.S, IT_BN));
+  p.kb_g = static_cast<int>(c.r_op.Kp / Cf::BK);
+  p.phi_part_stride = static_cast<int>(c.phi_op.Kp);
+  p.phiT_part_stride = static_cast<int>(c.phiT_op.Kp);
+  p.nsub_r = static_cast<int>(c.r_op.Kp / EPI_COLS);
+  p.r_block_w = Cf::BK;
+  p.prox = c.prox, p.group = c.group, p.use_momentum = c.use_momentum;
+  p.scalars = c.scalars;
+  p.stat = c.stat;
+  p.ablate = ablate_flags();
+  p.trace = g_iter_trace;
+  g_iter_trace = nullptr;  // one shot: only the next launch is traced
+  {
+    static int l2pf = -1;
+    if (l2pf < 0) {
+      const char* e = getenv("VTC_B200_ITER_L2PF");
+      l2pf = e ? atoi(e) : 0;
+    }
+    p.l2_prefetch = l2pf;
+  }
+  static bool attr_set_dev[64] = {};
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  bool& attr_set = attr_set_dev[dev & 63];
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(vtc_fista_iter2_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
+    attr_set = true;
+  }
+  long long max_pairs = info.sm_count / 2;
+  if (c.max_pairs > 0 && c.max_pairs < max_pairs) max_pairs = c.max_pairs;
+  const int pairs = static_cast<int>(p.num_panels < max_pairs ? p.num_panels : max_pairs);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(Cf::THREADS);
+  cfg.dynamicSmemBytes = Cf::SMEM_ALLOC;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (tune_flags() & TUNE_NO_PDL) ? 1 : 2;
+  if (c.k_count > 1) {
+    static int max_clusters_dev[64] = {};   // per instantiation and device
+    return launch_persistent(cfg, vtc_fista_iter2_kernel<P>, p, pairs, c.max_pairs == 0, dev, max_clusters_dev[dev & 63],
+                             stream);
+  }
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_fista_iter2_kernel<P>, p));
+  COUNT_LAUNCH();
+  return VTC_OK;
+}
+
 int launch_iter(const IterCall& c, cudaStream_t stream) {
   DeviceInfo info;
   TRY(require_sm100(&info));
   if (c.D > IT_RN) return fail(VTC_ERR_ARG, "fused iteration needs D <= %d", IT_RN);
+  if (c.qstate[1] != nullptr)
+    return parts_for(c.precision) == 1 ? launch_iter2_p<1>(c, info, stream) : launch_iter2_p<2>(c, info, stream);
   const bool one = parts_for(c.precision) == 1;
   switch (iter_variant(parts_for(c.precision))) {
     case 1: return one ? launch_iter_p<1, 1>(c, info, stream) : launch_iter_p<2, 1>(c, info, stream);
@@ -603,11 +739,12 @@ int grid_for(int64_t work, int threads, int sm_count) {
   if (g < 1) g = 1;
   return static_cast<int>(g);
 }
-int split_rows(const float* in, int64_t ld, int64_t R, int64_t C, const PartsMat& out, cudaStream_t st) {
+int split_rows(const float* in, int64_t ld, int64_t R, int64_t C, const PartsMat& out, cudaStream_t st,
+               float scale = 1.f) {
   DeviceInfo info;
   TRY(device_info(&info));
   split_rows_kernel<<<grid_for(R * out.Kp / 2, 256, info.sm_count), 256, 0, st>>>(
-      in, ld, R, C, out.Kp, out.parts, out.block, reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out.ptr)));
+      in, ld, R, C, out.Kp, out.parts, out.block, reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out.ptr)), scale);
   COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
@@ -696,6 +833,7 @@ int run_lipschitz(const float* dict, int64_t S, int64_t D, const LipschitzWs& w,
 
 // ---------------------------------------------------------------------------------------------- FISTA
 constexpr int kMaxFusedIters = 16384;   // iterations one persistent launch can run (size of the momentum table)
+constexpr int kStatSlots = 4096;        // ring of early-stopping statistics (one double per iteration)
 struct FistaWs {
   float* scalars;
   double* stats;
@@ -706,14 +844,17 @@ struct FistaWs {
   // bvec, X1, X2: tile-contiguous fp32 state [ceil(S/16)][B][16]; init_pad / out_pad / x_pad: row-major staging for
   // caller buffers that TMA cannot address directly (unaligned base or pitch)
   float *bvec, *X1, *X2, *init_pad, *out_pad, *x_pad;
+  float *Q0, *Q1, *Q2;   // quad-blocked state of the second-generation iteration kernel (Q0: converted warm start)
+  int64_t q_row_blocks, q_col_blocks;
   int64_t ldS, ldD;
 };
+bool iter2_ok(int64_t S, int64_t D, int precision);
 FistaWs carve_fista(Carver& cv, int64_t B, int64_t S, int64_t D, int precision) {
   FistaWs w;
   const int P = parts_for(precision);
   const int bk = (P == 1) ? 64 : 32;  // K block of the iteration GEMMs = block width of the streamed A operands
   w.scalars = static_cast<float*>(cv.take(64));
-  w.stats = static_cast<double*>(cv.take(8 * 4096));
+  w.stats = static_cast<double*>(cv.take(8 * kStatSlots));
   w.betas = static_cast<float*>(cv.take(sizeof(float) * (kMaxFusedIters + 1)));
   w.done = static_cast<int*>(cv.take(sizeof(int) * ceil_div(B, PAIR_M)));
   w.lip = carve_lipschitz(cv, D);
@@ -734,6 +875,21 @@ FistaWs carve_fista(Carver& cv, int64_t B, int64_t S, int64_t D, int precision) 
     w.x_pad = static_cast<float*>(cv.take(static_cast<size_t>(B) * w.ldD * 4));
     w.bvec = nullptr;
   }
+  w.Q0 = w.Q1 = w.Q2 = nullptr;
+  w.q_row_blocks = 2 * ceil_div(B, PAIR_M);
+  w.q_col_blocks = round_up(S, 32) / EPI_COLS;
+  if (iter2_ok(S, D, precision)) {
+    // second-generation kernel: three quad-blocked state arrays (whole 128-row x 32-atom blocks) and, for a warm start
+    // only, the operand parts of the starting point (r_0 = y_0 Phi - x by one GEMM)
+    const size_t qbytes = static_cast<size_t>(w.q_row_blocks) * w.q_col_blocks * EPI_ARRAY_BYTES;
+    w.yop[0] = carve_parts(cv, B, S, P, bk);
+    w.yop[1] = PartsMat();
+    w.Q0 = static_cast<float*>(cv.take(qbytes));
+    w.Q1 = static_cast<float*>(cv.take(qbytes));
+    w.Q2 = static_cast<float*>(cv.take(qbytes));
+    w.X1 = w.X2 = w.init_pad = w.out_pad = nullptr;
+    return w;
+  }
   w.yop[0] = carve_parts(cv, B, S, P, bk);
   w.yop[1] = carve_parts(cv, B, S, P, bk);
   w.X1 = static_cast<float*>(cv.take(state_blk));
@@ -744,6 +900,7 @@ FistaWs carve_fista(Carver& cv, int64_t B, int64_t S, int64_t D, int precision) 
 }
 
 bool tma_ok(const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld % 4) == 0; }
+bool iter2_ok(int64_t S, int64_t D, int precision) { return fused_iter_ok(S, D, precision) && iter_generation() == 2; }
 
 }  // namespace
 
@@ -755,6 +912,7 @@ long long vtc_launch_count(void) { return g_launches; }
 int vtc_profile_enable(int on) {
   g_prof.on = on != 0;
   g_prof.valid = false;
+  if (on) g_prof.calls = 0;
   return VTC_OK;
 }
 int vtc_set_formulation(int formulation) {
@@ -800,6 +958,33 @@ int vtc_profile_last(float* setup_ms, float* iter_ms, int* iter_launches, int* i
   if (first_launch_ms) *first_launch_ms = first;
   return VTC_OK;
 }
+// Every profiled vtc_fista_fc call since vtc_profile_enable(1), oldest first (a ring of kProfHistory calls): device
+// time of the setup, of the iteration launches and of the finishing copy, and the idle time of the stream between the
+// end of this call and the beginning of the next one (0 for the last).
+int vtc_profile_history_count(void) {
+  return static_cast<int>(g_prof.calls < kProfHistory ? g_prof.calls : kProfHistory);
+}
+int vtc_profile_history(int index, float* setup_ms, float* iter_ms, float* finish_ms, float* gap_to_next_ms) {
+  const int n = vtc_profile_history_count();
+  if (index < 0 || index >= n) return fail(VTC_ERR_ARG, "vtc_profile_history: index %d outside [0, %d)", index, n);
+  const long long first = g_prof.calls - n;
+  const int slot = static_cast<int>((first + index) % kProfHistory);
+  CUDA_TRY(cudaEventSynchronize(g_prof.h_end[slot]));
+  float a = 0.f, b = 0.f, c = 0.f, g = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&a, g_prof.h_begin[slot], g_prof.h_iter_begin[slot]));
+  CUDA_TRY(cudaEventElapsedTime(&b, g_prof.h_iter_begin[slot], g_prof.h_iter_end[slot]));
+  CUDA_TRY(cudaEventElapsedTime(&c, g_prof.h_iter_end[slot], g_prof.h_end[slot]));
+  if (index + 1 < n) {
+    const int next = static_cast<int>((first + index + 1) % kProfHistory);
+    CUDA_TRY(cudaEventSynchronize(g_prof.h_begin[next]));
+    CUDA_TRY(cudaEventElapsedTime(&g, g_prof.h_end[slot], g_prof.h_begin[next]));
+  }
+  if (setup_ms) *setup_ms = a;
+  if (iter_ms) *iter_ms = b;
+  if (finish_ms) *finish_ms = c;
+  if (gap_to_next_ms) *gap_to_next_ms = g;
+  return VTC_OK;
+}
 const char* vtc_last_error(void) { return g_err; }
 
 int vtc_device_info(int* sm_count, int* cc_major, int* cc_minor) {
@@ -842,6 +1027,7 @@ struct FistaCommon {
   int num_iters, variant, prox, group_size, precision, P;
   bool gram, early;
   bool fused_iter;  // one launch per iteration (fista_iter_kernel.cuh) instead of two
+  bool iter2;       // ... by the second-generation kernel (fista_iter2_kernel.cuh, quad-blocked state)
 };
 
 struct FistaChain {
@@ -910,11 +1096,39 @@ int chain_setup(const FistaCommon& cm, FistaChain& ch) {
     }
   } else {
     TRY(transpose_split(cm.dictionary, D, S, D, w.phiT_op, st));
-    CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.r_op.ptr), 0, w.r_op.bytes(), st));
+    if (!(cm.fused_iter && !ch.initial_codes))   // (from zero the fused schedule writes every element of r_0 itself)
+      CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.r_op.ptr), 0, w.r_op.bytes(), st));
     if (!tma_ok(ch.images, ch.ld_images)) {
       CUDA_TRY(cudaMemcpy2DAsync(w.x_pad, w.ldD * 4, ch.images, ch.ld_images * 4, D * 4, B, cudaMemcpyDeviceToDevice, st));
       ch.x_in = w.x_pad, ch.ld_x = w.ldD;
     }
+  }
+  if (cm.iter2) {
+    // second-generation panel-resident kernel: quad-blocked state. From zero nothing is initialised at all (iteration
+    // 1 reads no state, every block is written before it is read) and r_0 = -x is a split of the images; a warm
+    // start is converted once and r_0 = y_0 Phi - x comes from one GEMM.
+    if (ch.initial_codes) {
+      DeviceInfo info;
+      TRY(device_info(&info));
+      const int64_t slots = w.q_row_blocks * w.q_col_blocks * 512;
+      block_quad_kernel<<<grid_for(slots, 256, info.sm_count), 256, 0, st>>>(ch.initial_codes, ch.ld_codes, B, S,
+                                                                             w.q_row_blocks, w.q_col_blocks, w.Q0);
+      COUNT_LAUNCH();
+      CUDA_TRY(cudaGetLastError());
+      TRY(split_rows(ch.initial_codes, ch.ld_codes, B, S, w.yop[0], st));
+      GemmCall r;
+      r.precision = cm.precision;
+      r.max_pairs = ch.max_pairs;
+      r.A = w.yop[0], r.B = w.phiT_op;
+      r.M = B, r.N = D, r.K = S;
+      r.in[0] = F32Mat{ch.x_in, B, D, ch.ld_x}, r.in_mask = 1;
+      r.parts_out = w.r_op, r.n_parts = cm.P;
+      TRY(launch_gemm<EPI_STORE>(r, st));
+    } else {
+      TRY(split_rows(ch.x_in, ch.ld_x, B, D, w.r_op, st, -1.f));
+    }
+    if (cm.early) CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * kStatSlots, st));
+    return VTC_OK;
   }
   // state buffers
   ch.X1 = F32Mat{w.X1, B, S, 0, true};
@@ -933,12 +1147,17 @@ int chain_setup(const FistaCommon& cm, FistaChain& ch) {
   } else {
     // a_0 = 0: X2 doubles as a_0 (it is only overwritten, in place, when a_2 is produced)
     CUDA_TRY(cudaMemsetAsync(w.X2, 0, static_cast<size_t>(B) * round_up(S, EPI_COLS) * 4, st));
-    CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[0].ptr), 0, w.yop[0].bytes(), st));
+    // (the fused schedule starts from r_0 = -x and never reads the operand parts of y_0 = 0)
+    if (!cm.fused_iter) CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[0].ptr), 0, w.yop[0].bytes(), st));
     ch.init = ch.X2;
   }
-  if (cm.early) CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * cm.num_iters, st));
-  if (cm.fused_iter) {
-    // the fused schedule carries r_{k-1} = y_{k-1} Phi - x between launches: r_0 from the starting point, once
+  if (cm.early) CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * kStatSlots, st));
+  if (cm.fused_iter && !ch.initial_codes) {
+    // the fused schedule carries r_{k-1} = y_{k-1} Phi - x between launches; from zero r_0 = -x is a split of the
+    // images (no K = S contraction of an all-zero operand)
+    TRY(split_rows(ch.x_in, ch.ld_x, B, D, w.r_op, st, -1.f));
+  } else if (cm.fused_iter) {
+    // r_0 from the warm start, once
     GemmCall r;
     r.precision = cm.precision;
     r.max_pairs = ch.max_pairs;
@@ -954,7 +1173,7 @@ int chain_setup(const FistaCommon& cm, FistaChain& ch) {
 // Iterations k_first .. k_first + k_count - 1 of one chain in ONE launch of the panel-resident kernel. k_count > 1: the
 // persistent schedule (jobs = (iteration, panel) dealt round-robin to the SM pairs, no launch boundary and no panel
 // quantisation); the momentum table w.betas must have been uploaded, w.done is zeroed here.
-int chain_iterate_fused(const FistaCommon& cm, FistaChain& ch, int k_first, int k_count) {
+int chain_iterate_fused(const FistaCommon& cm, FistaChain& ch, int k_first, int k_count, int betas_k_lo = 0) {
   FistaWs& w = ch.w;
   IterCall c;
   c.r_op = w.r_op, c.phi_op = w.phi_op, c.phiT_op = w.phiT_op;
@@ -964,20 +1183,25 @@ int chain_iterate_fused(const FistaCommon& cm, FistaChain& ch, int k_first, int 
   c.x = F32Mat{ch.x_in, ch.B, cm.D, ch.ld_x};
   c.k_first = k_first, c.k_count = k_count;
   c.k_final = cm.early ? 0x7fffffff : cm.num_iters;
-  c.betas = w.betas;
+  c.betas = w.betas - betas_k_lo;   // the table holds entries betas_k_lo ..: indexed by absolute iteration
   if (k_count > 1) {
     CUDA_TRY(cudaMemsetAsync(w.done, 0, sizeof(int) * ceil_div(ch.B, PAIR_M), ch.st));
     c.done = w.done;
   }
   c.prox = cm.prox, c.group = cm.group_size, c.use_momentum = (cm.variant == VTC_VARIANT_FISTA);
   c.scalars = w.scalars;
-  c.stat = cm.early ? w.stats + (k_first - 1) : nullptr;
+  c.stat = cm.early ? w.stats + (k_first - 1) % kStatSlots : nullptr;
   c.max_pairs = ch.max_pairs;
+  if (cm.iter2) {
+    c.qstate[0] = w.Q0, c.qstate[1] = w.Q1, c.qstate[2] = w.Q2;
+    c.init_zero = ch.initial_codes == nullptr;
+  }
   return launch_iter(c, ch.st);
 }
 
 // iteration k (1-based) of one chain; `sample` >= 0 records profile events around its launches
-int chain_iterate(const FistaCommon& cm, FistaChain& ch, int k, float beta_prev, float beta_k, int sample) {
+int chain_iterate(const FistaCommon& cm, FistaChain& ch, int k, float beta_prev, float beta_k, int sample,
+                  int betas_k_lo = 0) {
   FistaWs& w = ch.w;
   cudaStream_t st = ch.st;
   const int64_t B = ch.B, S = cm.S, D = cm.D;
@@ -989,7 +1213,7 @@ int chain_iterate(const FistaCommon& cm, FistaChain& ch, int k, float beta_prev,
   if (sample >= 0) CUDA_TRY(cudaEventRecord(g_prof.k1_begin[sample], st));
   if (cm.fused_iter) {
     (void)a_prev, (void)a_prev2, (void)a_out, (void)beta_prev, (void)beta_k;
-    TRY(chain_iterate_fused(cm, ch, k, 1));
+    TRY(chain_iterate_fused(cm, ch, k, 1, betas_k_lo));
     if (sample >= 0) {
       CUDA_TRY(cudaEventRecord(g_prof.k1_end[sample], st));
       CUDA_TRY(cudaEventRecord(g_prof.k2_end[sample], st));
@@ -1031,7 +1255,7 @@ int chain_iterate(const FistaCommon& cm, FistaChain& ch, int k, float beta_prev,
   g.use_momentum = (cm.variant == VTC_VARIANT_FISTA);
   g.beta_prev = beta_prev, g.beta_next = beta_k;
   g.scalars = w.scalars;
-  g.stat = cm.early ? w.stats + (k - 1) : nullptr;
+  g.stat = cm.early ? w.stats + (k - 1) % kStatSlots : nullptr;
   TRY(launch_gemm<EPI_FISTA>(g, st));
   if (sample >= 0) {
     if (cm.gram) CUDA_TRY(cudaEventRecord(g_prof.k1_end[sample], st));
@@ -1042,6 +1266,16 @@ int chain_iterate(const FistaCommon& cm, FistaChain& ch, int k, float beta_prev,
 
 int chain_finish(const FistaCommon& cm, FistaChain& ch, int k_done) {
   const int64_t B = ch.B, S = cm.S;
+  if (cm.iter2) {
+    // the last iterate sits quad-blocked in the buffer of its parity: one pass back to the caller's row-major codes
+    DeviceInfo info;
+    TRY(device_info(&info));
+    unblock_quad_kernel<<<grid_for(B * S, 256, info.sm_count), 256, 0, ch.st>>>(
+        (k_done & 1) ? ch.w.Q1 : ch.w.Q2, B, S, ch.w.q_row_blocks, ch.codes_out, ch.ld_codes);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+    return VTC_OK;
+  }
   if (cm.early) {
     // the stopping iteration was not known in advance: the result sits in a tile-contiguous state buffer
     DeviceInfo info;
@@ -1123,9 +1357,9 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   cm.group_size = group_size;
   cm.precision = precision, cm.P = parts_for(precision);
   cm.gram = formulation_for(S, D) == FORM_GRAM;
-  cm.fused_iter = fused_iter_ok(S, D, precision) && num_iters <= kMaxFusedIters;  // else: the two-launch schedule
+  cm.iter2 = iter2_ok(S, D, precision);   // (takes runs longer than the momentum table in windows)
+  cm.fused_iter = cm.iter2 || (fused_iter_ok(S, D, precision) && num_iters <= kMaxFusedIters);  // else: two launches
   cm.early = early_stopping_epsilon >= 0.f;
-  if (cm.early && num_iters > 4096) return fail(VTC_ERR_UNSUPPORTED, "early stopping supports at most 4096 iterations");
 
   // the early-stopping statistic is global over the batch: one chain then
   const int chains = cm.early ? 1 : chains_for(B, S, D);
@@ -1147,17 +1381,26 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   }
   if (!workspace || !cv.fits()) return fail(VTC_ERR_WORKSPACE, "vtc_fista_fc: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
 
+  int prof_slot = 0;
   if (g_prof.on) {
-    if (!g_prof.begin) {
-      CUDA_TRY(cudaEventCreate(&g_prof.begin));
-      CUDA_TRY(cudaEventCreate(&g_prof.iter_begin));
-      CUDA_TRY(cudaEventCreate(&g_prof.iter_end));
+    if (!g_prof.events_made) {
+      for (int i = 0; i < kProfHistory; ++i) {
+        CUDA_TRY(cudaEventCreate(&g_prof.h_begin[i]));
+        CUDA_TRY(cudaEventCreate(&g_prof.h_iter_begin[i]));
+        CUDA_TRY(cudaEventCreate(&g_prof.h_iter_end[i]));
+        CUDA_TRY(cudaEventCreate(&g_prof.h_end[i]));
+      }
+      g_prof.events_made = true;
       for (int i = 0; i < kProfSamples; ++i) {
         CUDA_TRY(cudaEventCreate(&g_prof.k1_begin[i]));
         CUDA_TRY(cudaEventCreate(&g_prof.k1_end[i]));
         CUDA_TRY(cudaEventCreate(&g_prof.k2_end[i]));
       }
     }
+    prof_slot = static_cast<int>(g_prof.calls % kProfHistory);
+    g_prof.begin = g_prof.h_begin[prof_slot];
+    g_prof.iter_begin = g_prof.h_iter_begin[prof_slot];
+    g_prof.iter_end = g_prof.h_iter_end[prof_slot];
     g_prof.samples = 0;
     g_prof.valid = false;
     CUDA_TRY(cudaEventRecord(g_prof.begin, st));
@@ -1185,20 +1428,38 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   double t_k = 1.0;
   float beta_prev = 0.f;
   int k_done = 0;
+  const int table_iters = num_iters < kMaxFusedIters ? num_iters : kMaxFusedIters;
   if (cm.fused_iter) {
     // the panel-resident kernel takes the momentum coefficients from a device table: betas[k], betas[0] = 0
     for (int c = 0; c < chains; ++c) {
-      fista_betas_kernel<<<1, 32, 0, ch[c].st>>>(ch[c].w.betas, num_iters, variant == VTC_VARIANT_FISTA ? 1 : 0);
+      fista_betas_kernel<<<1, 32, 0, ch[c].st>>>(ch[c].w.betas, table_iters, variant == VTC_VARIANT_FISTA ? 1 : 0, 0);
       COUNT_LAUNCH();
     }
     CUDA_TRY(cudaGetLastError());
   }
+  int betas_k_lo = 0;   // first iteration index held by the device table (runs longer than the table: windows)
+  auto betas_window = [&](int k) -> int {   // makes the table cover iterations k - 1 .. ; returns 0 or an error
+    if (k <= betas_k_lo + table_iters && k - 1 >= betas_k_lo) return VTC_OK;
+    betas_k_lo = k - 1;
+    const int hi = (num_iters - betas_k_lo < kMaxFusedIters) ? num_iters : betas_k_lo + kMaxFusedIters;
+    for (int c = 0; c < chains; ++c) {
+      fista_betas_kernel<<<1, 32, 0, ch[c].st>>>(ch[c].w.betas, hi, variant == VTC_VARIANT_FISTA ? 1 : 0, betas_k_lo);
+      COUNT_LAUNCH();
+    }
+    CUDA_TRY(cudaGetLastError());
+    return VTC_OK;
+  };
   if (g_prof.on) CUDA_TRY(cudaEventRecord(g_prof.iter_begin, st));
   const bool persistent = cm.fused_iter && !cm.early && chains == 1 && persistent_iterations_enabled();
   if (persistent) {
-    // every iteration of every panel in ONE launch
+    // every iteration of every panel in ONE launch (runs longer than the momentum table: one launch per window)
     if (g_prof.on) CUDA_TRY(cudaEventRecord(g_prof.k1_begin[0], st));
-    TRY(chain_iterate_fused(cm, ch[0], 1, num_iters));
+    int launches = 0;
+    for (int k0 = 1; k0 <= num_iters; k0 += kMaxFusedIters, ++launches) {
+      TRY(betas_window(k0));
+      const int count = (num_iters - k0 + 1 < kMaxFusedIters) ? num_iters - k0 + 1 : kMaxFusedIters;
+      TRY(chain_iterate_fused(cm, ch[0], k0, count, betas_k_lo));
+    }
     if (g_prof.on) {
       CUDA_TRY(cudaEventRecord(g_prof.k1_end[0], st));
       CUDA_TRY(cudaEventRecord(g_prof.k2_end[0], st));
@@ -1212,7 +1473,10 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
     const float beta_k = (variant == VTC_VARIANT_FISTA) ? static_cast<float>((t_k - 1.0) / t_next) : 0.f;
     t_k = t_next;
     const int sample = (g_prof.on && k > num_iters / 2 && g_prof.samples < kProfSamples) ? g_prof.samples : -1;
-    for (int c = 0; c < chains; ++c) TRY(chain_iterate(cm, ch[c], k, beta_prev, beta_k, c == 0 ? sample : -1));
+    if (cm.fused_iter) TRY(betas_window(k));
+    if (cm.early && k > 1 && (k - 1) % kStatSlots == 0)   // the ring of statistics wraps: every slot has been read
+      CUDA_TRY(cudaMemsetAsync(ch[0].w.stats, 0, sizeof(double) * kStatSlots, st));
+    for (int c = 0; c < chains; ++c) TRY(chain_iterate(cm, ch[c], k, beta_prev, beta_k, c == 0 ? sample : -1, betas_k_lo));
     if (sample >= 0) {
       g_prof.samples = sample + 1;
       g_prof.two_launches = !cm.gram && !cm.fused_iter;
@@ -1221,19 +1485,22 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
     k_done = k;
     if (cm.early) {
       double sum_abs = 0.0;
-      CUDA_TRY(cudaMemcpyAsync(&sum_abs, ch[0].w.stats + (k - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(&sum_abs, ch[0].w.stats + (k - 1) % kStatSlots, sizeof(double), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
       const double avg = sum_abs / (static_cast<double>(B) * static_cast<double>(S)) / static_cast<double>(eta_host);
       if (avg < static_cast<double>(early_stopping_epsilon) && k > 1) break;
     }
   }
+  if (g_prof.on && chains == 1) CUDA_TRY(cudaEventRecord(g_prof.iter_end, st));
   for (int c = 0; c < chains; ++c) TRY(chain_finish(cm, ch[c], k_done));
   if (chains == 2) {  // join: the caller's stream continues only after the side chain is done
     CUDA_TRY(cudaEventRecord(side->join, side->stream));
     CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
   }
   if (g_prof.on) {
-    CUDA_TRY(cudaEventRecord(g_prof.iter_end, st));
+    if (chains == 2) CUDA_TRY(cudaEventRecord(g_prof.iter_end, st));
+    CUDA_TRY(cudaEventRecord(g_prof.h_end[prof_slot], st));
+    ++g_prof.calls;
     g_prof.iter_launches = persistent ? 1 : k_done * ((cm.gram || cm.fused_iter) ? 1 : 2) * chains;
     g_prof.launch_iters = persistent ? k_done : 1;
     g_prof.iters = k_done;
@@ -1538,7 +1805,7 @@ ConvWs carve_conv(Carver& cv, const ConvShape& cs, int precision) {
   const int bk = (P == 1) ? 64 : 32;
   const int64_t Sp = round_up(g.s, 64), Dbp = round_up(g.db, 64);
   w.scalars = static_cast<float*>(cv.take(64));
-  w.stats = static_cast<double*>(cv.take(8 * 4096));
+  w.stats = static_cast<double*>(cv.take(8 * kStatSlots));
   w.lip = carve_lipschitz(cv, cs.per_kernel);
   w.phiA_op = carve_parts(cv, g.s, cs.nq * Dbp, 3);
   w.phiS_op = carve_parts(cv, g.db, cs.nq * Sp, 3);
