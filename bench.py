@@ -9,8 +9,10 @@ A "step" is one full inference call (step size, Gram/drive GEMMs, 300 fused iter
 Inference needs no communication, so N GPUs run N independent shards of an N-times larger batch (weak scaling);
 `value` is the whole-job patches/sec with inputs resident in HBM, timed with CUDA events on the launching stream
 between barriers, max over ranks. `e2e` is the same call made through the public drop-in API from pinned HOST
-buffers, host<->device copies inside the timed region. `--impl reference` times the CPU float32 restatement of the
-reference (oracle/vtc_oracle.py; the reference itself is Python/torch and is not on the GPU box) on a bounded sample.
+buffers, host<->device copies of every step inside the timed region (vision_transform_codes_b200.host_pipeline keeps two
+steps in flight so that the copies of one step run under the compute of its neighbours). `--impl reference` times the
+UNMODIFIED reference (staged under oracle/_ref by tools/stage_reference.py; kind "reference") on all host cores, each
+step a bounded sample of the same workload; without the staged copy it falls back to the oracle port (kind "port").
 """
 import argparse
 import json
@@ -32,6 +34,13 @@ TRAIN_GLOBAL_BATCH = 524288
 WORKLOAD = ('configs[1]: fully-connected FISTA, 16x16 whitened patches (D=256), 1024 atoms, '
             'batch 65536 per GPU, 300 iters, lambda 0.1')
 CPU_SAMPLE = int(os.environ.get('VTC_BENCH_CPU_SAMPLE', '32768'))  # patches per CPU step (the contract test shrinks it)
+
+
+def shared_config(batch_per_gpu):
+  """The `config` of BOTH arms (this one and --impl reference): the workload only, nothing implementation-specific."""
+  return {'workload': WORKLOAD, 'batch_per_gpu': batch_per_gpu, 'atoms': S, 'pixels': D, 'iters': T,
+          'sparsity_weight': LAM, 'variant': 'fista', 'patches': 'synthetic whitened (oracle.synthetic_patches, seed = rank)',
+          'dictionary': 'unit-norm Gaussian rows (oracle.synthetic_dictionary, seed 1)'}
 CONV_IMAGES_PER_GPU, CONV_LAM = 128, 0.05
 
 
@@ -87,20 +96,38 @@ class ClockSampler:
             'samples': len(sm)}
 
 
+def cpu_reference_kind():
+  from oracle import reference
+  return 'reference' if reference.available() else 'port'
+
+
 def cpu_reference_patches_per_sec(sample, repeats=1):
-  """The reference's float32 CPU path (restated in oracle/vtc_oracle.py) on `sample` patches of the same workload."""
+  """The reference's own float32 CPU implementation (analysis_transforms/fully_connected/ista_fista.py:14-148, staged
+  unmodified under oracle/_ref) on `sample` patches of the same workload, all host cores; the oracle port only when
+  the staged copy is absent. Returns (patches/s, cores, seconds, kind)."""
+  from oracle import reference
   from oracle import vtc_oracle as oracle
   cores = os.cpu_count() or 1
   torch.set_num_threads(cores)
   phi = oracle.synthetic_dictionary(S, D)
   x = oracle.synthetic_patches(sample, D, kind='whitened')
-  oracle.ista_fista(x[:64], phi, LAM, 3)  # warm the thread pool
-  best = float('inf')
-  for _ in range(repeats):
-    t0 = time.perf_counter()
-    oracle.ista_fista(x, phi, LAM, T)
-    best = min(best, time.perf_counter() - t0)
-  return sample / best, cores, best
+  kind = cpu_reference_kind()
+
+  def timed_runs(run):
+    run(x[:64], phi, LAM, 3)  # warm the thread pool
+    best = float('inf')
+    for _ in range(repeats):
+      t0 = time.perf_counter()
+      run(x, phi, LAM, T)
+      best = min(best, time.perf_counter() - t0)
+    return best
+
+  if kind == 'reference':
+    with reference.reference_only():
+      best = timed_runs(reference.load('analysis_transforms.fully_connected.ista_fista').run)
+  else:
+    best = timed_runs(oracle.ista_fista)
+  return sample / best, cores, best, kind
 
 
 def conv_benchmark(world, rank, dev, timed, pk, precision, images_per_gpu=CONV_IMAGES_PER_GPU):
@@ -194,12 +221,22 @@ def config0_benchmark(rank, world, dev, timed, precision):
   out = {'workload': 'configs[0]: batch 250, 256 atoms, D=256, 300 FISTA iterations', 'ms_per_call': ms / 10,
          'patches_per_sec': 250 / (ms / 10 * 1e-3), 'gpu_launches_per_call': int(launches // 10)}
   if rank == 0 and world == 1:
+    from oracle import reference
     torch.set_num_threads(os.cpu_count() or 1)
-    oracle.ista_fista(x, phi, LAM, 10)
-    t0 = time.perf_counter()
-    oracle.ista_fista(x, phi, LAM, T)
-    cpu_ms = (time.perf_counter() - t0) * 1e3
-    out.update({'cpu_reference_ms_per_call': cpu_ms, 'cpu_cores': os.cpu_count() or 1,
+    kind = cpu_reference_kind()
+
+    def cpu_call(run):
+      run(x, phi, LAM, 10)
+      t0 = time.perf_counter()
+      run(x, phi, LAM, T)
+      return (time.perf_counter() - t0) * 1e3
+
+    if kind == 'reference':
+      with reference.reference_only():
+        cpu_ms = cpu_call(reference.load('analysis_transforms.fully_connected.ista_fista').run)
+    else:
+      cpu_ms = cpu_call(oracle.ista_fista)
+    out.update({'cpu_reference_ms_per_call': cpu_ms, 'cpu_cores': os.cpu_count() or 1, 'cpu_kind': kind,
                 'speedup_over_cpu_reference': cpu_ms / (ms / 10)})
   return out
 
@@ -241,9 +278,9 @@ def run_reference(args, rank):
   sample = CPU_SAMPLE if steps <= 6 else max(4096, (CPU_SAMPLE * 6 // steps) // 256 * 256)
   for _ in range(max(0, min(args.warmup, 1))):
     cpu_reference_patches_per_sec(256)
-  vals, secs, cores = [], [], 1
+  vals, secs, cores, kind = [], [], 1, 'port'
   for _ in range(steps):
-    v, cores, s = cpu_reference_patches_per_sec(sample)
+    v, cores, s, kind = cpu_reference_patches_per_sec(sample)
     vals.append(v)
     secs.append(s)
   value = sample * len(vals) / sum(secs)
@@ -251,13 +288,15 @@ def run_reference(args, rank):
       'impl': 'reference', 'metric': 'fista_patches_per_sec', 'value': value, 'unit': 'patches/s',
       'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(secs) / len(secs),
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': WORKLOAD, 'note': 'CPU float32 torch path of the reference (oracle port), all host '
-                 'threads; each step is a %d-patch sample of the workload, throughput is linear in the batch'
-                 % sample},
-      'cpu_baseline': {'value': value, 'unit': 'patches/s', 'cores': cores, 'kind': 'port',
-                       'sample': '%d of 65536 patches x 300 iterations per step' % sample},
       'e2e': {'value': value, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
+      'cpu_baseline': {'value': value, 'unit': 'patches/s', 'cores': cores, 'kind': kind,
+                       'sample': '%d of %d patches x %d iterations per step; throughput is linear in the batch '
+                                 '(every patch is an independent problem)' % (sample, args.batch, T),
+                       'what': ('the unmodified reference, analysis_transforms/fully_connected/ista_fista.py run() '
+                                'staged under oracle/_ref, float32 torch on all host threads') if kind == 'reference'
+                               else 'oracle port of the reference (oracle/_ref not staged), float32 torch on all host threads'},
+      'config': shared_config(args.batch),
   }
   emit(line)
 
@@ -348,122 +387,157 @@ def main():
     barrier()
     return max_over_ranks(e0.elapsed_time(e1)), lib.vtc_launch_count() - n0
 
-  # ---- headline: inputs resident in HBM
+  # ---- headline: inputs resident in HBM. The library records its own CUDA events (setup / iteration launches /
+  #      finishing copy of EVERY call, on the launching stream) inside this same timed loop, so the per-kernel figures
+  #      below are of the timed region itself, not of a separate call made afterwards.
+  import ctypes
   sampler = ClockSampler(local_rank)
   if rank == 0:
     sampler.start()
-  total_ms, launches = timed(lambda: ista_fista.run(x, phi, LAM, T), args.steps, args.warmup)
+  for _ in range(args.warmup):
+    ista_fista.run(x, phi, LAM, T)
+  barrier()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  n0 = lib.vtc_launch_count()
+  lib.vtc_profile_enable(1)
+  e0.record()
+  for _ in range(args.steps):
+    ista_fista.run(x, phi, LAM, T)
+  e1.record()
+  barrier()
+  total_ms, launches = max_over_ranks(e0.elapsed_time(e1)), lib.vtc_launch_count() - n0
   clocks = sampler.stop() if rank == 0 else None
   ms_per_step = total_ms / args.steps
   value = world * Bn / (ms_per_step * 1e-3)
+  per_step = []
+  f = [ctypes.c_float() for _ in range(4)]
+  for i in range(lib.vtc_profile_history_count()):
+    _lib.check(lib.vtc_profile_history(i, *[ctypes.byref(v) for v in f]))
+    per_step.append({'setup_ms': f[0].value, 'iter_ms': f[1].value, 'finish_ms': f[2].value, 'gap_to_next_ms': f[3].value})
+  setup_ms, iter_ms, n_launch, n_iter, fused_ms, first_ms = (ctypes.c_float(), ctypes.c_float(), ctypes.c_int(),
+                                                             ctypes.c_int(), ctypes.c_float(), ctypes.c_float())
+  _lib.check(lib.vtc_profile_last(ctypes.byref(setup_ms), ctypes.byref(iter_ms), ctypes.byref(n_launch),
+                                  ctypes.byref(n_iter), ctypes.byref(fused_ms), ctypes.byref(first_ms)))
+  lib.vtc_profile_enable(0)
+  n_launch, n_iter, first_ms = n_launch.value, n_iter.value, first_ms.value
+  mean = lambda key: sum(r[key] for r in per_step) / max(1, len(per_step))  # noqa: E731
+  setup_ms, iter_ms, finish_ms = mean('setup_ms'), mean('iter_ms'), mean('finish_ms')
+  gap_ms = sum(r['gap_to_next_ms'] for r in per_step) / max(1, len(per_step) - 1)
+  accounted_ms = setup_ms + iter_ms + finish_ms + gap_ms
 
-  # ---- the dominant kernel: CUDA events recorded by the library, on the launching stream, around 16 sampled launches
-  #      of the fused ISTA/FISTA kernel in the middle of one more call (and around all iteration launches together)
-  import ctypes
   pk = peaks()
   nprod = pkg.PRECISIONS[args.precision]
   nparts = {1: 1, 3: 2, 6: 3}[nprod]
   form = {1: 'gram', 2: 'synthesis'}[lib.vtc_get_formulation(S, D)]
   fused_iter = form == 'synthesis' and bool(lib.vtc_get_fused_iteration(S, D, nprod))
-
-  def profile_call():
-    lib.vtc_profile_enable(1)
-    ista_fista.run(x, phi, LAM, T)
-    setup_ms, iter_ms, fused_ms, first_ms = (ctypes.c_float() for _ in range(4))
-    n_launch, n_iter = ctypes.c_int(), ctypes.c_int()
-    _lib.check(lib.vtc_profile_last(ctypes.byref(setup_ms), ctypes.byref(iter_ms), ctypes.byref(n_launch),
-                                    ctypes.byref(n_iter), ctypes.byref(fused_ms), ctypes.byref(first_ms)))
-    lib.vtc_profile_enable(0)
-    return setup_ms.value, iter_ms.value, n_launch.value, n_iter.value, fused_ms.value, first_ms.value
-
-  setup_ms, iter_ms, n_launch, n_iter, fused_ms, first_ms = profile_call()
-  gram_flops_iter = 2.0 * Bn * S * S       # north-star (Gram form) algorithmic flops of one iteration
-  synth_flops_iter = 4.0 * Bn * S * D      # the reference's own two-contraction form
-  flops_iter = gram_flops_iter if form == 'gram' else synth_flops_iter
-  iter_ms_each = iter_ms / max(1, n_iter)
+  persistent = fused_iter and n_launch == 1
+  gram_flops_iter = 2.0 * Bn * S * S       # north-star (Gram form) algorithmic flops of one iteration (SURVEY 8d)
+  synth_flops_iter = 4.0 * Bn * S * D      # the reference's own two-contraction form (what is executed, x products)
+  launch_iters = n_iter if persistent else 1
+  launch_ms = iter_ms if persistent else fused_ms.value   # the dominant kernel's launch: all iterations, or one
   if form == 'gram':
-    # one launch per iteration: y G - b and the fused update. fp32 state 12 B read + 4 B written, bf16 parts 2P + 2P
-    bytes_fused = Bn * S * (16 + 4 * nparts)
-    flops_fused = gram_flops_iter
-    bound = 'hbm' if nprod == 1 else 'tensor'
+    bytes_iter = Bn * S * (16 + 4 * nparts)
   elif fused_iter:
-    # ONE launch per iteration (fista_iter_kernel.cuh): reads a_{k-1}, a_{k-2} (8 B) and writes a_k (4 B) per code
-    # element; per pixel reads x (4 B), reads r_{k-1} parts (2P B) and writes r_k parts (2P B). y_k stays on chip.
-    bytes_fused = Bn * S * 12 + Bn * D * (4 + 4 * nparts)
-    flops_fused = synth_flops_iter
-    hbm_ms = bytes_fused / (pk['hbm_gbs'] * 1e9) * 1e3
-    tensor_ms = nprod * flops_fused / (pk['bf16_sustained'] * 1e12) * 1e3
-    bound = 'hbm' if hbm_ms >= tensor_ms else 'tensor'
+    # per iteration: reads a_{k-1}, a_{k-2} (8 B) and writes a_k (4 B) per code element; per pixel reads x (4 B), reads
+    # r_{k-1} parts (2P B) and writes r_k parts (2P B). y_k stays on chip.
+    bytes_iter = Bn * S * 12 + Bn * D * (4 + 4 * nparts)
   else:
-    # fused launch: acc = r Phi^T (K = D) + update. reads a_k, a_{k-1} (8 B) and r parts; writes a (4 B) + y parts (2P)
-    bytes_fused = Bn * S * (12 + 2 * nparts) + Bn * D * 2 * nparts
-    flops_fused = 2.0 * Bn * S * D
-    bound = 'hbm'
-  if bound == 'hbm':
-    achieved = bytes_fused / (fused_ms * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                'frac': achieved / pk['hbm_gbs'], 'peak_source': pk['source'] + ' hbm_gbs (copy bandwidth)',
-                'algorithmic_bytes_per_launch': bytes_fused}
-  else:
-    achieved = flops_fused / (fused_ms * 1e-3) / 1e12
-    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk['bf16_sustained'], 'peak_source': pk['source'] + ' bf16_tflops_sustained',
-                'algorithmic_flops_per_launch': flops_fused,
-                'executed_frac': nprod * achieved / pk['bf16_sustained']}
+    bytes_iter = Bn * S * (12 + 2 * nparts) + Bn * D * 2 * nparts
+  executed_flops_iter = nprod * (gram_flops_iter if form == 'gram' else synth_flops_iter)
+  # primary roofline, SURVEY 8(d): Gram-form algorithmic flops of the launch / its duration, against the measured
+  # sustained cuBLAS bf16 throughput (the kernel is timed inside a long step)
+  achieved = launch_iters * gram_flops_iter / (launch_ms * 1e-3) / 1e12
   traffic = None  # DRAM bytes per launch of this kernel from the committed ncu --set full capture of the same shape
-  tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+  tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
   if os.path.exists(tpath) and form == 'synthesis' and Bn == B_PER_GPU:
-    traffic = json.load(open(tpath)).get(args.precision, {}).get('iter_bytes' if fused_iter else 'fused_bytes')
-  roofline.update({
-      'kernel': ('vtc_fista_iter_kernel<%d> (panel-resident, y_k on chip; launch_ms is per iteration)' % nparts) if fused_iter else
-                'vtc_gemm_kernel<EPI_FISTA,%d> (%s form)' % (nparts, form), 'traffic': traffic,
-      'launch_ms': fused_ms, 'first_launch_ms': first_ms if (form == 'synthesis' and not fused_iter) else None,
-      'algorithmic_bytes_per_launch': bytes_fused, 'executed_mma_flops_per_launch': nprod * flops_fused,
-      'hbm_floor_ms': bytes_fused / (pk['hbm_gbs'] * 1e9) * 1e3,
-      'tensor_floor_ms': nprod * flops_fused / (pk['bf16_sustained'] * 1e12) * 1e3,
-      'formulation': form, 'launches_per_iteration': n_launch / max(1, n_iter), 'ms_per_iteration': iter_ms_each,
-      'setup_ms_per_step': setup_ms,
-      # whole iteration loop against the tensor roofline, both flop conventions
-      'iteration_tflops_executed_form': flops_iter / (iter_ms_each * 1e-3) / 1e12,
-      'iteration_tflops_gram_equivalent': gram_flops_iter / (iter_ms_each * 1e-3) / 1e12,
-      'iteration_frac_of_tensor_peak_gram_equivalent':
-          gram_flops_iter / (iter_ms_each * 1e-3) / 1e12 / pk['bf16_sustained'],
-      'executed_mma_products_per_fp32_product': nprod,
-      'gram_form_flops_per_iteration': gram_flops_iter, 'reference_form_flops_per_iteration': synth_flops_iter,
-  })
+    per_iter = json.load(open(tpath)).get(args.precision, {}).get('iter_bytes')
+    traffic = per_iter * launch_iters if per_iter else None
+  hbm_gbs = launch_iters * bytes_iter / (launch_ms * 1e-3) / 1e9
+  roofline = {
+      'bound': 'tensor', 'achieved': achieved, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
+      'frac': achieved / pk['bf16_sustained'], 'peak_source': pk['source'] + ' bf16_tflops_sustained (cuBLAS)',
+      'basis': 'Gram-form algorithmic flops 2 B S^2 per iteration (SURVEY 8d) x %d iterations per launch' % launch_iters,
+      'traffic': traffic,
+      'kernel': ('vtc_fista_iter_kernel<%d> (panel-resident, y_k on chip; %s)' %
+                 (nparts, 'ONE launch = all %d iterations' % n_iter if persistent else 'one launch per iteration'))
+                if fused_iter else 'vtc_gemm_kernel<EPI_FISTA,%d> (%s form)' % (nparts, form),
+      'launch_ms': launch_ms, 'iterations_per_launch': launch_iters, 'ms_per_iteration': launch_ms / launch_iters,
+      'frac_of_burst_peak': achieved / pk['bf16_burst'] if pk['bf16_burst'] else None,
+      'executed_mma': {'tflops': launch_iters * executed_flops_iter / (launch_ms * 1e-3) / 1e12,
+                       'frac': launch_iters * executed_flops_iter / (launch_ms * 1e-3) / 1e12 / pk['bf16_sustained'],
+                       'products_per_fp32_product': nprod, 'form': form,
+                       'note': 'the %s form executes %.0f%% of the Gram-form flops, times %d bf16 products' %
+                               (form, 100 * (1.0 if form == 'gram' else synth_flops_iter / gram_flops_iter), nprod)},
+      'hbm': {'achieved': hbm_gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': hbm_gbs / pk['hbm_gbs'],
+              'algorithmic_bytes_per_iteration': bytes_iter, 'algorithmic_bytes_per_launch': launch_iters * bytes_iter,
+              'floor_ms_per_iteration': bytes_iter / (pk['hbm_gbs'] * 1e9) * 1e3},
+      'tensor_floor_ms_per_iteration_executed': executed_flops_iter / (pk['bf16_sustained'] * 1e12) * 1e3,
+      'first_launch_ms': first_ms if (form == 'synthesis' and not fused_iter) else None,
+      # where a timed step goes (means over the %d timed steps, library events on the launching stream)
+      'step_breakdown': {'setup_ms': setup_ms, 'iter_ms': iter_ms, 'finish_ms': finish_ms, 'gap_to_next_ms': gap_ms,
+                         'sum_ms': accounted_ms, 'ms_per_step': ms_per_step,
+                         'unaccounted_frac': (ms_per_step - accounted_ms) / ms_per_step,
+                         'per_step': per_step[:8]},
+  }
 
-  # ---- end to end through the public API from pinned host memory
-  codes_host = torch.empty((Bn, S), dtype=torch.float32).pin_memory()
+  # ---- end to end through the public API from pinned host memory: every step uploads its images and downloads its
+  #      codes; two steps are in flight (host_pipeline), so the copies of step i run under the compute of i - 1 / i + 1
+  from vision_transform_codes_b200.host_pipeline import HostPipeline
   pkg.config.check_finite = True  # the default user-facing behaviour
+  depth = 2
+  codes_host = [torch.empty((Bn, S), dtype=torch.float32).pin_memory() for _ in range(depth)]
+  pipe = HostPipeline(dev, depth=depth)
+  e2e_steps = max(4, min(args.steps, 8))
 
-  def e2e_step():
+  def e2e_run(n):
+    for i in range(n):
+      pipe.submit(x_host, phi, LAM, T, out=codes_host[i % depth])
+    pipe.synchronize()
+
+  e2e_run(2)
+  barrier()
+  s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  s0.record(pipe.upload)       # the first upload starts after this ...
+  e2e_run(e2e_steps)
+  s1.record(pipe.download)     # ... and the last download has finished before this
+  barrier()
+  e2e_ms = max_over_ranks(s0.elapsed_time(s1)) / e2e_steps
+  e2e = {'value': world * Bn / (e2e_ms * 1e-3), 'unit': 'patches/s', 'ms_per_step': e2e_ms, 'steps': e2e_steps,
+         'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': codes_host[0].numel() * 4,
+         'how': 'HostPipeline depth 2: per step one pinned H2D copy of the images, one ista_fista.run, one D2H copy of '
+                'the dense fp32 codes; CUDA events from before the first upload to after the last download, max over ranks',
+         'frac_of_device_resident_value': (world * Bn / (e2e_ms * 1e-3)) / value}
+  # the same without overlap (one step at a time, synchronised): what a naive caller gets
+  def serial_step():
     xd = x_host.to(dev, non_blocking=True)
     codes = ista_fista.run(xd, phi, LAM, T)
-    codes_host.copy_(codes, non_blocking=True)
+    codes_host[0].copy_(codes, non_blocking=True)
     torch.cuda.current_stream().synchronize()
 
-  e2e_ms, _ = timed(e2e_step, max(2, min(args.steps, 3)), 1)
-  e2e_ms /= max(2, min(args.steps, 3))
-  e2e = {'value': world * Bn / (e2e_ms * 1e-3), 'unit': 'patches/s', 'ms_per_step': e2e_ms,
-         'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': codes_host.numel() * 4}
+  ser_ms, _ = timed(serial_step, 2, 1)
+  e2e['serial_ms_per_step'] = ser_ms / 2
   pkg.config.check_finite = False
+  del pipe
 
   line = {
       'metric': 'fista_patches_per_sec', 'value': value, 'unit': 'patches/s', 'n_gpus': world, 'steps': args.steps,
       'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': args.precision + ' (bf16 products, fp32 accumulate)', 'data': 'synthetic',
-      'config': {'workload': WORKLOAD, 'batch_per_gpu': Bn, 'atoms': S, 'pixels': D, 'iters': T,
-                 'precision': args.precision, 'formulation': form,
-                 'schedule': ('one persistent launch for all %d iterations' % n_iter if n_launch == 1 else
-                              'one launch per iteration') if fused_iter else
-                             '%d launch(es) per iteration' % (n_launch // max(1, n_iter)),
-                 'parallelism': 'batch sharded over %d GPU(s), dictionary replicated, '
-                 'no data-path collective' % world,
-                 'l2': 'inputs larger than L2 (per-iteration state %.0f MB vs 126 MB L2)' % (Bn * S * 4 * 3 / 1e6)},
-      'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'clocks': clocks,
+      'e2e': e2e, 'gpu_launches': int(launches), 'train_step': None, 'roofline': roofline, 'clocks': clocks,
+      'cpu_baseline': None, 'config': shared_config(Bn),
+      'implementation': {'precision': args.precision, 'formulation': form,
+                         'schedule': ('one persistent launch for all %d iterations' % n_iter if persistent else
+                                      'one launch per iteration') if fused_iter else
+                                     '%d launch(es) per iteration' % (n_launch // max(1, n_iter)),
+                         'parallelism': 'batch sharded over %d GPU(s), dictionary replicated, no data-path '
+                                        'collective' % world,
+                         'l2': 'inputs larger than L2 (per-iteration state %.0f MB vs 126 MB L2)' % (Bn * S * 4 * 3 / 1e6)},
   }
 
   if not args.no_extras:
+    # the collective-bearing number first (it must survive truncated logs): configs[2], one full train step
+    from vision_transform_codes_b200.lean import sparse_coding as trainer
+    line['train_step'] = trainer.benchmark_train_step(TRAIN_GLOBAL_BATCH, S, D, T, LAM, world, rank, dev, timed)
     # separately toleranced plain-bf16 path (1 MMA pass per product)
     if args.precision != 'bf16':
       pkg.config.precision = 'bf16'
@@ -473,7 +547,7 @@ def main():
                            'tflops_gram_equivalent_whole_call': (T * gram_flops_iter) / (ms * 1e-3) / 1e12,
                            'frac_of_tensor_peak_gram_equivalent':
                                (T * gram_flops_iter) / (ms * 1e-3) / 1e12 / pk['bf16_sustained'],
-                           'tolerance': 'codes rel-L2 <= 5e-2, reconstructions <= 1e-2 (tests/test_gpu_parity.py)'}
+                           'tolerance': 'codes rel-L2 <= 1.4e-2, reconstructions <= 4e-3 (tests/test_gpu_parity.py)'}
       if fused_iter:
         # the plain-bf16 iteration kernel is HBM-bound: fp32 state 12 B per code element + x, r parts per pixel; the
         # whole call (setup included) against the measured copy bandwidth
@@ -483,18 +557,13 @@ def main():
                                          'frac': gbs / pk['hbm_gbs'], 'algorithmic_bytes_per_iteration': bytes_bf16,
                                          'basis': 'whole call / %d iterations' % T}
       pkg.config.precision = args.precision
-    try:
-      from vision_transform_codes_b200.lean import sparse_coding as trainer
-      line['train_step'] = trainer.benchmark_train_step(TRAIN_GLOBAL_BATCH, S, D, T, LAM, world, rank, dev, timed)
-    except ImportError:
-      pass
     line['conv_path'] = conv_benchmark(world, rank, dev, timed, pk, args.precision)
     line['subspace_path'] = subspace_benchmark(world, rank, dev, timed, pk, args.precision)
     line['config0'] = config0_benchmark(rank, world, dev, timed, args.precision)
     line['metrics_path'] = metrics_benchmark(rank, world, dev, timed, ista_fista.run(x, phi, LAM, T), x, phi)
     if rank == 0 and world == 1:
-      v, cores, secs = cpu_reference_patches_per_sec(CPU_SAMPLE)
-      line['cpu_baseline'] = {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': 'port',
+      v, cores, secs, kind = cpu_reference_patches_per_sec(CPU_SAMPLE)
+      line['cpu_baseline'] = {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': kind,
                               'sample': '%d of %d patches x %d iterations (%.1f s), float32 torch on the host'
                               % (CPU_SAMPLE, Bn, T, secs)}
   if rank == 0:

@@ -29,8 +29,15 @@ def test_reference_arm_prints_one_json_line():
   assert line['metric'] == 'fista_patches_per_sec' and line['unit'] == 'patches/s' and line['higher_is_better'] is True
   assert line['steps'] == 2 and line['warmup'] == 1 and line['n_gpus'] == 1 and line['vs_baseline'] is None
   assert line['value'] > 0 and line['ms_per_step'] > 0 and 'workload' in line['config']
-  assert set(line['cpu_baseline']) >= {'value', 'unit', 'cores', 'kind', 'sample'} and line['cpu_baseline']['kind'] == 'port'
+  assert set(line['cpu_baseline']) >= {'value', 'unit', 'cores', 'kind', 'sample'}
+  # the unmodified reference when it is staged (oracle/_ref, tools/stage_reference.py), else the oracle port
+  from oracle import reference
+  assert line['cpu_baseline']['kind'] == ('reference' if reference.available() else 'port')
   assert line['e2e'] == {'value': line['value'], 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+  # both arms describe the SAME workload in `config` (nothing implementation-specific in it)
+  sys.path.insert(0, ROOT)
+  import bench
+  assert line['config'] == bench.shared_config(bench.B_PER_GPU)
 
 
 def test_reference_arm_other_ranks_print_nothing():
@@ -51,3 +58,10 @@ def test_b200_arm_prints_one_json_line():
   assert set(line['e2e']) >= {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'}
   assert line['e2e']['h2d_bytes_per_step'] == 8192 * 256 * 4 and line['e2e']['d2h_bytes_per_step'] == 8192 * 1024 * 4
   assert set(line['clocks']) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
+  assert line['roofline']['bound'] == 'tensor' and set(line['roofline']['hbm']) >= {'achieved', 'peak', 'frac'}
+  # the library's own events of the timed steps add up to the driver-timed step (10.7 % was unaccounted)
+  br = line['roofline']['step_breakdown']
+  assert abs(br['unaccounted_frac']) < 0.05, br
+  sys.path.insert(0, ROOT)
+  import bench
+  assert line['config'] == bench.shared_config(8192)

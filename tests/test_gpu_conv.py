@@ -228,15 +228,48 @@ def test_conv_error_behaviour():
     ista_fista.run(x, phi, (8, 8), pad, 0.1, 3, variant='lista')
   with pytest.raises(UnboundLocalError):
     ista_fista.run(x, phi, (8, 8), pad, 0.1, 0)
-  with pytest.raises(NotImplementedError):
-    # kernel not a multiple of the stride: not on the GEMM path
-    ista_fista.run(torch.zeros(1, 1, 31, 31).cuda(), phi, (5, 5), pad, 0.1, 3)
+  # (a kernel size that is not a multiple of the stride is supported: test_conv_kernel_not_a_multiple_of_the_stride)
   with pytest.raises(RuntimeError):
     ista_fista.run(torch.zeros(1, 1, 35, 32).cuda(), phi, (8, 8), pad, 0.1, 3)
   bad = phi.clone()
   bad[2, 0, 3, 3] = float('inf')
   with pytest.raises(RuntimeError):
     ista_fista.run(x, bad, (8, 8), pad, 0.1, 3)
+
+
+def test_conv_kernel_not_a_multiple_of_the_stride():
+  """The reference takes any kernel size whose strides tile the padded image (analysis_transforms/convolutional/
+  ista_fista.py:119-122; ceil in utils/convolutions.py:14-15): 12 x 10 kernels at stride (8, 4), two channels. Codes,
+  both dictionary updates and the Hessian mean against the CPU oracle (torch conv2d / conv_transpose2d)."""
+  ista_fista, cheap, steepest = modules()
+  from vision_transform_codes_b200.dict_update_rules.convolutional import _common
+  g = torch.Generator().manual_seed(11)
+  kh, kw, st = 12, 10, (8, 4)
+  pad = ((4, 4), (6, 2))
+  h, w = kh + 4 * st[0], kw + 9 * st[1]          # (h - kh) % sy == 0: 5 x 10 code positions
+  img = torch.zeros(3, 2, h, w)
+  img[:, :, pad[0][0]:h - pad[0][1], pad[1][0]:w - pad[1][1]] = 0.3 * torch.randn(
+      3, 2, h - sum(pad[0]), w - sum(pad[1]), generator=g)
+  phi = torch.randn(7, 2, kh, kw, generator=g)
+  yy = (torch.arange(kh) - (kh - 1) / 2)[:, None] / (0.18 * kh)
+  xx = (torch.arange(kw) - (kw - 1) / 2)[None, :] / (0.18 * kw)
+  phi = phi * torch.exp(-0.5 * (yy**2 + xx**2))
+  phi = phi / phi.flatten(1).norm(dim=1)[:, None, None, None]
+  for variant, kw_ in (('fista', {}), ('ista', {'nonnegative_only': True})):
+    want = oracle.conv_ista_fista(img, phi, st, pad, 0.05, 30, variant=variant, **kw_)
+    got = ista_fista.run(img.cuda(), phi.cuda(), st, pad, 0.05, 30, variant=variant, **kw_)
+    assert tuple(got.shape) == (3, 7, 5, 10)
+    check(got, want, case='12x10 kernels, stride (8, 4), ' + variant)
+  codes = oracle.conv_ista_fista(img, phi, st, pad, 0.05, 30)
+  hd = torch.mean(torch.sum(codes**2, dim=(2, 3)), dim=0) / 100
+  d = phi.cuda()
+  cheap.run(img.cuda(), d, codes.cuda(), hd.cuda(), st, pad, stepsize=0.05, num_iters=2)
+  assert oracle.relative_l2(d.cpu(), oracle.conv_sc_dictionary_update(img, phi, codes, st, pad, hd, stepsize=0.05,
+                                                                    num_iters=2)) < DICT_TOL
+  d = phi.cuda()
+  steepest.run(img.cuda(), d, codes.cuda(), st, pad, stepsize=0.05)
+  assert oracle.relative_l2(d.cpu(), oracle.conv_sc_dictionary_update(img, phi, codes, st, pad, None, stepsize=0.05)) < DICT_TOL
+  assert tuple(_common.dictionary_gradient(img.cuda(), phi.cuda(), codes.cuda(), st, pad).shape) == (7, 2, kh, kw)
 
 
 def test_conv_determinism_and_image_shard_independence():

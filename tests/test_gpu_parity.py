@@ -17,8 +17,8 @@ pytestmark = pytest.mark.gpu
 
 CODE_TOL = 1e-4       # north_star: relative L2 on codes, float32-parity path
 RECON_TOL = 1e-4      # north_star: relative L2 on reconstructions
-BF16_CODE_TOL = 3e-2  # separately toleranced plain-bf16 path: <= 2x the largest value measured over this suite
-BF16_RECON_TOL = 6e-3  # (profiles/parity_r02.json: codes 1.5e-2, reconstructions 2.8e-3 on the overcomplete shape)
+BF16_CODE_TOL = 1.4e-2  # separately toleranced plain-bf16 path: 2x what it measures on the overcomplete shape
+BF16_RECON_TOL = 4e-3   # (profiles/parity_r02.json: codes 6.8e-3, reconstructions 1.9e-3, 166 support flips of 98 304)
 GUARD_BAND = 1e-4     # a support flip whose non-zero side is below this is a tie at the threshold
 
 

@@ -169,3 +169,32 @@ def test_tools_and_entry_points_compile():
   assert len(files) > 10
   for f in files:
     py_compile.compile(f, doraise=True)
+
+
+def test_dataset_pickle_reader_takes_the_references_format(tmp_path):
+  """{'training': {'patches': ndarray, ...}, 'validation': {...}} (tests/dset_generation_1.py:13-25)."""
+  import pickle
+  import numpy as np
+  from vision_transform_codes_b200.utils import dataset_generation as dg
+  rng = np.random.RandomState(0)
+  raw = {'training': {'patches': rng.randn(103, 64).astype('float32'), 'local_contrasts': rng.randn(103, 1)},
+         'validation': {'patches': rng.randn(40, 64).astype('float32')}}
+  path = tmp_path / 'field_white_8x8.p'
+  pickle.dump(raw, open(path, 'wb'))
+  got = dg.load_patch_dataset(path, 'cpu')
+  assert torch.equal(got['training'], torch.from_numpy(raw['training']['patches']))
+  assert torch.equal(got['validation'], torch.from_numpy(raw['validation']['patches']))
+  assert set(got['extras']['training']) == {'local_contrasts'}
+  batched = dg.load_patch_dataset(path, 'cpu', batch_size=25, shuffle=True)
+  seen = torch.cat(list(batched['training']))
+  assert len(batched['training']) == 5 and seen.shape == (103, 64)
+  assert torch.equal(seen.sort(dim=0).values, got['training'].sort(dim=0).values)   # a permutation of the patches
+  assert [b.size(0) for b in dg.DeviceBatches(got['training'], 25, drop_last=True)] == [25] * 4
+  assert [b.size(0) for b in batched['validation']] == [40]
+  # unflattened (padded) image patches keep their (N, c, h, w) shape (tests/dset_generation_1.py:44-63)
+  raw4 = {'training': {'patches': rng.randn(6, 1, 24, 24).astype('float32')}}
+  pickle.dump(raw4, open(path, 'wb'))
+  assert dg.load_patch_dataset(path, 'cpu')['training'].shape == (6, 1, 24, 24)
+  pickle.dump({'nope': 1}, open(path, 'wb'))
+  with pytest.raises(ValueError):
+    dg.load_patch_dataset(path, 'cpu')

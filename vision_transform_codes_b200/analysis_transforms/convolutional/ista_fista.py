@@ -47,12 +47,31 @@ def geometry(images_padded, dictionary, kernel_stride, padding_dims):
   return (B, C, H, W, S, KH, KW, SY, SX) + pads + (SH, SW)
 
 
+def align_to_stride(images_padded, dictionary, geo):
+  """
+  The kernels treat a kernel as ceil(k / stride) taps of one stride each, so a kernel size that is not a multiple of
+  the stride (the reference takes any, analysis_transforms/convolutional/ista_fista.py:119-122 with the ceil of
+  utils/convolutions.py:14-15) is zero-padded at its trailing edge up to the next multiple, and the images get the
+  same number of trailing zero rows / columns, counted as padding (masked). Nothing changes numerically: the extra taps
+  multiply zeros in the analysis, the extra pixels of the synthesis lie in the masked border, the code grid and the
+  Gram matrix of the flattened kernels (step size) are the same. Returns (images, dictionary, geometry) to compute with.
+  """
+  B, C, H, W, S, KH, KW, SY, SX, pt, pb, pl, pr, SH, SW = geo
+  ey, ex = (-KH) % SY, (-KW) % SX
+  if ey == 0 and ex == 0:
+    return images_padded, dictionary, geo
+  images_padded = torch.nn.functional.pad(images_padded, (0, ex, 0, ey))
+  dictionary = torch.nn.functional.pad(dictionary, (0, ex, 0, ey))
+  return images_padded, dictionary, (B, C, H + ey, W + ex, S, KH + ey, KW + ex, SY, SX, pt, pb + ey, pl, pr + ex, SH, SW)
+
+
 def infer(images_padded, dictionary, kernel_stride, padding_dims, sparsity_weight, num_iters, variant,
           initial_codes, early_stopping_epsilon, nonnegative_only, hard_threshold, precision=None):
   """Returns (codes, iterations actually run)."""
   _lib.require_cuda_f32(images_padded, 'images_padded')
   _lib.require_cuda_f32(dictionary, 'dictionary')
   geo = geometry(images_padded, dictionary, kernel_stride, padding_dims)
+  images_padded, dictionary, geo = align_to_stride(images_padded, dictionary, geo)
   B, C, H, W, S, KH, KW, SY, SX, pt, pb, pl, pr, SH, SW = geo
   if num_iters < 1:
     # the reference falls out of its while loop and returns a name that was never bound (ista_fista.py:141,197)
@@ -112,7 +131,7 @@ def run(images_padded, dictionary, kernel_stride, padding_dims,
   dictionary : torch.Tensor(float32, size=(s, c, kh, kw))
       The kernels; s is the number of channels of the code.
   kernel_stride : tuple(int, int)
-      Vertical and horizontal stride of the kernels. The kernel size must be a multiple of the stride.
+      Vertical and horizontal stride of the kernels.
   padding_dims : tuple(tuple(int, int), tuple(int, int))
       (leading, trailing) padding of the images, vertical then horizontal: the reconstruction error in this border is
       ignored (utils.convolutions.create_mask).

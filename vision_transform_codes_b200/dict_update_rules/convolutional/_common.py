@@ -6,12 +6,12 @@ import torch
 
 try:
   from vision_transform_codes_b200 import _lib, config
-  from vision_transform_codes_b200.analysis_transforms.convolutional.ista_fista import geometry
+  from vision_transform_codes_b200.analysis_transforms.convolutional.ista_fista import align_to_stride, geometry
   from vision_transform_codes_b200.dict_update_rules.fully_connected._common import global_batch_size
 except ImportError:
   sys.path.append(os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
   from vision_transform_codes_b200 import _lib, config
-  from vision_transform_codes_b200.analysis_transforms.convolutional.ista_fista import geometry
+  from vision_transform_codes_b200.analysis_transforms.convolutional.ista_fista import align_to_stride, geometry
   from vision_transform_codes_b200.dict_update_rules.fully_connected._common import global_batch_size
 
 
@@ -19,19 +19,30 @@ def dictionary_gradient(images_padded, dictionary, codes, kernel_stride, padding
   """Gradient of the reconstruction error w.r.t. the kernels, summed over this batch (not divided by it), (s, c, kh, kw)."""
   lib = _lib.load()
   device = dictionary.device
-  B, C, H, W, S, KH, KW, SY, SX, pt, pb, pl, pr, SH, SW = geometry(images_padded, dictionary, kernel_stride,
-                                                                    padding_dims)
+  geo = geometry(images_padded, dictionary, kernel_stride, padding_dims)
+  kh, kw = dictionary.size(2), dictionary.size(3)
+  # a kernel size that is not a multiple of the stride: zero taps up to the next multiple (align_to_stride); the
+  # gradient of those taps is not part of the dictionary and is cropped away
+  images_padded, dictionary, geo = align_to_stride(images_padded, dictionary, geo)
+  B, C, H, W, S, KH, KW, SY, SX, pt, pb, pl, pr, SH, SW = geo
+  aligned = (KH, KW) != (kh, kw)
   if tuple(codes.shape) != (B, S, SH, SW):
     raise ValueError('codes must have shape %s, got %s' % ((B, S, SH, SW), tuple(codes.shape)))
-  if out is None:
-    out = torch.empty((S, C, KH, KW), dtype=torch.float32, device=device)
+  full = out if (out is not None and not aligned) else torch.empty((S, C, KH, KW), dtype=torch.float32, device=device)
   prec = config.precision_code('update_precision')
   with torch.cuda.device(device):
     nbytes = max(16, lib.vtc_conv_dict_grad_workspace_bytes(B, C, H, W, S, KH, KW, SY, SX, prec))
     ws = _lib.workspace(nbytes, device, 'conv_dict_grad')
     _lib.check(lib.vtc_sc_conv_dict_grad(
-        _lib.ptr(images_padded.contiguous()), _lib.ptr(dictionary), _lib.ptr(codes.contiguous()), _lib.ptr(out),
-        B, C, H, W, S, KH, KW, SY, SX, pt, pb, pl, pr, prec, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(device)))
+        _lib.ptr(images_padded.contiguous()), _lib.ptr(dictionary.contiguous()), _lib.ptr(codes.contiguous()),
+        _lib.ptr(full), B, C, H, W, S, KH, KW, SY, SX, pt, pb, pl, pr, prec, _lib.ptr(ws), ws.numel(),
+        _lib.stream_ptr(device)))
+  if not aligned:
+    return full
+  cropped = full[:, :, :kh, :kw]
+  if out is None:
+    return cropped.contiguous()
+  out.copy_(cropped)
   return out
 
 

@@ -260,6 +260,45 @@ def train_dictionary(training_image_dataset, validation_image_dataset, init_dict
   return hessian_diag
 
 
+def sharded_equivalence(S, D, num_iters, sparsity_weight, world, rank, device, reduced_batch=16384, steps=2):
+  """
+  SURVEY section 4(v) made visible to the driver: `steps` train steps on a reduced global batch, once sharded over the
+  `world` ranks (dictionary-gradient all-reduce over NCCL) and once unsharded on rank 0 alone; returns the relative L2
+  difference of the two dictionaries (rank 0; 0.0 by construction at world == 1). The shards are seeded per rank so
+  that rank 0 can rebuild the whole batch.
+  """
+  shard = reduced_batch // world
+
+  def shard_of(r):
+    g = torch.Generator(device=device).manual_seed(500 + r)
+    return 0.3 * torch.randn(shard, D, generator=g, device=device)
+
+  def init():
+    g = torch.Generator().manual_seed(1)
+    phi = torch.randn(S, D, generator=g)
+    return (phi / phi.norm(dim=1, keepdim=True)).to(device), torch.zeros(S, device=device)
+
+  def steps_on(x, phi, h, batch_global):
+    state = _UpdateState(phi)
+    for _ in range(steps):
+      codes = ista_fista.run(x, phi, sparsity_weight, num_iters)
+      update_dictionary(x, phi, codes, h, 0.1, 1, state, batch_global=batch_global)
+
+  was_parallel, was_group = config.data_parallel, config.process_group
+  try:
+    phi_sharded, h = init()
+    config.data_parallel, config.process_group = world > 1, None
+    steps_on(shard_of(rank), phi_sharded, h, shard * world)
+    config.data_parallel = False
+    if rank != 0:
+      return None
+    phi_single, h1 = init()
+    steps_on(torch.cat([shard_of(r) for r in range(world)]), phi_single, h1, shard * world)
+    return float(torch.norm(phi_sharded - phi_single) / torch.norm(phi_single))
+  finally:
+    config.data_parallel, config.process_group = was_parallel, was_group
+
+
 def benchmark_train_step(global_batch, S, D, num_iters, sparsity_weight, world, rank, device, timed, steps=2):
   """
   bench.py helper: BASELINE.json configs[2], one full train step = FISTA inference on this rank's shard of a
@@ -295,7 +334,9 @@ def benchmark_train_step(global_batch, S, D, num_iters, sparsity_weight, world, 
     same = torch.tensor([int(torch.equal(ref, phi))], device=device)
     dist.all_reduce(same, op=dist.ReduceOp.MIN)
     replicas_identical = bool(same.item())
+  equivalence = sharded_equivalence(S, D, num_iters, sparsity_weight, world, rank, device)
   return {'steps_per_sec': 1e3 / ms, 'ms_per_step': ms, 'global_batch': global_batch, 'shard_per_gpu': shard,
+          'phi_rel_l2_vs_single_gpu': equivalence,
           'scaling': 'strong', 'update_rule': 'sc_cheap_quadratic_descent', 'allreduce_bytes_per_step': 4 * (S * D + S),
           'patches_per_sec': global_batch * 1e3 / ms, 'gpu_launches': int(launches),
           'replicas_bit_identical': replicas_identical,

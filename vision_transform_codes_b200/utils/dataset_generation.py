@@ -73,3 +73,65 @@ def sample_patches(images, num_samples, patch_dimensions, edge_buffer, generator
   n, h, w = images.shape[:3]
   corners = draw_patch_corners(num_samples, n, (h, w), patch_dimensions, edge_buffer, generator, images.device)
   return extract_patches(images, corners, patch_dimensions, flatten_patches)
+
+
+class DeviceBatches:
+  """Iterable of training batches cut from a patch matrix that lives on the device (what the reference's examples
+  build from a DataLoader over ``OneOutputDset``, examples/train_sparse_coding.py:83-92): every pass reshuffles the
+  patches (one ``randperm`` + one gather on the device) and yields ``(batch, ...)`` tensors; the last, smaller batch is
+  kept unless ``drop_last``. ``train_dictionary`` only iterates its dataset argument, so this is a drop-in for it."""
+
+  def __init__(self, patches, batch_size, shuffle=True, drop_last=False, generator=None):
+    self.patches, self.batch_size, self.shuffle, self.drop_last = patches, int(batch_size), shuffle, drop_last
+    self.generator = generator
+
+  def __len__(self):
+    n = self.patches.size(0)
+    return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+  def __iter__(self):
+    n = self.patches.size(0)
+    data = self.patches
+    if self.shuffle:
+      data = data[torch.randperm(n, device=data.device, generator=self.generator)]
+    for i in range(len(self)):
+      yield data[i * self.batch_size:(i + 1) * self.batch_size]
+
+
+def load_patch_dataset(path, device, batch_size=None, validation_batch_size=None, shuffle=True, drop_last=False):
+  """
+  Reads a dataset pickle in the reference's format and puts it on the device.
+
+  The reference's dataset scripts (tests/dset_generation_1.py:13-25, :28-40, :44-63) pickle
+  ``{'training': {'patches': float32 ndarray, ...}, 'validation': {'patches': ...}}`` where ``patches`` is ``(N, D)``
+  for flattened patches or ``(N, c, h, w)`` for (padded) image patches; extra keys of the inner dictionaries
+  (``local_contrasts``, ``original_component_means``, ... utils/dataset_generation.py:314-333) are kept as numpy arrays.
+
+  Returns ``{'training': ..., 'validation': ...}``: device tensors when ``batch_size`` is None, else ``DeviceBatches``
+  iterables ready to be passed to ``train_dictionary`` (validation batches default to ten training batches, as in
+  examples/train_sparse_coding.py:88-90), plus ``'extras'`` with the remaining arrays per split.
+  """
+  import pickle
+
+  import numpy as np
+  with open(str(path), 'rb') as f:
+    raw = pickle.load(f)
+  if not isinstance(raw, dict) or 'training' not in raw:
+    raise ValueError("not a dataset pickle of the reference's format: expected a dict with a 'training' entry")
+  out, extras = {}, {}
+  for split in ('training', 'validation'):
+    if split not in raw:
+      continue
+    entry = raw[split]
+    if not isinstance(entry, dict) or 'patches' not in entry:
+      raise ValueError("dataset split %r has no 'patches' array" % split)
+    patches = torch.from_numpy(np.ascontiguousarray(entry['patches'], dtype=np.float32)).to(device)
+    extras[split] = {k: v for k, v in entry.items() if k != 'patches'}
+    if batch_size is None:
+      out[split] = patches
+    elif split == 'training':
+      out[split] = DeviceBatches(patches, batch_size, shuffle=shuffle, drop_last=drop_last)
+    else:
+      out[split] = DeviceBatches(patches, validation_batch_size or 10 * batch_size, shuffle=False)
+  out['extras'] = extras
+  return out
