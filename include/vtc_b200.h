@@ -76,6 +76,11 @@ int vtc_get_formulation(int64_t S, int64_t D);
  * whether a problem of this shape would run the one-launch schedule. */
 int vtc_set_fused_iteration(int on);
 int vtc_get_fused_iteration(int64_t S, int64_t D, int precision);
+/* Small problems in the Gram form (S <= 256 atoms, at most 2368 patches, scalar threshold, no early stopping, bf16 or
+ * bf16x3; e.g. BASELINE configs[0]) run ALL iterations in one launch with G, the drive, both iterates and the operand y
+ * resident on chip (csrc/fista_small_kernel.cuh); 0 keeps the tiled schedule (one launch per iteration) for them.
+ * Identical results either way. Also VTC_B200_SMALL. */
+int vtc_set_small_batch_kernel(int on);
 /* Debug aid (tools/iter_trace.py): four threads of CTA 0 of the NEXT one-launch iteration kernel write a timeline into
  * device_buffer (4 regions of 2048 uint64 words: [0] = event count, then event id << 48 | SM clock), zeroed by the
  * caller. One shot: the pointer is dropped after that launch. */

@@ -153,3 +153,38 @@ def test_whitening_against_reference_outputs_and_oracle():
   assert float(std.min()) == 0.0 and float(std.max()) == 1.0
   with pytest.raises(RuntimeError):
     image_processing.whiten_center_surround(batch, cut)   # CPU tensor: no fallback
+
+
+def test_small_batch_kernel_equals_the_tiled_schedule():
+  """csrc/fista_small_kernel.cuh (everything on chip, one launch for the whole run; what BASELINE configs[0] takes) and
+  the tiled Gram-form schedule (one launch per iteration) are the same arithmetic: bit-identical codes, for ragged
+  batch sizes, fewer than 256 atoms, a warm start, ISTA and the non-negative threshold, in both parity precisions."""
+  import vision_transform_codes_b200 as pkg
+  from vision_transform_codes_b200 import _lib
+  from vision_transform_codes_b200.analysis_transforms.fully_connected import ista_fista
+  lib = _lib.load()
+  saved = pkg.config.precision
+  try:
+    for precision in ('bf16x3', 'bf16'):
+      pkg.config.precision = precision
+      for (b, s, d) in ((250, 256, 256), (33, 200, 128), (1, 64, 64), (700, 256, 200)):
+        x = oracle.synthetic_patches(b, d, seed=b).cuda()
+        phi = oracle.synthetic_dictionary(s, d).cuda()
+        warm = ista_fista.run(x, phi, 0.1, 3)
+        for kw in ({}, {'variant': 'ista'}, {'nonnegative_only': True}, {'initial_codes': warm}):
+          got = {}
+          for small in (1, 0):
+            _lib.check(lib.vtc_set_small_batch_kernel(small))
+            n0 = lib.vtc_launch_count()
+            got[small] = ista_fista.run(x, phi, 0.1, 40, **kw)
+            got[small, 'launches'] = lib.vtc_launch_count() - n0
+          assert torch.equal(got[1], got[0]), (precision, b, s, d, kw)
+          assert got[1, 'launches'] < got[0, 'launches'] - 30   # one launch instead of forty
+    # the oracle agrees (this shape is tests/golden/inference_config1.npz's)
+    pkg.config.precision = 'bf16x3'
+    x, phi = oracle.synthetic_patches(250, 256), oracle.synthetic_dictionary(256, 256)
+    want = oracle.ista_fista(x, phi, 0.1, 60)
+    assert oracle.relative_l2(ista_fista.run(x.cuda(), phi.cuda(), 0.1, 60).cpu(), want) < 1e-4
+  finally:
+    lib.vtc_set_small_batch_kernel(1)
+    pkg.config.precision = saved

@@ -567,3 +567,28 @@ def test_inference_call_is_capturable_into_a_cuda_graph():
     assert torch.equal(conv_captured, conv_eager)
   finally:
     pkg.config.check_finite = saved
+
+
+def test_subspace_groups_wider_than_sixteen():
+  """subspace_ista_fista.py:94-96 takes groups of any size; beyond 16 atoms the group norm spans several epilogue
+  sub-tiles and the update runs as its own pass (wide_group_prox_kernel). In-order groups of 64, ragged / overlapping
+  groups of up to 20 (padded to 32), ISTA and FISTA, a warm start and early stopping, against the oracle."""
+  subspace = modules()[1]
+  b, n, s, T, lam = 40, 96, 256, 40, 0.1
+  x, phi = oracle.synthetic_patches(b, n, seed=3), oracle.synthetic_dictionary(s, n)
+  xd, pd = x.cuda(), phi.cuda()
+  in_order = [list(map(int, g)) for g in np.array_split(np.arange(s), s // 64)]
+  rng = np.random.RandomState(5)
+  ragged = [sorted(rng.choice(s, size=k, replace=False).tolist()) for k in (20, 3, 17, 9, 20, 1, 12)]
+  for name, groups in (('in-order groups of 64', in_order), ('ragged groups up to 20', ragged)):
+    for variant in ('fista', 'ista'):
+      want = oracle.subspace_ista_fista(x, phi, groups, lam, T, variant=variant)
+      got = subspace.run(xd, pd, groups, lam, T, variant=variant)
+      check_codes(got, want, phi, case='%s, %s' % (name, variant))
+  warm = oracle.subspace_ista_fista(x, phi, ragged, lam, 5)
+  check_codes(subspace.run(xd, pd, ragged, lam, T, initial_codes=warm.cuda()),
+              oracle.subspace_ista_fista(x, phi, ragged, lam, T, initial_codes=warm), phi, case='ragged, warm start')
+  want, want_iters = oracle.subspace_ista_fista(x, phi, in_order, lam, 1000, variant='ista', early_stopping_epsilon=1e-3,
+                                                return_iters=True)
+  got = subspace.run(xd, pd, in_order, lam, 1000, variant='ista', early_stopping_epsilon=1e-3)
+  check_codes(got, want, phi, tol=2e-3, recon_tol=2e-3, band=None, case='groups of 64, early stopping')

@@ -26,6 +26,7 @@ SIGNATURES = {
     'vtc_set_formulation': (_int, [_int]),
     'vtc_get_formulation': (_int, [_i64, _i64]),
     'vtc_set_fused_iteration': (_int, [_int]),
+    'vtc_set_small_batch_kernel': (_int, [_int]),
     'vtc_get_fused_iteration': (_int, [_i64, _i64, _int]),
     'vtc_debug_iter_trace': (_int, [_ptr]),
     'vtc_get_chains': (_int, [_i64, _i64, _i64]),

@@ -20,8 +20,6 @@ except ImportError:
   from vision_transform_codes_b200 import _lib, config
 from vision_transform_codes_b200.analysis_transforms.fully_connected import ista_fista as _vanilla
 
-MAX_GROUP_WIDTH = 16  # one epilogue sub-tile
-
 
 def _slot_table(group_assignments, num_atoms):
   """Atom index of every (group, position) slot, -1 for padding; width = max group size rounded up to 2^k."""
@@ -75,9 +73,9 @@ def run(images, dictionary, group_assignments, sparsity_weight,
   _lib.require_cuda_f32(images, 'images')
   _lib.require_cuda_f32(dictionary, 'dictionary')
   S = dictionary.size(0)
+  # groups of up to 16 elements shrink inside the GEMM epilogue; wider ones (padded to 32, 64, ...) take a separate
+  # pass per iteration (vtc_fista_fc, wide_group_prox_kernel)
   table, max_size, width = _slot_table(group_assignments, S)
-  if width > MAX_GROUP_WIDTH:
-    raise NotImplementedError('groups of more than %d elements are not supported yet' % MAX_GROUP_WIDTH)
   n_slots = table.size
   identity = (n_slots == S and np.array_equal(table.reshape(-1), np.arange(S, dtype=np.int32)))
   # the reference averages |delta|/stepsize over b * num_groups * max_size slots (:172-177); padding slots stay 0

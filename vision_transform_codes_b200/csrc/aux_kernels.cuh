@@ -261,54 +261,75 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int ns
 // (subspace_sc_cheap_quadratic_descent.py:91-127). One block per group; slots[g*W + i] is the atom of member i or -1.
 //   normalised dictionary:  grad_i = sum_j sign(c_ij) (phi_j - c_ij phi_i),            c = phi phi^T
 //   general:                grad_i = sum_j sign(c_ij) (phi_j / (n_i n_j) - c_ij / n_i^2 phi_i),  c_ij = phi_i.phi_j / (n_i n_j)
-// Contributions are accumulated with atomics because an atom may belong to several groups (:66-70).
+// One block per ATOM: it walks the groups in order and, for every group the atom belongs to, adds that group's
+// contribution to the atom's row -- the order of the reference's loop (:66-70: accum[group] = accum[group] + ...), no
+// atomics, so the result is bit-reproducible whatever the group structure (an atom in three or more groups made the
+// earlier atomicAdd version order-dependent, which broke the bit-identity of data-parallel replicas).
 __global__ void alignment_grad_kernel(const float* __restrict__ dict, int64_t D, const int32_t* __restrict__ slots,
-                                      int W, int normalized, float* __restrict__ accum) {
+                                      int num_groups, int W, int normalized, float* __restrict__ accum) {
   extern __shared__ float sm[];
-  float* rows = sm;                 // [W][D]
-  float* dots = sm + static_cast<size_t>(W) * D;  // [W][W]
-  float* norms = dots + W * W;      // [W]
-  const int g = blockIdx.x;
-  const int32_t* members = slots + static_cast<int64_t>(g) * W;
-  for (int64_t i = threadIdx.x; i < static_cast<int64_t>(W) * D; i += blockDim.x) {
-    const int m = static_cast<int>(i / D);
-    const int32_t a = members[m];
-    rows[i] = (a >= 0) ? dict[static_cast<int64_t>(a) * D + (i - m * D)] : 0.f;
-  }
-  __syncthreads();
+  float* rows = sm;                                // [W][D]: the rows of the current group
+  float* dots = sm + static_cast<size_t>(W) * D;   // [W]: <phi_m, phi_j> for this atom m
+  float* norms = dots + W;                         // [W]
+  __shared__ int member_pos;
+  const int32_t atom = static_cast<int32_t>(blockIdx.x);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int pair = warp; pair < W * W; pair += nwarps) {
-    const int i = pair / W, j = pair % W;
-    float acc = 0.f;
-    for (int64_t d = lane; d < D; d += 32) acc += rows[i * D + d] * rows[j * D + d];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) dots[pair] = acc;
-  }
-  __syncthreads();
-  if (threadIdx.x < W) norms[threadIdx.x] = sqrtf(dots[threadIdx.x * W + threadIdx.x]);
-  __syncthreads();
-  for (int64_t i = threadIdx.x; i < static_cast<int64_t>(W) * D; i += blockDim.x) {
-    const int m = static_cast<int>(i / D);
-    const int64_t d = i - static_cast<int64_t>(m) * D;
-    const int32_t a = members[m];
-    if (a < 0) continue;
-    float grad = 0.f;
-    for (int j = 0; j < W; ++j) {
-      if (members[j] < 0) continue;
-      float c, t;
-      if (normalized) {
-        c = dots[m * W + j];
-        t = rows[j * D + d] - c * rows[m * D + d];
-      } else {
-        const float nn = norms[m] * norms[j];
-        c = dots[m * W + j] / nn;
-        t = rows[j * D + d] / nn - (c / (norms[m] * norms[m])) * rows[m * D + d];
-      }
-      const float sgn = (c > 0.f) ? 1.f : (c < 0.f) ? -1.f : 0.f;
-      grad += sgn * t;
+  for (int g = 0; g < num_groups; ++g) {
+    const int32_t* members = slots + static_cast<int64_t>(g) * W;
+    if (threadIdx.x == 0) {
+      int pos = -1;
+      for (int j = 0; j < W; ++j)
+        if (members[j] == atom) {
+          pos = j;
+          break;
+        }
+      member_pos = pos;
     }
-    atomicAdd(accum + static_cast<int64_t>(a) * D + d, grad);
+    __syncthreads();
+    const int m = member_pos;
+    if (m < 0) {
+      __syncthreads();   // (member_pos is rewritten by the next group)
+      continue;
+    }
+    for (int64_t i = threadIdx.x; i < static_cast<int64_t>(W) * D; i += blockDim.x) {
+      const int j = static_cast<int>(i / D);
+      const int32_t a = members[j];
+      rows[i] = (a >= 0) ? dict[static_cast<int64_t>(a) * D + (i - static_cast<int64_t>(j) * D)] : 0.f;
+    }
+    __syncthreads();
+    for (int j = warp; j < W; j += nwarps) {
+      float acc = 0.f, nn = 0.f;
+      for (int64_t d = lane; d < D; d += 32) {
+        acc += rows[m * D + d] * rows[j * D + d];
+        nn += rows[j * D + d] * rows[j * D + d];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        nn += __shfl_xor_sync(0xffffffffu, nn, o);
+      }
+      if (lane == 0) dots[j] = acc, norms[j] = sqrtf(nn);
+    }
+    __syncthreads();
+    for (int64_t d = threadIdx.x; d < D; d += blockDim.x) {
+      float grad = 0.f;
+      for (int j = 0; j < W; ++j) {
+        if (members[j] < 0) continue;
+        float c, t;
+        if (normalized) {
+          c = dots[j];
+          t = rows[j * D + d] - c * rows[m * D + d];
+        } else {
+          const float nn = norms[m] * norms[j];
+          c = dots[j] / nn;
+          t = rows[j * D + d] / nn - (c / (norms[m] * norms[m])) * rows[m * D + d];
+        }
+        const float sgn = (c > 0.f) ? 1.f : (c < 0.f) ? -1.f : 0.f;
+        grad += sgn * t;
+      }
+      accum[static_cast<int64_t>(atom) * D + d] += grad;   // this block owns the row
+    }
+    __syncthreads();
   }
 }
 
@@ -838,6 +859,71 @@ __global__ void spectrum_filter_kernel(float2* __restrict__ spectrum, int64_t n,
     float2 v = spectrum[i];
     v.x *= f, v.y *= f;
     spectrum[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Subspace (group) shrinkage for groups WIDER than one epilogue sub-tile (more than 16 atoms; subspace_ista_fista.py:
+// 94-96 takes any width): the update of one iteration as a pass of its own over row-major arrays, one warp per
+// (patch, group):   y = a1 + beta_prev (a1 - a2);  u = y - eta * grad;  a = u * max(1 - theta / ||u_g||, 0)  with
+// ||u_g|| = 0 -> 1 (subspace_ista_fista.py:144-156);  y' = a + beta_next (a - a1)  -> bf16 parts (the next operand).
+// a is written over a2 (every element is read before it is written, by the same thread). W = group width (a multiple
+// of 32), ld = pitch of the fp32 arrays, y parts in the operand layout of split_rows_kernel.
+__global__ void wide_group_prox_kernel(const float* __restrict__ grad, const float* __restrict__ a1, float* a2_out,
+                                       int64_t ld, int64_t B, int64_t S, int W, const float* __restrict__ scalars,
+                                       float beta_prev, float beta_next, int use_momentum, int has_prev2,
+                                       __nv_bfloat16* __restrict__ yparts, int64_t Kp, int nparts, int block,
+                                       double* __restrict__ stat) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t groups_per_row = S / W;
+  const float eta = scalars[0], theta = scalars[1];
+  float stat_local = 0.f;
+  for (int64_t item = warp; item < B * groups_per_row; item += nwarps) {
+    const int64_t r = item / groups_per_row;
+    const int64_t c0 = (item - r * groups_per_row) * W;
+    float ss = 0.f;
+    for (int c = lane; c < W; c += 32) {
+      const int64_t i = r * ld + c0 + c;
+      const float ak = a1[i];
+      float y = ak;
+      if (has_prev2) y = __fadd_rn(ak, __fmul_rn(beta_prev, __fsub_rn(ak, a2_out[i])));
+      const float u = __fsub_rn(y, __fmul_rn(eta, grad[i]));
+      ss = __fadd_rn(ss, __fmul_rn(u, u));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    float nrm = sqrtf(ss);
+    if (nrm == 0.f) nrm = 1.f;
+    const float scale = fmaxf(__fsub_rn(1.f, __fdiv_rn(theta, nrm)), 0.f);
+    for (int c = lane; c < W; c += 32) {
+      const int64_t col = c0 + c;
+      const int64_t i = r * ld + col;
+      const float ak = a1[i];
+      float y = ak;
+      if (has_prev2) y = __fadd_rn(ak, __fmul_rn(beta_prev, __fsub_rn(ak, a2_out[i])));
+      const float u = __fsub_rn(y, __fmul_rn(eta, grad[i]));
+      const float a = __fmul_rn(u, scale);
+      const float d = __fsub_rn(a, ak);
+      float v = use_momentum ? __fadd_rn(a, __fmul_rn(beta_next, d)) : a;
+      a2_out[i] = a;
+      stat_local += fabsf(d);
+      if (yparts != nullptr) {
+        for (int p = 0; p < nparts; ++p) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          v = __fsub_rn(v, __bfloat162float(h));
+          const int64_t idx = block ? ((p * (Kp / block) + col / block) * B + r) * block + col % block
+                                    : r * (static_cast<int64_t>(nparts) * Kp) + p * Kp + col;
+          yparts[idx] = h;
+        }
+      }
+    }
+  }
+  if (stat != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) stat_local += __shfl_xor_sync(0xffffffffu, stat_local, o);
+    if (lane == 0) atomicAdd(stat, static_cast<double>(stat_local));
   }
 }
 

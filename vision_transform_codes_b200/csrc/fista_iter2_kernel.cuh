@@ -196,9 +196,14 @@ __global__ void __launch_bounds__(Iter2Cfg<P>::THREADS, 1) vtc_fista_iter2_kerne
   auto wait_for_previous = [&](const Job& j, bool for_tma) {
     if (p.done != nullptr && j.wait_target > 0) {
       if (lane == 0) {
+        // The predecessor runs on another CTA pair of this launch (the whole grid is resident: launch_iter_p). Almost
+        // never taken; when it is, back off instead of hammering L2, and give up only after about a minute -- other
+        // work sharing the GPU (another stream, NCCL, MPS) may legitimately delay a pair for a long time, and a trap
+        // takes the whole CUDA context down.
         uint32_t spins = 0;
         while (ld_acquire_gpu(p.done + j.panel) < j.wait_target) {
-          if (++spins > (1u << 28)) {
+          if (++spins > 1024u) asm volatile("nanosleep.u32 256;" ::: "memory");
+          if (spins > (1u << 28)) {
             printf("vtc_b200: job (k %d, panel %d) never saw its predecessor (block %d)\n", j.k, j.panel, (int)blockIdx.x);
             __trap();
           }

@@ -16,6 +16,7 @@
 #include "gemm_kernel.cuh"
 #include "fista_iter_kernel.cuh"
 #include "fista_iter2_kernel.cuh"
+#include "fista_small_kernel.cuh"
 
 namespace {
 
@@ -716,6 +717,71 @@ int launch_iter2_p(const IterCall& c, const DeviceInfo& info, cudaStream_t strea
   return VTC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- small-batch kernel
+// VTC_B200_SMALL=0 keeps the tiled Gram-form schedule for small problems (one launch per iteration)
+constexpr int64_t kSmallMaxRows = 74 * SM_ROWS;   // one pair per 32 patches, at most one wave of pairs
+int g_small_kernel = -1;   // vtc_set_small_batch_kernel / VTC_B200_SMALL
+bool small_kernel_ok(int64_t B, int64_t S, int64_t D, int precision, int group_size, bool early) {
+  if (g_small_kernel < 0) {
+    const char* e = getenv("VTC_B200_SMALL");
+    g_small_kernel = e ? (atoi(e) != 0) : 1;
+  }
+  return g_small_kernel && formulation_for(S, D) == FORM_GRAM && S <= SM_K && B <= kSmallMaxRows && group_size == 1 &&
+         !early && parts_for(precision) <= 2;
+}
+struct SmallCall {
+  PartsMat G_op;
+  const float* b = nullptr;
+  const float* init = nullptr;
+  int64_t ld_init = 0;
+  float* out = nullptr;
+  int64_t ld_out = 0;
+  int64_t B = 0, S = 0;
+  int num_iters = 0, prox = 0, use_momentum = 0, precision = VTC_PRECISION_BF16X3;
+  const float* betas = nullptr;
+  const float* scalars = nullptr;
+};
+template <int P>
+int launch_small_p(const SmallCall& c, cudaStream_t stream) {
+  using Cf = SmallCfg<P>;
+  SmallParams p;
+  memset(&p, 0, sizeof(p));
+  if (c.G_op.block != 0 || c.G_op.Kp > SM_K || c.G_op.Kp % 64 != 0)
+    return fail(VTC_ERR_ARG, "small kernel: G operand must be row-major with at most %d padded columns", SM_K);
+  TRY(map_operand(&p.tmG, c.G_op, SM_BK, "Gram operand"));
+  p.g_part_stride = static_cast<int>(c.G_op.Kp);
+  p.k_blocks = static_cast<int>(c.G_op.Kp / SM_BK);
+  p.b = c.b, p.init = c.init, p.ld_init = c.ld_init, p.out = c.out, p.ld_out = c.ld_out;
+  p.B = static_cast<int>(c.B), p.S = static_cast<int>(c.S);
+  p.num_iters = c.num_iters, p.betas = c.betas, p.prox = c.prox, p.use_momentum = c.use_momentum;
+  p.scalars = c.scalars;
+  static bool attr_set_dev[64] = {};
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (!attr_set_dev[dev & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(vtc_fista_small_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
+    attr_set_dev[dev & 63] = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * static_cast<unsigned>(ceil_div(c.B, SM_ROWS)));
+  cfg.blockDim = dim3(Cf::THREADS);
+  cfg.dynamicSmemBytes = Cf::SMEM_ALLOC;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (tune_flags() & TUNE_NO_PDL) ? 1 : 2;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_fista_small_kernel<P>, p));
+  COUNT_LAUNCH();
+  return VTC_OK;
+}
+
 int launch_iter(const IterCall& c, cudaStream_t stream) {
   DeviceInfo info;
   TRY(require_sm100(&info));
@@ -925,6 +991,10 @@ int vtc_set_fused_iteration(int on) {
   g_fused_iter = on != 0;
   return VTC_OK;
 }
+int vtc_set_small_batch_kernel(int on) {
+  g_small_kernel = on != 0;
+  return VTC_OK;
+}
 int vtc_debug_iter_trace(void* device_buffer) {
   g_iter_trace = static_cast<unsigned long long*>(device_buffer);
   return VTC_OK;
@@ -1028,6 +1098,7 @@ struct FistaCommon {
   bool gram, early;
   bool fused_iter;  // one launch per iteration (fista_iter_kernel.cuh) instead of two
   bool iter2;       // ... by the second-generation kernel (fista_iter2_kernel.cuh, quad-blocked state)
+  bool small;       // the whole run in one launch with everything on chip (fista_small_kernel.cuh: S <= 256, small batch)
 };
 
 struct FistaChain {
@@ -1094,6 +1165,7 @@ int chain_setup(const FistaCommon& cm, FistaChain& ch) {
       g.max_pairs = ch.max_pairs;
       TRY(launch_gemm<EPI_STORE>(g, st));
     }
+    if (cm.small) return VTC_OK;   // the resident kernel needs G, b and the step size only: no state buffers
   } else {
     TRY(transpose_split(cm.dictionary, D, S, D, w.phiT_op, st));
     if (!(cm.fused_iter && !ch.initial_codes))   // (from zero the fused schedule writes every element of r_0 itself)
@@ -1313,6 +1385,135 @@ int side_stream(SideStream** out) {
 
 }  // namespace
 
+namespace {
+// ---- subspace groups wider than one epilogue sub-tile (more than 16 atoms; subspace_ista_fista.py:94-96 takes any
+// width): the group norm spans several sub-tiles, so the update is a pass of its own (wide_group_prox_kernel) after the
+// two contractions of the synthesis form -- three launches per iteration, any S and D. Rare in practice (the
+// reference's examples use groups of 2 to 8), kept simple.
+struct WideWs {
+  float* scalars;
+  double* stats;
+  LipschitzWs lip;
+  PartsMat phi_op, phiT_op, r_op, yop[2];
+  float *x_pad, *acc, *A0, *A1;
+  int64_t ldS, ldD;
+};
+WideWs carve_wide(Carver& cv, int64_t B, int64_t S, int64_t D, int precision) {
+  WideWs w;
+  const int P = parts_for(precision);
+  const int bk = (P == 1) ? 64 : 32;
+  w.scalars = static_cast<float*>(cv.take(64));
+  w.stats = static_cast<double*>(cv.take(8 * kStatSlots));
+  w.lip = carve_lipschitz(cv, D);
+  w.phi_op = carve_parts(cv, S, D, 3);
+  w.phiT_op = carve_parts(cv, D, S, 3);
+  w.r_op = carve_parts(cv, B, D, P, bk);
+  w.yop[0] = carve_parts(cv, B, S, P, bk);
+  w.yop[1] = carve_parts(cv, B, S, P, bk);
+  w.ldS = round_up(S, 4), w.ldD = round_up(D, 4);
+  w.x_pad = static_cast<float*>(cv.take(static_cast<size_t>(B) * w.ldD * 4));
+  const size_t state = static_cast<size_t>(B) * w.ldS * 4;
+  w.acc = static_cast<float*>(cv.take(state));
+  w.A0 = static_cast<float*>(cv.take(state));
+  w.A1 = static_cast<float*>(cv.take(state));
+  return w;
+}
+bool wide_groups(int group_size) { return group_size > EPI_COLS; }
+
+int run_wide_groups(const float* images, int64_t ld_images, const float* dictionary, const float* initial_codes,
+                    float* codes_out, int64_t ld_codes, int64_t B, int64_t S, int64_t D, float sparsity_weight,
+                    int num_iters, int variant, int W, float early_stopping_epsilon, int precision, void* workspace,
+                    size_t workspace_bytes, int* iters_run, float* lipschitz_out, cudaStream_t st) {
+  if (W % 32 != 0 || S % W != 0)
+    return fail(VTC_ERR_UNSUPPORTED, "wide groups: the (padded) group width must be a multiple of 32 dividing the grouped code size; got %d", W);
+  Carver cv(workspace, workspace_bytes);
+  WideWs w = carve_wide(cv, B, S, D, precision);
+  if (!workspace || !cv.fits()) return fail(VTC_ERR_WORKSPACE, "vtc_fista_fc: workspace too small (%zu < %zu)", workspace_bytes, cv.off);
+  DeviceInfo info;
+  TRY(require_sm100(&info));
+  const int P = parts_for(precision);
+  const bool early = early_stopping_epsilon >= 0.f;
+  const bool fista = variant == VTC_VARIANT_FISTA;
+  TRY(run_lipschitz(dictionary, S, D, w.lip, sparsity_weight, w.scalars, nullptr, st));
+  TRY(split_rows(dictionary, D, S, D, w.phi_op, st));
+  TRY(transpose_split(dictionary, D, S, D, w.phiT_op, st));
+  const float* x_in = images;
+  int64_t ld_x = ld_images;
+  if (!tma_ok(images, ld_images)) {
+    CUDA_TRY(cudaMemcpy2DAsync(w.x_pad, w.ldD * 4, images, ld_images * 4, D * 4, B, cudaMemcpyDeviceToDevice, st));
+    x_in = w.x_pad, ld_x = w.ldD;
+  }
+  const size_t state = static_cast<size_t>(B) * w.ldS * 4;
+  CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.r_op.ptr), 0, w.r_op.bytes(), st));
+  CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[1].ptr), 0, w.yop[1].bytes(), st));
+  CUDA_TRY(cudaMemsetAsync(w.A1, 0, state, st));
+  if (initial_codes) {
+    CUDA_TRY(cudaMemsetAsync(w.A0, 0, state, st));
+    CUDA_TRY(cudaMemcpy2DAsync(w.A0, w.ldS * 4, initial_codes, ld_codes * 4, S * 4, B, cudaMemcpyDeviceToDevice, st));
+    TRY(split_rows(initial_codes, ld_codes, B, S, w.yop[0], st));
+  } else {
+    CUDA_TRY(cudaMemsetAsync(w.A0, 0, state, st));
+    CUDA_TRY(cudaMemsetAsync(const_cast<void*>(w.yop[0].ptr), 0, w.yop[0].bytes(), st));
+  }
+  if (early) CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * kStatSlots, st));
+  float eta_host = 0.f;
+  if (early || lipschitz_out) {
+    float sc_host[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(sc_host, w.scalars, sizeof(sc_host), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    eta_host = sc_host[0];
+    if (lipschitz_out) *lipschitz_out = sc_host[2];
+    if (sc_host[3] != 0.f || !isfinite(sc_host[2]))
+      return fail(VTC_ERR_NONFINITE, "largest eigenvalue of dictionary^T dictionary is %g: a dictionary element overflowed", sc_host[2]);
+  }
+  double t_k = 1.0;
+  float beta_prev = 0.f;
+  int k_done = 0;
+  for (int k = 1; k <= num_iters; ++k) {
+    const double t_next = (1.0 + sqrt(1.0 + 4.0 * t_k * t_k)) / 2.0;
+    const float beta_k = fista ? static_cast<float>((t_k - 1.0) / t_next) : 0.f;
+    t_k = t_next;
+    float* prev = (k & 1) ? w.A0 : w.A1;    // a_{k-1}
+    float* other = (k & 1) ? w.A1 : w.A0;   // a_{k-2}, overwritten by a_k
+    GemmCall r;   // r = y_{k-1} Phi - x, as bf16 parts
+    r.precision = precision;
+    r.A = w.yop[(k - 1) & 1], r.B = w.phiT_op;
+    r.M = B, r.N = D, r.K = S;
+    r.in[0] = F32Mat{x_in, B, D, ld_x}, r.in_mask = 1;
+    r.parts_out = w.r_op, r.n_parts = P;
+    TRY(launch_gemm<EPI_STORE>(r, st));
+    GemmCall g;   // gradient = r Phi^T, fp32
+    g.precision = precision;
+    g.A = w.r_op, g.B = w.phi_op;
+    g.M = B, g.N = S, g.K = D;
+    g.out = F32Mat{w.acc, B, S, w.ldS, false}, g.store_out = true;
+    TRY(launch_gemm<EPI_STORE>(g, st));
+    if (early && k > 1 && (k - 1) % kStatSlots == 0) CUDA_TRY(cudaMemsetAsync(w.stats, 0, sizeof(double) * kStatSlots, st));
+    const PartsMat& yo = w.yop[k & 1];
+    wide_group_prox_kernel<<<grid_for(B * (S / W) * 32, 256, info.sm_count), 256, 0, st>>>(
+        w.acc, prev, other, w.ldS, B, S, W, w.scalars, beta_prev, beta_k, fista ? 1 : 0,
+        (fista && beta_prev != 0.f) ? 1 : 0,
+        k < num_iters ? reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(yo.ptr)) : nullptr, yo.Kp, yo.parts, yo.block,
+        early ? w.stats + (k - 1) % kStatSlots : nullptr);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+    beta_prev = beta_k;
+    k_done = k;
+    if (early) {
+      double sum_abs = 0.0;
+      CUDA_TRY(cudaMemcpyAsync(&sum_abs, w.stats + (k - 1) % kStatSlots, sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      const double avg = sum_abs / (static_cast<double>(B) * static_cast<double>(S)) / static_cast<double>(eta_host);
+      if (avg < static_cast<double>(early_stopping_epsilon) && k > 1) break;
+    }
+  }
+  const float* result = (k_done & 1) ? w.A1 : w.A0;
+  CUDA_TRY(cudaMemcpy2DAsync(codes_out, ld_codes * 4, result, w.ldS * 4, S * 4, B, cudaMemcpyDeviceToDevice, st));
+  if (iters_run) *iters_run = k_done;
+  return VTC_OK;
+}
+}  // namespace
+
 extern "C" {
 
 size_t vtc_fista_workspace_bytes(int64_t B, int64_t S, int64_t D, int precision) {
@@ -1323,7 +1524,11 @@ size_t vtc_fista_workspace_bytes(int64_t B, int64_t S, int64_t D, int precision)
   Carver two(nullptr, 0);
   const int chains = chains_for(B, S, D);
   for (int c = 0; c < chains; ++c) carve_fista(two, chain_rows(B, chains, c), S, D, precision);
-  return (one.off > two.off ? one.off : two.off) + 2048;
+  Carver wide(nullptr, 0);   // (the group width is not an argument here: room for the wide-group schedule as well)
+  carve_wide(wide, B, S, D, precision);
+  size_t need = one.off > two.off ? one.off : two.off;
+  if (wide.off > need) need = wide.off;
+  return need + 2048;
 }
 
 int vtc_get_chains(int64_t B, int64_t S, int64_t D) { return chains_for(B, S, D); }
@@ -1342,8 +1547,12 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   if (group_size < 1) return fail(VTC_ERR_ARG, "group_size must be >= 1");
   if (group_size > 1) {
     if (hard_threshold) return fail(VTC_ERR_UNSUPPORTED, "hard threshold is not implemented for the subspace variant");
+    if (wide_groups(group_size))   // the norm spans several epilogue sub-tiles: the three-launch schedule
+      return run_wide_groups(images, ld_images, dictionary, initial_codes, codes_out, ld_codes, B, S, D, sparsity_weight,
+                             num_iters, variant, group_size, early_stopping_epsilon, precision, workspace,
+                             workspace_bytes, iters_run, lipschitz_out, st);
     if (EPI_COLS % group_size != 0 || S % group_size != 0)
-      return fail(VTC_ERR_UNSUPPORTED, "group_size must divide 16 and the (grouped) code size; got %d", group_size);
+      return fail(VTC_ERR_UNSUPPORTED, "group_size must divide 16 (or be a multiple of 32) and divide the (grouped) code size; got %d", group_size);
   }
   if (S > (1 << 20) || B > (1ll << 31) - 256) return fail(VTC_ERR_ARG, "problem too large for 32-bit tile coordinates");
   DeviceInfo info;
@@ -1357,6 +1566,7 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   cm.group_size = group_size;
   cm.precision = precision, cm.P = parts_for(precision);
   cm.gram = formulation_for(S, D) == FORM_GRAM;
+  cm.small = small_kernel_ok(B, S, D, precision, group_size, early_stopping_epsilon >= 0.f) && num_iters <= kMaxFusedIters;
   cm.iter2 = iter2_ok(S, D, precision);   // (takes runs longer than the momentum table in windows)
   cm.fused_iter = cm.iter2 || (fused_iter_ok(S, D, precision) && num_iters <= kMaxFusedIters);  // else: two launches
   cm.early = early_stopping_epsilon >= 0.f;
@@ -1429,6 +1639,32 @@ int vtc_fista_fc(const float* images, int64_t ld_images, const float* dictionary
   float beta_prev = 0.f;
   int k_done = 0;
   const int table_iters = num_iters < kMaxFusedIters ? num_iters : kMaxFusedIters;
+  if (cm.small) {
+    // everything on chip for the whole run: one launch, result straight into the caller's codes
+    FistaWs& w = ch[0].w;
+    fista_betas_kernel<<<1, 32, 0, st>>>(w.betas, num_iters, variant == VTC_VARIANT_FISTA ? 1 : 0, 0);
+    COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+    if (g_prof.on) CUDA_TRY(cudaEventRecord(g_prof.iter_begin, st));
+    SmallCall sc;
+    sc.G_op = w.G_op, sc.b = w.bvec, sc.init = initial_codes, sc.ld_init = ld_codes, sc.out = codes_out, sc.ld_out = ld_codes;
+    sc.B = B, sc.S = S, sc.num_iters = num_iters, sc.prox = cm.prox, sc.use_momentum = (variant == VTC_VARIANT_FISTA);
+    sc.precision = precision, sc.betas = w.betas, sc.scalars = w.scalars;
+    if (g_prof.on) CUDA_TRY(cudaEventRecord(g_prof.k1_begin[0], st));
+    TRY(cm.P == 1 ? launch_small_p<1>(sc, st) : launch_small_p<2>(sc, st));
+    if (g_prof.on) {
+      CUDA_TRY(cudaEventRecord(g_prof.k1_end[0], st));
+      CUDA_TRY(cudaEventRecord(g_prof.k2_end[0], st));
+      CUDA_TRY(cudaEventRecord(g_prof.iter_end, st));
+      CUDA_TRY(cudaEventRecord(g_prof.h_end[prof_slot], st));
+      ++g_prof.calls;
+      g_prof.samples = 1, g_prof.two_launches = false;
+      g_prof.iter_launches = 1, g_prof.launch_iters = num_iters, g_prof.iters = num_iters;
+      g_prof.valid = true;
+    }
+    if (iters_run) *iters_run = num_iters;
+    return VTC_OK;
+  }
   if (cm.fused_iter) {
     // the panel-resident kernel takes the momentum coefficients from a device table: betas[k], betas[0] = 0
     for (int c = 0; c < chains; ++c) {
@@ -1619,13 +1855,14 @@ int vtc_subspace_alignment_grad(const float* dictionary, int64_t S, int64_t D, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!dictionary || !group_slots || !alignment_grad || S <= 0 || D <= 0 || num_groups <= 0 || group_width <= 0)
     return fail(VTC_ERR_ARG, "vtc_subspace_alignment_grad: bad argument");
-  const size_t smem = (static_cast<size_t>(group_width) * D + group_width * group_width + group_width) * sizeof(float);
+  const size_t smem = (static_cast<size_t>(group_width) * D + 2 * group_width) * sizeof(float);
   if (smem > 200 * 1024) return fail(VTC_ERR_UNSUPPORTED, "group of %lld atoms x %lld pixels does not fit in shared memory", (long long)group_width, (long long)D);
   if (smem > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(alignment_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   CUDA_TRY(cudaMemsetAsync(alignment_grad, 0, static_cast<size_t>(S) * D * sizeof(float), st));
-  alignment_grad_kernel<<<static_cast<unsigned>(num_groups), 256, smem, st>>>(
-      dictionary, D, group_slots, static_cast<int>(group_width), dictionary_is_normalized, alignment_grad);
+  alignment_grad_kernel<<<static_cast<unsigned>(S), 256, smem, st>>>(
+      dictionary, D, group_slots, static_cast<int>(num_groups), static_cast<int>(group_width), dictionary_is_normalized,
+      alignment_grad);
   COUNT_LAUNCH();
   CUDA_TRY(cudaGetLastError());
   return VTC_OK;
