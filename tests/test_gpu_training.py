@@ -46,6 +46,22 @@ def test_trainer_matches_reference_trainer_outputs(capsys):
   assert oracle.relative_l2(phi.cpu(), g['subspace_cheap_aligned']) < 1e-4
 
 
+def test_lean_trainer_updates_a_non_contiguous_dictionary_correctly():
+  """a strided init_dictionary (a transposed view) must be updated through a contiguous working copy, not
+  read and written as if it were dense -- same result, in place in the caller's storage."""
+  from vision_transform_codes_b200.lean import sparse_coding as trainer
+  g = load_golden('training_small')
+  batches, phi0 = g['batches'].cuda(), g['dictionary']
+  storage = phi0.t().contiguous().cuda()        # (n, s) storage ...
+  phi_view = storage.t()                        # ... seen as a (s, n) dictionary with strides (1, s)
+  assert not phi_view.is_contiguous()
+  trainer.train_dictionary(batches, batches[:1], phi_view, params('fista', 'sc_cheap_quadratic_descent'))
+  assert oracle.relative_l2(phi_view.cpu(), g['fista_cheap']) < 1e-4
+  assert oracle.relative_l2(storage.t().cpu(), g['fista_cheap']) < 1e-4   # the caller's own storage was updated
+  with pytest.raises(RuntimeError):   # no CPU fallback: a host dictionary is refused before anything runs
+    trainer.train_dictionary(batches.cpu(), None, phi0.clone(), params('fista', 'sc_cheap_quadratic_descent'))
+
+
 def test_checkpoint_format_matches_reference(tmp_path):
   import pickle
   from vision_transform_codes_b200.lean import sparse_coding as trainer

@@ -67,6 +67,13 @@ struct Cfg {
   // epilogue math groups (four warps each). (A third group for the 64-wide halo tiles, which have only four sub-tiles
   // each, measured neutral: 0.238 against 0.232 ms per convolutional iteration, it costs an operand stage.)
   static constexpr int GROUPS = NUM_MATH_GROUPS;
+  // RES < 0 ("deep operand ring", NIN = 2 only): the fused update behind a LONG K = D contraction (D = 1024, configs[3]).
+  // The default NIN = 2 split (2 operand stages, 6 input stages) is made for K = 256, where the launch is HBM-bound; with
+  // 32 K blocks per tile two operand stages make every K block an L2 round trip -- ncu: tensor pipe 55 % active against
+  // 96 % for the r = y Phi - x launch of the same flops (profiles/r02_config3_ncu_details.txt). Deep: 4 operand stages,
+  // 4 input stages, 2 output stages. (A third math group measured neutral there: not epilogue-bound.)
+  static constexpr bool DEEP = (RES < 0);
+  static_assert(!DEEP || (NIN == 2 && NBANDS == 0), "the deep operand ring is a variant of the NIN = 2 split");
   static constexpr int MATH_WARPS = 4 * GROUPS;
   static constexpr int THREADS = 128 + 32 * MATH_WARPS;
   static_assert(NBANDS == 0 || RES > 0, "halo staging needs the resident B");
@@ -81,20 +88,20 @@ struct Cfg {
   static constexpr int STAGE_BYTES = NBANDS > 0 ? NBANDS * P * BAND_BYTES
                                    : RES > 0 ? P * TILE_BYTES : P * (TILE_BYTES + B_TILE_BYTES);
   static constexpr int BRES_KB_BYTES = P * B_TILE_BYTES;        // one K block of the resident B
-  static constexpr int BRES_BYTES = RES * BRES_KB_BYTES;
+  static constexpr int BRES_BYTES = (RES > 0 ? RES : 0) * BRES_KB_BYTES;
   static constexpr int IN_STAGE_BYTES = NIN * EPI_ARRAY_BYTES;
   static constexpr int OP_STAGES = NBANDS > 0 ? (NIN == 1 ? 3 : 2)
                                  : RES > 0 ? (NIN == 1 ? 6 : (P == 3 ? 2 : 3))
                                  : NIN == 3 ? ((P == 3) ? 2 : 3)
-                                 : NIN == 2 ? 2
+                                 : NIN == 2 ? (DEEP ? (P == 3 ? 2 : 4) : 2)
                                             : ((P == 3) ? 3 : 4);
   // IN_STAGES is a multiple of NUM_MATH_GROUPS: every input stage is always consumed by the same math group, so a
   // group sees the phases of "its" stages strictly in order (parity waits must never run a whole phase ahead).
   static constexpr int IN_STAGES = NBANDS > 0 ? (NIN == 1 ? 6 : 4)
                                  : NIN == 3 ? ((P == 3) ? 2 : 4)
-                                 : NIN == 2 ? ((P == 3) ? 4 : 6)
+                                 : NIN == 2 ? (DEEP ? 4 : (P == 3) ? 4 : 6)
                                             : ((P == 3) ? 2 : 6);
-  static constexpr int OUT_STAGES = (NBANDS > 0 && NIN == 1) ? 2 : (NIN == 3 && P != 3) ? 2 : 3;
+  static constexpr int OUT_STAGES = (NBANDS > 0 && NIN == 1) ? 2 : (NIN == 3 && P != 3) ? 2 : DEEP ? 2 : 3;
   static_assert(IN_STAGES % GROUPS == 0, "input stages must have a fixed owner group");
   // output stages: with two groups the in-order storer keeps a stage's barrier at most one phase behind any waiter
   // (three stages are fine); with three groups a slow group can leave it two phases behind, so every stage then needs a
@@ -487,7 +494,7 @@ vtc_gemm_kernel(const __grid_constant__ GemmParams p) {
               tma_load_2d_pair(dst + q * C::TILE_BYTES, &p.tmA, full_bar(s), q * p.a_part_stride + kba * C::BK, arow,
                                kEvictNormal);
           }
-          if (RES == 0) {
+          if (RES <= 0) {
 #pragma unroll
             for (int q = 0; q < P; ++q)
               tma_load_2d_pair(dst + P * C::TILE_BYTES + q * C::B_TILE_BYTES, &p.tmB, full_bar(s),

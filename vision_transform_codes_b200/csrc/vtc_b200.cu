@@ -415,6 +415,11 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
         default: return launch_gemm_p<EPI_FISTA, 3, 2, 128>(c, info, stream);
       }
     }
+    // a long contraction (D >= 512, configs[3]): the deep operand ring (Cfg RES = -1); K = 256 keeps the split made
+    // for the HBM-bound case
+    if (c.K >= 512 && c.nseg == 0 && P <= 2)
+      return P == 1 ? launch_gemm_p<EPI_FISTA, 1, 2, 256, -1>(c, info, stream)
+                    : launch_gemm_p<EPI_FISTA, 2, 2, 256, -1>(c, info, stream);
     switch (P) {
       case 1: return launch_gemm_p<EPI_FISTA, 1, 2, 256>(c, info, stream);
       case 2: return launch_gemm_p<EPI_FISTA, 2, 2, 256>(c, info, stream);
