@@ -1,51 +1,63 @@
-// Panel-resident ISTA/FISTA iterations, second generation (sm_100a). Same algorithm, job structure, persistent schedule
-// and bit-exact arithmetic as fista_iter_kernel.cuh (read that header first); what changed is how the epilogue is fed,
-// after the round-2 ablations (profiles/README.md) showed that the first kernel was bound by its own handshakes and by
-// the bytes its rings could keep in flight, not by HBM, the tensor pipe or shared-memory bandwidth:
+// Panel-resident ISTA/FISTA iterations, second generation (sm_100a): the default for S > 2 D, D <= 256, bf16 / bf16x3.
+// Same algorithm, job structure, persistent schedule and bit-exact arithmetic as fista_iter_kernel.cuh (read that
+// header first); what changed is how the epilogue is fed, after the round-2 ablations (profiles/README.md) showed
+// that the first kernel was bound by its own handshakes and by the latency its shallow rings exposed (two G stages:
+// an L2 round trip per K block; two input stages per math group, each held from the load through the math to the end
+// of the store), not by HBM, the tensor pipe or shared-memory bandwidth:
 //
-//   * work unit of the epilogue = one 32-atom CHUNK (two 16-column sub-tiles), owned by ONE group of four warps: the
-//     y stage of a chunk has a single writer group, and the y-ring handshake (wait for the stage, publish it to the R
-//     issuer across the CTA pair) happens once per chunk instead of once per sub-tile and group;
-//   * a_{k-2} does not go through shared memory: the math warps read it with coalesced ld.global (prefetched one
+//   * a_{k-2} does not go through shared memory: the math warps read it with coalesced ld.global.cg (prefetched one
 //     sub-tile ahead into registers) from a state layout made for it -- every sub-tile is one contiguous 8 KB block
 //     [4 column quads][128 rows][4 floats], so a warp's 128-bit load covers 512 contiguous bytes. Only a_{k-1} is
 //     staged (1-D bulk copy, no tensor map) and a_k is written over it in place (each thread touches its own row
-//     only): in/out stages are 8 KB instead of 16, twelve of them (four per group) fit where six did;
+//     only): in/out stages are 8 KB instead of 16;
+//   * the shared memory that frees goes where the latency was exposed: nine input stages (three per math group
+//     instead of two) and THREE G stages instead of two (bf16x3; plain bf16: twelve input stages);
+//   * setmaxnreg moves registers from the eight non-math warps (40 each) to the math warps (128 each with three
+//     groups): room for the prefetch registers without spills;
 //   * G and R MMAs are issued by two warps that block on their own barriers; the operand "full" barriers take one
-//     arrival (the leader's expect_tx for both CTAs' bytes) instead of a cross-CTA arrive per stage.
+//     arrival (the leader's expect_tx for both CTAs' bytes) instead of a cross-CTA arrive per stage;
+//   * starting from zero nothing is initialised: iteration 1 loads no state, every block is written before it is read.
+//
+// (The first version of this kernel used 32-atom chunks as the epilogue's work unit -- one y-ring handshake per chunk --
+// and read x with plain loads at the panel end: 9 % SLOWER than the first generation, because four chunks on three
+// groups made one group the critical path of every tile and the panel end took twice as long. Work units are 16-column
+// sub-tiles again and the panel end is staged by TMA.)
 //
 // State buffers (IterParams2::state) are "quad-blocked": [col block cb = atom / 16][row block rb = row / 128][quad][row % 128][4].
 // The caller converts a warm start into that layout and the result back to row-major (block_quad / unblock_quad
 // kernels in aux_kernels.cuh); rows beyond the batch and atoms beyond S are zero and stay zero.
 //
-// Warp roles (20 warps):
-//   0        TMA producer of the G operand ring (r_op K blocks + Phi tile halves), both CTAs
-//   1        tcgen05.mma issuer of G (leader CTA)
-//   2        TMEM allocator, then bulk / TMA stores (a_k sub-tiles, r_op parts)
-//   3        bulk loader of a_{k-1}
-//   4 .. 15  epilogue math, three groups of four warps (one warp per TMEM lane quarter) on chunks round-robin
-//   16       TMA producer of the Phi^T chunk ring (B operand of R), both CTAs
-//   17       tcgen05.mma issuer of R (leader CTA)
-//   18, 19   none (they complete the fifth warpgroup)
+// Warp roles (4 NG + 8 warps, NG = 3 or 4 math groups):
+//   0          TMA producer of the G operand ring (r_op K blocks + Phi tile halves), both CTAs
+//   1          tcgen05.mma issuer of G (leader CTA)
+//   2          TMEM allocator, then bulk / TMA stores (a_k sub-tiles, r_op parts)
+//   3          bulk loader of a_{k-1} (x at the panel end)
+//   4 ..       epilogue math, NG groups of four warps (one warp per TMEM lane quarter) on sub-tiles round-robin
+//   4 NG + 4   TMA producer of the Phi^T chunk ring (B operand of R), both CTAs
+//   4 NG + 5   tcgen05.mma issuer of R (leader CTA)
+//   last two   none (they complete the last warpgroup: setmaxnreg is warpgroup-wide)
 #pragma once
 #include "fista_iter_kernel.cuh"
 
 namespace vtc {
 
-template <int P>
+template <int P, int NG = 3>
 struct Iter2Cfg {
   static_assert(P == 1 || P == 2, "parts");
-  static constexpr int GROUPS = 3;
+  static_assert(NG == 3 || NG == 4, "math groups");
+  static constexpr int GROUPS = NG;
   static constexpr int MATH_WARPS = 4 * GROUPS;
   static constexpr int PT_WARP = 4 + MATH_WARPS;
   static constexpr int R_WARP = PT_WARP + 1;
-  // 20 warps = five whole warpgroups (setmaxnreg is a warpgroup-wide instruction); warps 18 and 19 have no role
-  static constexpr int THREADS = 32 * 20;
+  // whole warpgroups (setmaxnreg is a warpgroup-wide instruction): 20 / 24 warps, the last two have no role
+  static constexpr int THREADS = 32 * (MATH_WARPS + 8);
+  static constexpr int LAUNCH_REGS = (65536 / THREADS) / 8 * 8;   // what the launch gives every thread (96 / 80)
   // The launch gives every warp the compiled 96 registers (5 warps per scheduler): the CTA's pool is 20 x 32 x 96 =
   // 61440 registers. The eight non-math warps hand most of theirs back and the twelve math warps take 128:
   // (8 x 40 + 12 x 128) x 32 = 59392 <= 61440 (setmaxnreg.inc blocks for ever when the pool cannot cover it).
-  static constexpr int REGS_MATH = 128, REGS_OTHER = 40;
-  static_assert((8 * REGS_OTHER + MATH_WARPS * REGS_MATH) * 32 <= THREADS * 96, "register pool of the CTA");
+  static constexpr int REGS_OTHER = 40;
+  static constexpr int REGS_MATH = ((THREADS * LAUNCH_REGS - 8 * 32 * REGS_OTHER) / (MATH_WARPS * 32)) / 8 * 8;  // 128 / 96
+  static_assert((8 * REGS_OTHER + MATH_WARPS * REGS_MATH) * 32 <= THREADS * LAUNCH_REGS, "register pool of the CTA");
   static constexpr int BK = (P == 1) ? 64 : 32;          // K extent of a G stage
   static constexpr int SPAN = BK * 2;
   static constexpr int A_TILE = BLOCK_M * SPAN;           // one part of this CTA's 128 rows of r_op
@@ -57,10 +69,16 @@ struct Iter2Cfg {
   static constexpr int PT_TILE = (IT_RN / 2) * CHUNK * 2; // one part of this CTA's 128 pixel rows of Phi^T
   static constexpr int PT_STAGE = P * PT_TILE;
   static constexpr int IN_STAGE = EPI_ARRAY_BYTES;        // a_{k-1} in, a_k (or the r parts of a panel-end sub-tile) out
-  static constexpr int IN_STAGES = 12;                    // four per group: two chunks
-  static constexpr int G_STAGES = (P == 2) ? 2 : 3;
-  static constexpr int Y_STAGES = 3;
+  // three groups: 3 input stages each, 3 G stages, 3 y stages; four groups: 2 input stages each, 4 G stages, 2 y
+  // stages (a y stage then always has the same two writer groups). Plain bf16 (half the operand bytes) spends what is
+  // left on a deeper input ring: it is HBM-bound
+  static constexpr int IN_STAGES = (NG == 4) ? (P == 1 ? 12 : 8) : (P == 1 ? 12 : 9);
+  static constexpr int G_STAGES = (NG == 4 && P == 2) ? 4 : 3;
+  static constexpr int Y_STAGES = (NG == 4) ? 2 : 3;
   static constexpr int PT_STAGES = (P == 2) ? 2 : 4;
+  // panel-end sub-tiles are padded to a multiple of this, so that the running sub-tile index (math group, in/out stage)
+  // and the running y chunk index stay congruent from job to job: every y stage always has the same writer groups
+  static constexpr int PANEL_END_PAD = (NG == 4) ? 4 : 6;
   static constexpr int OFF_G = 0;
   static constexpr int OFF_Y = OFF_G + G_STAGES * G_STAGE;
   static constexpr int OFF_PT = OFF_Y + Y_STAGES * Y_STAGE;
@@ -86,7 +104,7 @@ struct Iter2Cfg {
   static constexpr int STORES_IN_FLIGHT = 1;
   // a stage is always consumed by the same group (stage e belongs to group (e % 6) / 2): a group sees the phases of
   // its stages' barriers strictly in order
-  static_assert(IN_STAGES % (2 * GROUPS) == 0, "input stages must have a fixed owner group");
+  static_assert(IN_STAGES % GROUPS == 0, "input stages must have a fixed owner group");
   static_assert(P * EPI_PART_BYTES <= IN_STAGE, "r parts must fit a stage");
   static_assert(SMEM_ALLOC <= 232448, "over the 227 KB shared memory limit");
 };
@@ -96,6 +114,7 @@ struct IterParams2 {
   CUtensorMap tmPhi;    // phi_op (S x parts*Dp, row-major): box BK x 64, B operand of G
   CUtensorMap tmPhiT;   // phiT_op (D x parts*Sp, row-major): box 32 x 128, SWIZZLE_64B, B operand of R
   CUtensorMap tmROut;   // r_op as a store target: box 16 x 128, SWIZZLE_32B
+  CUtensorMap tmX;      // images (B x D fp32, row-major), box 16 x 128, SWIZZLE_64B
   float* state[3];      // quad-blocked fp32 code arrays: [0] the starting point a_0 (unused when init_zero), [1] a_k
                         // for odd k, [2] a_k for even k (a_k overwrites a_{k-2} in place; the final iterate too)
   const float* x;       // images, row-major (B x D), pitch ld_x floats (16-byte aligned rows)
@@ -146,9 +165,9 @@ __device__ __forceinline__ float4 ldg_nc_v4(const float* p) {
   return v;
 }
 
-template <int P>
-__global__ void __launch_bounds__(Iter2Cfg<P>::THREADS, 1) vtc_fista_iter2_kernel(const __grid_constant__ IterParams2 p) {
-  using C = Iter2Cfg<P>;
+template <int P, int NG>
+__global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2_kernel(const __grid_constant__ IterParams2 p) {
+  using C = Iter2Cfg<P, NG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sG = sbase + C::OFF_G, sY = sbase + C::OFF_Y, sPT = sbase + C::OFF_PT;
@@ -215,9 +234,11 @@ __global__ void __launch_bounds__(Iter2Cfg<P>::THREADS, 1) vtc_fista_iter2_kerne
   };
   // chunks of tile nt (whole chunks; atoms at or beyond S are zero everywhere)
   auto tile_chunks = [&](int nt) { return (min(IT_BN, p.S - nt * IT_BN) + C::CHUNK - 1) / C::CHUNK; };
-  int state_units = 0;   // chunks of one job
-  for (int nt = 0; nt < NT; ++nt) state_units += tile_chunks(nt);
-  const int pe_units = (p.nsub_r + 1) / 2;          // panel-end units: two 16-pixel sub-tiles of r each
+  int state_subs = 0;    // 16-atom sub-tiles of one job (whole 32-atom chunks)
+  for (int nt = 0; nt < NT; ++nt) state_subs += 2 * tile_chunks(nt);
+  // panel-end sub-tiles padded to a multiple of 6, so that the running sub-tile index (math group, in/out stage) and
+  // the running y chunk index stay congruent from job to job: every y stage always has the same two writer groups
+  const int nsub_r_pad = (p.nsub_r + C::PANEL_END_PAD - 1) / C::PANEL_END_PAD * C::PANEL_END_PAD;
   const long long row_blocks = static_cast<long long>(p.num_panels) * 2;
   // float offset of sub-tile (col block cb, this CTA's row block of panel) in a quad-blocked state array
   auto state_offset = [&](int panel, int cb) {
@@ -229,6 +250,7 @@ __global__ void __launch_bounds__(Iter2Cfg<P>::THREADS, 1) vtc_fista_iter2_kerne
     tma_prefetch_desc(&p.tmPhi);
     tma_prefetch_desc(&p.tmPhiT);
     tma_prefetch_desc(&p.tmROut);
+    tma_prefetch_desc(&p.tmX);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::G_STAGES; ++s) {
@@ -242,7 +264,7 @@ __global__ void __launch_bounds__(Iter2Cfg<P>::THREADS, 1) vtc_fista_iter2_kerne
       mbar_init(bar(C::B_PT_EMPTY + s), 1);
     }
     for (int s = 0; s < C::Y_STAGES; ++s) {
-      mbar_init(bar(C::B_Y_FULL + s), 2 * 4);     // 2 CTAs x the 4 warps of the chunk's group (leader's barrier)
+      mbar_init(bar(C::B_Y_FULL + s), 2 * 2 * 4);  // 2 CTAs x the two sub-tiles of a chunk x 4 warps (leader's barrier)
       mbar_init(bar(C::B_Y_EMPTY + s), 1);        // multicast tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -420,32 +442,36 @@ __global__ void __launch_bounds__(Iter2Cfg<P>::THREADS, 1) vtc_fista_iter2_kerne
       }
     }
   } else if (warp == 3) {
-    // ================================ loader of a_{k-1} ================================
-    uint32_t q = 0;   // running sub-tile index: stage q % IN_STAGES
+    // ================================ loader of a_{k-1} (and x at the panel end) ================================
+    uint32_t q = 0;   // running sub-tile index: stage q % IN_STAGES, math group q % GROUPS
     for (int ji = 0; ji < my_jobs; ++ji) {
       const Job job = job_at(ji);
       wait_for_previous(job, true);   // a_{k-1} (and the block a_k overwrites) belong to the previous iterations
       const float* src = p.state[job.prev];
       const float* src2 = p.state[job.prev2];
-      const int units = state_units + (job.do_r ? pe_units : 0);
-      for (int u = 0; u < units; ++u) {
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h, ++q) {
-          const int e = q % C::IN_STAGES;
-          mbar_wait(bar(C::B_IN_FREE + e), ((q / C::IN_STAGES) & 1) ^ 1);
-          if (elect_one_sync()) {
-            const uint32_t full = bar(C::B_IN_FULL + e);
-            if (u < state_units && job.has_prev && !(ablate_of(p) & ABL_STATE_LOAD)) {
-              const long long off = state_offset(job.panel, 2 * u + h);
+      const int nsub = state_subs + (job.do_r ? nsub_r_pad : 0);
+      for (int j = 0; j < nsub; ++j, ++q) {
+        const int e = q % C::IN_STAGES;
+        mbar_wait(bar(C::B_IN_FREE + e), ((q / C::IN_STAGES) & 1) ^ 1);
+        if (elect_one_sync()) {
+          const uint32_t full = bar(C::B_IN_FULL + e);
+          if (j < state_subs) {
+            if (job.has_prev && !(ablate_of(p) & ABL_STATE_LOAD)) {
+              const long long off = state_offset(job.panel, j);
               mbar_arrive_expect_tx(full, EPI_ARRAY_BYTES);
               bulk_load_1d(sIn + e * C::IN_STAGE, src + off, EPI_ARRAY_BYTES, full);
               if (p.l2_prefetch && job.has_prev2) bulk_prefetch_l2(src2 + off, EPI_ARRAY_BYTES);
             } else {
-              mbar_arrive(full);   // nothing staged: iteration 1 from zero, or a panel-end sub-tile (x is read directly)
+              mbar_arrive(full);   // iteration 1 from zero: nothing staged
             }
+          } else if (j - state_subs < p.nsub_r) {
+            mbar_arrive_expect_tx(full, EPI_ARRAY_BYTES);
+            tma_load_2d(sIn + e * C::IN_STAGE, &p.tmX, full, (j - state_subs) * EPI_COLS, job.m0, kEvictNormal);
+          } else {
+            mbar_arrive(full);     // padding sub-tile of the panel end
           }
-          __syncwarp();
         }
+        __syncwarp();
       }
     }
   } else if (warp == 2) {
@@ -454,34 +480,28 @@ __global__ void __launch_bounds__(Iter2Cfg<P>::THREADS, 1) vtc_fista_iter2_kerne
     for (int ji = 0; ji < my_jobs; ++ji) {
       const Job job = job_at(ji);
       float* dst = p.state[job.out];
-      const int units = state_units + (job.do_r ? pe_units : 0);
-      for (int u = 0; u < units; ++u) {
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h, ++q) {
-          const int e = q % C::IN_STAGES;
-          mbar_wait(bar(C::B_OUT_FULL + e), (q / C::IN_STAGES) & 1);
-          const uint32_t src = sIn + e * C::IN_STAGE;
-          if (elect_one_sync()) {
-            if (u < state_units) {
-              if (!(ablate_of(p) & ABL_STATE_STORE)) bulk_store_1d(dst + state_offset(job.panel, 2 * u + h), src, EPI_ARRAY_BYTES);
-            } else {
-              const int j = 2 * (u - state_units) + h;   // 16-pixel sub-tile of r
-              if (j < p.nsub_r) {
-                const int col = j * EPI_COLS;
+      const int nsub = state_subs + (job.do_r ? nsub_r_pad : 0);
+      for (int j = 0; j < nsub; ++j, ++q) {
+        const int e = q % C::IN_STAGES;
+        mbar_wait(bar(C::B_OUT_FULL + e), (q / C::IN_STAGES) & 1);
+        const uint32_t src = sIn + e * C::IN_STAGE;
+        if (elect_one_sync()) {
+          if (j < state_subs) {
+            if (!(ablate_of(p) & ABL_STATE_STORE)) bulk_store_1d(dst + state_offset(job.panel, j), src, EPI_ARRAY_BYTES);
+          } else if (j - state_subs < p.nsub_r) {
+            const int col = (j - state_subs) * EPI_COLS;
 #pragma unroll
-                for (int part = 0; part < P; ++part)
-                  tma_store_3d(&p.tmROut, src + part * EPI_PART_BYTES, col % p.r_block_w, job.m0,
-                               part * p.kb_g + col / p.r_block_w);
-              }
-            }
-            bulk_commit();
-            if (q >= C::STORES_IN_FLIGHT) {
-              bulk_wait_read<C::STORES_IN_FLIGHT>();
-              mbar_arrive(bar(C::B_IN_FREE + (q - C::STORES_IN_FLIGHT) % C::IN_STAGES));
-            }
+            for (int part = 0; part < P; ++part)
+              tma_store_3d(&p.tmROut, src + part * EPI_PART_BYTES, col % p.r_block_w, job.m0,
+                           part * p.kb_g + col / p.r_block_w);
           }
-          __syncwarp();
+          bulk_commit();
+          if (q >= C::STORES_IN_FLIGHT) {
+            bulk_wait_read<C::STORES_IN_FLIGHT>();
+            mbar_arrive(bar(C::B_IN_FREE + (q - C::STORES_IN_FLIGHT) % C::IN_STAGES));
+          }
         }
+        __syncwarp();
       }
       if (p.done != nullptr) {
         // every store of this job has been performed: publish it to the pair that runs the panel's next iteration
@@ -510,7 +530,7 @@ __global__ void __launch_bounds__(Iter2Cfg<P>::THREADS, 1) vtc_fista_iter2_kerne
     ua.want_stat = p.stat != nullptr;
     float stat_local = 0.f;
     Tracer trace(p, 2, warp == 4 && lane == 0);
-    uint32_t uq = 0;    // running unit index (all units of all jobs): group uq % 3, stages 2 uq, 2 uq + 1 (mod 12)
+    uint32_t q = 0;     // running sub-tile index (all sub-tiles of all jobs): group q % 3, stage q % IN_STAGES
     uint32_t yc = 0;    // running chunk index of the jobs with an R: y stage yc % 3
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t row_in = row * 16;            // this thread's 16 bytes inside a quad plane of a stage
@@ -523,8 +543,8 @@ __global__ void __launch_bounds__(Iter2Cfg<P>::THREADS, 1) vtc_fista_iter2_kerne
       ua.beta_prev = job.beta_prev, ua.beta_next = job.beta_next;
       if (has_prev2) wait_for_previous(job, false);   // a_{k-2} is read with plain loads by this warp
       const float* prev2 = p.state[job.prev2] + row * 4;
-      // a_{k-2} of this group's NEXT sub-tile, loaded one sub-tile ahead (the group's units inside a job are
-      // u_first, u_first + 3, ...; column block of (unit u, half h) = 2 u + h)
+      // a_{k-2} of this group's NEXT sub-tile, loaded one sub-tile ahead (its sub-tiles inside a job are s_first,
+      // s_first + 3, ...; sub-tile s is column block s of the panel's state)
       float4 pf[4];
       auto prefetch_prev2 = [&](int cb) {
         const float* src = prev2 + state_offset(job.panel, cb);
@@ -532,201 +552,170 @@ __global__ void __launch_bounds__(Iter2Cfg<P>::THREADS, 1) vtc_fista_iter2_kerne
         for (int ch = 0; ch < 4; ++ch) pf[ch] = ldg_cg_v4(src + ch * (BLOCK_M * 4));
       };
       {
-        const int u_first = (group + C::GROUPS - static_cast<int>(uq % C::GROUPS)) % C::GROUPS;
-        if (has_prev2 && u_first < state_units) prefetch_prev2(2 * u_first);
+        const int s_first = (group + C::GROUPS - static_cast<int>(q % C::GROUPS)) % C::GROUPS;
+        if (has_prev2 && s_first < state_subs) prefetch_prev2(s_first);
       }
-      int u = 0;   // unit inside the job
+      int s0 = 0;   // first sub-tile of the current tile inside the job
       for (int nt = 0; nt < NT; ++nt, ++t) {
-        const int nch = tile_chunks(nt);
+        const int nsub = 2 * tile_chunks(nt);
         const int acc = t & 1;
         mbar_wait(bar(C::B_ACCG_FULL + acc), (t >> 1) & 1);
         tc_fence_after();
         trace(TR_E_BEGIN, pi * (NT + 1) + nt);
         const uint32_t t_row = lane_base + acc * IT_BN;
         const uint32_t drained_bar = bar(C::B_ACCG_EMPTY + acc);
-        // chunks of this tile that belong to this warp's group: c0, c0 + 3, ...
-        const int c0 = (group + C::GROUPS - static_cast<int>((uq + u) % C::GROUPS)) % C::GROUPS;
-        const int c_last = (c0 < nch) ? c0 + ((nch - 1 - c0) / C::GROUPS) * C::GROUPS : -1;
-        if (c_last < 0) {
+        const uint32_t q0 = q;
+        const int j_first = static_cast<int>((group + C::GROUPS - q0 % C::GROUPS) % C::GROUPS);
+        const int j_last = (j_first < nsub) ? j_first + ((nsub - 1 - j_first) / C::GROUPS) * C::GROUPS : -1;
+        if (j_last < 0) {
           __syncwarp();
           if (lane == 0) {
             tc_fence_before();
             mbar_arrive_remote(drained_bar, 0);
           }
         }
-        for (int c = c0; c < nch; c += C::GROUPS) {
-          const uint32_t unit = uq + u + c;
-          const uint32_t chunk = yc + u + c;
+        q = q0 + nsub;
+        for (int j = j_first; j < nsub; j += C::GROUPS) {
+          const uint32_t qq = q0 + j;
+          const int e = qq % C::IN_STAGES;
+          const int s = s0 + j;                    // sub-tile inside the job = column block
+          const uint32_t chunk = yc + (s >> 1);
           const int ys = chunk % C::Y_STAGES;
-          bool y_ready = !job.do_r;
-          const uint32_t ystage = sY + ys * C::Y_STAGE + row * (C::CHUNK * 2);
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t q = 2 * unit + h;
-            const int e = q % C::IN_STAGES;
-            uint32_t v[16];
-            trace(TR_E_SUB, 2 * c + h);
-            if (!(ablate_of(p) & ABL_TMEM_LD)) tmem_ld16(t_row + (2 * c + h) * EPI_COLS, v);
-            else {
+          uint32_t v[16];
+          trace(TR_E_SUB, j);
+          if (!(ablate_of(p) & ABL_TMEM_LD)) tmem_ld16(t_row + j * EPI_COLS, v);
+          else {
 #pragma unroll
-              for (int x = 0; x < 16; ++x) v[x] = 0u;
-            }
-            float in[3][16];
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              const float4 b = has_prev2 ? pf[ch] : make_float4(0.f, 0.f, 0.f, 0.f);
-              in[2][4 * ch + 0] = b.x, in[2][4 * ch + 1] = b.y, in[2][4 * ch + 2] = b.z, in[2][4 * ch + 3] = b.w;
-            }
-            if (has_prev2) {
-              const int un = (h == 0) ? u + c : u + c + C::GROUPS;   // unit of this group's next sub-tile
-              if (un < state_units) prefetch_prev2(2 * un + (h == 0 ? 1 : 0));
-            }
-            mbar_wait(bar(C::B_IN_FULL + e), (q / C::IN_STAGES) & 1);
-            trace(TR_E_IN, 2 * c + h);
-            const uint32_t in_stage = sIn + e * C::IN_STAGE + row_in;
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (has_prev && !(ablate_of(p) & ABL_STATE_LSU)) a = lds128(in_stage + ch * (BLOCK_M * 16));
-              in[0][4 * ch + 0] = a.x, in[0][4 * ch + 1] = a.y, in[0][4 * ch + 2] = a.z, in[0][4 * ch + 3] = a.w;
-              in[1][4 * ch + 0] = 0.f, in[1][4 * ch + 1] = 0.f, in[1][4 * ch + 2] = 0.f, in[1][4 * ch + 3] = 0.f;
-            }
-            tmem_ld_wait();
-            trace(TR_E_LD, 2 * c + h);
-            if (c == c_last && h == 1) {   // this warp has drained its share of the accumulator
-              __syncwarp();
-              if (lane == 0) {
-                tc_fence_before();
-                mbar_arrive_remote(drained_bar, 0);
-              }
-            }
-            float outv[16], partv[16];
-            fista_update16(ua, v, in, outv, partv, stat_local);
-            trace(TR_E_CMP, 2 * c + h);
-            // a_k over a_{k-1}, in place: every thread reads and writes its own 4 x 16 bytes only
-            if (!(ablate_of(p) & ABL_STATE_LSU)) {
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch)
-                sts128(in_stage + ch * (BLOCK_M * 16), outv[4 * ch], outv[4 * ch + 1], outv[4 * ch + 2], outv[4 * ch + 3]);
-            }
-            if (job.do_r) {
-              // y_k parts straight into the A operand of R: K-major 64-byte rows (SWIZZLE_64B), this sub-tile is the
-              // 32-byte half h of the row
-              if (!y_ready) {
-                mbar_wait(bar(C::B_Y_EMPTY + ys), ((chunk / C::Y_STAGES) & 1) ^ 1);
-                y_ready = true;
-              }
-              trace(TR_E_YW, 2 * c + h);
-              const uint32_t c2 = 2 * h;
-              if (!(ablate_of(p) & ABL_Y_STS)) split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
-                const uint32_t prow = ystage + part * C::Y_TILE;
-                sts128u(prow + (((c2 + 0) ^ sw64) << 4), w32[0], w32[1], w32[2], w32[3]);
-                sts128u(prow + (((c2 + 1) ^ sw64) << 4), w32[4], w32[5], w32[6], w32[7]);
-              });
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(bar(C::B_OUT_FULL + e));
-              if (h == 1 && job.do_r) mbar_arrive_remote(bar(C::B_Y_FULL + ys), 0);
-            }
-            trace(TR_E_ARR, 2 * c + h);
+            for (int x = 0; x < 16; ++x) v[x] = 0u;
           }
-        }
-        trace(TR_E_END, pi * (NT + 1) + nt);
-        u += nch;
-      }
-      uq += state_units;
-      if (job.do_r) {
-        yc += state_units;
-        // ---- panel end: r_k = acc_r - x -> bf16 parts -> r_op[panel]. x is read straight from the caller's row-major
-        // images, one sub-tile ahead (the first one before the wait for the synthesis accumulator)
-        const long long grow = static_cast<long long>(job.m0) + row;
-        const float* xrow = p.x + grow * p.ld_x;
-        const bool row_ok = grow < p.B;
-        float4 px[4];
-        auto prefetch_x = [&](int j) {
+          float in[3][16];
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
-            const int col = j * EPI_COLS + 4 * ch;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row_ok) {
-              if (col + 4 <= p.D) {
-                a = ldg_nc_v4(xrow + col);
-              } else {
-                if (col + 0 < p.D) a.x = __ldg(xrow + col + 0);
-                if (col + 1 < p.D) a.y = __ldg(xrow + col + 1);
-                if (col + 2 < p.D) a.z = __ldg(xrow + col + 2);
-              }
-            }
-            px[ch] = a;
+            const float4 b = has_prev2 ? pf[ch] : make_float4(0.f, 0.f, 0.f, 0.f);
+            in[2][4 * ch + 0] = b.x, in[2][4 * ch + 1] = b.y, in[2][4 * ch + 2] = b.z, in[2][4 * ch + 3] = b.w;
           }
-        };
-        {
-          const int c_first = (group + C::GROUPS - static_cast<int>(uq % C::GROUPS)) % C::GROUPS;
-          if (2 * c_first < p.nsub_r) prefetch_x(2 * c_first);
+          if (has_prev2 && s + C::GROUPS < state_subs) prefetch_prev2(s + C::GROUPS);
+          mbar_wait(bar(C::B_IN_FULL + e), (qq / C::IN_STAGES) & 1);
+          trace(TR_E_IN, j);
+          const uint32_t in_stage = sIn + e * C::IN_STAGE + row_in;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_prev && !(ablate_of(p) & ABL_STATE_LSU)) a = lds128(in_stage + ch * (BLOCK_M * 16));
+            in[0][4 * ch + 0] = a.x, in[0][4 * ch + 1] = a.y, in[0][4 * ch + 2] = a.z, in[0][4 * ch + 3] = a.w;
+            in[1][4 * ch + 0] = 0.f, in[1][4 * ch + 1] = 0.f, in[1][4 * ch + 2] = 0.f, in[1][4 * ch + 3] = 0.f;
+          }
+          tmem_ld_wait();
+          trace(TR_E_LD, j);
+          if (j == j_last) {   // this warp has drained its share of the accumulator
+            __syncwarp();
+            if (lane == 0) {
+              tc_fence_before();
+              mbar_arrive_remote(drained_bar, 0);
+            }
+          }
+          float outv[16], partv[16];
+          if (ua.prox == 0 && ua.group <= 1)
+            soft_update16<false, true, true>(v, in, ua.eta, ua.theta, has_prev2 ? ua.beta_prev : 0.f,
+                                             ua.use_momentum ? ua.beta_next : 0.f, outv, partv, stat_local, ua.want_stat);
+          else
+            fista_update16(ua, v, in, outv, partv, stat_local);
+          trace(TR_E_CMP, j);
+          // a_k over a_{k-1}, in place: every thread reads and writes its own 4 x 16 bytes only
+          if (!(ablate_of(p) & ABL_STATE_LSU)) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              sts128(in_stage + ch * (BLOCK_M * 16), outv[4 * ch], outv[4 * ch + 1], outv[4 * ch + 2], outv[4 * ch + 3]);
+          }
+          uint32_t yfull = 0;
+          if (job.do_r) {
+            // y_k parts straight into the A operand of R: K-major 64-byte rows (SWIZZLE_64B), this sub-tile is the
+            // 32-byte half s & 1 of the row
+            mbar_wait(bar(C::B_Y_EMPTY + ys), ((chunk / C::Y_STAGES) & 1) ^ 1);
+            trace(TR_E_YW, j);
+            const uint32_t ystage = sY + ys * C::Y_STAGE + row * (C::CHUNK * 2);
+            const uint32_t c2 = 2 * (s & 1);
+            if (!(ablate_of(p) & ABL_Y_STS)) split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
+              const uint32_t prow = ystage + part * C::Y_TILE;
+              sts128u(prow + (((c2 + 0) ^ sw64) << 4), w32[0], w32[1], w32[2], w32[3]);
+              sts128u(prow + (((c2 + 1) ^ sw64) << 4), w32[4], w32[5], w32[6], w32[7]);
+            });
+            yfull = bar(C::B_Y_FULL + ys);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar(C::B_OUT_FULL + e));
+            if (job.do_r) mbar_arrive_remote(yfull, 0);
+          }
+          trace(TR_E_ARR, j);
         }
+        trace(TR_E_END, pi * (NT + 1) + nt);
+        s0 += nsub;
+      }
+      if (job.do_r) {
+        yc += state_subs / 2;
+        // ---- panel end: r_k = acc_r - x -> bf16 parts -> r_op[panel]; x staged by TMA like a state sub-tile
         mbar_wait(bar(C::B_ACCR_FULL), r_jobs & 1);
         tc_fence_after();
         trace(TR_E_BEGIN, pi * (NT + 1) + NT);
         ++r_jobs;
         const uint32_t t_row = lane_base + 2 * IT_BN;
         const uint32_t drained_bar = bar(C::B_ACCR_EMPTY);
-        const int c0 = (group + C::GROUPS - static_cast<int>(uq % C::GROUPS)) % C::GROUPS;
-        const int c_last = (c0 < pe_units) ? c0 + ((pe_units - 1 - c0) / C::GROUPS) * C::GROUPS : -1;
-        if (c_last < 0) {
+        const uint32_t q0 = q;
+        const int j_first = static_cast<int>((group + C::GROUPS - q0 % C::GROUPS) % C::GROUPS);
+        const int j_last = (j_first < p.nsub_r) ? j_first + ((p.nsub_r - 1 - j_first) / C::GROUPS) * C::GROUPS : -1;
+        if (j_last < 0) {
           __syncwarp();
           if (lane == 0) {
             tc_fence_before();
             mbar_arrive_remote(drained_bar, 0);
           }
         }
-        for (int c = c0; c < pe_units; c += C::GROUPS) {
-          const uint32_t unit = uq + c;
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t q = 2 * unit + h;
-            const int e = q % C::IN_STAGES;
-            const int j = 2 * c + h;   // 16-pixel sub-tile of r
-            const bool real = j < p.nsub_r;
-            uint32_t v[16];
-            float xin[16];
-            if (real) {
-              tmem_ld16(t_row + j * EPI_COLS, v);
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch)
-                xin[4 * ch + 0] = px[ch].x, xin[4 * ch + 1] = px[ch].y, xin[4 * ch + 2] = px[ch].z, xin[4 * ch + 3] = px[ch].w;
-              // x of this group's next sub-tile of r
-              const int jn = (h == 0) ? j + 1 : 2 * (c + C::GROUPS);
-              if (jn < p.nsub_r) prefetch_x(jn);
-            }
-            mbar_wait(bar(C::B_IN_FULL + e), (q / C::IN_STAGES) & 1);
-            if (real) {
-              tmem_ld_wait();
-              if (c == c_last && (h == 1 || j + 1 >= p.nsub_r)) {
-                __syncwarp();
-                if (lane == 0) {
-                  tc_fence_before();
-                  mbar_arrive_remote(drained_bar, 0);
-                }
-              }
-              float partv[16];
-#pragma unroll
-              for (int x = 0; x < 16; ++x) partv[x] = __uint_as_float(v[x]) - xin[x];  // r_k = y_k Phi - x
-              const uint32_t out_stage = sIn + e * C::IN_STAGE;
-              split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
-                const uint32_t prow = out_stage + part * EPI_PART_BYTES + row * 32;
-                sts128u(prow + ((0 ^ sw32) << 4), w32[0], w32[1], w32[2], w32[3]);
-                sts128u(prow + ((1 ^ sw32) << 4), w32[4], w32[5], w32[6], w32[7]);
-              });
-              fence_proxy_async_smem();
-            }
+        q = q0 + nsub_r_pad;
+        for (int j = j_first; j < nsub_r_pad; j += C::GROUPS) {
+          const uint32_t qq = q0 + j;
+          const int e = qq % C::IN_STAGES;
+          if (j >= p.nsub_r) {   // padding sub-tile: pass the stage on
+            mbar_wait(bar(C::B_IN_FULL + e), (qq / C::IN_STAGES) & 1);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(C::B_OUT_FULL + e));
+            continue;
           }
+          uint32_t v[16];
+          tmem_ld16(t_row + j * EPI_COLS, v);
+          mbar_wait(bar(C::B_IN_FULL + e), (qq / C::IN_STAGES) & 1);
+          const uint32_t stage = sIn + e * C::IN_STAGE;
+          float xin[16];
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const float4 a = lds128(stage + row * 64 + ((ch ^ sw64) << 4));   // TMA box 16 x 128 fp32, SWIZZLE_64B
+            xin[4 * ch + 0] = a.x, xin[4 * ch + 1] = a.y, xin[4 * ch + 2] = a.z, xin[4 * ch + 3] = a.w;
+          }
+          // the r parts go over the same stage, where a part row of this thread lies on other threads' x rows: all
+          // four warps of the group must have read their x first
+          named_bar_sync(1 + group, 128);
+          tmem_ld_wait();
+          if (j == j_last) {
+            __syncwarp();
+            if (lane == 0) {
+              tc_fence_before();
+              mbar_arrive_remote(drained_bar, 0);
+            }
+          }
+          float partv[16];
+#pragma unroll
+          for (int x = 0; x < 16; ++x) partv[x] = __uint_as_float(v[x]) - xin[x];  // r_k = y_k Phi - x
+          split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
+            const uint32_t prow = stage + part * EPI_PART_BYTES + row * 32;
+            sts128u(prow + ((0 ^ sw32) << 4), w32[0], w32[1], w32[2], w32[3]);
+            sts128u(prow + ((1 ^ sw32) << 4), w32[4], w32[5], w32[6], w32[7]);
+          });
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(C::B_OUT_FULL + e));
         }
         trace(TR_E_END, pi * (NT + 1) + NT);
-        uq += pe_units;
       }
     }
     if (p.stat) {

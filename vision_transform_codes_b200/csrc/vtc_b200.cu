@@ -483,15 +483,15 @@ bool fused_iter_ok(int64_t S, int64_t D, int precision) {
   return fused_iter_enabled() && formulation_for(S, D) == FORM_SYNTHESIS && D <= IT_RN && parts_for(precision) <= 2;
 }
 
-// VTC_B200_ITER_GEN=2 selects the experimental second-generation panel-resident kernel (fista_iter2_kernel.cuh:
-// chunk-granular epilogue, a_{k-2} read directly, 8 KB in/out stages; measured 9 % slower than the default on
-// configs[1], profiles/README.md); default 1 (fista_iter_kernel.cuh)
+// The panel-resident kernel: default 2 = fista_iter2_kernel.cuh (a_{k-2} read directly from a coalescing-friendly state
+// layout, 8 KB in/out stages, three G stages: -9.5 % against the first generation on configs[1] bf16x3, same-box,
+// profiles/README.md); VTC_B200_ITER_GEN=1 = fista_iter_kernel.cuh
 int iter_generation() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = getenv("VTC_B200_ITER_GEN");
-    cached = e ? atoi(e) : 1;
-    if (cached != 2) cached = 1;
+    cached = e ? atoi(e) : 2;
+    if (cached != 1) cached = 2;
   }
   return cached;
 }
@@ -642,9 +642,9 @@ int launch_persistent(cudaLaunchConfig_t& cfg, Kernel kernel, const Params& p, i
   return VTC_OK;
 }
 
-template <int P>
+template <int P, int NG>
 int launch_iter2_p(const IterCall& c, const DeviceInfo& info, cudaStream_t stream) {
-  using Cf = Iter2Cfg<P>;
+  using Cf = Iter2Cfg<P, NG>;
   IterParams2 p;
   memset(&p, 0, sizeof(p));
   if (c.r_op.block != Cf::BK) return fail(VTC_ERR_ARG, "fused iteration: r_op must be tile-contiguous with block %d", Cf::BK);
@@ -652,6 +652,7 @@ int launch_iter2_p(const IterCall& c, const DeviceInfo& info, cudaStream_t strea
   TRY(map_operand(&p.tmPhi, c.phi_op, Cf::BK, "dictionary operand", IT_BN / 2));
   TRY(map_operand(&p.tmPhiT, c.phiT_op, Cf::CHUNK, "transposed dictionary operand", IT_RN / 2));
   TRY(map_parts_out(&p.tmROut, c.r_op, "r parts output"));
+  TRY(map_f32(&p.tmX, c.x, "images"));
   for (int i = 0; i < 3; ++i) p.state[i] = c.qstate[i];
   p.init_zero = c.init_zero ? 1 : 0;
   if (!p.state[1] || !p.state[2] || (!p.init_zero && !p.state[0])) return fail(VTC_ERR_ARG, "fused iteration: state arrays missing");
@@ -691,7 +692,7 @@ int launch_iter2_p(const IterCall& c, const DeviceInfo& info, cudaStream_t strea
   CUDA_TRY(cudaGetDevice(&dev));
   bool& attr_set = attr_set_dev[dev & 63];
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(vtc_fista_iter2_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
+    CUDA_TRY(cudaFuncSetAttribute(vtc_fista_iter2_kernel<P, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM_ALLOC));
     attr_set = true;
   }
   long long max_pairs = info.sm_count / 2;
@@ -714,10 +715,10 @@ int launch_iter2_p(const IterCall& c, const DeviceInfo& info, cudaStream_t strea
   cfg.numAttrs = (tune_flags() & TUNE_NO_PDL) ? 1 : 2;
   if (c.k_count > 1) {
     static int max_clusters_dev[64] = {};   // per instantiation and device
-    return launch_persistent(cfg, vtc_fista_iter2_kernel<P>, p, pairs, c.max_pairs == 0, dev, max_clusters_dev[dev & 63],
+    return launch_persistent(cfg, vtc_fista_iter2_kernel<P, NG>, p, pairs, c.max_pairs == 0, dev, max_clusters_dev[dev & 63],
                              stream);
   }
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_fista_iter2_kernel<P>, p));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, vtc_fista_iter2_kernel<P, NG>, p));
   COUNT_LAUNCH();
   return VTC_OK;
 }
@@ -791,8 +792,16 @@ int launch_iter(const IterCall& c, cudaStream_t stream) {
   DeviceInfo info;
   TRY(require_sm100(&info));
   if (c.D > IT_RN) return fail(VTC_ERR_ARG, "fused iteration needs D <= %d", IT_RN);
-  if (c.qstate[1] != nullptr)
-    return parts_for(c.precision) == 1 ? launch_iter2_p<1>(c, info, stream) : launch_iter2_p<2>(c, info, stream);
+  if (c.qstate[1] != nullptr) {
+    static int groups = -1;   // VTC_B200_ITER_GROUPS: math groups of the second-generation kernel (3 or 4)
+    if (groups < 0) {
+      const char* e = getenv("VTC_B200_ITER_GROUPS");
+      groups = (e && atoi(e) == 4) ? 4 : 3;
+    }
+    if (groups == 4)
+      return parts_for(c.precision) == 1 ? launch_iter2_p<1, 4>(c, info, stream) : launch_iter2_p<2, 4>(c, info, stream);
+    return parts_for(c.precision) == 1 ? launch_iter2_p<1, 3>(c, info, stream) : launch_iter2_p<2, 3>(c, info, stream);
+  }
   const bool one = parts_for(c.precision) == 1;
   switch (iter_variant(parts_for(c.precision))) {
     case 1: return one ? launch_iter_p<1, 1>(c, info, stream) : launch_iter_p<2, 1>(c, info, stream);
