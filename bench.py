@@ -458,8 +458,9 @@ def main():
       'frac': achieved / pk['bf16_sustained'], 'peak_source': pk['source'] + ' bf16_tflops_sustained (cuBLAS)',
       'basis': 'Gram-form algorithmic flops 2 B S^2 per iteration (SURVEY 8d) x %d iterations per launch' % launch_iters,
       'traffic': traffic,
-      'kernel': ('vtc_fista_iter_kernel<%d> (panel-resident, y_k on chip; %s)' %
-                 (nparts, 'ONE launch = all %d iterations' % n_iter if persistent else 'one launch per iteration'))
+      'kernel': ('%s<%d> (panel-resident, y_k on chip; %s)' %
+                 ('vtc_fista_iter_kernel' if os.environ.get('VTC_B200_ITER_GEN') == '1' else 'vtc_fista_iter2_kernel',
+                  nparts, 'ONE launch = all %d iterations' % n_iter if persistent else 'one launch per iteration'))
                 if fused_iter else 'vtc_gemm_kernel<EPI_FISTA,%d> (%s form)' % (nparts, form),
       'launch_ms': launch_ms, 'iterations_per_launch': launch_iters, 'ms_per_iteration': launch_ms / launch_iters,
       'frac_of_burst_peak': achieved / pk['bf16_burst'] if pk['bf16_burst'] else None,
@@ -504,9 +505,9 @@ def main():
   e2e_ms = max_over_ranks(s0.elapsed_time(s1)) / e2e_steps
   e2e = {'value': world * Bn / (e2e_ms * 1e-3), 'unit': 'patches/s', 'ms_per_step': e2e_ms, 'steps': e2e_steps,
          'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': codes_host[0].numel() * 4,
+         'frac_of_device_resident_value': (world * Bn / (e2e_ms * 1e-3)) / value,
          'how': 'HostPipeline depth 2: per step one pinned H2D copy of the images, one ista_fista.run, one D2H copy of '
-                'the dense fp32 codes; CUDA events from before the first upload to after the last download, max over ranks',
-         'frac_of_device_resident_value': (world * Bn / (e2e_ms * 1e-3)) / value}
+                'the dense fp32 codes; CUDA events from before the first upload to after the last download, max over ranks'}
   # the same without overlap (one step at a time, synchronised): what a naive caller gets
   def serial_step():
     xd = x_host.to(dev, non_blocking=True)
@@ -523,7 +524,8 @@ def main():
       'metric': 'fista_patches_per_sec', 'value': value, 'unit': 'patches/s', 'n_gpus': world, 'steps': args.steps,
       'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': args.precision + ' (bf16 products, fp32 accumulate)', 'data': 'synthetic',
-      'e2e': e2e, 'gpu_launches': int(launches), 'train_step': None, 'roofline': roofline, 'clocks': clocks,
+      'train_step': None,   # (filled below; early in the line so that it survives truncated logs)
+      'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'clocks': clocks,
       'cpu_baseline': None, 'config': shared_config(Bn),
       'implementation': {'precision': args.precision, 'formulation': form,
                          'schedule': ('one persistent launch for all %d iterations' % n_iter if persistent else

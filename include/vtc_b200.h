@@ -13,7 +13,12 @@
  *    never allocates or frees device memory;
  *  - every call is enqueued on `stream` and returns without synchronising, except where stated;
  *  - return value 0 = success; anything else is an error, text via vtc_last_error();
- *  - there is no CPU fallback: without an sm_100 device every compute entry point fails with VTC_ERR_CUDA.
+ *  - there is no CPU fallback: without an sm_100 device every compute entry point fails with VTC_ERR_CUDA;
+ *  - threading: compute calls may be issued concurrently on DIFFERENT streams with different workspaces (the error
+ *    text is per thread). The tuning switches (vtc_set_formulation, vtc_set_fused_iteration,
+ *    vtc_set_small_batch_kernel and the VTC_B200_* environment variables), the profile recorder (vtc_profile_*),
+ *    the launch counter and the debug trace hook are process-global and not synchronised: set them before the threads
+ *    start, and profile from one thread.
  */
 #ifndef VTC_B200_H_
 #define VTC_B200_H_

@@ -72,8 +72,14 @@ struct Iter2Cfg {
   // three groups: 3 input stages each, 3 G stages, 3 y stages; four groups: 2 input stages each, 4 G stages, 2 y
   // stages (a y stage then always has the same two writer groups). Plain bf16 (half the operand bytes) spends what is
   // left on a deeper input ring: it is HBM-bound
-  static constexpr int IN_STAGES = (NG == 4) ? (P == 1 ? 12 : 8) : (P == 1 ? 12 : 9);
-  static constexpr int G_STAGES = (NG == 4 && P == 2) ? 4 : 3;
+#ifndef VTC_IT2_IN3
+#define VTC_IT2_IN3 9   // (tuning builds: tools/ab_build.sh with NVCC_EXTRA=-DVTC_IT2_IN3=.. -DVTC_IT2_G3=..)
+#endif
+#ifndef VTC_IT2_G3
+#define VTC_IT2_G3 3
+#endif
+  static constexpr int IN_STAGES = (NG == 4) ? (P == 1 ? 12 : 8) : (P == 1 ? 12 : VTC_IT2_IN3);
+  static constexpr int G_STAGES = (NG == 4 && P == 2) ? 4 : (P == 2 ? VTC_IT2_G3 : 3);
   static constexpr int Y_STAGES = (NG == 4) ? 2 : 3;
   static constexpr int PT_STAGES = (P == 2) ? 2 : 4;
   // panel-end sub-tiles are padded to a multiple of this, so that the running sub-tile index (math group, in/out stage)

@@ -336,8 +336,7 @@ def benchmark_train_step(global_batch, S, D, num_iters, sparsity_weight, world, 
     replicas_identical = bool(same.item())
   equivalence = sharded_equivalence(S, D, num_iters, sparsity_weight, world, rank, device)
   return {'steps_per_sec': 1e3 / ms, 'ms_per_step': ms, 'global_batch': global_batch, 'shard_per_gpu': shard,
-          'phi_rel_l2_vs_single_gpu': equivalence,
+          'phi_rel_l2_vs_single_gpu': equivalence, 'replicas_bit_identical': replicas_identical,
           'scaling': 'strong', 'update_rule': 'sc_cheap_quadratic_descent', 'allreduce_bytes_per_step': 4 * (S * D + S),
           'patches_per_sec': global_batch * 1e3 / ms, 'gpu_launches': int(launches),
-          'replicas_bit_identical': replicas_identical,
           'workload': 'configs[2]: FISTA-300 inference + SC quadratic-descent update, 16x16 patches, 1024 atoms'}
