@@ -1,6 +1,7 @@
 // Small HBM-bound helper kernels around the tcgen05 GEMM: bf16 operand splitting, transposes, the Lipschitz constant
 // (largest eigenvalue of dictionary^T dictionary) in fp64, the dictionary apply step, gathers/scatters for subspaces.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -202,6 +203,84 @@ __global__ void square_fp64_kernel(const double* __restrict__ A, int n, const do
     if (i == j) tr += acc[q];
   }
   if (i0 == j0 && tr != 0.0) atomicAdd(trace_out, tr);
+}
+
+// The Gram matrix and ALL squarings in one cooperative launch (grid-wide barriers between the steps) instead of one
+// launch per step: the thirty dependent launches were a third of a small call (BASELINE configs[0]). Same tiles, same
+// arithmetic and the same stopping rule as gram_fp64_kernel / square_fp64_kernel above; the Rayleigh quotient stays in
+// lipschitz_finalize_kernel (one block, fixed summation order). Launched with cudaLaunchCooperativeKernel: the whole
+// grid is resident or the launch fails (the caller then takes the per-step launches).
+__global__ void lipschitz_squarings_kernel(const float* __restrict__ phi, int64_t S, int64_t D, int n,
+                                           double* __restrict__ M, double* __restrict__ A0, double* __restrict__ A1,
+                                           double* __restrict__ traces, int squarings) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double As[32][33], Bs[32][33];
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  {
+    double acc[4] = {0, 0, 0, 0};
+    for (int64_t s0 = 0; s0 < S; s0 += 32) {
+      for (int r = ty; r < 32; r += 8) {
+        const int64_t s = s0 + r;
+        As[r][tx] = (s < S && i0 + tx < D) ? static_cast<double>(phi[s * D + i0 + tx]) : 0.0;
+        Bs[r][tx] = (s < S && j0 + tx < D) ? static_cast<double>(phi[s * D + j0 + tx]) : 0.0;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) {
+        const double b = Bs[k][tx];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] += As[k][ty + 8 * q] * b;
+      }
+      __syncthreads();
+    }
+    double tr = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + ty + 8 * q, j = j0 + tx;
+      M[static_cast<int64_t>(i) * n + j] = acc[q];
+      if (i == j) tr += acc[q];
+    }
+    if (i0 == j0 && tr != 0.0) atomicAdd(traces + 0, tr);
+  }
+  grid.sync();
+  const double* src = M;
+  double* dst = A0;
+  for (int step = 0; step < squarings; ++step) {
+    const double trace_in = traces[step];
+    if (step >= 1 && 1.0 - trace_in < kLipschitzConverged) {   // the same value in every block: a uniform exit
+      if (blockIdx.x == 0 && blockIdx.y == 0 && tx == 0 && ty == 0) traces[squarings + 1] = static_cast<double>(step);
+      break;
+    }
+    const double scale = 1.0 / trace_in;
+    double acc[4] = {0, 0, 0, 0};
+    for (int k0 = 0; k0 < n; k0 += 32) {
+      for (int r = ty; r < 32; r += 8) {
+        As[r][tx] = src[static_cast<int64_t>(k0 + r) * n + i0 + tx] * scale;
+        Bs[r][tx] = src[static_cast<int64_t>(k0 + r) * n + j0 + tx] * scale;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) {
+        const double b = Bs[k][tx];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] += As[k][ty + 8 * q] * b;
+      }
+      __syncthreads();
+    }
+    double tr = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + ty + 8 * q, j = j0 + tx;
+      dst[static_cast<int64_t>(i) * n + j] = acc[q];
+      if (i == j) tr += acc[q];
+    }
+    if (i0 == j0 && tr != 0.0) atomicAdd(traces + step + 1, tr);
+    grid.sync();
+    src = dst;
+    dst = (dst == A0) ? A1 : A0;
+  }
 }
 
 // scalars[0] = eta = 1/L, [1] = theta = lambda * eta, [2] = L, [3] = status bits (1 = non-finite / non-positive L)

@@ -893,16 +893,56 @@ int run_lipschitz(const float* dict, int64_t S, int64_t D, const LipschitzWs& w,
                   float* lipschitz_dev, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(w.traces, 0, (kSquarings + 2) * sizeof(double), st));
   const dim3 grid(w.n / 32, w.n / 32), block(32, 8);
-  gram_fp64_kernel<<<grid, block, 0, st>>>(dict, S, D, w.n, w.M, w.traces + 0);
-  COUNT_LAUNCH();
-  const double* src = w.M;
-  double* dst = w.A0;
-  for (int j = 0; j < kSquarings; ++j) {
-    square_fp64_kernel<<<grid, block, 0, st>>>(src, w.n, w.traces + j, dst, w.traces + j + 1, j,
-                                               w.traces + kSquarings + 1);
+  // One cooperative launch for the Gram matrix and every squaring when the whole grid can be resident (and the stream is
+  // not being captured into a graph: a refused launch would invalidate the capture); else one launch per step.
+  bool fused = false;
+  {
+    static int coop_dev[64] = {};   // 0 unknown, 1 usable, -1 not
+    static int blocks_per_sm_dev[64] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int& coop = coop_dev[dev & 63];
+    if (coop == 0) {
+      int supported = 0;
+      CUDA_TRY(cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, dev));
+      const char* e = getenv("VTC_B200_LIPSCHITZ_FUSED");
+      coop = (supported && !(e && atoi(e) == 0)) ? 1 : -1;
+      if (coop == 1)
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm_dev[dev & 63], lipschitz_squarings_kernel,
+                                                               256, 0));
+    }
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    CUDA_TRY(cudaStreamIsCapturing(st, &capturing));
+    DeviceInfo info;
+    TRY(device_info(&info));
+    if (coop == 1 && capturing == cudaStreamCaptureStatusNone &&
+        static_cast<long long>(grid.x) * grid.y <= static_cast<long long>(blocks_per_sm_dev[dev & 63]) * info.sm_count) {
+      int n = w.n, squarings = kSquarings;
+      int64_t S_ = S, D_ = D;
+      double *M = w.M, *A0 = w.A0, *A1 = w.A1, *traces = w.traces;
+      void* args[] = {&dict, &S_, &D_, &n, &M, &A0, &A1, &traces, &squarings};
+      if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lipschitz_squarings_kernel), grid, block, args, 0, st) ==
+          cudaSuccess) {
+        COUNT_LAUNCH();
+        fused = true;
+      } else {
+        (void)cudaGetLastError();   // refused (e.g. the device is shared): the per-step launches below
+        CUDA_TRY(cudaMemsetAsync(w.traces, 0, (kSquarings + 2) * sizeof(double), st));
+      }
+    }
+  }
+  if (!fused) {
+    gram_fp64_kernel<<<grid, block, 0, st>>>(dict, S, D, w.n, w.M, w.traces + 0);
     COUNT_LAUNCH();
-    src = dst;
-    dst = (dst == w.A0) ? w.A1 : w.A0;
+    const double* src = w.M;
+    double* dst = w.A0;
+    for (int j = 0; j < kSquarings; ++j) {
+      square_fp64_kernel<<<grid, block, 0, st>>>(src, w.n, w.traces + j, dst, w.traces + j + 1, j,
+                                                 w.traces + kSquarings + 1);
+      COUNT_LAUNCH();
+      src = dst;
+      dst = (dst == w.A0) ? w.A1 : w.A0;
+    }
   }
   lipschitz_finalize_kernel<<<1, 1024, 0, st>>>(w.A0, w.A1, w.M, w.n, w.traces, kSquarings, sparsity_weight,
                                                        scalars, lipschitz_dev);
