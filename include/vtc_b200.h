@@ -88,7 +88,8 @@ int vtc_get_fused_iteration(int64_t S, int64_t D, int precision);
 int vtc_set_small_batch_kernel(int on);
 /* Debug aid (tools/iter_trace.py): four threads of CTA 0 of the NEXT one-launch iteration kernel write a timeline into
  * device_buffer (4 regions of 2048 uint64 words: [0] = event count, then event id << 48 | SM clock), zeroed by the
- * caller. One shot: the pointer is dropped after that launch. */
+ * caller. One shot: the pointer is dropped after that launch. Only in a library built with -DVTC_TRACE (the shipped
+ * kernels carry no trace points); VTC_ERR_ARG otherwise. */
 int vtc_debug_iter_trace(void* device_buffer);
 
 /* Number of concurrent half-batch chains vtc_fista_fc uses for this problem (1 unless VTC_B200_CHAINS=2 asks for two;

@@ -1,5 +1,7 @@
 """Timeline of CTA 0 of one launch of the one-launch iteration kernel (vtc_debug_iter_trace).
-usage: python tools/iter_trace.py [B] [precision]"""
+Needs a library with the trace points compiled in:
+  NVCC_EXTRA=-DVTC_TRACE tools/ab_build.sh HEAD trace
+  VTC_B200_LIB=tools/ab/libvtc_b200_trace.so python tools/iter_trace.py [B] [precision]"""
 import os
 import sys
 
@@ -23,7 +25,7 @@ buf = torch.zeros(4 * 2048, dtype=torch.int64, device='cuda')
 # trace a middle iteration only: run 4 untraced, then 1 traced via a warm start
 warm = ista_fista.run(x, phi, 0.1, 4)
 torch.cuda.synchronize()
-lib.vtc_debug_iter_trace(_lib.ptr(buf))
+_lib.check(lib.vtc_debug_iter_trace(_lib.ptr(buf)))   # fails on a library without -DVTC_TRACE
 ista_fista.run(x, phi, 0.1, 2, initial_codes=warm)   # the first launch is traced (the last one would skip R)
 torch.cuda.synchronize()
 host = buf.cpu().tolist()

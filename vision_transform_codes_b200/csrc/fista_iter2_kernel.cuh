@@ -525,6 +525,12 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
   } else {
     // ================================ epilogue math ================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_MATH));
+    // this role's own copies of the thread index and the shared-memory base, pinned in registers (pin_u32)
+    const uint32_t tid = pin_u32(threadIdx.x);
+    const int warp = static_cast<int>(tid >> 5), lane = static_cast<int>(tid & 31);
+    const uint32_t sbase_m = pin_u32(sbase);
+    const uint32_t sY = sbase_m + C::OFF_Y, sIn = sbase_m + C::OFF_IN, bar0 = sbase_m + C::OFF_BAR;
+    auto bar = [&](int idx) { return bar0 + 8 * idx; };
     const int group = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
@@ -540,6 +546,8 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
     uint32_t yc = 0;    // running chunk index of the jobs with an R: y stage yc % 3
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t row_in = row * 16;            // this thread's 16 bytes inside a quad plane of a stage
+    const long long cb_stride = row_blocks * (EPI_ARRAY_BYTES / 4);   // floats between column blocks of the state
+    const bool fast_soft = ua.prox == 0 && ua.group <= 1;
     int t = 0;          // running atom tile: accumulator t & 1
     int r_jobs = 0;
     for (int pi = 0; pi < my_jobs; ++pi) {
@@ -548,12 +556,17 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
       ua.in_mask = has_prev2 ? 5 : 1;
       ua.beta_prev = job.beta_prev, ua.beta_next = job.beta_next;
       if (has_prev2) wait_for_previous(job, false);   // a_{k-2} is read with plain loads by this warp
-      const float* prev2 = p.state[job.prev2] + row * 4;
+      const float bp_fast = has_prev2 ? ua.beta_prev : 0.f, bn_fast = ua.use_momentum ? ua.beta_next : 0.f;
+      const bool do_r = job.do_r;
       // a_{k-2} of this group's NEXT sub-tile, loaded one sub-tile ahead (its sub-tiles inside a job are s_first,
-      // s_first + 3, ...; sub-tile s is column block s of the panel's state)
+      // s_first + 3, ...; sub-tile s is column block s of the panel's state: one pointer per job, one multiply-add per
+      // sub-tile). Without an a_{k-2} (first iterations, ISTA) the registers stay zero and beta_prev is 0.
+      const float* prev2 = pin_ptr(p.state[job.prev2] + row * 4 + state_offset(job.panel, 0));
       float4 pf[4];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) pf[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
       auto prefetch_prev2 = [&](int cb) {
-        const float* src = prev2 + state_offset(job.panel, cb);
+        const float* src = prev2 + cb * cb_stride;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) pf[ch] = ldg_cg_v4(src + ch * (BLOCK_M * 4));
       };
@@ -575,7 +588,7 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
         const int j_last = (j_first < nsub) ? j_first + ((nsub - 1 - j_first) / C::GROUPS) * C::GROUPS : -1;
         if (j_last < 0) {
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one_sync()) {
             tc_fence_before();
             mbar_arrive_remote(drained_bar, 0);
           }
@@ -597,7 +610,7 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
           float in[3][16];
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
-            const float4 b = has_prev2 ? pf[ch] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b = pf[ch];
             in[2][4 * ch + 0] = b.x, in[2][4 * ch + 1] = b.y, in[2][4 * ch + 2] = b.z, in[2][4 * ch + 3] = b.w;
           }
           if (has_prev2 && s + C::GROUPS < state_subs) prefetch_prev2(s + C::GROUPS);
@@ -615,15 +628,16 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
           trace(TR_E_LD, j);
           if (j == j_last) {   // this warp has drained its share of the accumulator
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one_sync()) {
               tc_fence_before();
               mbar_arrive_remote(drained_bar, 0);
             }
           }
           float outv[16], partv[16];
-          if (ua.prox == 0 && ua.group <= 1)
-            soft_update16<false, true, true>(v, in, ua.eta, ua.theta, has_prev2 ? ua.beta_prev : 0.f,
-                                             ua.use_momentum ? ua.beta_next : 0.f, outv, partv, stat_local, ua.want_stat);
+          if (fast_soft && !ua.want_stat)
+            soft_update16<false, true, true, 0>(v, in, ua.eta, ua.theta, bp_fast, bn_fast, outv, partv, stat_local);
+          else if (fast_soft)
+            soft_update16<false, true, true, 1>(v, in, ua.eta, ua.theta, bp_fast, bn_fast, outv, partv, stat_local);
           else
             fista_update16(ua, v, in, outv, partv, stat_local);
           trace(TR_E_CMP, j);
@@ -634,7 +648,7 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
               sts128(in_stage + ch * (BLOCK_M * 16), outv[4 * ch], outv[4 * ch + 1], outv[4 * ch + 2], outv[4 * ch + 3]);
           }
           uint32_t yfull = 0;
-          if (job.do_r) {
+          if (do_r) {
             // y_k parts straight into the A operand of R: K-major 64-byte rows (SWIZZLE_64B), this sub-tile is the
             // 32-byte half s & 1 of the row
             mbar_wait(bar(C::B_Y_EMPTY + ys), ((chunk / C::Y_STAGES) & 1) ^ 1);
@@ -650,16 +664,16 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one_sync()) {
             mbar_arrive(bar(C::B_OUT_FULL + e));
-            if (job.do_r) mbar_arrive_remote(yfull, 0);
+            if (do_r) mbar_arrive_remote(yfull, 0);
           }
           trace(TR_E_ARR, j);
         }
         trace(TR_E_END, pi * (NT + 1) + nt);
         s0 += nsub;
       }
-      if (job.do_r) {
+      if (do_r) {
         yc += state_subs / 2;
         // ---- panel end: r_k = acc_r - x -> bf16 parts -> r_op[panel]; x staged by TMA like a state sub-tile
         mbar_wait(bar(C::B_ACCR_FULL), r_jobs & 1);
@@ -673,7 +687,7 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
         const int j_last = (j_first < p.nsub_r) ? j_first + ((p.nsub_r - 1 - j_first) / C::GROUPS) * C::GROUPS : -1;
         if (j_last < 0) {
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one_sync()) {
             tc_fence_before();
             mbar_arrive_remote(drained_bar, 0);
           }
@@ -685,7 +699,7 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
           if (j >= p.nsub_r) {   // padding sub-tile: pass the stage on
             mbar_wait(bar(C::B_IN_FULL + e), (qq / C::IN_STAGES) & 1);
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(C::B_OUT_FULL + e));
+            if (elect_one_sync()) mbar_arrive(bar(C::B_OUT_FULL + e));
             continue;
           }
           uint32_t v[16];
@@ -704,7 +718,7 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
           tmem_ld_wait();
           if (j == j_last) {
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one_sync()) {
               tc_fence_before();
               mbar_arrive_remote(drained_bar, 0);
             }
@@ -719,7 +733,7 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
           });
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(C::B_OUT_FULL + e));
+          if (elect_one_sync()) mbar_arrive(bar(C::B_OUT_FULL + e));
         }
         trace(TR_E_END, pi * (NT + 1) + NT);
       }

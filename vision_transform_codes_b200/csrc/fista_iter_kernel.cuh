@@ -192,6 +192,10 @@ enum TraceKind { TR_G_BEGIN = 1, TR_G_END = 2, TR_R_ISSUE = 3, TR_E_BEGIN = 4, T
                  TR_START = 8, TR_STOP = 9, TR_E_IN = 10, TR_E_LD = 11, TR_E_CMP = 12, TR_E_YW = 13, TR_E_ARR = 14 };
 // Each tracing thread owns a region of 2048 words (role = 0 G producer, 1 issuer, 2 math warp 4, 3 thread 0) and a private
 // counter: plain stores, no atomics, so that the trace perturbs the timeline as little as possible.
+// Compiled in only with -DVTC_TRACE (tools/ab_build.sh): a run-time "is tracing on" test at every trace point cost the
+// math warps ~45 of their ~450 instructions per sub-tile and a tenth of their time (ncu stall samples on the
+// BSSY / BRA / BSYNC of the tests), so the shipped kernels carry none.
+#ifdef VTC_TRACE
 struct Tracer {
   unsigned long long* base;
   uint32_t n;
@@ -206,6 +210,13 @@ struct Tracer {
     }
   }
 };
+#else
+struct Tracer {
+  template <typename Params>
+  __device__ __forceinline__ Tracer(const Params&, int, bool) {}
+  __device__ __forceinline__ void operator()(int, int) const {}
+};
+#endif
 
 // completion flags between jobs of one launch (a panel's iteration k may run on another CTA pair than k - 1)
 __device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {

@@ -236,10 +236,11 @@ __device__ __forceinline__ void group_shrink(const float (&u)[16], float (&o)[16
 // fma(b, -1, a): the product is exact, one rounding), so the result is bit-identical to the unpacked sequence and to
 // the reference's separate multiply and add; only the issue slots are halved.
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
-template <bool HASB, bool PREV, bool MOM>
+// STAT: 1 / 0 = the convergence statistic is (not) accumulated, decided at compile time; -1 = want_stat decides.
+template <bool HASB, bool PREV, bool MOM, int STAT = -1>
 __device__ __forceinline__ void soft_update16(const uint32_t (&v)[16], const float (&in)[3][16], float eta, float theta,
                                               float beta_prev, float beta_next, float (&outv)[16],
-                                              float (&partv)[16], float& stat_local, bool want_stat) {
+                                              float (&partv)[16], float& stat_local, bool want_stat = false) {
   const float2 eta2 = make_float2(eta, eta), bp2 = make_float2(beta_prev, beta_prev);
   const float2 bn2 = make_float2(beta_next, beta_next);
 #pragma unroll
@@ -259,7 +260,7 @@ __device__ __forceinline__ void soft_update16(const uint32_t (&v)[16], const flo
     const float2 yn = MOM ? __fadd2_rn(a, __fmul2_rn(bn2, d)) : a;
     partv[x] = yn.x;
     partv[x + 1] = yn.y;
-    if (want_stat) stat_local += fabsf(d.x) + fabsf(d.y);
+    if (STAT > 0 || (STAT < 0 && want_stat)) stat_local += fabsf(d.x) + fabsf(d.y);
   }
 }
 

@@ -38,6 +38,17 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// ptxas re-derives "cheap" values at every use when registers are tight: in the math loop of the iteration kernel that
+// was three S2R of the thread index, the shared-window base (S2UR + 4 ALU) three times and an indexed constant-bank
+// load of a state pointer PER SUB-TILE, all of them long-latency links in a latency-bound chain. A value that went
+// through a shuffle (from the thread's own lane: the identity) cannot be re-derived and stays in its register.
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, threadIdx.x & 31); }
+__device__ __forceinline__ const float* pin_ptr(const float* ptr) {
+  const unsigned long long a = reinterpret_cast<unsigned long long>(ptr);
+  const uint32_t lo = pin_u32(static_cast<uint32_t>(a)), hi = pin_u32(static_cast<uint32_t>(a >> 32));
+  return reinterpret_cast<const float*>((static_cast<unsigned long long>(hi) << 32) | lo);
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -67,7 +78,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug traps (clean launch failure) instead of hanging the GPU. try_wait suspends the thread
 // in hardware for a while when the phase is not complete, so the loop turns over rarely and a plain counter is a
 // cheap enough bound (no clock reads on the hot path).
+// (The report must stay inline: a __noinline__ helper is a real ABI call, and ptxas then allocates the WHOLE kernel
+// for the smallest setmaxnreg budget of its warp-specialised roles -- the math loops spilled everything.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;   // the common case: one test, no loop state
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 22)) {  // x the suspend hint: seconds

@@ -1050,8 +1050,13 @@ int vtc_set_small_batch_kernel(int on) {
   return VTC_OK;
 }
 int vtc_debug_iter_trace(void* device_buffer) {
+#ifdef VTC_TRACE
   g_iter_trace = static_cast<unsigned long long*>(device_buffer);
   return VTC_OK;
+#else
+  (void)device_buffer;
+  return fail(VTC_ERR_ARG, "vtc_debug_iter_trace: this library was built without -DVTC_TRACE (tools/ab_build.sh)");
+#endif
 }
 int vtc_get_fused_iteration(int64_t S, int64_t D, int precision) {
   return valid_precision(precision) && fused_iter_ok(S, D, precision) ? 1 : 0;
