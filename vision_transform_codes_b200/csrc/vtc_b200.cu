@@ -1401,7 +1401,7 @@ int chain_finish(const FistaCommon& cm, FistaChain& ch, int k_done) {
     // the last iterate sits quad-blocked in the buffer of its parity: one pass back to the caller's row-major codes
     DeviceInfo info;
     TRY(device_info(&info));
-    unblock_quad_kernel<<<grid_for(B * S, 256, info.sm_count), 256, 0, ch.st>>>(
+    unblock_quad_kernel<<<grid_for(ch.w.q_row_blocks * ((S + 15) / 16) * 512, 256, info.sm_count), 256, 0, ch.st>>>(
         (k_done & 1) ? ch.w.Q1 : ch.w.Q2, B, S, ch.w.q_row_blocks, ch.codes_out, ch.ld_codes);
     COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
