@@ -81,17 +81,24 @@ class ClockSampler:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
     self.proc.terminate()
     self.thread.join(timeout=2)
-    sm, smax, reasons = [], None, set()
+    sm, power, smax, reasons = [], [], None, set()
     for r in self.rows:
       try:
         sm.append(float(r[0]))
         smax = float(r[1])
       except (ValueError, IndexError):
         continue
+      try:
+        power.append(float(r[2]))
+      except (ValueError, IndexError):
+        power.append(0.0)
       for name, cell in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
         if cell.lower().startswith('active'):
           reasons.add(name)
-    busy = [v for v in sm if smax and v > 0.3 * smax] or sm
+    # "under load" = the samples drawing at least 60 % of the highest power seen: an idle GPU of this pool sits at its
+    # maximum clock, and a short timed region under torchrun leaves many idle samples around it
+    top = max(power) if power else 0.0
+    busy = [v for v, w in zip(sm, power) if top > 0 and w >= 0.6 * top] or sm
     return {'sm_mhz': statistics.median(busy) if busy else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons),
             'samples': len(sm)}
 
