@@ -188,3 +188,22 @@ def test_small_batch_kernel_equals_the_tiled_schedule():
   finally:
     lib.vtc_set_small_batch_kernel(1)
     pkg.config.precision = saved
+
+
+@pytest.mark.gpu
+def test_workspace_cache_grows_and_gives_back():
+  """The scratch cache grows to the largest request of a (device, stream, tag), is reused for smaller ones, and a
+  buffer far larger than the request is replaced instead of staying pinned (_lib.workspace)."""
+  from vision_transform_codes_b200 import _lib
+  dev = torch.device('cuda:0')
+  _lib.release_workspaces()
+  floor = _lib.WORKSPACE_SHRINK_FLOOR
+  a = _lib.workspace(1 << 20, dev, 'test_ws')
+  assert a.numel() == 1 << 20
+  b = _lib.workspace(2 * floor, dev, 'test_ws')          # grows
+  assert b.numel() == 2 * floor
+  assert _lib.workspace(floor, dev, 'test_ws') is b      # within the factor: reused
+  c = _lib.workspace(1 << 20, dev, 'test_ws')            # far smaller than the cached buffer: given back
+  assert c.numel() == 1 << 20 and c is not b
+  assert _lib.workspace(1 << 20, dev, 'other_tag') is not c
+  _lib.release_workspaces()

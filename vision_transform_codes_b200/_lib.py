@@ -126,12 +126,20 @@ def row_major(t):
 _workspaces = {}
 
 
+WORKSPACE_SHRINK_FACTOR = 4          # a cached buffer this many times the request (and over the floor) is given back
+WORKSPACE_SHRINK_FLOOR = 256 << 20
+
+
 def workspace(nbytes, device, tag):
-  """Grow-only scratch buffer per (device, current stream, tag); the library never allocates device memory itself.
+  """Scratch buffer per (device, current stream, tag); the library never allocates device memory itself.
   Keyed by stream so that calls enqueued on different streams never share scratch memory (calls on one stream are
-  ordered, so one buffer per stream is enough)."""
+  ordered, so one buffer per stream is enough). The buffer grows to the largest request and is reused; one large call
+  does not pin its gigabytes for ever, though: a buffer several times larger than what is asked for goes back to
+  torch's allocator (where other tensors can use it) and a fitting one takes its place."""
   key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
   buf = _workspaces.get(key)
+  if buf is not None and buf.numel() > WORKSPACE_SHRINK_FLOOR and buf.numel() > WORKSPACE_SHRINK_FACTOR * nbytes:
+    buf = None
   if buf is None or buf.numel() < nbytes:
     _workspaces.pop(key, None)
     buf = None

@@ -5,7 +5,7 @@ Drop-in for the reference module of the same dotted name
 (vision_transform_codes/analysis_transforms/fully_connected/ista_fista.py:14-148): same signature, same return
 value, same exceptions. The arithmetic runs in ``vtc_fista_fc`` (include/vtc_b200.h), which picks the contraction
 with fewer flops: for s > 2 n the reference's own synthesis form ``a <- prox(y - eta ((y Phi - x) Phi^T))`` -- all
-iterations in ONE persistent launch of the panel-resident tcgen05 kernel when n <= 256 (csrc/fista_iter_kernel.cuh),
+iterations in ONE persistent launch of the panel-resident tcgen05 kernel when n <= 256 (csrc/fista_iter2_kernel.cuh),
 two launches per iteration otherwise -- and for s <= 2 n the Gram form ``a <- prox(y - eta (y G - b))`` with
 ``G = Phi Phi^T`` and ``b = x Phi^T`` precomputed by tcgen05 GEMMs. In every schedule the gradient step, the threshold
 and the FISTA momentum are the epilogue of the contraction (DESIGN.md sections 2 and 4).
