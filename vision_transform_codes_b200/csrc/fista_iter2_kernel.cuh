@@ -63,16 +63,8 @@ struct Iter2Cfg {
   static constexpr int A_TILE = BLOCK_M * SPAN;           // one part of this CTA's 128 rows of r_op
   static constexpr int B_TILE = (IT_BN / 2) * SPAN;       // one part of this CTA's 64 atoms of the Phi tile
   static constexpr int G_STAGE = P * (A_TILE + B_TILE);
-  // atoms per y stage = K extent of one group of R MMAs: 32 (SWIZZLE_64B rows, two sub-tiles per chunk) or 16
-  // (SWIZZLE_32B rows, one sub-tile per chunk: half the bytes in the y and Phi^T rings -- the shared memory goes to the
-  // G operand ring, see G_STAGES)
-#ifndef VTC_IT2_CHUNK
-#define VTC_IT2_CHUNK 32
-#endif
-  static constexpr int CHUNK = VTC_IT2_CHUNK;
-  static_assert(CHUNK == 32 || CHUNK == 16, "y chunk width");
-  static constexpr int SUBS_PER_CHUNK = CHUNK / EPI_COLS;
-  static constexpr int Y_TILE = BLOCK_M * CHUNK * 2;      // one part of y: 128 rows x CHUNK atoms
+  static constexpr int CHUNK = 32;                        // atoms per epilogue unit = K extent of one group of R MMAs
+  static constexpr int Y_TILE = BLOCK_M * CHUNK * 2;      // one part of y: 128 rows x 32 atoms, SWIZZLE_64B
   static constexpr int Y_STAGE = P * Y_TILE;
   static constexpr int PT_TILE = (IT_RN / 2) * CHUNK * 2; // one part of this CTA's 128 pixel rows of Phi^T
   static constexpr int PT_STAGE = P * PT_TILE;
@@ -88,14 +80,8 @@ struct Iter2Cfg {
 #endif
   static constexpr int IN_STAGES = (NG == 4) ? (P == 1 ? 12 : 8) : (P == 1 ? 12 : VTC_IT2_IN3);
   static constexpr int G_STAGES = (NG == 4 && P == 2) ? 4 : (P == 2 ? VTC_IT2_G3 : 3);
-#ifndef VTC_IT2_Y
-#define VTC_IT2_Y 3
-#endif
-  static constexpr int Y_STAGES = (NG == 4) ? 2 : VTC_IT2_Y;
-#ifndef VTC_IT2_PT
-#define VTC_IT2_PT ((P == 2) ? 2 : 4)
-#endif
-  static constexpr int PT_STAGES = VTC_IT2_PT;
+  static constexpr int Y_STAGES = (NG == 4) ? 2 : 3;
+  static constexpr int PT_STAGES = (P == 2) ? 2 : 4;
   // panel-end sub-tiles are padded to a multiple of this, so that the running sub-tile index (math group, in/out stage)
   // and the running y chunk index stay congruent from job to job: every y stage always has the same writer groups
   static constexpr int PANEL_END_PAD = (NG == 4) ? 4 : 6;
@@ -255,7 +241,7 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
   // chunks of tile nt (whole chunks; atoms at or beyond S are zero everywhere)
   auto tile_chunks = [&](int nt) { return (min(IT_BN, p.S - nt * IT_BN) + C::CHUNK - 1) / C::CHUNK; };
   int state_subs = 0;    // 16-atom sub-tiles of one job (whole 32-atom chunks)
-  for (int nt = 0; nt < NT; ++nt) state_subs += C::SUBS_PER_CHUNK * tile_chunks(nt);
+  for (int nt = 0; nt < NT; ++nt) state_subs += 2 * tile_chunks(nt);
   // panel-end sub-tiles padded to a multiple of 6, so that the running sub-tile index (math group, in/out stage) and
   // the running y chunk index stay congruent from job to job: every y stage always has the same two writer groups
   const int nsub_r_pad = (p.nsub_r + C::PANEL_END_PAD - 1) / C::PANEL_END_PAD * C::PANEL_END_PAD;
@@ -284,7 +270,7 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
       mbar_init(bar(C::B_PT_EMPTY + s), 1);
     }
     for (int s = 0; s < C::Y_STAGES; ++s) {
-      mbar_init(bar(C::B_Y_FULL + s), 2 * C::SUBS_PER_CHUNK * 4);  // 2 CTAs x the sub-tiles of a chunk x 4 warps (leader's barrier)
+      mbar_init(bar(C::B_Y_FULL + s), 2 * 2 * 4);  // 2 CTAs x the two sub-tiles of a chunk x 4 warps (leader's barrier)
       mbar_init(bar(C::B_Y_EMPTY + s), 1);        // multicast tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -590,7 +576,7 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
       }
       int s0 = 0;   // first sub-tile of the current tile inside the job
       for (int nt = 0; nt < NT; ++nt, ++t) {
-        const int nsub = C::SUBS_PER_CHUNK * tile_chunks(nt);
+        const int nsub = 2 * tile_chunks(nt);
         const int acc = t & 1;
         mbar_wait(bar(C::B_ACCG_FULL + acc), (t >> 1) & 1);
         tc_fence_after();
@@ -612,7 +598,7 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
           const uint32_t qq = q0 + j;
           const int e = qq % C::IN_STAGES;
           const int s = s0 + j;                    // sub-tile inside the job = column block
-          const uint32_t chunk = yc + s / C::SUBS_PER_CHUNK;
+          const uint32_t chunk = yc + (s >> 1);
           const int ys = chunk % C::Y_STAGES;
           uint32_t v[16];
           trace(TR_E_SUB, j);
@@ -668,14 +654,11 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
             mbar_wait(bar(C::B_Y_EMPTY + ys), ((chunk / C::Y_STAGES) & 1) ^ 1);
             trace(TR_E_YW, j);
             const uint32_t ystage = sY + ys * C::Y_STAGE + row * (C::CHUNK * 2);
-            // 16-byte pieces of this sub-tile inside the row and the row's swizzle (32-atom chunks: 64-byte rows,
-            // SWIZZLE_64B, the sub-tile is half s & 1 of the row; 16-atom chunks: 32-byte rows, SWIZZLE_32B)
-            const uint32_t c2 = (C::CHUNK == 32) ? 2 * (s & 1) : 0;
-            const uint32_t swy = (C::CHUNK == 32) ? sw64 : sw32;
+            const uint32_t c2 = 2 * (s & 1);
             if (!(ablate_of(p) & ABL_Y_STS)) split_parts16(partv, P, [&](int part, const uint32_t (&w32)[8]) {
               const uint32_t prow = ystage + part * C::Y_TILE;
-              sts128u(prow + (((c2 + 0) ^ swy) << 4), w32[0], w32[1], w32[2], w32[3]);
-              sts128u(prow + (((c2 + 1) ^ swy) << 4), w32[4], w32[5], w32[6], w32[7]);
+              sts128u(prow + (((c2 + 0) ^ sw64) << 4), w32[0], w32[1], w32[2], w32[3]);
+              sts128u(prow + (((c2 + 1) ^ sw64) << 4), w32[4], w32[5], w32[6], w32[7]);
             });
             yfull = bar(C::B_Y_FULL + ys);
           }
@@ -691,7 +674,7 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
         s0 += nsub;
       }
       if (do_r) {
-        yc += state_subs / C::SUBS_PER_CHUNK;
+        yc += state_subs / 2;
         // ---- panel end: r_k = acc_r - x -> bf16 parts -> r_op[panel]; x staged by TMA like a state sub-tile
         mbar_wait(bar(C::B_ACCR_FULL), r_jobs & 1);
         tc_fence_after();
