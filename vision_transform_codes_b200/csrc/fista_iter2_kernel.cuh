@@ -80,8 +80,14 @@ struct Iter2Cfg {
 #endif
   static constexpr int IN_STAGES = (NG == 4) ? (P == 1 ? 12 : 8) : (P == 1 ? 12 : VTC_IT2_IN3);
   static constexpr int G_STAGES = (NG == 4 && P == 2) ? 4 : (P == 2 ? VTC_IT2_G3 : 3);
-  static constexpr int Y_STAGES = (NG == 4) ? 2 : 3;
-  static constexpr int PT_STAGES = (P == 2) ? 2 : 4;
+#ifndef VTC_IT2_Y
+#define VTC_IT2_Y 3
+#endif
+  static constexpr int Y_STAGES = (NG == 4) ? 2 : (P == 2 ? VTC_IT2_Y : 3);
+#ifndef VTC_IT2_PT
+#define VTC_IT2_PT 2
+#endif
+  static constexpr int PT_STAGES = (P == 2) ? VTC_IT2_PT : 4;
   // panel-end sub-tiles are padded to a multiple of this, so that the running sub-tile index (math group, in/out stage)
   // and the running y chunk index stay congruent from job to job: every y stage always has the same writer groups
   static constexpr int PANEL_END_PAD = (NG == 4) ? 4 : 6;
