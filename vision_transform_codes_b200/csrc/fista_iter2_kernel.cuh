@@ -87,7 +87,7 @@ struct Iter2Cfg {
 #ifndef VTC_IT2_PT
 #define VTC_IT2_PT 2
 #endif
-  static constexpr int PT_STAGES = (P == 2) ? VTC_IT2_PT : 4;
+  static constexpr int PT_STAGES = (P == 2) ? (NG == 3 ? VTC_IT2_PT : 2) : 4;
   // panel-end sub-tiles are padded to a multiple of this, so that the running sub-tile index (math group, in/out stage)
   // and the running y chunk index stay congruent from job to job: every y stage always has the same writer groups
   static constexpr int PANEL_END_PAD = (NG == 4) ? 4 : 6;
