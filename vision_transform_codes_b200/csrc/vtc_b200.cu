@@ -697,6 +697,16 @@ int launch_iter2_p(const IterCall& c, const DeviceInfo& info, cudaStream_t strea
   }
   long long max_pairs = info.sm_count / 2;
   if (c.max_pairs > 0 && c.max_pairs < max_pairs) max_pairs = c.max_pairs;
+  {
+    // measurement aid: fewer SM pairs (how the iteration time scales with the SMs used tells a per-SM bound from a
+    // chip-wide one, profiles/README.md)
+    static int limit = -1;
+    if (limit < 0) {
+      const char* e = getenv("VTC_B200_ITER_PAIRS");
+      limit = e ? atoi(e) : 0;
+    }
+    if (limit > 0 && limit < max_pairs) max_pairs = limit;
+  }
   const int pairs = static_cast<int>(p.num_panels < max_pairs ? p.num_panels : max_pairs);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
