@@ -154,13 +154,28 @@ struct IterParams2 {
 };
 
 // ---- 1-D bulk copies (no tensor map): contiguous global <-> shared, sizes and addresses multiples of 16 bytes
+// VTC_IT2_STATE_HINT (tuning builds): 1 = the state streams carry an L2 evict-first policy (they are read once per
+// iteration and never hit: 0.8 GB per iteration through a 126 MB L2 that also has to keep r_op and the dictionary)
+#ifndef VTC_IT2_STATE_HINT
+#define VTC_IT2_STATE_HINT 0
+#endif
 __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+#if VTC_IT2_STATE_HINT
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar), "l"(kEvictFirst) : "memory");
+#else
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t smem_src, uint32_t bytes) {
+#if VTC_IT2_STATE_HINT
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               ::"l"(gdst), "r"(smem_src), "r"(bytes), "l"(kEvictFirst) : "memory");
+#else
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
                : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
@@ -168,7 +183,12 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t byte
 // state written by another SM earlier in this launch: L2 is the point of coherence, never a (possibly stale) L1 line
 __device__ __forceinline__ float4 ldg_cg_v4(const float* p) {
   float4 v;
+#if VTC_IT2_STATE_HINT
+  asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(kEvictFirst));
+#else
   asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#endif
   return v;
 }
 __device__ __forceinline__ float4 ldg_nc_v4(const float* p) {
