@@ -159,6 +159,12 @@ struct IterParams2 {
 #ifndef VTC_IT2_STATE_HINT
 #define VTC_IT2_STATE_HINT 0
 #endif
+// VTC_IT2_R_HINT (tuning builds): 1 = r_op (67 MB at configs[1], rewritten in place every iteration and read eight
+// times per job) is stored and loaded with an L2 evict-last policy, so that it can stay in the 126 MB L2 instead of
+// making the round trip through HBM
+#ifndef VTC_IT2_R_HINT
+#define VTC_IT2_R_HINT 0
+#endif
 __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
 #if VTC_IT2_STATE_HINT
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
@@ -354,7 +360,8 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
             trace(TR_G_LOAD, nt * p.kb_g + kb);
 #pragma unroll
             for (int q = 0; q < P; ++q)
-              if (load_a) tma_load_3d_pair(dst + q * C::A_TILE, &p.tmR, full, 0, m0, q * p.kb_g + kb, kEvictNormal);
+              if (load_a) tma_load_3d_pair(dst + q * C::A_TILE, &p.tmR, full, 0, m0, q * p.kb_g + kb,
+                                           VTC_IT2_R_HINT ? kEvictLast : kEvictNormal);
 #pragma unroll
             for (int q = 0; q < P; ++q)
               if (load_b) tma_load_2d_pair(dst + P * C::A_TILE + q * C::B_TILE, &p.tmPhi, full,
@@ -524,8 +531,13 @@ __global__ void __launch_bounds__((Iter2Cfg<P, NG>::THREADS), 1) vtc_fista_iter2
             const int col = (j - state_subs) * EPI_COLS;
 #pragma unroll
             for (int part = 0; part < P; ++part)
+#if VTC_IT2_R_HINT
+              tma_store_3d_hint(&p.tmROut, src + part * EPI_PART_BYTES, col % p.r_block_w, job.m0,
+                                part * p.kb_g + col / p.r_block_w, kEvictLast);
+#else
               tma_store_3d(&p.tmROut, src + part * EPI_PART_BYTES, col % p.r_block_w, job.m0,
                            part * p.kb_g + col / p.r_block_w);
+#endif
           }
           bulk_commit();
           if (q >= C::STORES_IN_FLIGHT) {
