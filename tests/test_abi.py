@@ -89,3 +89,17 @@ def test_dropin_names_resolve_through_install():
     for name in list(sys.modules):
       if name.split('.')[0] in ('analysis_transforms', 'dict_update_rules'):
         del sys.modules[name]
+
+
+def test_shipped_library_has_no_trace_points():
+  """The timeline hook of tools/iter_trace.py exists only in a -DVTC_TRACE build: the shipped kernels carry no trace
+  points, and asking the shipped library for a trace fails loudly instead of silently recording nothing."""
+  from vision_transform_codes_b200 import _lib
+  if not os.path.exists(_lib.LIB_PATH):
+    pytest.skip('library not built yet: run __graft_entry__.build()')
+  lib = _lib.load()
+  rc = lib.vtc_debug_iter_trace(None)
+  assert rc == _lib.VTC_ERR_ARG
+  assert b'VTC_TRACE' in lib.vtc_last_error()
+  with pytest.raises(ValueError):
+    _lib.check(rc)
