@@ -207,3 +207,48 @@ def test_workspace_cache_grows_and_gives_back():
   assert c.numel() == 1 << 20 and c is not b
   assert _lib.workspace(1 << 20, dev, 'other_tag') is not c
   _lib.release_workspaces()
+
+
+@pytest.mark.gpu
+def test_c_abi_writes_only_the_codes_it_owns():
+  """vtc_fista_fc with a PITCHED output inside a larger buffer: every float outside the (B, S) block -- the pitch
+  padding of every row and guard zones before and after -- keeps its canary, the images, the dictionary and the warm
+  start are not written (include/vtc_b200.h), and the block equals the dense call. All schedules: the panel-resident
+  kernel (S > 2 D), the Gram form, the small-batch kernel, ragged shapes."""
+  import vision_transform_codes_b200 as pkg
+  from vision_transform_codes_b200 import _lib
+  from vision_transform_codes_b200.analysis_transforms.fully_connected import ista_fista
+  lib = _lib.load()
+  dev = torch.device('cuda:0')
+  prec = pkg.config.precision_code()
+  canary = 12345.0
+  for (b, s, d, warm) in ((600, 1024, 256, False), (257, 1000, 250, True), (250, 256, 256, False), (33, 200, 128, True),
+                          (1500, 520, 64, False)):
+    x = oracle.synthetic_patches(b, d, seed=b).to(dev)
+    phi = oracle.synthetic_dictionary(s, d).to(dev)
+    init = (0.01 * torch.randn(b, s, generator=torch.Generator().manual_seed(1))).to(dev) if warm else None
+    want = ista_fista.run(x, phi, 0.1, 12, initial_codes=init)
+    ld = s + 12                      # multiple of 4 floats: rows stay 16-byte aligned
+    guard = 4096
+    buf = torch.full((guard + b * ld + guard,), canary, dtype=torch.float32, device=dev)
+    out = buf[guard:guard + b * ld].view(b, ld)
+    x0, phi0 = x.clone(), phi.clone()
+    init_p = None
+    if warm:
+      init_buf = torch.full((b, ld), canary, dtype=torch.float32, device=dev)
+      init_buf[:, :s] = init
+      init_p, init0 = init_buf, init_buf.clone()
+    with torch.cuda.device(dev):
+      nbytes = lib.vtc_fista_workspace_bytes(b, s, d, prec)
+      ws = _lib.workspace(nbytes, dev, 'fista_guard_test')
+      iters = ctypes.c_int(0)
+      _lib.check(lib.vtc_fista_fc(_lib.ptr(x), d, _lib.ptr(phi), _lib.ptr(init_p), _lib.ptr(out), ld, b, s, d, 0.1, 12, 1,
+                                  0, 0, 1, -1.0, prec, _lib.ptr(ws), ws.numel(), ctypes.byref(iters), None,
+                                  _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, :s], want), (b, s, d, warm)
+    assert bool((out[:, s:] == canary).all()), 'pitch padding written'
+    assert bool((buf[:guard] == canary).all()) and bool((buf[guard + b * ld:] == canary).all()), 'guard zone written'
+    assert torch.equal(x, x0) and torch.equal(phi, phi0)
+    if warm:
+      assert torch.equal(init_p, init0)
