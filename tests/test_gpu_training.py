@@ -112,3 +112,45 @@ def test_two_gpu_train_step_equals_one_gpu(tmp_path):
                         os.path.join(ROOT, 'tools', 'dp_equivalence.py')], capture_output=True, text=True, timeout=600)
   assert out.returncode == 0, out.stdout + out.stderr
   assert 'DP_EQUIVALENCE_OK' in out.stdout
+
+
+@pytest.mark.gpu
+def test_dictionary_gradient_writes_only_its_output():
+  """vtc_sc_dict_grad writing into the middle of a larger buffer: the guard zones keep their canaries, the pitched
+  images and codes are not written, and the result equals the dense call (ragged shapes, both update precisions)."""
+  import ctypes
+  import vision_transform_codes_b200 as pkg
+  from vision_transform_codes_b200 import _lib
+  from vision_transform_codes_b200.dict_update_rules.fully_connected import _common
+  lib = _lib.load()
+  dev = torch.device('cuda:0')
+  canary = 54321.0
+  saved = pkg.config.update_precision
+  try:
+    for precision in ('bf16x3', 'bf16x6'):
+      pkg.config.update_precision = precision
+      prec = pkg.config.precision_code('update_precision')
+      for (b, s, d) in ((1000, 300, 100), (4096, 1024, 256), (77, 64, 20)):
+        x = oracle.synthetic_patches(b, d, seed=3).to(dev)
+        phi = oracle.synthetic_dictionary(s, d).to(dev)
+        codes = torch.relu(torch.randn(b, s, generator=torch.Generator().manual_seed(2)) - 1.0).to(dev)
+        want = _common.dictionary_gradient(x, phi, codes)
+        ldx, ldc, guard = d + 4, s + 8, 2048
+        xb = torch.full((b, ldx), canary, device=dev)
+        xb[:, :d] = x
+        cb = torch.full((b, ldc), canary, device=dev)
+        cb[:, :s] = codes
+        x0, c0 = xb.clone(), cb.clone()
+        buf = torch.full((guard + s * d + guard,), canary, device=dev)
+        out = buf[guard:guard + s * d].view(s, d)
+        with torch.cuda.device(dev):
+          nbytes = lib.vtc_dict_grad_workspace_bytes(b, s, d, prec)
+          ws = _lib.workspace(nbytes, dev, 'dict_grad_guard_test')
+          _lib.check(lib.vtc_sc_dict_grad(_lib.ptr(xb), ldx, _lib.ptr(phi), _lib.ptr(cb), ldc, _lib.ptr(out), b, s, d, prec,
+                                          _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+        torch.cuda.synchronize()
+        assert torch.equal(out, want), (precision, b, s, d)
+        assert bool((buf[:guard] == canary).all()) and bool((buf[guard + s * d:] == canary).all()), 'guard zone written'
+        assert torch.equal(xb, x0) and torch.equal(cb, c0)
+  finally:
+    pkg.config.update_precision = saved
