@@ -349,3 +349,47 @@ def test_conv_tile_variants_agree(env):
   out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, **env))
   assert out.returncode == 0 and 'VARIANT_OK' in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_conv_c_abi_writes_only_the_codes_it_owns():
+  """vtc_fista_conv writing its codes into the middle of a larger buffer: the guard zones keep their canaries, the
+  padded images, the dictionary and the warm start are not written, and the codes equal the front end's."""
+  import ctypes
+  import vision_transform_codes_b200 as pkg
+  from vision_transform_codes_b200 import _lib
+  from vision_transform_codes_b200.analysis_transforms.convolutional import ista_fista
+  lib = _lib.load()
+  dev = torch.device('cuda:0')
+  prec = pkg.config.precision_code()
+  canary = 777.0
+  for (b, c, h, w, s, k, st, warm) in ((3, 1, 40, 56, 24, (8, 8), (4, 4), False), (2, 2, 32, 32, 16, (16, 16), (8, 8), True),
+                                       (5, 1, 64, 48, 64, (16, 16), (8, 8), False)):
+    x, pad = oracle.synthetic_padded_images(b, c, h, w, k, st, seed=b)
+    x = x.to(dev)
+    phi = oracle.synthetic_conv_dictionary(s, c, k[0], k[1]).to(dev)
+    geo = ista_fista.geometry(x, phi, st, pad)
+    B, C, H, W, S, KH, KW, SY, SX, pt, pb, pl, pr, SH, SW = geo
+    init = None
+    if warm:
+      init = (0.01 * torch.randn(B, S, SH, SW, generator=torch.Generator().manual_seed(4))).to(dev)
+    want = ista_fista.run(x, phi, st, pad, 0.05, 10, initial_codes=init)
+    n, guard = B * S * SH * SW, 4096
+    buf = torch.full((guard + n + guard,), canary, device=dev)
+    out = buf[guard:guard + n].view(B, S, SH, SW)
+    x0, phi0 = x.clone(), phi.clone()
+    init0 = init.clone() if warm else None
+    with torch.cuda.device(dev):
+      nbytes = lib.vtc_fista_conv_workspace_bytes(B, C, H, W, S, KH, KW, SY, SX, prec)
+      assert nbytes > 0
+      ws = _lib.workspace(nbytes, dev, 'fista_conv_guard_test')
+      iters = ctypes.c_int(0)
+      _lib.check(lib.vtc_fista_conv(_lib.ptr(x), _lib.ptr(phi), _lib.ptr(init), _lib.ptr(out), B, C, H, W, S, KH, KW, SY, SX,
+                                    pt, pb, pl, pr, 0.05, 10, 1, 0, 0, -1.0, prec, _lib.ptr(ws), ws.numel(),
+                                    ctypes.byref(iters), None, _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert torch.equal(out, want), (b, c, h, w, s, k, st)
+    assert bool((buf[:guard] == canary).all()) and bool((buf[guard + n:] == canary).all()), 'guard zone written'
+    assert torch.equal(x, x0) and torch.equal(phi, phi0)
+    if warm:
+      assert torch.equal(init, init0)
